@@ -1,0 +1,93 @@
+// jb_internal.cuh -- structures shared by the translation units of libjasper_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/jasper_b200.h"
+#include "jb_header.hpp"
+#include "jb_kmer.cuh"
+
+namespace jb {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+#define JB_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return jb::fail(JB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+void note_timing(const char* what, double ms);
+void note_counter(const char* what, int64_t v);
+void add_counter(const char* what, int64_t v);
+
+// ---- resident table ---------------------------------------------------------------------------
+// 16-byte slot {key.lo, key.hi : 32 | count : 32}; count == 0 <=> empty.  Two slots = one
+// 32-byte sector, the unit a probe loads (32 algorithmic bytes per lookup).
+struct __align__(16) Slot {
+  uint64_t lo;
+  uint32_t hi;
+  uint32_t count;
+};
+
+struct TableView {
+  const Slot* slots;
+  const uint64_t* lut;   // key_bytes * 256 entries
+  TableGeom g;
+  Key mask;
+};
+
+// Probe: starting at the sector of the home slot, scan slots until the key or an empty slot.
+// 256-bit loads (LDG.E.256) fetch exactly one 32-byte sector per step.
+__device__ __forceinline__ uint32_t table_find(const TableView& t, const Key& key, uint64_t home, int* steps = nullptr) {
+  const ulonglong4* sec = reinterpret_cast<const ulonglong4*>(t.slots) + (home >> 1);
+  int n = 0;
+  while (true) {
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(sec));
+    ++n;
+    uint32_t c0 = (uint32_t)(w1 >> 32), c1 = (uint32_t)(w3 >> 32);
+    uint32_t r;
+    bool done = true;
+    if (c0 == 0) r = 0;
+    else if (w0 == key.lo && (uint32_t)w1 == (uint32_t)key.hi) r = c0;
+    else if (c1 == 0) r = 0;
+    else if (w2 == key.lo && (uint32_t)w3 == (uint32_t)key.hi) r = c1;
+    else { done = false; r = 0; }
+    if (done) { if (steps) *steps = n; return r; }
+    ++sec;
+  }
+}
+
+__device__ __forceinline__ uint32_t table_count(const TableView& t, const Key& canonical) {
+  uint64_t pos = hash_lut(t.lut, t.g.key_bytes, canonical);
+  return table_find(t, canonical, home_slot(t.g, pos, canonical));
+}
+
+}  // namespace jb
+
+struct jb_db {
+  jb::JfHeader hdr;
+  int device = 0;
+  jb::Slot* slots = nullptr;
+  uint64_t n_slots = 0;        // cap + tail + guard
+  uint64_t cap = 0;
+  uint64_t* lut = nullptr;     // device
+  jb::TableGeom geom{};
+  uint64_t n_records = 0;
+  uint64_t max_disp = 0;
+  double load_seconds = 0, build_ms = 0;
+  cudaStream_t stream = nullptr;
+  jb::TableView view() const {
+    jb::TableView v;
+    v.slots = slots; v.lut = lut; v.g = geom; v.mask = jb::key_mask(hdr.k());
+    return v;
+  }
+};

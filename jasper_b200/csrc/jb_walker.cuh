@@ -1,0 +1,814 @@
+// jb_walker.cuh -- K4: the per-contig walker.  One WARP owns one contig and runs the reference's
+// sequential state machine (src/jasper.py:50-104 scan, :150-223 handle_bad_kmers, :226-332
+// fixing_sid, :340-583 the fix_* family, :585-599 check_sequence) with warp-uniform control flow;
+// the 32 lanes cooperate on everything that is data-parallel:
+//   * hopping over good sequence: 32 strided event bits per step (bitmask from k_scan),
+//   * weak-run walks: 32 consecutive windows looked up per wave (speculative window cache),
+//   * candidate scoring: all sampled k-mers of a trial string probed in one wave,
+//   * de-Bruijn bridging: 8 paths x 4 extensions probed per wave,
+//   * splicing edits into the output buffer.
+// The mutating sequence is  out[0:olen] ++ in[ipos:]  (materialised prefix + untouched suffix);
+// nothing is ever memmoved beyond the few bases between an edit and the materialised frontier.
+//
+// The same source compiles for the host (one "lane loop" instead of a warp): that build exists
+// only for differential debugging in tests/ (tests/hostsim) and is never linked into the product.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/jasper_b200.h"
+#include "jb_kmer.cuh"
+
+#if defined(__CUDACC__)
+#define JB_W __device__
+#else
+#define JB_W
+#endif
+#if defined(__CUDA_ARCH__)
+#define JB_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
+#define JB_SYNC() __syncwarp()
+#else
+#define JB_LANES(l) for (int l = 0; l < 32; ++l)
+#define JB_SYNC() ((void)0)
+#endif
+
+namespace jb {
+
+constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check string fits (<= 3k + 8)
+constexpr int kPathCap = 4 * JB_MAX_PATHS + 64;  // a round can at most quadruple the path list
+constexpr uint32_t kDeadNode = 0xFFFFFFFFu;
+
+enum RowKind : uint32_t { kRowPlain = 0, kRowBridge = 1 };
+
+struct DevRow {              // one fix event as logged by the walker
+  int64_t coord;
+  uint32_t unit;
+  uint32_t seqno;            // emission order inside the unit
+  uint32_t kind;
+  uint16_t fb_len, orig_len;
+  uint64_t aux_off;          // kRowBridge: patch then original bytes in the aux arena
+  uint32_t aux_patch_len, aux_orig_len;
+  char fb[48];
+  char orig[48];
+};
+
+struct RowSink {
+  DevRow* rows;
+  unsigned long long cap;
+  unsigned long long* used;
+  uint8_t* aux;
+  unsigned long long aux_cap;
+  unsigned long long* aux_used;
+};
+
+struct BridgeScratch {       // global memory, one per resident walker
+  Key km[2][kPathCap];
+  uint32_t node[2][kPathCap];
+  uint32_t* trie;            // (parent << 2) | base
+  uint32_t trie_cap;
+  uint8_t* patch;            // room for the recovered patch
+  uint32_t patch_cap;
+};
+
+struct WarpScratch {         // shared memory (device) / plain struct (host)
+  uint8_t t[kStrCap];        // to_be_fixed
+  uint8_t b[kStrCap];        // trial
+  uint8_t c[kStrCap];        // check string / window staging
+  uint32_t wc[32];           // window-count cache
+  int64_t px[32];            // point queries
+  uint32_t pr[32];
+  uint32_t flag[32];
+};
+
+struct UnitIO {
+  const uint8_t* in;
+  int64_t in_len;
+  uint8_t* out;
+  int64_t out_cap;
+  const uint32_t* ev;        // event words of this unit (bit p of the pass-start sequence); may be null
+  uint32_t unit;
+  // results
+  int64_t fin_olen, fin_ipos; // new sequence = out[0:fin_olen] ++ in[fin_ipos:]
+  int64_t out_len;
+  int64_t wrong;
+  int32_t status;
+  uint32_t n_rows;
+  unsigned long long lookups;
+  unsigned long long events;
+};
+
+template <class DB>
+struct Walker {
+  const DB& db;
+  const int k;
+  const int step;
+  const int64_t solid;
+  const bool fix;
+  const Key mask;
+  UnitIO& u;
+  WarpScratch& s;
+  BridgeScratch* bs;
+  RowSink sink;
+
+  int64_t i = 0, olen = 0, ipos = 0, L = 0, clean_from = 0;
+  int64_t wrong = 0;
+  int status = 0;
+  bool brk = false;
+  int64_t wc_base = 0;
+  int wc_n = 0;
+  bool have_empty = false;
+  uint32_t empty_count = 0;
+  uint32_t seqno = 0;
+  unsigned long long lookups = 0, events = 0;
+
+  JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
+               BridgeScratch* bs_, RowSink sink_)
+      : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), bs(bs_), sink(sink_) {}
+
+  // ---------------------------------------------------------------------------- sequence access
+  JB_W uint8_t get(int64_t x) const { return x < olen ? u.out[x] : u.in[ipos + (x - olen)]; }
+
+  // dst[0:n] = seq[a:b] clamped to [0, L); returns n
+  JB_W int load(uint8_t* dst, int64_t a, int64_t b) {
+    if (a < 0) a = 0;
+    if (b > L) b = L;
+    int n = b > a ? (int)(b - a) : 0;
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < n; q += 32) dst[q] = get(a + q); if (l == 0) dst[n] = 0; }
+    JB_SYNC();
+    return n;
+  }
+
+  JB_W uint32_t count_in(const uint8_t* buf, int len, int m) const {
+    Key key = key_from_chars(buf + m, (int64_t)len - m, k, mask);
+    return db.count(key_canonical(key, k));
+  }
+
+  // ---------------------------------------------------------------------------- lookups
+  JB_W uint32_t C_empty() {
+    if (!have_empty) { Key z = {0, 0}; empty_count = db.count(z); have_empty = true; ++lookups; }
+    return empty_count;
+  }
+
+  // C(seq[x:x+k]); a miss refills the cache with 32 consecutive windows in direction `dir`.
+  JB_W uint32_t Cw(int64_t x, int dir) {
+    if (x < 0) return C_empty();                     // the slices with negative starts are empty (L >= k)
+    if (x >= wc_base && x < wc_base + wc_n) return s.wc[x - wc_base];
+    int64_t base = dir > 0 ? x : (x - 31 > 0 ? x - 31 : 0);
+    int len = load(s.c, base, base + 32 + k - 1);
+    JB_LANES(l) { s.wc[l] = count_in(s.c, len, l < len ? l : len); }
+    JB_SYNC();
+    lookups += 32;
+    wc_base = base; wc_n = 32;
+    return s.wc[x - base];
+  }
+
+  // n <= 32 windows at arbitrary starts s.px[0..n) (non-negative, within a span that fits s.c)
+  JB_W void Cpts(int n) {
+    int64_t lo = s.px[0], hi = s.px[0];
+    for (int q = 1; q < n; ++q) { lo = s.px[q] < lo ? s.px[q] : lo; hi = s.px[q] > hi ? s.px[q] : hi; }
+    if (hi + k - lo > kStrCap - 8) {                 // cannot happen for the call sites below; stay exact anyway
+      for (int q = 0; q < n; ++q) s.pr[q] = Cw(s.px[q], +1);
+      return;
+    }
+    int len = load(s.c, lo, hi + k);
+    JB_LANES(l) { if (l < n) { int m = (int)(s.px[l] - lo); s.pr[l] = count_in(s.c, len, m < len ? m : len); } }
+    JB_SYNC();
+    lookups += n;
+  }
+
+  // src/jasper.py:585-599 on a string in scratch memory
+  JB_W bool check_sequence(const uint8_t* buf, int len, int64_t thr) {
+    // sample starts: 0, max(0,len-k), then step, 2*step, ... < len-k
+    int n_mid = 0;
+    for (int m = step; m < len - k; m += step) ++n_mid;
+    int total = 2 + n_mid;
+    bool ok = true;
+    for (int w0 = 0; w0 < total && ok; w0 += 32) {
+      JB_SYNC();
+      JB_LANES(l) {
+        int q = w0 + l;
+        uint32_t f = 0;
+        if (q < total) {
+          int m = q == 0 ? 0 : (q == 1 ? (len - k > 0 ? len - k : 0) : step * (q - 1));
+          f = (int64_t)count_in(buf, len, m) < thr ? 1u : 0u;
+        }
+        s.flag[l] = f;
+      }
+      JB_SYNC();
+      int cnt = total - w0 < 32 ? total - w0 : 32;
+      lookups += cnt;
+      for (int q = 0; q < cnt; ++q) ok = ok && !s.flag[q];
+    }
+    return ok;
+  }
+
+  // number of windows of buf (all of them) below thr
+  JB_W int count_weak(const uint8_t* buf, int len, int64_t thr) {
+    int total = len - k + 1, bad = 0;
+    for (int w0 = 0; w0 < total; w0 += 32) {
+      JB_SYNC();
+      JB_LANES(l) {
+        int q = w0 + l;
+        s.flag[l] = (q < total && (int64_t)count_in(buf, len, q) < thr) ? 1u : 0u;
+      }
+      JB_SYNC();
+      int cnt = total - w0 < 32 ? total - w0 : 32;
+      lookups += cnt;
+      for (int q = 0; q < cnt; ++q) bad += (int)s.flag[q];
+    }
+    return bad;
+  }
+
+  // ---------------------------------------------------------------------------- edits
+  JB_W bool ensure_out(int64_t upto) {               // materialise seq[olen:upto) into out
+    if (upto <= olen) return true;
+    if (upto > u.out_cap) { status = JB_E_SCRATCH; return false; }
+    int64_t n = upto - olen;
+    JB_SYNC();
+    JB_LANES(l) { for (int64_t q = l; q < n; q += 32) u.out[olen + q] = u.in[ipos + q]; }
+    JB_SYNC();
+    ipos += n; olen = upto;
+    return true;
+  }
+
+  // seq = seq[:a] + repl + seq[e:]
+  JB_W bool apply_edit(int64_t a, int64_t e, const uint8_t* repl, int64_t rlen) {
+    if (!ensure_out(e)) return false;
+    const int64_t delta = rlen - (e - a);
+    const int64_t tail = olen - e;
+    if (olen + delta > u.out_cap) { status = JB_E_SCRATCH; return false; }
+    if (delta != 0 && tail > 0) {
+      // shift out[e:olen) by delta, 32 bytes per step, in the safe direction
+      if (delta > 0) {
+        for (int64_t hi = tail; hi > 0; hi -= 32) {
+          int64_t lo = hi - 32 > 0 ? hi - 32 : 0;
+          uint8_t v = 0;
+          JB_SYNC();
+#if defined(__CUDA_ARCH__)
+          { int l = threadIdx.x & 31; if (lo + l < hi) v = u.out[e + lo + l]; __syncwarp(); if (lo + l < hi) u.out[e + lo + l + delta] = v; }
+#else
+          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = u.out[e + lo + l];
+            for (int l = 0; l < 32; ++l) if (lo + l < hi) u.out[e + lo + l + delta] = tmp[l]; (void)v; }
+#endif
+        }
+      } else {
+        for (int64_t lo = 0; lo < tail; lo += 32) {
+          int64_t hi = lo + 32 < tail ? lo + 32 : tail;
+          uint8_t v = 0;
+          JB_SYNC();
+#if defined(__CUDA_ARCH__)
+          { int l = threadIdx.x & 31; if (lo + l < hi) v = u.out[e + lo + l]; __syncwarp(); if (lo + l < hi) u.out[e + lo + l + delta] = v; }
+#else
+          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = u.out[e + lo + l];
+            for (int l = 0; l < 32; ++l) if (lo + l < hi) u.out[e + lo + l + delta] = tmp[l]; (void)v; }
+#endif
+        }
+      }
+    }
+    JB_SYNC();
+    JB_LANES(l) { for (int64_t q = l; q < rlen; q += 32) u.out[a + q] = repl[q]; }
+    JB_SYNC();
+    olen += delta; L += delta;
+    int64_t shifted = clean_from + delta;
+    clean_from = a + rlen > shifted ? a + rlen : shifted;
+    wc_n = 0;
+    return true;
+  }
+
+  JB_W void emit_row(int64_t coord, const uint8_t* fb, int fb_len, uint8_t tag, const uint8_t* orig, int orig_len) {
+    JB_SYNC();
+    unsigned long long slot = 0;
+#if defined(__CUDA_ARCH__)
+    if ((threadIdx.x & 31) == 0) slot = atomicAdd(sink.used, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+#else
+    slot = (*sink.used)++;
+#endif
+    if (slot >= sink.cap) { status = JB_E_SCRATCH; return; }
+    DevRow& r = sink.rows[slot];
+    JB_LANES(l) {
+      if (l == 0) {
+        r.coord = coord; r.unit = u.unit; r.seqno = seqno; r.kind = kRowPlain;
+        r.fb_len = (uint16_t)fb_len; r.orig_len = (uint16_t)(orig_len + 1);
+        r.aux_off = 0; r.aux_patch_len = 0; r.aux_orig_len = 0;
+        r.orig[0] = (char)tag;
+      }
+      for (int q = l; q < fb_len; q += 32) r.fb[q] = (char)fb[q];
+      for (int q = l; q < orig_len; q += 32) r.orig[1 + q] = (char)orig[q];
+    }
+    JB_SYNC();
+    ++seqno;
+  }
+
+  // ---------------------------------------------------------------------------- fix_* family
+  // All take the to_be_fixed string in s.t (length n) that starts at sequence position s0.
+
+  JB_W void copy_t_to_b(int n) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < n; q += 32) s.b[q] = s.t[q]; } JB_SYNC(); }
+  JB_W void set_b(int at, uint8_t v) { JB_SYNC(); JB_LANES(l) { if (l == 0) s.b[at] = v; } JB_SYNC(); }
+  // b = t[:at] + ins(len m, same char v) + t[at:]
+  JB_W void b_from_t_insert(int n, int at, uint8_t v, int m) {
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < n + m; q += 32) s.b[q] = q < at ? s.t[q] : (q < at + m ? v : s.t[q - m]); }
+    JB_SYNC();
+  }
+  // b = t[:at] + t[at+m:]
+  JB_W void b_from_t_delete(int n, int at, int m) {
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < n - m; q += 32) s.b[q] = q < at ? s.t[q] : s.t[q + m]; }
+    JB_SYNC();
+  }
+
+  // src/jasper.py:392-406 then :409-419
+  JB_W bool fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
+    const uint8_t bad = s.t[k - 1];
+    const uint8_t before = get(ga - 1);
+    const char order[4] = {'A', 'C', 'T', 'G'};
+    for (int o = 0; o < 4; ++o) {
+      uint8_t bb = (uint8_t)order[o];
+      if (bb == bad) continue;
+      copy_t_to_b(n);
+      set_b(k - 1, bb);
+      if (check_sequence(s.b, n, thr)) {
+        if (!apply_edit(s0 + k - 1, s0 + k, &bb, 1)) return true;
+        emit_row(ga - 1, &bb, 1, 's', &before, 1);
+        return true;
+      }
+    }
+    b_from_t_delete(n, k - 1, 1);
+    if (check_sequence(s.b, n - 1, thr)) {
+      if (!apply_edit(s0 + k - 1, s0 + k, nullptr, 0)) return true;
+      uint8_t dash = '-';
+      emit_row(ga - 1, &dash, 1, 'i', &before, 1);
+      return true;
+    }
+    return false;
+  }
+
+  // src/jasper.py:422-431
+  JB_W bool fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
+    const char order[4] = {'A', 'T', 'C', 'G'};
+    for (int o = 0; o < 4; ++o) {
+      uint8_t bb = (uint8_t)order[o];
+      b_from_t_insert(n, k - 1, bb, 1);
+      if (check_sequence(s.b, n + 1, thr)) {
+        if (!apply_edit(s0 + k - 1, s0 + k - 1, &bb, 1)) return true;
+        uint8_t dash = '-';
+        emit_row(ga, &bb, 1, 'd', &dash, 1);
+        return true;
+      }
+    }
+    return false;
+  }
+
+  // src/jasper.py:340-388
+  JB_W bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
+    const uint8_t left_bad = s.t[n - k], right_bad = s.t[k - 1];
+    const int64_t g0 = gb - k + 1 > 0 ? gb - k + 1 : 0;
+    const int na = (2 * k - 1 - n) / 2;
+    int64_t a0, a1;
+    if (ga + k - 1 + na < L) { a0 = ga + k - 1; a1 = ga + k - 1 + na; }
+    else { a0 = (L - 1 < ga + k - 1) ? L - 1 : ga + k - 1; a1 = L; }
+    const int bl = (int)(a1 > a0 ? a1 - a0 : 0);
+    const int64_t b0 = g0 - bl + 1 > 0 ? g0 - bl + 1 : 0;
+    const int nb = (int)(g0 + 1 - b0);
+    // check string c = before + trial + after ; we stage before/after once
+    const uint8_t seq_ga1 = get(ga - 1), seq_gb1 = get(gb + 1);
+    JB_SYNC();
+    JB_LANES(l) {
+      for (int q = l; q < nb; q += 32) s.c[q] = get(b0 + q);
+      for (int q = l; q < bl; q += 32) s.c[nb + n + q] = get(a0 + q);
+    }
+    JB_SYNC();
+    const char order[4] = {'A', 'C', 'T', 'G'};
+    for (int xo = 0; xo < 4; ++xo)
+      for (int yo = 0; yo < 4; ++yo) {
+        uint8_t x = (uint8_t)order[xo], y = (uint8_t)order[yo];
+        if (x == left_bad && y == right_bad) continue;
+        if (x != left_bad && y != right_bad) continue;
+        JB_SYNC();
+        JB_LANES(l) {
+          for (int q = l; q < n; q += 32) s.c[nb + q] = (q == n - k) ? x : ((q == k - 1) ? y : s.t[q]);
+        }
+        JB_SYNC();
+        if (check_sequence(s.c, nb + n + bl, thr)) {
+          // one edit covering both positions: t[n-k : k] with x / y substituted
+          JB_SYNC();
+          JB_LANES(l) { for (int q = l; q < 2 * k - n; q += 32) s.b[q] = s.c[nb + (n - k) + q]; }
+          JB_SYNC();
+          if (!apply_edit(s0 + n - k, s0 + k, s.b, 2 * k - n)) return true;
+          if (x == left_bad) emit_row(gb + 1, &y, 1, 's', &seq_gb1, 1);     // "e": the right-hand base changed
+          else emit_row(ga - 1, &x, 1, 's', &seq_ga1, 1);                   // "s": the left-hand base changed
+          return true;
+        }
+      }
+    return false;
+  }
+
+  // src/jasper.py:434-477
+  JB_W bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
+    if (thr > solid) return false;
+    const uint8_t sb = s.t[k - 2];
+    const int start_bad = n - k + 1;
+    int cur = start_bad, added = 0;
+    while (added < start_bad) {
+      ++added;
+      b_from_t_insert(n, k - 1, sb, added);
+      int nbw = count_weak(s.b, n + added, thr);
+      if (nbw == 0) {
+        if (!apply_edit(s0 + k - 1, s0 + k - 1, s.b + (k - 1), added)) return true;
+        uint8_t dash = '-';
+        emit_row(k - 1 + s0, s.b + (k - 1), added, 'd', &dash, 1);
+        return true;
+      }
+      if (nbw >= cur) break;
+      cur = nbw;
+    }
+    const char order[4] = {'A', 'T', 'C', 'G'};
+    for (int o = 0; o < 4; ++o) {
+      uint8_t bb = (uint8_t)order[o];
+      b_from_t_insert(n, k - 2, bb, 1);
+      if (check_sequence(s.b, n + 1, thr)) {
+        if (!apply_edit(s0 + k - 2, s0 + k - 2, &bb, 1)) return true;
+        uint8_t dash = '-';
+        emit_row(k - 2 + s0, &bb, 1, 'd', &dash, 1);
+        return true;
+      }
+    }
+    return false;
+  }
+
+  // src/jasper.py:479-524
+  JB_W bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
+    if (thr > solid) return false;
+    const uint8_t sb = s.t[k - 1];
+    const int start_bad = n - k + 1;
+    int cur = start_bad, removed = 0;
+    while (removed < start_bad) {
+      --cur; ++removed;
+      if (n - removed == k) break;
+      b_from_t_delete(n, k - 1, removed);
+      int nbw = count_weak(s.b, n - removed, thr);
+      if (nbw == 0) {
+        if (!apply_edit(s0 + k - 1, s0 + k - 1 + removed, nullptr, 0)) return true;
+        JB_SYNC();
+        JB_LANES(l) { for (int q = l; q < removed; q += 32) s.c[q] = sb; }
+        JB_SYNC();
+        uint8_t dash = '-';
+        emit_row(k - 1 + s0, &dash, 1, 'i', s.c, removed);
+        return true;
+      }
+      if (nbw >= cur) break;
+      cur = nbw;
+    }
+    for (int m = n - k; m < n - 1; ++m) {
+      b_from_t_delete(n, m, 1);
+      if (check_sequence(s.b, n - 1, thr)) {
+        uint8_t gone = s.t[m];
+        if (!apply_edit(s0 + m, s0 + m + 1, nullptr, 0)) return true;
+        uint8_t dash = '-';
+        emit_row(m + s0, &dash, 1, 'i', &gone, 1);
+        return true;
+      }
+    }
+    return false;
+  }
+
+  // ---------------------------------------------------------------------------- base_extension
+  // src/jasper.py:527-583.  Paths live as (packed last k-1 bases, trie leaf); s.t holds good_kmer_before
+  // (k chars), s.b holds good_k_mer_after (k chars).  Returns patch length (>= 1) with the patch in
+  // bs->patch, 0 for "None".
+  JB_W uint32_t trie_new(uint32_t parent, uint32_t base, uint32_t& n_nodes) {
+    if (n_nodes >= bs->trie_cap) { status = JB_E_SCRATCH; return 0; }
+    uint32_t id = n_nodes++;
+    JB_LANES(l) { if (l == 0) bs->trie[id] = (parent << 2) | base; }
+    return id;
+  }
+
+  JB_W int64_t base_extension(int len_tbf, int64_t thr) {
+    if (thr > solid || !bs) { if (!bs) status = JB_E_SCRATCH; return 0; }
+    const uint8_t* G = s.t;          // good_kmer_before
+    const uint8_t* A = s.b;          // good_k_mer_after
+    const int64_t span = (int64_t)len_tbf - 2 * k;
+    const int64_t max_ext = (int64_t)rint((double)span * 1.2) + JB_MIN_OVERLAP + JB_SLACK;
+    const int64_t min_patch = (int64_t)rint((double)span / 1.2) - JB_SLACK;
+    // Codes of "ACGT" upper case for the overlap test
+    const char up[4] = {'A', 'C', 'G', 'T'};
+    uint32_t n_nodes = 1;            // node 0 = root = the single start path (its char is G[k-1], kept raw)
+    int cur = 0;
+    // km1 at round 1 = G[1:k]
+    Key km0 = {0, 0};
+    for (int q = 1; q < k; ++q) km0 = key_push(km0, base_valid(G[q]) ? base_code(G[q]) : 0u, mask);
+    const Key mask_km1 = key_mask(k - 1);
+    km0.lo &= mask_km1.lo; km0.hi &= mask_km1.hi;
+    JB_SYNC();
+    JB_LANES(l) { if (l == 0) { bs->km[0][0] = km0; bs->node[0][0] = 0; bs->trie[0] = 0; } }
+    JB_SYNC();
+    int n_paths = 1;
+    for (int64_t it = 1; it < max_ext; ++it) {
+      // ---- paths = [l for l in paths if len(l) > 0]
+      {
+        int nxt = cur ^ 1, w = 0;
+        for (int p0 = 0; p0 < n_paths; p0 += 32) {
+          JB_SYNC();
+          JB_LANES(l) { s.flag[l] = (p0 + l < n_paths && bs->node[cur][p0 + l] != kDeadNode) ? 1u : 0u; }
+          JB_SYNC();
+          int run = w;
+          JB_LANES(l) {
+            if (s.flag[l]) {
+              int off = 0;
+              for (int q = 0; q < l; ++q) off += (int)s.flag[q];
+              bs->km[nxt][w + off] = bs->km[cur][p0 + l];
+              bs->node[nxt][w + off] = bs->node[cur][p0 + l];
+            }
+          }
+          for (int q = 0; q < 32; ++q) run += (int)s.flag[q];
+          w = run;
+          JB_SYNC();
+        }
+        cur = nxt; n_paths = w;
+      }
+      if (n_paths > JB_MAX_PATHS) return 0;
+      if (n_paths == 0) return 0;                      // the reference keeps looping over an empty list: None
+      // first invalid base of km1 = G[it:k] ++ new bases (only G can hold invalid bytes)
+      int first_inv = -1;
+      for (int q = (int)it; q < k; ++q) if (!base_valid(G[q])) { first_inv = q - (int)it; break; }
+      const bool overlap_round = it >= JB_MIN_OVERLAP && it >= min_patch;
+      const int last_path = n_paths;
+      for (int p0 = 0; p0 < last_path; p0 += 8) {
+        // ---- 8 paths x 4 bases per wave
+        JB_SYNC();
+        JB_LANES(l) {
+          int p = p0 + (l >> 2);
+          uint32_t ok = 0;
+          if (p < last_path) {
+            Key full = key_push(bs->km[cur][p], (uint32_t)(l & 3), mask);   // km1 + base: k bases
+            if (first_inv >= 0) {                                          // MerDNA stops at the invalid byte
+              int keep = first_inv;                                        // bases kept
+              Key trimmed = {0, 0};
+              if (keep > 0) {
+                int drop = 2 * (k - keep);
+                if (drop >= 64) { trimmed.hi = (full.hi >> (drop - 64)) << (drop - 64); trimmed.lo = 0; }
+                else { trimmed.hi = full.hi; trimmed.lo = (full.lo >> drop) << drop; }
+              }
+              full = trimmed;
+            }
+            ok = (int64_t)db.count(key_canonical(full, k)) >= thr ? 1u : 0u;
+          }
+          s.flag[l] = ok;
+        }
+        JB_SYNC();
+        int np = last_path - p0 < 8 ? last_path - p0 : 8;
+        lookups += 4 * np;
+        for (int pp = 0; pp < np; ++pp) {
+          const int p = p0 + pp;
+          const uint32_t old_node = bs->node[cur][p];
+          const Key old_km = bs->km[cur][p];
+          int extended = 0;
+          for (int j = 0; j < 4; ++j) {
+            if (!s.flag[pp * 4 + j]) continue;
+            Key nk = key_push(old_km, (uint32_t)j, mask_km1);
+            if (overlap_round) {
+              // (km1 + base)[-5:] == good_k_mer_after[0:5]: four upper-case path bases then base j
+              bool same = (uint8_t)up[j] == A[JB_MIN_OVERLAP - 1];
+              for (int q = 0; q < JB_MIN_OVERLAP - 1 && same; ++q) {
+                uint32_t code = (uint32_t)((old_km.lo >> (2 * (JB_MIN_OVERLAP - 2 - q))) & 3u);
+                same = (uint8_t)up[code] == A[q];
+              }
+              if (same) {
+                // body = path string of old_node (length it).  Rebuild the last k+3 chars of
+                // stem + body into s.c, append base j and good_k_mer_after[-(k-5):]  (2k-1 chars)
+                const int need = k + 3;                     // chars of (stem + body) that survive [-(2k-1):]
+                JB_SYNC();
+                JB_LANES(l) {
+                  if (l == 0) {
+                    uint32_t nd = old_node;
+                    int64_t depth = it;                     // body has `it` chars; body[0] = G[k-1]
+                    for (int q = need - 1; q >= 0; --q) {
+                      uint8_t ch;
+                      if (depth > 1) { ch = (uint8_t)up[bs->trie[nd] & 3u]; nd = bs->trie[nd] >> 2; --depth; }
+                      else if (depth == 1) { ch = G[k - 1]; --depth; }
+                      else { int64_t gi = (k - 1) - (int64_t)(need - (int64_t)it - q) ; ch = G[gi]; }
+                      s.c[q] = ch;
+                    }
+                    s.c[need] = (uint8_t)up[j];
+                    for (int q = 0; q < k - JB_MIN_OVERLAP; ++q) s.c[need + 1 + q] = A[JB_MIN_OVERLAP + q];
+                  }
+                }
+                JB_SYNC();
+                if (check_sequence(s.c, 2 * k - 1, thr)) {
+                  if (it == JB_MIN_OVERLAP) return 0;
+                  // patch = (body + base)[1:-5] : it - 5 chars, recovered through the trie
+                  const int64_t plen = it - JB_MIN_OVERLAP;
+                  if ((uint64_t)plen > bs->patch_cap) { status = JB_E_SCRATCH; return 0; }
+                  JB_SYNC();
+                  JB_LANES(l) {
+                    if (l == 0) {
+                      // (body + base) has it+1 chars; drop the last 5 => chars [1, it-4)
+                      uint32_t nd = old_node;
+                      int64_t idx = it - 1;                 // index of body's last char
+                      // skip the 4 body chars that fall in the dropped tail (base j is the 5th)
+                      for (int q = 0; q < JB_MIN_OVERLAP - 1; ++q) { nd = bs->trie[nd] >> 2; --idx; }
+                      for (; idx >= 1; --idx) { bs->patch[idx - 1] = (uint8_t)up[bs->trie[nd] & 3u]; nd = bs->trie[nd] >> 2; }
+                    }
+                  }
+                  JB_SYNC();
+                  return plen;
+                }
+              }
+            }
+            if (!extended) {
+              uint32_t nn = trie_new(old_node, (uint32_t)j, n_nodes);
+              if (status) return 0;
+              JB_SYNC();
+              JB_LANES(l) { if (l == 0) { bs->km[cur][p] = nk; bs->node[cur][p] = nn; } }
+              extended = 1;
+            } else {
+              if (n_paths >= kPathCap) { status = JB_E_SCRATCH; return 0; }
+              uint32_t nn = trie_new(old_node, (uint32_t)j, n_nodes);
+              if (status) return 0;
+              JB_SYNC();
+              JB_LANES(l) { if (l == 0) { bs->km[cur][n_paths] = nk; bs->node[cur][n_paths] = nn; } }
+              ++n_paths;
+            }
+          }
+          if (!extended) { JB_SYNC(); JB_LANES(l) { if (l == 0) bs->node[cur][p] = kDeadNode; } }
+        }
+        JB_SYNC();
+      }
+    }
+    return 0;
+  }
+
+  // ---------------------------------------------------------------------------- fixing_sid
+  JB_W void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
+    const int64_t n64 = ga + k - 1 - s0;
+    if (nbad == k) {
+      int n = load(s.t, s0, ga + k - 1);
+      fix_k_case(n, thr, s0, ga);
+    } else if (nbad == k - 1) {
+      int n = load(s.t, s0, ga + k - 1);
+      if (!fix_del(n, thr, s0, ga))
+        if (!fix_diploid(n, thr, s0, gb, ga)) fix_same_base_insertion(n, thr, s0);
+    } else if (nbad < k - 1 && nbad > 1 && n64 >= k) {
+      int n = load(s.t, s0, ga + k - 1);
+      if (!fix_same_base_del(n, thr, s0))
+        if (!fix_diploid(n, thr, s0, gb, ga)) fix_same_base_insertion(n, thr, s0);
+    } else if (nbad > k) {
+      if (gb - k + 1 < 0) return;                          // good_kmer_before comes out shorter than k
+      int ng = load(s.t, gb - k + 1, gb + 1);
+      int na = load(s.b, ga, ga + k);
+      if (ng < k || na < k) return;
+      if (n64 > 0x7fffffff) return;
+      int64_t plen = base_extension((int)n64, thr);
+      if (status || plen <= 0) return;
+      // row material: patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
+      const int64_t olen_old = ga - (gb + 1);
+      unsigned long long off = 0, rslot = 0;
+      JB_SYNC();
+#if defined(__CUDA_ARCH__)
+      if ((threadIdx.x & 31) == 0) { off = atomicAdd(sink.aux_used, (unsigned long long)(plen + olen_old)); rslot = atomicAdd(sink.used, 1ull); }
+      off = __shfl_sync(0xffffffffu, off, 0); rslot = __shfl_sync(0xffffffffu, rslot, 0);
+#else
+      off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old); rslot = (*sink.used)++;
+#endif
+      if (off + plen + olen_old > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; return; }
+      JB_LANES(l) {
+        for (int64_t q = l; q < plen; q += 32) sink.aux[off + q] = bs->patch[q];
+        for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + plen + q] = get(gb + 1 + q);
+        if (l == 0) {
+          DevRow& r = sink.rows[rslot];
+          r.coord = gb + 1; r.unit = u.unit; r.seqno = seqno; r.kind = kRowBridge; r.fb_len = 0; r.orig_len = 0;
+          r.aux_off = off; r.aux_patch_len = (uint32_t)plen; r.aux_orig_len = (uint32_t)olen_old;
+        }
+      }
+      JB_SYNC();
+      seqno += 2;                                         // at most two csv rows come out of one patch
+      apply_edit(gb + 1, ga, bs->patch, plen);
+    }
+  }
+
+  // ---------------------------------------------------------------------------- handle_bad_kmers
+  JB_W void handle_bad_kmers(int64_t rolling_thre) {
+    ++events;
+    const int64_t thre = rolling_thre > 0 ? rolling_thre : solid;
+    int64_t j = i - 1;
+    uint32_t occ = Cw(j, -1);
+    while ((int64_t)occ < thre && j >= 0) { --j; occ = Cw(j, -1); }
+    int64_t gb = j + k - 1;
+    uint64_t prev = occ;
+    uint32_t cur = Cw(i, +1);
+    if (j == -1) gb = -1;
+    if (rolling_thre == 0) {
+      while ((int64_t)cur < thre && i < L - k + 1) { ++i; cur = Cw(i, +1); }
+    } else {
+      while ((int64_t)cur < thre && i < L - k + 1) {
+        if (i - j > k) { i = i + 1; return; }
+        ++i; cur = Cw(i, +1);
+      }
+    }
+    int64_t ga = i;
+    if (2 * (int64_t)Cw(gb - k + 2, +1) < solid && 2 * (int64_t)Cw(gb - k + 3, +1) < solid) {
+      // "too low" -- flag only
+    } else if (rolling_thre == 0) {
+      while (2 * (uint64_t)Cw(gb - k + 2, +1) >= prev && gb - k + 1 < ga) {
+        if (gb == -1) break;
+        if (2 * (int64_t)prev >= thre && 2 * (int64_t)Cw(gb - k + 2, +1) < thre && 2 * (int64_t)Cw(gb - k + 3, +1) < thre) break;
+        prev = Cw(gb - k + 2, +1);
+        ++gb;
+      }
+      if (gb >= L - 1) { brk = true; return; }
+    }
+    const int64_t s0 = gb - k + 2 > 0 ? gb - k + 2 : 0;
+    if (s0 + k + k >= L) { i = s0 + k + k; brk = true; return; }
+    s.px[0] = s0 + 1; s.px[1] = s0 + k - 2; s.px[2] = s0 + k - 1; s.px[3] = s0 + k;
+    JB_SYNC();
+    Cpts(4);
+    if ((int64_t)s.pr[0] < thre && (int64_t)s.pr[1] < thre && (int64_t)s.pr[2] < thre && (int64_t)s.pr[3] >= thre) ga = s0 + k;
+    const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
+    wrong += nbad;
+    if (fix) {
+      if (gb < 0) return;
+      fixing_sid(s0, nbad, thre, gb, ga);
+    }
+  }
+
+  // ---------------------------------------------------------------------------- scan loop
+  // Fast hop: while the walker is in untouched territory, 32 strided event bits decide in one step
+  // how far the plain `i += k-1` branch carries it.
+  JB_W bool fast_hop() {
+    if (!u.ev || i - k < clean_from) return false;
+    const int64_t shift = olen - ipos;                 // new = old + shift for everything >= clean_from
+    const int64_t p = i - shift;
+    const int64_t stride = k - 1;
+    JB_SYNC();
+    JB_LANES(l) {
+      int64_t q = p + (int64_t)l * stride;
+      uint32_t f = 1;
+      if (q <= u.in_len) f = (u.ev[q >> 5] >> (q & 31)) & 1u;
+      s.flag[l] = f;
+    }
+    JB_SYNC();
+    int l = 0;
+    while (l < 32 && !s.flag[l]) ++l;
+    i += (int64_t)l * stride;
+    return l == 32;                                     // all clear: keep hopping
+  }
+
+  JB_W void run() {
+    i = 0; olen = 0; ipos = 0; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; wc_n = 0;
+    while (i < L - k + 1 && !brk && !status) {
+      if (fast_hop()) continue;
+      if (!(i < L - k + 1)) break;
+      // ---- the reference's loop body at position i (src/jasper.py:56-100)
+      int n = load(s.t, i, i + k);                      // n == k here
+      int firstN = -1, firstn = -1, bad = 0;
+      for (int q = 0; q < n; ++q) {
+        uint8_t c = s.t[q];
+        if (c == 'N' && firstN < 0) firstN = q;
+        if (c == 'n' && firstn < 0) firstn = q;
+        if (!base_valid(c)) bad = 1;
+      }
+      if (firstN >= 0) {
+        i += firstN + 1;
+        // a run of N: every following window starts with 'N' and advances by one; jump the run
+        while (i < L - k + 1 && get(i) == 'N') ++i;
+        continue;
+      }
+      if (firstn >= 0) { i += firstn + 1; continue; }
+      if (bad) { i += 1; continue; }
+      s.px[0] = i; s.px[1] = i - k > 0 ? i - k : 0;
+      JB_SYNC();
+      Cpts(i > 0 ? 2 : 1);
+      const int64_t occ = s.pr[0];
+      if (occ < solid) {
+        handle_bad_kmers(0);
+      } else if (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)s.pr[1]) {
+        int64_t ind = i - k > 0 ? i - k : 0;
+        int num = 0;
+        while (ind < i) { ind += step; s.px[num] = ind; ++num; }
+        JB_SYNC();
+        Cpts(num);
+        uint64_t sum = 0;
+        for (int q = 0; q < num; ++q) sum += s.pr[q];
+        const double mean = (double)sum / (double)num;
+        const int64_t rt = (int64_t)rint(mean / (double)JB_DIVISOR);
+        if (occ < rt) handle_bad_kmers((int64_t)rint(mean / 2.0));
+        else i += k - 1;
+      } else {
+        i += k - 1;
+      }
+    }
+    // the untouched rest in[ipos:] is appended to out[olen:] by k_finalize (whole-GPU copy)
+    u.fin_olen = olen; u.fin_ipos = ipos;
+    u.out_len = status ? 0 : L;
+    u.wrong = wrong;
+    u.status = status;
+    u.n_rows = seqno;
+    u.lookups = lookups;
+    u.events = events;
+  }
+};
+
+}  // namespace jb
