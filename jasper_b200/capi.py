@@ -1,0 +1,321 @@
+"""ctypes binding of libjasper_b200.so (include/jasper_b200.h).
+
+Mirrors the operator interface the reference polisher uses:
+
+    qf = QueryMerFile(path)          # JF!swig/mer_file.i:18-36  -> jb_db_open
+    qf[MerDNA(s).get_canonical()]    # JF!swig/mer_file.i:41     -> jb_lookup (one string)
+    qf.lookup(strings)               # the same for a batch, one kernel launch
+    qf.count_positions(seq)          # C(seq[i:i+k]) for every i
+    qf.polish(seqs, k, thre, passes) # src/jasper.py main()      -> jb_polish
+
+Errors surface as JasperError (a RuntimeError, like the SWIG binding's std::runtime_error);
+there is no fallback when the library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class JasperError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (jb error %d)" % (msg, code))
+        self.code = code
+
+
+class _DbInfo(C.Structure):
+    _fields_ = [("k", C.c_int32), ("key_bits", C.c_int32), ("counter_len", C.c_int32), ("canonical", C.c_int32),
+                ("matrix_r", C.c_int32), ("matrix_c", C.c_int32), ("matrix_identity", C.c_int32), ("device", C.c_int32),
+                ("hash_size", C.c_uint64), ("n_records", C.c_uint64), ("table_slots", C.c_uint64),
+                ("table_bytes", C.c_uint64), ("max_displacement", C.c_uint64), ("load_seconds", C.c_double),
+                ("build_kernel_ms", C.c_double)]
+
+
+class _Seq(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("seq", C.c_char_p), ("len", C.c_uint64)]
+
+
+class _FixRow(C.Structure):
+    _fields_ = [("seq_index", C.c_uint32), ("coord", C.c_int64), ("mutation", C.c_char * 64), ("original", C.c_char * 64)]
+
+
+# every symbol include/jasper_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "jb_init", "jb_device_count", "jb_last_error", "jb_version",
+    "jb_db_open", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
+    "jb_lookup", "jb_lookup_flat", "jb_count_positions",
+    "jb_polish", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
+    "jb_result_status", "jb_result_iterations", "jb_result_tally", "jb_result_num_rows", "jb_result_rows",
+    "jb_result_num_seqs", "jb_result_seq", "jb_result_free",
+    "jb_last_timing_ms", "jb_last_counter",
+    "jb_comm_unique_id", "jb_comm_init", "jb_allreduce_tallies", "jb_comm_destroy",
+    "jb_gather_bench",
+]
+
+
+def library_path() -> str:
+    return os.environ.get("JASPER_B200_LIB", os.path.join(_HERE, "libjasper_b200.so"))
+
+
+def load_library():
+    """Load libjasper_b200.so (built in-tree by __graft_entry__.build() / jasper_b200/build.py)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise JasperError(-4, "libjasper_b200.so is not built (%s): run `python -m jasper_b200.build`; "
+                              "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, u64p, u32p, i64p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)
+    sig = {
+        "jb_init": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+        "jb_device_count": (C.c_int, []),
+        "jb_last_error": (C.c_char_p, []),
+        "jb_version": (C.c_char_p, []),
+        "jb_db_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "jb_db_info": (C.c_int, [vp, C.POINTER(_DbInfo)]),
+        "jb_db_replicate": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
+        "jb_db_close": (None, [vp]),
+        "jb_db_dump": (C.c_int, [vp, u64p, u64p, u32p, C.c_uint64, u64p]),
+        "jb_db_histogram": (C.c_int, [vp, C.c_uint64, u64p]),
+        "jb_solid_threshold": (C.c_int, [u64p, u64p, C.c_size_t]),
+        "jb_lookup": (C.c_int, [vp, C.POINTER(C.c_char_p), C.c_size_t, u32p]),
+        "jb_lookup_flat": (C.c_int, [vp, C.c_char_p, u64p, C.c_size_t, u32p]),
+        "jb_count_positions": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p]),
+        "jb_polish": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]),
+        "jb_batch_upload": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.POINTER(vp)]),
+        "jb_batch_polish": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.c_int]),
+        "jb_batch_fetch": (C.c_int, [vp, C.POINTER(vp)]),
+        "jb_batch_free": (None, [vp]),
+        "jb_result_status": (C.c_int, [vp]),
+        "jb_result_iterations": (C.c_int, [vp]),
+        "jb_result_tally": (C.c_int, [vp, C.c_int, i64p, i64p]),
+        "jb_result_num_rows": (C.c_int64, [vp, C.c_int]),
+        "jb_result_rows": (C.c_int, [vp, C.c_int, C.POINTER(_FixRow), C.c_size_t]),
+        "jb_result_num_seqs": (C.c_int64, [vp]),
+        "jb_result_seq": (C.c_int, [vp, C.c_size_t, C.POINTER(C.c_void_p), u64p]),
+        "jb_result_free": (None, [vp]),
+        "jb_last_timing_ms": (C.c_double, [C.c_char_p]),
+        "jb_last_counter": (C.c_int64, [C.c_char_p]),
+        "jb_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "jb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int]),
+        "jb_allreduce_tallies": (C.c_int, [i64p]),
+        "jb_comm_destroy": (None, []),
+        "jb_gather_bench": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise JasperError(rc, load_library().jb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def timing_ms(what: str) -> float:
+    return load_library().jb_last_timing_ms(what.encode())
+
+
+def counter(what: str) -> int:
+    return load_library().jb_last_counter(what.encode())
+
+
+class MerDNA(object):
+    """Stand-in for jf.MerDNA: it only carries the string; packing, reverse complement and the
+    canonical choice happen on the device inside the lookup (JF!swig/mer_dna.i:15,71)."""
+    __slots__ = ("s",)
+
+    def __init__(self, s: str = ""):
+        self.s = s
+
+    def get_canonical(self):
+        return self
+
+    def __str__(self):
+        return self.s
+
+
+@dataclass
+class PolishResult:
+    status: int
+    tallies: list                      # [(wrong, total)] per iteration 0..p
+    rows: list                         # per iteration: [[name, coord, mutation, original], ...]
+    seqs: list                         # [(name, str)]
+    timings: dict = field(default_factory=dict)
+    counters: dict = field(default_factory=dict)
+
+
+class QueryMerFile(object):
+    """A Jellyfish binary/sorted database resident in the HBM of one GPU."""
+
+    def __init__(self, path: str, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.jb_init(1, (C.c_int * 1)(device)))
+        _check(self._lib.jb_db_open(os.fsencode(path), device, C.byref(self._h)))
+        info = _DbInfo()
+        _check(self._lib.jb_db_info(self._h, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in _DbInfo._fields_}
+        self.k = info.k
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.jb_db_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- qf[mer] ------------------------------------------------------------------------------
+    def __getitem__(self, mer) -> int:
+        return self.lookup([str(mer)])[0]
+
+    def lookup(self, strings) -> list:
+        n = len(strings)
+        enc = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in strings]
+        k = self.k
+        parts, offs, pos = [], [0], 0
+        for b in enc:
+            z = b.find(b"\0")
+            b = b[:k] if z < 0 else b[:min(k, z)]          # MerDNA(const char*) stops at NUL / k bytes
+            parts.append(b)
+            pos += len(b)
+            offs.append(pos)
+        flat = b"".join(parts)
+        out = (C.c_uint32 * max(1, n))()
+        _check(self._lib.jb_lookup_flat(self._h, flat, (C.c_uint64 * (n + 1))(*offs), n, out))
+        return list(out[:n])
+
+    def count_positions(self, seq):
+        import numpy as np
+        b = seq.encode("latin-1") if isinstance(seq, str) else bytes(seq)
+        out = np.empty(len(b) + 1, dtype=np.uint32)
+        _check(self._lib.jb_count_positions(self._h, b, len(b), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def dump(self):
+        import numpy as np
+        n = self.info["n_records"]
+        lo = np.empty(max(1, n), dtype=np.uint64)
+        hi = np.empty(max(1, n), dtype=np.uint64)
+        cnt = np.empty(max(1, n), dtype=np.uint32)
+        got = C.c_uint64()
+        p64, p32 = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+        _check(self._lib.jb_db_dump(self._h, lo.ctypes.data_as(p64), hi.ctypes.data_as(p64), cnt.ctypes.data_as(p32), n, C.byref(got)))
+        return lo[:n], hi[:n], cnt[:n]
+
+    def histogram(self, high: int = 10000):
+        """Rows (count, frequency) as `jellyfish histo` prints them."""
+        hist = (C.c_uint64 * (high + 2))()
+        _check(self._lib.jb_db_histogram(self._h, high, hist))
+        return [(c, hist[c]) for c in range(1, high + 2) if hist[c] > 0]
+
+    def gather_bench(self, n_probes: int = 1 << 28, sector_bytes: int = 32, iters: int = 3):
+        gbps, gps = C.c_double(), C.c_double()
+        _check(self._lib.jb_gather_bench(self._h, n_probes, sector_bytes, iters, C.byref(gbps), C.byref(gps)))
+        return gbps.value, gps.value
+
+    # -- polishing ----------------------------------------------------------------------------
+    def _seq_array(self, seqs):
+        n = len(seqs)
+        arr = (_Seq * max(1, n))()
+        keep = []
+        for i, (name, s) in enumerate(seqs):
+            b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
+            nb = name.encode("utf-8")
+            keep.append((b, nb))
+            arr[i].name = nb
+            arr[i].seq = b
+            arr[i].len = len(b)
+        return arr, keep
+
+    def _collect(self, res, names) -> PolishResult:
+        lib = self._lib
+        n_it = lib.jb_result_iterations(res)
+        tallies, rows = [], []
+        for ite in range(n_it):
+            w, t = C.c_int64(), C.c_int64()
+            _check(lib.jb_result_tally(res, ite, C.byref(w), C.byref(t)))
+            tallies.append((w.value, t.value))
+            nr = lib.jb_result_num_rows(res, ite)
+            buf = (_FixRow * max(1, nr))()
+            _check(lib.jb_result_rows(res, ite, buf, nr))
+            rows.append([[names[buf[i].seq_index], buf[i].coord, buf[i].mutation.decode("latin-1"), buf[i].original.decode("latin-1")]
+                         for i in range(nr)])
+        seqs = []
+        for i in range(lib.jb_result_num_seqs(res)):
+            p, ln = C.c_void_p(), C.c_uint64()
+            _check(lib.jb_result_seq(res, i, C.byref(p), C.byref(ln)))
+            seqs.append((names[i], C.string_at(p, ln.value).decode("latin-1") if ln.value else ""))
+        out = PolishResult(status=lib.jb_result_status(res), tallies=tallies, rows=rows, seqs=seqs)
+        for key in ("polish", "polish_scan", "polish_walk", "h2d", "d2h"):
+            out.timings[key] = timing_ms(key)
+        for key in ("scan_lookups", "walk_lookups", "kernel_launches", "events", "probe_steps", "h2d_bytes", "d2h_bytes"):
+            out.counters[key] = counter(key)
+        return out
+
+    def polish(self, seqs, k: int, solid_thre: int, passes: int, fix: bool = True) -> PolishResult:
+        """seqs: [(name, str)].  One call = the whole per-batch loop of src/jasper.py main()."""
+        arr, keep = self._seq_array(seqs)
+        res = C.c_void_p()
+        _check(self._lib.jb_polish(self._h, arr, len(seqs), k, solid_thre, passes, 1 if fix else 0, C.byref(res)))
+        try:
+            return self._collect(res, [n for n, _ in seqs])
+        finally:
+            self._lib.jb_result_free(res)
+
+    # split form: keep the batch resident and time the device part alone
+    def upload(self, seqs):
+        arr, keep = self._seq_array(seqs)
+        b = C.c_void_p()
+        _check(self._lib.jb_batch_upload(self._h, arr, len(seqs), C.byref(b)))
+        return _Batch(self, b, [n for n, _ in seqs])
+
+
+class _Batch(object):
+    def __init__(self, qf: QueryMerFile, handle, names):
+        self.qf, self.h, self.names = qf, handle, names
+
+    def polish(self, k, solid_thre, passes, fix=True):
+        _check(self.qf._lib.jb_batch_polish(self.h, k, solid_thre, passes, 1 if fix else 0))
+
+    def fetch(self) -> PolishResult:
+        res = C.c_void_p()
+        _check(self.qf._lib.jb_batch_fetch(self.h, C.byref(res)))
+        try:
+            return self.qf._collect(res, self.names)
+        finally:
+            self.qf._lib.jb_result_free(res)
+
+    def free(self):
+        if self.h:
+            self.qf._lib.jb_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def solid_threshold(rows) -> int:
+    """src/jellyfish.py on histogram rows [(count, freq)]; raises JasperError where the reference exits 1."""
+    n = len(rows)
+    cs = (C.c_uint64 * max(1, n))(*[r[0] for r in rows])
+    fs = (C.c_uint64 * max(1, n))(*[r[1] for r in rows])
+    return _check(load_library().jb_solid_threshold(cs, fs, n))

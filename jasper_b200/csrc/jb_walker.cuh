@@ -79,6 +79,7 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   int64_t px[32];            // point queries
   uint32_t pr[32];
   uint32_t flag[32];
+  uint32_t ext[32];          // extension verdicts of one bridging wave (check_sequence reuses flag)
 };
 
 struct UnitIO {
@@ -556,7 +557,7 @@ struct Walker {
             }
             ok = (int64_t)db.count(key_canonical(full, k)) >= thr ? 1u : 0u;
           }
-          s.flag[l] = ok;
+          s.ext[l] = ok;
         }
         JB_SYNC();
         int np = last_path - p0 < 8 ? last_path - p0 : 8;
@@ -567,7 +568,7 @@ struct Walker {
           const Key old_km = bs->km[cur][p];
           int extended = 0;
           for (int j = 0; j < 4; ++j) {
-            if (!s.flag[pp * 4 + j]) continue;
+            if (!s.ext[pp * 4 + j]) continue;
             Key nk = key_push(old_km, (uint32_t)j, mask_km1);
             if (overlap_round) {
               // (km1 + base)[-5:] == good_k_mer_after[0:5]: four upper-case path bases then base j

@@ -39,8 +39,8 @@ def random_genome(n: int, rng: np.random.Generator, homopolymers: int = 0, hp_le
     for _ in range(homopolymers):
         ln = int(rng.integers(hp_len[0], hp_len[1] + 1))
         at = int(rng.integers(0, max(1, n - ln)))
-        g[at:at + ln] = rng.integers(0, 4)
-    if repeat_copies:
+        g[at:min(n, at + ln)] = rng.integers(0, 4)
+    if repeat_copies and repeat_len < n:
         unit = rng.integers(0, 4, repeat_len, dtype=np.uint8)
         for _ in range(repeat_copies):
             at = int(rng.integers(0, max(1, n - repeat_len)))

@@ -1,0 +1,190 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import jasper_oracle as jo
+from jasper_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dbs(golden_cases):
+    out = {}
+    for name, case in golden_cases.items():
+        out[name] = capi.QueryMerFile(case["db"])
+    yield out
+    for q in out.values():
+        q.close()
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_table_holds_exactly_the_file_records(golden_cases, dbs, name):
+    """load -> dump == the record list of the file, in file order (the loader preserves (pos,key) order)."""
+    odb = helpers.OracleDB(golden_cases[name]["db"])
+    lo, hi, cnt = odb.records()
+    qf = dbs[name]
+    assert qf.k == odb.k and qf.info["n_records"] == odb.n_records
+    glo, ghi, gcnt = qf.dump()
+    assert np.array_equal(glo, lo) and np.array_equal(ghi, hi) and np.array_equal(gcnt.astype(np.uint64), cnt & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_histogram_matches_jellyfish_histo(golden_cases, dbs, name):
+    rows = [tuple(int(x) for x in l.split()) for l in open(os.path.join(golden_cases[name]["dir"], "histo.csv"))]
+    assert dbs[name].histogram() == rows
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_lookup_matches_binding_vectors_and_oracle(golden_cases, dbs, name):
+    case = golden_cases[name]
+    qf = dbs[name]
+    strings = [s for s, _, _ in case["lookups"]]
+    assert qf.lookup(strings) == [c for _, _, c in case["lookups"]]
+    odb = helpers.OracleDB(case["db"])
+    rng = np.random.default_rng(1)
+    seq = "".join(s for _, s in jo.read_fasta(case["fasta"]))
+    alphabet = "ACGTacgtNnRY-"
+    probes = []
+    for _ in range(5000):
+        if rng.random() < 0.6:
+            at = int(rng.integers(0, len(seq) - 100)); probes.append(seq[at:at + int(rng.integers(0, 2 * qf.k))])
+        else:
+            probes.append("".join(alphabet[int(x)] for x in rng.integers(0, len(alphabet), int(rng.integers(0, 60)))))
+    assert qf.lookup(probes) == [odb.count(s) for s in probes]
+    assert qf[capi.MerDNA(probes[0]).get_canonical()] == odb.count(probes[0])
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_count_positions_matches_oracle(golden_cases, dbs, name):
+    case = golden_cases[name]
+    odb = helpers.OracleDB(case["db"])
+    for _, s in jo.read_fasta(case["fasta"]):
+        got = dbs[name].count_positions(s)
+        assert np.array_equal(got, odb.count_positions(s))
+    assert np.array_equal(dbs[name].count_positions(""), odb.count_positions(""))
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_polish_reproduces_reference_bytes(golden_cases, dbs, name):
+    """fix.csv per pass, polished FASTA and tallies: byte-identical to the unmodified jasper.py run."""
+    case = golden_cases[name]
+    seqs = jo.read_fasta(case["fasta"])
+    res = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
+    assert res.status == 0
+    for ite in range(case["passes"]):
+        assert jo.format_fix_csv(res.rows[ite]) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+    assert jo.format_fasta(res.seqs) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+    assert ("%d %d\n" % res.tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
+    assert ("%d %d\n" % res.tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+    assert res.counters["kernel_launches"] >= 2 * (case["passes"] + 1)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_polish_fuzz_matches_oracle(tmp_path, seed):
+    k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
+    recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k)
+    odb = helpers.OracleDB(path)
+    want, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
+    qf = capi.QueryMerFile(path)
+    try:
+        if want is None:
+            res = qf.polish(recs, k, thr, 2)
+            assert res.status == -7
+            return
+        res = qf.polish(recs, k, thr, 2)
+        names = [n for n, _ in recs]
+        assert res.status == 0
+        assert helpers.product_rows_text(res.rows, names) == helpers.rows_text(want.passes, names)
+        assert [s for _, s in res.seqs] == [s for _, s in want.seqs]
+        assert res.tallies == [(p.wrong, p.total) for p in want.passes]
+    finally:
+        qf.close()
+
+
+def _mid_case(tmp_path, n, k, seed, err=0.001):
+    rng = np.random.default_rng(seed)
+    g = synth.random_genome(n, rng, homopolymers=n // 2000)
+    a = synth.inject_errors(g, err, rng)
+    lo, hi = synth.canonical_keys(g, k)
+    lo, hi, mult = synth.unique_keys(lo, hi)
+    cnt = np.maximum(1, rng.poisson(22.8, len(lo))) * mult
+    # singleton error k-mers: random keys (absent from the genome with overwhelming probability)
+    ne = len(lo) // 2
+    elo = rng.integers(0, 1 << 62, ne, dtype=np.uint64)
+    ehi = rng.integers(0, 1 << max(1, 2 * k - 64), ne, dtype=np.uint64) if 2 * k > 64 else np.zeros(ne, np.uint64)
+    if 2 * k < 64:
+        elo &= np.uint64((1 << (2 * k)) - 1)
+    lo2, hi2, c2 = synth.unique_keys(np.concatenate([lo, elo]), np.concatenate([hi, ehi]), np.concatenate([cnt, np.ones(ne, np.int64)]))
+    path = str(tmp_path / ("mid_%d_%d.jf" % (n, k)))
+    synth.write_jf(path, lo2, hi2, c2, k, seed=seed)
+    return synth.codes_to_bytes(a).decode(), path
+
+
+def test_polish_mid_size_matches_oracle(tmp_path):
+    """1 Mb contig + small ones, k=37, 3 passes: sequences, rows and tallies equal the oracle's."""
+    k = 37
+    s, path = _mid_case(tmp_path, 1_000_000, k, 77, err=0.002)
+    recs = [("big", s), ("part", s[5000:90000]), ("short", s[:30]), ("empty", "")]
+    odb = helpers.OracleDB(path)
+    want, _ = helpers.oracle_polish(odb, recs, k, 3, 3)
+    qf = capi.QueryMerFile(path)
+    res = qf.polish(recs, k, 3, 3)
+    names = [n for n, _ in recs]
+    assert res.status == 0 and want is not None
+    assert helpers.product_rows_text(res.rows, names) == helpers.rows_text(want.passes, names)
+    assert [x for _, x in res.seqs] == [x for _, x in want.seqs]
+    assert res.tallies == [(p.wrong, p.total) for p in want.passes]
+    # size-independent properties: a polished assembly is a fixed point of the count-only pass, and
+    # polishing again with fix=False changes nothing
+    again = qf.polish(res.seqs, k, 3, 0)
+    assert [x for _, x in again.seqs] == [x for _, x in res.seqs]
+    assert again.tallies[0] == res.tallies[-1]
+    qf.close()
+
+
+def test_count_positions_large_properties(tmp_path):
+    """8 Mb: every genome window is found with its exact count; reverse-complement symmetry."""
+    k = 37
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(8_000_000, rng)
+    lo, hi = synth.canonical_keys(g, k)
+    ulo, uhi, mult = synth.unique_keys(lo, hi)
+    path = str(tmp_path / "big.jf")
+    synth.write_jf(path, ulo, uhi, mult * 3, k, seed=1)
+    qf = capi.QueryMerFile(path)
+    s = synth.codes_to_bytes(g).decode()
+    c = qf.count_positions(s)
+    assert c.shape[0] == len(s) + 1
+    assert np.all(c[:len(s) - k + 1] >= 3) and np.all(c[:len(s) - k + 1] % 3 == 0)
+    rc = synth.codes_to_bytes((3 - g)[::-1]).decode()
+    c2 = qf.count_positions(rc)
+    n = len(s) - k + 1
+    assert np.array_equal(c[:n], c2[:n][::-1])
+    assert qf.info["max_displacement"] < 4096
+    qf.close()
+
+
+def test_errors_mirror_the_binding(tmp_path, golden_cases):
+    with pytest.raises(capi.JasperError) as e:
+        capi.QueryMerFile(str(tmp_path / "missing.jf"))
+    assert "Can't open file" in str(e.value)
+    bad = tmp_path / "bad.jf"
+    bad.write_bytes(b"000000031{\"format\":\"bloomcounter\"}\0\0\0\0\0\0")
+    with pytest.raises(capi.JasperError) as e:
+        capi.QueryMerFile(str(bad))
+    assert "Unsupported format" in str(e.value) or "format" in str(e.value)
+    case = golden_cases["k25_mix"]
+    qf = capi.QueryMerFile(case["db"])
+    with pytest.raises(capi.JasperError) as e:
+        qf.polish([("a", "ACGT" * 50)], 31, 3, 1)      # --ksize differs from the DB's k
+    assert e.value.code == -6
+    qf.close()
+
+
+def test_gather_roofline_probe(dbs):
+    gbps, gps = dbs["k37_mix"].gather_bench(n_probes=1 << 24, sector_bytes=32, iters=2)
+    assert gbps > 0 and gps > 0

@@ -1,0 +1,134 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports everything include/*.h
+declares, fails loudly without a GPU, and the walker state machine (the very source the GPU runs,
+compiled for the host in tests/hostsim -- test-only) agrees with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+import jasper_oracle as jo
+from jasper_b200 import capi, synth
+
+ROOT = helpers.ROOT
+
+
+def _built():
+    return os.path.exists(capi.library_path())
+
+
+def test_library_exports_every_declared_symbol():
+    if not _built():
+        from jasper_b200 import build
+        build.build()
+    header = open(os.path.join(ROOT, "include", "jasper_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(jb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 30
+    lib = C.CDLL(capi.library_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_no_cpu_fallback(golden_cases):
+    """Without a CUDA device the product refuses to compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load_library()
+    assert lib.jb_device_count() == 0
+    with pytest.raises(capi.JasperError) as e:
+        capi.QueryMerFile(golden_cases["k25_mix"]["db"])
+    assert e.value.code == -4 and "no CPU path" in str(e.value)
+
+
+def test_solid_threshold_entry_point():
+    rows = [(1, 100), (2, 50), (3, 20), (4, 10), (5, 12), (6, 30)]
+    assert capi.solid_threshold(rows) == synth.solid_threshold_from_histogram(rows) == 2
+    with pytest.raises(capi.JasperError):
+        capi.solid_threshold([(1, 100), (2, 50), (3, 60)])
+    with pytest.raises(capi.JasperError):
+        capi.solid_threshold([(1, 100), (2, 50), (3, 40)])
+
+
+def test_kmer_arithmetic_matches_oracle(hostsim_lib, oracle_lib):
+    """jb_kmer.cuh (2-bit pack with MerDNA padding, reverse complement, canonical) vs the C oracle."""
+    rng = np.random.default_rng(3)
+    alphabet = b"ACGTacgtNnRY-\0"
+    for k in (8, 20, 25, 31, 32, 33, 37, 48):
+        for _ in range(300):
+            s = bytes(alphabet[int(x)] for x in rng.integers(0, 9 if rng.random() < 0.7 else len(alphabet), int(rng.integers(0, 60))))
+            m, c, r = (C.c_uint64 * 2)(), (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
+            hostsim_lib.hostsim_mer(s, len(s), k, m, c, r)
+            om, oc, orc = (C.c_uint64 * 2)(), (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
+            oracle_lib.jfo_mer_from_chars(s, len(s), k, om)
+            oracle_lib.jfo_canonical(om, k, oc)
+            oracle_lib.jfo_revcomp(om, k, orc)
+            assert (m[0], m[1]) == (om[0], om[1]), (k, s)
+            assert (r[0], r[1]) == (orc[0], orc[1]), (k, s)
+            assert (c[0], c[1]) == (oc[0], oc[1]), (k, s)
+
+
+def test_alignment_matches_shim(hostsim_lib):
+    """jb_align.cpp vs oracle/Bio/pairwise2.py (both restate Bio.pairwise2; parity unpinned vs Biopython)."""
+    from Bio import pairwise2
+    rng = np.random.default_rng(11)
+    for _ in range(400):
+        n = int(rng.integers(1, 40))
+        a = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, n))
+        b = list(a)
+        for _ in range(int(rng.integers(0, 5))):
+            at = int(rng.integers(0, max(1, len(b))))
+            op = rng.integers(0, 3)
+            if op == 0 and b:
+                b[at] = "ACGT"[int(rng.integers(0, 4))]
+            elif op == 1:
+                b.insert(at, "ACGT"[int(rng.integers(0, 4))])
+            elif b:
+                del b[at]
+        b = "".join(b)
+        if not b:
+            continue
+        want = pairwise2.first_global_alignment(a, b)[0]
+        oa, ob = C.create_string_buffer(256), C.create_string_buffer(256)
+        assert hostsim_lib.hostsim_align(a.encode(), b.encode(), oa, ob, 256) == 1
+        assert (oa.value.decode(), ob.value.decode()) == (want[0], want[1]), (a, b)
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+@pytest.mark.parametrize("use_events", [0, 1])
+def test_walker_source_matches_golden(golden_cases, hostsim_lib, name, use_events):
+    case = golden_cases[name]
+    odb = helpers.OracleDB(case["db"])
+    seqs = jo.read_fasta(case["fasta"])
+    res, _ = helpers.oracle_polish(odb, seqs, case["k"], case["threshold"], case["passes"])
+    st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events)
+    assert st == 0
+    names = [n for n, _ in seqs]
+    assert txt == helpers.rows_text(res.passes, names)
+    assert out == [s for _, s in res.seqs]
+    assert tallies == [(p.wrong, p.total) for p in res.passes]
+    # and therefore the reference's own bytes
+    rows0 = [[names[int(f[1])], int(f[2]), f[3], f[4]] for f in (l.split("\t") for l in txt.splitlines()) if f[0] == "0"]
+    assert jo.format_fix_csv(rows0) == helpers.expected_file(case, "_iter0_asm.fa.fix.csv")
+    assert jo.format_fasta(list(zip(names, out))) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_walker_source_fuzz(tmp_path, hostsim_lib, seed):
+    """Random dirty genomes (N runs, lower case, IUPAC, repeats, heterozygosity, clustered errors)."""
+    k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
+    recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k)
+    odb = helpers.OracleDB(path)
+    res, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
+    for use_events in (0, 1):
+        st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, use_events)
+        if res is None:
+            assert st == -7          # JB_E_REFERENCE_CRASH
+            continue
+        assert st == 0
+        assert txt == helpers.rows_text(res.passes, [n for n, _ in recs])
+        assert out == [s for _, s in res.seqs]
+        assert tallies == [(p.wrong, p.total) for p in res.passes]
