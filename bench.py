@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the polishing hot path (BASELINE.json: assembly bp
+polished/sec and k-mer lookups/sec vs the reference's CPU path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--genome-mb M]
+
+One "step" = one pass of the hot path over one batch: the whole per-batch loop of src/jasper.py
+main() (p fixing passes + the final count-only pass) over the workload's contig chunks.
+Workload (configs[1]): synthetic 64 Mb chr20-scale assembly with 0.1 % injected errors, k-mer
+database of a simulated 30x Illumina read set written directly as a Jellyfish binary/sorted file,
+k = 37, p = 2, chunked exactly like src/jasper.sh does for -t 16.
+`value` is device-timed with the chunks already resident in HBM; `e2e` goes through the public
+call (host buffers in, polished host strings out) with both copies inside the timed region.
+Multi-GPU (torchrun, one rank per GPU): every rank holds a replica of the table and polishes its
+own assembly of the same size (weak scaling); the QV tallies are summed with one NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 37
+PASSES = 2
+SOLID_THRE = 5
+CHUNK_THREADS = 16            # the -t of src/jasper.sh that defines the chunking (src/jasper.sh:132-139)
+ASM_ERR = 0.001
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-mb", type=float, default=64.0)
+    ap.add_argument("--cpu-sample-kb", type=int, default=0, help="bases of the workload the CPU baseline polishes (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def build_workload(work_dir: str, genome_mb: float, rank: int, make_db: bool):
+    """Genome + .jf (rank 0 writes it once) + this rank's assembly, chunked like jasper.sh -t 16."""
+    from jasper_b200 import batching, synth_gpu
+    G = int(genome_mb * 1e6)
+    t0 = time.time()
+    if make_db:
+        w = synth_gpu.make_workload(work_dir, G, K, seed=20)
+        genome = w["genome"]
+        meta = {a: b for a, b in w.items() if a != "genome"}
+        import numpy as np
+        np.save(os.path.join(work_dir, "genome.npy"), genome)
+        json.dump(meta, open(os.path.join(work_dir, "meta.json"), "w"))
+    else:
+        import numpy as np
+        genome = np.load(os.path.join(work_dir, "genome.npy"))
+        meta = json.load(open(os.path.join(work_dir, "meta.json")))
+    asm = synth_gpu.make_assembly(genome, ASM_ERR, seed=1000 + rank).decode("latin-1")
+    bs = batching.batch_size(len(asm), CHUNK_THREADS)
+    chunks = batching.split_contigs([("chr20_like", asm)], bs)
+    meta["gen_seconds"] = time.time() - t0
+    meta["assembly_bp"] = len(asm)
+    meta["batch_size"] = bs
+    return meta, chunks
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle = checker, timed as the reference's CPU path)
+def _cpu_polish_worker(args):
+    db_path, seqs, k, thr, passes = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import jasper_oracle as jo
+    try:
+        import dna_jellyfish as jf             # the reference's own compiled Jellyfish binding (oracle/_ref)
+        qf = jf.QueryMerFile(db_path)
+        count = lambda s: qf[jf.MerDNA(s).get_canonical()]
+        kind = "reference-binding"
+    except Exception:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers
+        odb = helpers.OracleDB(db_path)
+        count = odb.count
+        kind = "port"
+    o = jo.PolishOracle(count, k, thr)
+    t0 = time.perf_counter()
+    res = o.polish(seqs, passes)
+    dt = time.perf_counter() - t0
+    return dt, res.lookups, sum(len(s) for _, s in seqs), [(p.wrong, p.total) for p in res.passes], kind, [s for _, s in res.seqs]
+
+
+def cpu_baseline(db_path, chunks, sample_bp: int, procs: int):
+    """The oracle (Python restatement of src/jasper.py over the reference's compiled lookup when
+    oracle/_ref is present) on a bounded sample: `procs` worker processes, one slice each --
+    the reference's own parallel model (xargs -P, src/jasper.sh:212)."""
+    import multiprocessing as mp
+    whole = "".join(s for _, s in chunks)
+    per = int(max(2000, min(sample_bp // procs, len(whole) // procs)))
+    jobs = []
+    for w in range(procs):
+        at = w * (len(whole) // procs)
+        piece = whole[at:at + per]
+        if len(piece) < 2 * K:
+            continue
+        jobs.append((db_path, [("slice_%d" % w, piece)], K, SOLID_THRE, PASSES))
+    t0 = time.perf_counter()
+    if len(jobs) == 1:
+        outs = [_cpu_polish_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            outs = pool.map(_cpu_polish_worker, jobs)
+    wall = time.perf_counter() - t0
+    bp = sum(o[2] for o in outs)
+    lookups = sum(o[1] for o in outs)
+    return {"wall": wall, "bp": bp, "lookups": lookups, "kind": outs[0][4], "procs": len(jobs), "jobs": jobs, "outs": outs}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    from jasper_b200 import capi
+    import ctypes as C
+
+    base = os.environ.get("JB_BENCH_DIR") or os.path.join(tempfile.gettempdir(), "jb_bench_%s" % os.environ.get("MASTER_PORT", "single"))
+    if rank == 0:
+        shutil.rmtree(base, ignore_errors=True)
+        os.makedirs(base, exist_ok=True)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        meta, chunks = build_workload(base, args.genome_mb, rank, make_db=True)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        meta, chunks = build_workload(base, args.genome_mb, rank, make_db=False)
+    db_path = os.path.join(base, "db.jf")
+
+    t0 = time.time()
+    qf = capi.QueryMerFile(db_path, device=local_rank)
+    open_s = time.time() - t0
+    lib = capi.load_library()
+    if world > 1:
+        uid = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            capi._check(lib.jb_comm_unique_id(buf))
+            uid = [buf.raw]
+        dist.broadcast_object_list(uid, src=0)
+        capi._check(lib.jb_comm_init(rank, world, uid[0], local_rank))
+
+    total_bp = sum(len(s) for _, s in chunks)
+
+    def device_step():
+        b = qf.upload(chunks)                         # not timed: `value` starts with the chunks resident
+        b.polish(K, SOLID_THRE, PASSES)
+        ms = capi.timing_ms("polish")
+        stats = {"scan_ms": capi.timing_ms("polish_scan"), "walk_ms": capi.timing_ms("polish_walk"),
+                 "scan_lookups": capi.counter("scan_lookups"), "walk_lookups": capi.counter("walk_lookups"),
+                 "launches": capi.counter("kernel_launches"), "probe_steps": capi.counter("probe_steps"), "events": capi.counter("events")}
+        return b, ms, stats
+
+    for _ in range(args.warmup):
+        b, _, _ = device_step()
+        b.free()
+    # ---- timed: K steps, device time (CUDA events on the library's stream), max over ranks
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, last_stats, last_batch = 0.0, None, None
+    for step in range(args.steps):
+        if last_batch is not None:
+            last_batch.free()
+        last_batch, ms, last_stats = device_step()
+        dev_ms += ms
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    res = last_batch.fetch()
+    last_batch.free()
+    # ---- e2e: the public call, host strings in -> polished host strings out, K steps, wall clock
+    e2e_t0 = time.perf_counter()
+    for step in range(args.steps):
+        r2 = qf.polish(chunks, K, SOLID_THRE, PASSES)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e2e_t0
+    h2d, d2h = r2.counters["h2d_bytes"], r2.counters["d2h_bytes"]
+    clocks = sampler.stop() if rank == 0 else None
+
+    tallies = (C.c_int64 * 4)(res.tallies[0][0], res.tallies[0][1], res.tallies[-1][0], res.tallies[-1][1])
+    if world > 1:
+        capi._check(lib.jb_allreduce_tallies(tallies))
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        tb = torch.tensor([total_bp], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb)
+        job_bp = float(tb[0])
+    else:
+        job_bp = float(total_bp)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    value = job_bp * PASSES / (ms_per_step * 1e-3)
+    e2e_value = job_bp * PASSES / (e2e_s / args.steps)
+
+    # ---- roofline of the probe kernel (k_scan): algorithmic bytes = 32 B per lookup
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    gather_gbps, gather_gps = qf.gather_bench(n_probes=1 << 28, sector_bytes=32, iters=3)
+    scan_ms_per_launch = last_stats["scan_ms"] / (PASSES + 1)
+    lookups_per_launch = last_stats["scan_lookups"] / (PASSES + 1)
+    achieved = lookups_per_launch * 32 / (scan_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_scan<events>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback 6650",
+                "traffic": None,
+                "lookups_per_s": lookups_per_launch / (scan_ms_per_launch * 1e-3),
+                "random_sector_peak_GBps": gather_gbps, "frac_of_random_sector_peak": achieved / gather_gbps if gather_gbps else None,
+                "ms_per_launch": scan_ms_per_launch, "share_of_step": last_stats["scan_ms"] / (dev_ms / args.steps),
+                "sectors_per_lookup": last_stats["probe_steps"] / max(1, last_stats["scan_lookups"])}
+
+    # ---- CPU baseline beside it (bounded sample of the same workload, all host cores)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        sample = (args.cpu_sample_kb * 1000) or min(total_bp, 3_000_000 * cores)
+        cb = cpu_baseline(db_path, chunks, sample, cores)
+        cpu = {"value": cb["bp"] * PASSES / cb["wall"], "unit": "bp polished/s", "cores": cb["procs"],
+               "kind": "reference" if cb["kind"] == "reference-binding" else "port",
+               "sample": "%d slices of %d bp of the same chunks, k=%d p=%d, python oracle over %s, %.1f s wall" % (
+                   cb["procs"], cb["bp"] // max(1, cb["procs"]), K, PASSES,
+                   "the reference's compiled Jellyfish binding (oracle/_ref)" if cb["kind"] == "reference-binding" else "oracle/libjf_oracle.so", cb["wall"]),
+               "lookups_per_s": cb["lookups"] / cb["wall"]}
+
+    line = {
+        "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64/u8 (2-bit packed k-mers, 32-bit counts)", "data": "synthetic",
+        "config": {"workload": "synthetic %.0f Mb chr20-scale assembly, 0.1%% injected errors, simulated 30x Illumina .jf (%d records), k=%d, p=%d, chunked as jasper.sh -t %d (%d chunks of <= %d bp), solid_thre=%d; one assembly per GPU against a replicated table"
+                   % (args.genome_mb, meta["n_records"], K, PASSES, CHUNK_THREADS, len(chunks), meta["batch_size"], SOLID_THRE),
+                   "l2_policy": "inputs larger than L2: %.1f GB table probed at random, fresh upload every step" % (qf.info["table_bytes"] / 1e9)},
+        "e2e": {"value": e2e_value, "unit": "bp polished/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(last_stats["launches"] * args.steps),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "lookups_per_s": (last_stats["scan_lookups"] + last_stats["walk_lookups"]) / (ms_per_step * 1e-3) * world,
+        "detail": {"scan_ms": last_stats["scan_ms"], "walk_ms": last_stats["walk_ms"], "events": last_stats["events"],
+                   "walk_lookups": last_stats["walk_lookups"], "db_open_s": open_s, "table_gb": qf.info["table_bytes"] / 1e9,
+                   "workload_gen_s": meta["gen_seconds"], "qv_tallies_all_ranks": list(tallies),
+                   "fix_rows_pass0": len(res.rows[0]), "fix_rows_pass1": len(res.rows[1]) if len(res.rows) > 1 else 0},
+    }
+    print(json.dumps(line))
+    qf.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores."""
+    if rank != 0:
+        return
+    base = os.path.join(tempfile.gettempdir(), "jb_bench_ref")
+    shutil.rmtree(base, ignore_errors=True)
+    os.makedirs(base, exist_ok=True)
+    meta, chunks = build_workload(base, args.genome_mb, 0, make_db=True)
+    db_path = os.path.join(base, "db.jf")
+    cores = len(os.sched_getaffinity(0))
+    total_bp = sum(len(s) for _, s in chunks)
+    sample = (args.cpu_sample_kb * 1000) or min(total_bp, 1_000_000 * cores)
+    walls, bps, kind, procs = [], [], "port", cores
+    for step in range(args.warmup + args.steps):
+        cb = cpu_baseline(db_path, chunks, sample, cores)
+        if step >= args.warmup:
+            walls.append(cb["wall"]); bps.append(cb["bp"])
+        kind, procs = cb["kind"], cb["procs"]
+    wall = sum(walls)
+    value = sum(bps) * PASSES / wall
+    line = {
+        "impl": "reference", "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "python int / uint64", "data": "synthetic",
+        "config": {"workload": "bounded sample of: synthetic %.0f Mb chr20-scale assembly, 0.1%% injected errors, simulated 30x Illumina .jf (%d records), k=%d, p=%d, solid_thre=%d"
+                   % (args.genome_mb, meta["n_records"], K, PASSES, SOLID_THRE)},
+        "cpu_baseline": {"value": value, "unit": "bp polished/s", "cores": procs, "kind": "reference" if kind == "reference-binding" else "port",
+                         "sample": "each step: %d worker processes x %d bp slices of the workload's chunks (python restatement of src/jasper.py over %s)"
+                                   % (procs, bps[-1] // max(1, procs), "the reference's compiled Jellyfish binding" if kind == "reference-binding" else "oracle/libjf_oracle.so")},
+        "e2e": {"value": value, "unit": "bp polished/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
