@@ -1,0 +1,99 @@
+// jb_plan.hpp -- host-side planning and assembly around the segment walkers (shared by the
+// product's orchestration in jb_polish.cu and by the test-only host build of the walker).
+//
+// One pass over a batch:
+//   scan (event / weak bits)  ->  first anchor of every seg_block positions  ->  plan_segments
+//   ->  one walker per segment  ->  contigs with a seam violation are re-walked as one segment
+//   ->  place_segments (prefix sums of the segments' new lengths)  ->  concat + fix rows.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "jb_rows.hpp"
+
+namespace jb {
+
+struct SegPlan {
+  uint32_t unit, seg, n_segs;
+  int64_t base, next_anchor;      // next_anchor = -1 for the last segment of the contig
+  int64_t stage_off, stage_cap;   // where the segment materialises edited bases, relative to the contig's staging region
+};
+
+struct BlockRef { uint32_t unit; uint32_t pad; uint64_t start; };
+
+// the blocks k_find_anchors inspects: every seg_block positions of every contig long enough to split
+inline std::vector<BlockRef> make_blocks(const std::vector<int64_t>& lens, int64_t seg_block) {
+  std::vector<BlockRef> b;
+  for (size_t u = 0; u < lens.size(); ++u)
+    for (int64_t s = seg_block; s < lens[u]; s += seg_block) b.push_back(BlockRef{(uint32_t)u, 0, (uint64_t)s});
+  return b;
+}
+
+// anchors[i] belongs to blocks[i] (-1 = none).  caps[u] = bytes of contig u's staging region.
+inline std::vector<SegPlan> plan_segments(const std::vector<int64_t>& lens, const std::vector<int64_t>& caps,
+                                          const std::vector<BlockRef>& blocks, const long long* anchors) {
+  constexpr int64_t kPadMax = 1024, kPadMin = 96;   // growth room of one segment before it needs the whole-contig fallback
+  std::vector<SegPlan> plan;
+  size_t bi = 0;
+  for (size_t u = 0; u < lens.size(); ++u) {
+    std::vector<int64_t> cuts{0};
+    for (; bi < blocks.size() && blocks[bi].unit == u; ++bi)
+      if (anchors && anchors[bi] > cuts.back()) cuts.push_back((int64_t)anchors[bi]);
+    int64_t pad = std::min<int64_t>(kPadMax, (caps[u] - lens[u]) / (int64_t)cuts.size());
+    while (pad < kPadMin && cuts.size() > 1) {       // not enough slack for that many segments: keep every other cut
+      size_t w = 1;
+      for (size_t q = 2; q < cuts.size(); q += 2) cuts[w++] = cuts[q];
+      cuts.resize(w);
+      pad = std::min<int64_t>(kPadMax, (caps[u] - lens[u]) / (int64_t)cuts.size());
+    }
+    const uint32_t n = (uint32_t)cuts.size();
+    for (uint32_t s = 0; s < n; ++s) {
+      SegPlan p;
+      p.unit = (uint32_t)u; p.seg = s; p.n_segs = n;
+      p.base = cuts[s]; p.next_anchor = s + 1 < n ? cuts[s + 1] : -1;
+      const int64_t end = s + 1 < n ? cuts[s + 1] : lens[u];
+      p.stage_off = cuts[s] + (int64_t)s * pad;
+      p.stage_cap = n == 1 ? caps[u] : (end - cuts[s]) + pad;
+      plan.push_back(p);
+    }
+  }
+  return plan;
+}
+
+inline SegPlan whole_contig(uint32_t unit, int64_t cap) { return SegPlan{unit, 0, 1, 0, -1, 0, cap}; }
+
+// After the walkers: per segment the offset of its new bases inside the new contig and the
+// coordinate shift its rows need (segment-local new coordinate + shift = coordinate in the new contig).
+struct SegPlace { int64_t new_off; int64_t row_shift; };
+
+// segs: accepted segments in (unit, seg) order.
+inline std::vector<SegPlace> place_segments(const std::vector<UnitIO>& segs, std::vector<int64_t>* new_lens) {
+  std::vector<SegPlace> out(segs.size());
+  int64_t run = 0;
+  for (size_t i = 0; i < segs.size(); ++i) {
+    if (segs[i].seg == 0) run = 0;
+    out[i].new_off = run;
+    out[i].row_shift = run - segs[i].base;          // bases before `base` moved by the earlier segments' net change
+    run += segs[i].new_len;
+    if (i + 1 == segs.size() || segs[i + 1].seg == 0) (*new_lens)[segs[i].unit] = run;
+  }
+  return out;
+}
+
+// Keep the rows of the accepted launch of every contig and move them into contig coordinates.
+// first_seg[u] = index of contig u's first accepted segment in segs / place.
+inline void settle_rows(std::vector<DevRow>* rows, const std::vector<UnitIO>& segs, const std::vector<SegPlace>& place,
+                        const std::vector<size_t>& first_seg) {
+  size_t w = 0;
+  for (size_t i = 0; i < rows->size(); ++i) {
+    DevRow r = (*rows)[i];
+    const size_t s0 = first_seg[r.unit];
+    if (segs[s0].gen != r.gen) continue;             // superseded attempt
+    r.coord += place[s0 + r.seg].row_shift;
+    (*rows)[w++] = r;
+  }
+  rows->resize(w);
+}
+
+}  // namespace jb

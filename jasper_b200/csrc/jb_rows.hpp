@@ -13,11 +13,15 @@ namespace jb {
 struct HostRow { uint32_t seq_index; int64_t coord; std::string mutation, original; };
 struct PassOut { int64_t wrong = 0, total = 0; std::vector<HostRow> rows; };
 
-// Sorts `rows` by (unit, emission order) and appends the csv rows to out.  Returns false when the
+// Sorts `rows` by (contig, segment, emission order) and appends the csv rows to out.  Returns false when the
 // reference would have crashed (IndexError at src/jasper.py:221 / :309 -> exit 1).
 inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
   bool ok = true;
-  std::sort(rows.begin(), rows.end(), [](const DevRow& x, const DevRow& y) { return x.unit != y.unit ? x.unit < y.unit : x.seqno < y.seqno; });
+  std::sort(rows.begin(), rows.end(), [](const DevRow& x, const DevRow& y) {
+    if (x.unit != y.unit) return x.unit < y.unit;
+    if (x.seg != y.seg) return x.seg < y.seg;
+    return x.seqno < y.seqno;
+  });
   for (const DevRow& r : rows) {
     if (r.kind == kRowPlain) {
       out->push_back(HostRow{r.unit, r.coord, std::string(r.fb, r.fb_len), std::string(r.orig, r.orig_len)});

@@ -43,6 +43,8 @@ struct ScanArgs {
   uint32_t n_tiles;
   uint32_t* counts;        // may be null
   uint32_t* events;        // may be null (bit words)
+  uint32_t* weak;          // with events: bit p = window all-ACGT and count < solid_thre ("pure weak")
+  uint32_t* events_l1;     // with events: bit b = any event among flat bit positions [1024 b, 1024 b + 1024); pre-zeroed
   uint32_t solid_thre;
   unsigned long long* probe_steps;   // optional statistics: total sector loads
 };
@@ -153,16 +155,22 @@ k_scan(TableView t, ScanArgs a) {
     if (kEvents) {
       __syncthreads();
       for (int q = threadIdx.x; q < kTile; q += kScanThreads) {
-        bool ev = false;
+        bool ev = false, wk = false;
         if (q < n_out) {
           const uint64_t p = tile.start + q;
           const uint32_t c = s_cnt[q + back];
+          wk = s_ok[q + back] && c < a.solid_thre;
           ev = !s_ok[q + back] || p < (uint64_t)k || c < a.solid_thre;
           if (!ev) ev = (unsigned long long)c * JB_DIVISOR < (unsigned long long)s_cnt[q];   // count at p - k
         }
-        unsigned int word = __ballot_sync(0xffffffffu, ev);
-        if ((threadIdx.x & 31) == 0 && q < n_out + 31)
-          a.events[(u.out_off + tile.start + q) >> 5] = word;
+        const unsigned int word = __ballot_sync(0xffffffffu, ev);
+        const unsigned int wword = __ballot_sync(0xffffffffu, wk);
+        if ((threadIdx.x & 31) == 0 && q < n_out) {
+          const uint64_t f = u.out_off + tile.start + q;       // flat bit index, multiple of 32
+          a.events[f >> 5] = word;
+          a.weak[f >> 5] = wword;
+          if (word) atomicOr(&a.events_l1[f >> 15], 1u << ((f >> 10) & 31));
+        }
       }
     }
   }

@@ -19,6 +19,7 @@
 
 #include "../../include/jasper_b200.h"
 #include "jb_kmer.cuh"
+#include "jb_segments.cuh"
 
 #if defined(__CUDACC__)
 #define JB_W __device__
@@ -44,7 +45,9 @@ enum RowKind : uint32_t { kRowPlain = 0, kRowBridge = 1 };
 struct DevRow {              // one fix event as logged by the walker
   int64_t coord;
   uint32_t unit;
-  uint32_t seqno;            // emission order inside the unit
+  uint32_t seg;              // segment of the contig that emitted it
+  uint32_t seqno;            // emission order inside the segment
+  uint32_t gen;              // which launch of the pass produced it (a re-run supersedes the first attempt)
   uint32_t kind;
   uint16_t fb_len, orig_len;
   uint64_t aux_off;          // kRowBridge: patch then original bytes in the aux arena
@@ -71,6 +74,12 @@ struct BridgeScratch {       // global memory, one per resident walker
   uint32_t patch_cap;
 };
 
+struct BridgePool {          // bridging scratch is borrowed only while a multi-error patch is being searched
+  BridgeScratch* slots;
+  uint32_t n;
+  uint32_t* busy;            // device: 0 = free, 1 = held
+};
+
 struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint8_t t[kStrCap];        // to_be_fixed
   uint8_t b[kStrCap];        // trial
@@ -82,16 +91,22 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint32_t ext[32];          // extension verdicts of one bridging wave (check_sequence reuses flag)
 };
 
-struct UnitIO {
-  const uint8_t* in;
+struct UnitIO {               // one SEGMENT of one contig (a whole contig is the one-segment case)
+  const uint8_t* in;         // the contig at the start of the pass
   int64_t in_len;
-  uint8_t* out;
+  uint8_t* out;              // new bases of old range [base, ...): materialised part
   int64_t out_cap;
-  const uint32_t* ev;        // event words of this unit (bit p of the pass-start sequence); may be null
-  uint32_t unit;
-  // results
-  int64_t fin_olen, fin_ipos; // new sequence = out[0:fin_olen] ++ in[fin_ipos:]
-  int64_t out_len;
+  const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
+  const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
+  uint64_t ev_bit_base;      // flat bit index of contig position 0
+  int64_t base;              // old coordinate where this segment starts (0 or an anchor)
+  int64_t next_anchor;       // old coordinate of the next segment's anchor, or -1 for the last segment
+  uint32_t unit;             // contig index
+  uint32_t seg;              // segment index inside the contig
+  uint32_t gen;
+  // results: new bases of old [base, end_old) = out[0:fin_olen] ++ in[fin_ipos:end_old]
+  int64_t fin_olen, fin_ipos, end_old;
+  int64_t new_len;
   int64_t wrong;
   int32_t status;
   uint32_t n_rows;
@@ -109,13 +124,18 @@ struct Walker {
   const Key mask;
   UnitIO& u;
   WarpScratch& s;
-  BridgeScratch* bs;
+  BridgePool pool;
+  BridgeScratch* bs = nullptr;
+  int bs_slot = -1;
   RowSink sink;
 
   int64_t i = 0, olen = 0, ipos = 0, L = 0, clean_from = 0;
+  int64_t base = 0, seam_margin = 0;   // seam_margin: how far before `base` this walker may read / how far before the
+                                       // next anchor the previous walker must have stopped editing
   int64_t wrong = 0;
   int status = 0;
   bool brk = false;
+  bool seam_bad = false;
   int64_t wc_base = 0;
   int wc_n = 0;
   bool have_empty = false;
@@ -124,11 +144,52 @@ struct Walker {
   unsigned long long lookups = 0, events = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
-               BridgeScratch* bs_, RowSink sink_)
-      : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), bs(bs_), sink(sink_) {}
+               BridgePool pool_, RowSink sink_)
+      : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), pool(pool_), sink(sink_) {}
+
+  // ---------------------------------------------------------------------------- bridging scratch
+  JB_W bool acquire_bridge() {
+    if (!pool.slots || !pool.n) { status = JB_E_SCRATCH; return false; }
+#if defined(__CUDA_ARCH__)
+    int got = -1;
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t at = (uint32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % pool.n;
+      while (got < 0) {                                  // holders never wait on anything, so this terminates
+        for (uint32_t tries = 0; tries < pool.n && got < 0; ++tries) {
+          if (atomicCAS(&pool.busy[at], 0u, 1u) == 0u) got = (int)at;
+          else at = at + 1 == pool.n ? 0 : at + 1;
+        }
+        if (got < 0) __nanosleep(500);
+      }
+      __threadfence();
+    }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    bs_slot = got;
+#else
+    bs_slot = 0;
+#endif
+    bs = pool.slots + bs_slot;
+    return true;
+  }
+  JB_W void release_bridge() {
+    if (bs_slot < 0) return;
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { __threadfence(); atomicExch(&pool.busy[bs_slot], 0u); }
+#endif
+    bs = nullptr; bs_slot = -1;
+  }
 
   // ---------------------------------------------------------------------------- sequence access
-  JB_W uint8_t get(int64_t x) const { return x < olen ? u.out[x] : u.in[ipos + (x - olen)]; }
+  // new sequence (segment-local coordinates) = in[0:base) ++ out[0:olen) ++ in[ipos:)
+  JB_W uint8_t get(int64_t x) {
+    if (x < base) {                                   // bases the previous segment's walker owns
+      if (x < base - seam_margin) seam_bad = true;    // ...and may have edited: the contig is re-walked whole
+      return u.in[x];
+    }
+    const int64_t y = x - base;
+    return y < olen ? u.out[y] : u.in[ipos + (y - olen)];
+  }
 
   // dst[0:n] = seq[a:b] clamped to [0, L); returns n
   JB_W int load(uint8_t* dst, int64_t a, int64_t b) {
@@ -223,7 +284,8 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- edits
-  JB_W bool ensure_out(int64_t upto) {               // materialise seq[olen:upto) into out
+  JB_W bool ensure_out(int64_t upto_abs) {           // materialise seq[base+olen : upto_abs) into out
+    const int64_t upto = upto_abs - base;
     if (upto <= olen) return true;
     if (upto > u.out_cap) { status = JB_E_SCRATCH; return false; }
     int64_t n = upto - olen;
@@ -235,8 +297,10 @@ struct Walker {
   }
 
   // seq = seq[:a] + repl + seq[e:]
-  JB_W bool apply_edit(int64_t a, int64_t e, const uint8_t* repl, int64_t rlen) {
-    if (!ensure_out(e)) return false;
+  JB_W bool apply_edit(int64_t a_abs, int64_t e_abs, const uint8_t* repl, int64_t rlen) {
+    if (a_abs < base) { status = kSeamViolation; return false; }
+    if (!ensure_out(e_abs)) return false;
+    const int64_t a = a_abs - base, e = e_abs - base;   // offsets into out
     const int64_t delta = rlen - (e - a);
     const int64_t tail = olen - e;
     if (olen + delta > u.out_cap) { status = JB_E_SCRATCH; return false; }
@@ -273,7 +337,7 @@ struct Walker {
     JB_SYNC();
     olen += delta; L += delta;
     int64_t shifted = clean_from + delta;
-    clean_from = a + rlen > shifted ? a + rlen : shifted;
+    clean_from = a_abs + rlen > shifted ? a_abs + rlen : shifted;
     wc_n = 0;
     return true;
   }
@@ -291,7 +355,7 @@ struct Walker {
     DevRow& r = sink.rows[slot];
     JB_LANES(l) {
       if (l == 0) {
-        r.coord = coord; r.unit = u.unit; r.seqno = seqno; r.kind = kRowPlain;
+        r.coord = coord; r.unit = u.unit; r.seg = u.seg; r.gen = u.gen; r.seqno = seqno; r.kind = kRowPlain;
         r.fb_len = (uint16_t)fb_len; r.orig_len = (uint16_t)(orig_len + 1);
         r.aux_off = 0; r.aux_patch_len = 0; r.aux_orig_len = 0;
         r.orig[0] = (char)tag;
@@ -488,7 +552,7 @@ struct Walker {
   }
 
   JB_W int64_t base_extension(int len_tbf, int64_t thr) {
-    if (thr > solid || !bs) { if (!bs) status = JB_E_SCRATCH; return 0; }
+    if (thr > solid) return 0;
     const uint8_t* G = s.t;          // good_kmer_before
     const uint8_t* A = s.b;          // good_k_mer_after
     const int64_t span = (int64_t)len_tbf - 2 * k;
@@ -662,8 +726,10 @@ struct Walker {
       int na = load(s.b, ga, ga + k);
       if (ng < k || na < k) return;
       if (n64 > 0x7fffffff) return;
+      if (thr > solid) return;                             // base_extension returns None (src/jasper.py:529)
+      if (!acquire_bridge()) return;
       int64_t plen = base_extension((int)n64, thr);
-      if (status || plen <= 0) return;
+      if (status || plen <= 0) { release_bridge(); return; }
       // row material: patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
       const int64_t olen_old = ga - (gb + 1);
       unsigned long long off = 0, rslot = 0;
@@ -674,19 +740,20 @@ struct Walker {
 #else
       off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old); rslot = (*sink.used)++;
 #endif
-      if (off + plen + olen_old > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; return; }
+      if (off + plen + olen_old > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; release_bridge(); return; }
       JB_LANES(l) {
         for (int64_t q = l; q < plen; q += 32) sink.aux[off + q] = bs->patch[q];
         for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + plen + q] = get(gb + 1 + q);
         if (l == 0) {
           DevRow& r = sink.rows[rslot];
-          r.coord = gb + 1; r.unit = u.unit; r.seqno = seqno; r.kind = kRowBridge; r.fb_len = 0; r.orig_len = 0;
+          r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = u.gen; r.seqno = seqno; r.kind = kRowBridge; r.fb_len = 0; r.orig_len = 0;
           r.aux_off = off; r.aux_patch_len = (uint32_t)plen; r.aux_orig_len = (uint32_t)olen_old;
         }
       }
       JB_SYNC();
       seqno += 2;                                         // at most two csv rows come out of one patch
       apply_edit(gb + 1, ga, bs->patch, plen);
+      release_bridge();
     }
   }
 
@@ -740,7 +807,7 @@ struct Walker {
   // how far the plain `i += k-1` branch carries it.
   JB_W bool fast_hop() {
     if (!u.ev || i - k < clean_from) return false;
-    const int64_t shift = olen - ipos;                 // new = old + shift for everything >= clean_from
+    const int64_t shift = base + olen - ipos;          // new = old + shift for everything >= clean_from
     const int64_t p = i - shift;
     const int64_t stride = k - 1;
     JB_SYNC();
@@ -754,14 +821,47 @@ struct Walker {
     int l = 0;
     while (l < 32 && !s.flag[l]) ++l;
     i += (int64_t)l * stride;
-    return l == 32;                                     // all clear: keep hopping
+    if (l < 32) return false;                           // an event (or the end) at the new i
+    if (u.ev_l1) {
+      // 32 clear strides: consult the level-1 summary to leap over event-free 1024-position blocks
+      const int64_t p2 = i - shift;
+      const uint64_t blk = (u.ev_bit_base + (uint64_t)p2) >> 10;
+      const uint64_t last_blk = (u.ev_bit_base + (uint64_t)u.in_len) >> 10;
+      JB_SYNC();
+      JB_LANES(l2) {
+        uint64_t bq = blk + (uint64_t)l2;
+        s.flag[l2] = bq > last_blk ? 1u : ((u.ev_l1[bq >> 5] >> (bq & 31)) & 1u);
+      }
+      JB_SYNC();
+      int m = 0;
+      while (m < 32 && !s.flag[m]) ++m;
+      if (m >= 2) {
+        const int64_t T = (int64_t)(((blk + (uint64_t)m) << 10) - u.ev_bit_base);   // first position of a non-empty block
+        if (T - 1 > p2) i += ((T - 1 - p2) / stride) * stride;
+      }
+    }
+    return true;                                        // all clear: keep hopping
   }
 
   JB_W void run() {
-    i = 0; olen = 0; ipos = 0; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; wc_n = 0;
+    base = u.base; seam_margin = seam_read_margin(k);
+    i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; wc_n = 0;
+    bool reached = false;
     while (i < L - k + 1 && !brk && !status) {
+      if (u.next_anchor >= 0) {
+        const int64_t i_old = i - (L - u.in_len);
+        if (i_old >= u.next_anchor) {
+          // the next segment starts here: we must arrive clean and land inside its anchor run
+          // (everything from seam_margin before the anchor on is untouched, so the next walker reads pass-start bases)
+          const int64_t a_new = u.next_anchor + (L - u.in_len);
+          if (clean_from > a_new - seam_margin || i_old > u.next_anchor + k - 2) status = kSeamViolation;
+          reached = true;
+          break;
+        }
+      }
       if (fast_hop()) continue;
       if (!(i < L - k + 1)) break;
+      if (u.next_anchor >= 0 && i - (L - u.in_len) >= u.next_anchor) continue;   // re-check the seam first
       // ---- the reference's loop body at position i (src/jasper.py:56-100)
       int n = load(s.t, i, i + k);                      // n == k here
       int firstN = -1, firstn = -1, bad = 0;
@@ -801,9 +901,16 @@ struct Walker {
         i += k - 1;
       }
     }
-    // the untouched rest in[ipos:] is appended to out[olen:] by k_finalize (whole-GPU copy)
-    u.fin_olen = olen; u.fin_ipos = ipos;
-    u.out_len = status ? 0 : L;
+#if defined(__CUDA_ARCH__)
+    seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdict warp-uniform
+#endif
+    if (!status && seam_bad) status = kSeamViolation;
+    if (!status && u.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
+    const int64_t end_old = u.next_anchor >= 0 ? u.next_anchor : u.in_len;
+    if (!status && ipos > end_old) status = kSeamViolation;
+    // new bases of old [base, end_old) = out[0:olen) ++ in[ipos:end_old); k_concat streams both parts
+    u.fin_olen = olen; u.fin_ipos = ipos; u.end_old = end_old;
+    u.new_len = status ? 0 : olen + (end_old - ipos);
     u.wrong = wrong;
     u.status = status;
     u.n_rows = seqno;

@@ -117,13 +117,18 @@ def hostsim_lib():
     sim.hostsim_seq.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     sim.hostsim_tally.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     sim.hostsim_free.argtypes = [C.c_void_p]
+    sim.hostsim_segments.restype = C.c_ulonglong
+    sim.hostsim_segments.argtypes = [C.c_void_p]
+    sim.hostsim_reruns.restype = C.c_ulonglong
+    sim.hostsim_reruns.argtypes = [C.c_void_p]
     sim.hostsim_mer.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     sim.hostsim_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     return sim
 
 
-def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1):
-    """Run the CPU build of the device walker; returns (status, rows_text, seqs, tallies)."""
+def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=None):
+    """Run the CPU build of the device walker; returns (status, rows_text, seqs, tallies).
+    use_events: 0 = no event bitmask, 1 = bitmask, >= 64 = also split contigs into segments (one anchor per that many bases)."""
     n = len(seqs)
     enc = [s.encode("latin-1") for _, s in seqs]
     arr = (C.c_char_p * max(1, n))(*enc)
@@ -144,6 +149,9 @@ def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1):
             w, t = C.c_longlong(), C.c_longlong()
             sim.hostsim_tally(r, ite, C.byref(w), C.byref(t))
             tallies.append((w.value, t.value))
+        if stats is not None:
+            stats["segments"] = sim.hostsim_segments(r)
+            stats["reruns"] = sim.hostsim_reruns(r)
         return st, txt, out, tallies
     finally:
         sim.hostsim_free(r)

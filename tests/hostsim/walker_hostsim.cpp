@@ -4,11 +4,12 @@
 // compare the device state machine against oracle/jasper_oracle.py without a GPU.
 // It is never linked into libjasper_b200.so and nothing in jasper_b200/ loads it.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "../../jasper_b200/csrc/jb_rows.hpp"
+#include "../../jasper_b200/csrc/jb_plan.hpp"
 
 using namespace jb;
 
@@ -25,11 +26,11 @@ struct SimResult {
   std::vector<PassOut> passes;
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
-  unsigned long long lookups = 0, events = 0;
+  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0;
 };
 
-// event bitmask exactly as k_scan<.,true> defines it (jb_scan.cuh)
-static std::vector<uint32_t> event_bits(const HostDB& db, const std::string& seq, int k, uint32_t solid) {
+// event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
+static void scan_bits(const HostDB& db, const std::string& seq, int k, uint32_t solid, std::vector<uint32_t>* ev, std::vector<uint32_t>* weak) {
   const int64_t L = (int64_t)seq.size();
   std::vector<uint32_t> cnt(L + 1);
   std::vector<uint8_t> ok(L + 1);
@@ -41,58 +42,125 @@ static std::vector<uint32_t> event_bits(const HostDB& db, const std::string& seq
     for (int q = 0; v && q < k; ++q) v = base_valid((uint8_t)seq[p + q]);
     ok[p] = v;
   }
-  std::vector<uint32_t> ev((L + 1 + 31) / 32 + 1, 0);
+  ev->assign((L + 1 + 31) / 32 + 1, 0);
+  weak->assign((L + 1 + 31) / 32 + 1, 0);
   for (int64_t p = 0; p <= L; ++p) {
     bool e = !ok[p] || p < k || cnt[p] < solid;
     if (!e) e = (unsigned long long)cnt[p] * JB_DIVISOR < (unsigned long long)cnt[p - k];
-    if (e) ev[p >> 5] |= 1u << (p & 31);
+    if (e) (*ev)[p >> 5] |= 1u << (p & 31);
+    if (ok[p] && cnt[p] < solid) (*weak)[p >> 5] |= 1u << (p & 31);
   }
-  return ev;
 }
 
+// use_events: 0 = the walker evaluates every position itself, 1 = event bitmask + 1-per-1024 summary,
+// >= 64 = additionally split every contig into segments at the first anchor of every `use_events` positions
 extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint32_t solid, int passes, int fix,
                                      int n_seqs, const char* const* seqs, const uint64_t* lens, int use_events) {
   HostDB db{fn, dbh};
   auto* res = new SimResult();
-  std::vector<std::string> cur(n_seqs);
-  for (int i = 0; i < n_seqs; ++i) cur[i].assign(seqs[i], lens[i]);
+  const size_t n = (size_t)n_seqs;
+  std::vector<std::string> cur(n);
+  for (size_t i = 0; i < n; ++i) cur[i].assign(seqs[i], lens[i]);
   std::vector<DevRow> rows(1 << 16);
   std::vector<uint8_t> aux(1 << 22);
   static BridgeScratch bs;                     // large: keep off the stack
   std::vector<uint32_t> trie(1u << 20);
   std::vector<uint8_t> patch(1u << 18);
   bs.trie = trie.data(); bs.trie_cap = (uint32_t)trie.size(); bs.patch = patch.data(); bs.patch_cap = (uint32_t)patch.size();
+  BridgePool pool{&bs, 1, nullptr};
   WarpScratch ws;
+  const int64_t seg_block = use_events >= 64 ? use_events : 0;
+  int64_t margin = anchor_margin(k);
+  if (const char* e = getenv("JB_ANCHOR_MARGIN")) margin = atol(e);   // tests shrink it to provoke seam re-runs
+  std::vector<int64_t> caps(n);
+  for (size_t i = 0; i < n; ++i) { int64_t L = (int64_t)cur[i].size(); caps[i] = L + L / 8 + 4096; }
   for (int ite = 0; ite <= passes; ++ite) {
     const bool do_fix = fix && ite != passes;
     PassOut po;
     unsigned long long used = 0, aux_used = 0;
     RowSink sink{rows.data(), rows.size(), &used, aux.data(), aux.size(), &aux_used};
-    for (int i = 0; i < n_seqs; ++i) {
-      const int64_t L = (int64_t)cur[i].size();
-      po.total += L - k + 1;
-      std::vector<uint32_t> ev;
-      if (use_events) ev = event_bits(db, cur[i], k, solid);
-      std::vector<uint8_t> out((size_t)(L + L / 8 + 4096));
+    std::vector<int64_t> len(n);
+    std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n);
+    std::vector<std::vector<uint8_t>> stage(n);
+    for (size_t i = 0; i < n; ++i) {
+      len[i] = (int64_t)cur[i].size();
+      po.total += len[i] - k + 1;
+      stage[i].resize((size_t)caps[i] + 64);
+      if (!use_events) continue;
+      scan_bits(db, cur[i], k, solid, &ev[i], &weak[i]);
+      // level-1 summary over this contig's own bit positions (ev_bit_base = 0)
+      l1[i].assign((size_t)(len[i] + 1) / 32768 + 2, 0);
+      for (int64_t p = 0; p <= len[i]; ++p)
+        if (bit_at(ev[i].data(), p)) l1[i][p >> 15] |= 1u << ((p >> 10) & 31);
+    }
+    std::vector<BlockRef> blocks;
+    if (seg_block) blocks = make_blocks(len, seg_block);
+    std::vector<long long> anchors(blocks.size(), -1);
+    for (size_t q = 0; q < blocks.size(); ++q) {
+      const size_t u = blocks[q].unit;
+      const int64_t lo = (int64_t)blocks[q].start, hi = std::min<int64_t>(lo + seg_block, len[u]);
+      anchors[q] = first_anchor(ev[u].data(), weak[u].data(), lo, hi, k, len[u], margin);
+    }
+    std::vector<SegPlan> plan = plan_segments(len, caps, blocks, anchors.data());
+    auto make_seg = [&](const SegPlan& p, uint32_t gen) {
       UnitIO u;
       memset(&u, 0, sizeof u);
-      u.in = (const uint8_t*)cur[i].data(); u.in_len = L; u.out = out.data(); u.out_cap = (int64_t)out.size();
-      u.ev = use_events ? ev.data() : nullptr; u.unit = (uint32_t)i;
-      Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, &bs, sink);
+      const size_t i = p.unit;
+      u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
+      u.out = stage[i].data() + p.stage_off; u.out_cap = p.stage_cap;
+      u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
+      u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
+      return u;
+    };
+    std::vector<UnitIO> segs(plan.size());
+    std::vector<uint8_t> redo(n, 0);
+    bool any_redo = false;
+    for (size_t q = 0; q < plan.size(); ++q) {
+      segs[q] = make_seg(plan[q], 0);
+      Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, segs[q], ws, pool, sink);
       w.run();
-      if (u.status) { res->status = u.status; return res; }
-      po.wrong += u.wrong;
-      res->lookups += u.lookups; res->events += u.events;
-      if (do_fix) {
-        std::string next((const char*)out.data(), (size_t)u.fin_olen);
-        next.append(cur[i].data() + u.fin_ipos, (size_t)(L - u.fin_ipos));
-        if ((int64_t)next.size() != u.out_len) { res->status = -100; return res; }
-        cur[i].swap(next);
+      if (segs[q].status) {
+        if (plan[q].n_segs > 1 && (segs[q].status == kSeamViolation || segs[q].status == JB_E_SCRATCH)) { redo[plan[q].unit] = 1; any_redo = true; }
+        else { res->status = segs[q].status; return res; }
       }
     }
+    res->segments += plan.size();
+    if (any_redo) {
+      std::vector<UnitIO> merged;
+      for (size_t q = 0; q < segs.size();) {
+        const uint32_t unit = segs[q].unit;
+        if (!redo[unit]) { merged.push_back(segs[q++]); continue; }
+        UnitIO u = make_seg(whole_contig(unit, caps[unit]), 1);
+        Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink);
+        w.run();
+        if (u.status) { res->status = u.status; return res; }
+        merged.push_back(u);
+        ++res->reruns;
+        while (q < segs.size() && segs[q].unit == unit) ++q;
+      }
+      segs.swap(merged);
+    }
+    for (const UnitIO& u : segs) { po.wrong += u.wrong; res->lookups += u.lookups; res->events += u.events; }
     if (do_fix) {
+      std::vector<int64_t> new_lens(len);
+      std::vector<SegPlace> place = place_segments(segs, &new_lens);
+      std::vector<size_t> first_seg(n, 0);
+      std::vector<std::string> next(n);
+      for (size_t q = 0; q < segs.size(); ++q) {
+        const UnitIO& u = segs[q];
+        if (u.seg == 0) first_seg[u.unit] = q;
+        std::string& dst = next[u.unit];
+        if ((int64_t)dst.size() != place[q].new_off) { res->status = -100; return res; }
+        dst.append((const char*)u.out, (size_t)u.fin_olen);
+        dst.append((const char*)u.in + u.fin_ipos, (size_t)(u.end_old - u.fin_ipos));
+      }
+      for (size_t i = 0; i < n; ++i) {
+        if ((int64_t)next[i].size() != new_lens[i] || new_lens[i] > caps[i]) { res->status = -100; return res; }
+        cur[i].swap(next[i]);
+      }
       std::vector<DevRow> got(rows.begin(), rows.begin() + used);
       std::vector<uint8_t> a2(aux.begin(), aux.begin() + aux_used);
+      settle_rows(&got, segs, place, first_seg);
       if (!rows_from_log(got, a2, &po.rows)) res->status = JB_E_REFERENCE_CRASH;
     }
     for (const HostRow& r : po.rows) {
@@ -113,6 +181,8 @@ extern "C" int hostsim_iterations(const SimResult* r) { return (int)r->passes.si
 extern "C" void hostsim_tally(const SimResult* r, int ite, long long* wrong, long long* total) { *wrong = r->passes[ite].wrong; *total = r->passes[ite].total; }
 extern "C" const char* hostsim_seq(const SimResult* r, int i, uint64_t* len) { *len = r->seqs[i].size(); return r->seqs[i].data(); }
 extern "C" unsigned long long hostsim_lookups(const SimResult* r) { return r->lookups; }
+extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->segments; }
+extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
 extern "C" void hostsim_free(SimResult* r) { delete r; }
 
 // also expose the shared k-mer arithmetic for unit tests

@@ -83,6 +83,58 @@ def test_polish_reproduces_reference_bytes(golden_cases, dbs, name):
     assert res.counters["kernel_launches"] >= 2 * (case["passes"] + 1)
 
 
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+@pytest.mark.parametrize("seg_block,margin", [("0", None), ("64", None), ("256", "0"), ("2048", None)])
+def test_polish_golden_is_independent_of_segmentation(golden_cases, dbs, name, seg_block, margin, monkeypatch):
+    """The same bytes whether contigs are walked whole (JB_SEG_BLOCK=0) or split into segments at anchors."""
+    monkeypatch.setenv("JB_SEG_BLOCK", seg_block)
+    if margin is not None:
+        monkeypatch.setenv("JB_ANCHOR_MARGIN", margin)
+    case = golden_cases[name]
+    seqs = jo.read_fasta(case["fasta"])
+    res = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
+    assert res.status == 0
+    for ite in range(case["passes"]):
+        assert jo.format_fix_csv(res.rows[ite]) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+    assert jo.format_fasta(res.seqs) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+    assert ("%d %d\n" % res.tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+    if seg_block != "0":
+        assert res.counters["segments"] > (case["passes"] + 1) * len(seqs)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_polish_big_fuzz_segmented_matches_hostsim_and_oracle(tmp_path, hostsim_lib, seed, monkeypatch):
+    """Bigger dirty genomes, many seams: device result == sequential host build of the walker (== oracle for
+    the first seeds), for the default anchor margin and for margin 0 (seam re-runs)."""
+    k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
+    recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k, big=True)
+    odb = helpers.OracleDB(path)
+    st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, 1)
+    names = [n for n, _ in recs]
+    if seed < 104:
+        want, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
+        if want is not None:
+            assert st == 0 and out == [s for _, s in want.seqs] and txt == helpers.rows_text(want.passes, names)
+    qf = capi.QueryMerFile(path)
+    try:
+        reruns = 0
+        for seg_block, margin in (("128", None), ("128", "0"), ("1024", "0")):
+            monkeypatch.setenv("JB_SEG_BLOCK", seg_block)
+            if margin is None:
+                monkeypatch.delenv("JB_ANCHOR_MARGIN", raising=False)
+            else:
+                monkeypatch.setenv("JB_ANCHOR_MARGIN", margin)
+            res = qf.polish(recs, k, thr, 2)
+            assert res.status == (0 if st == 0 else st)
+            if st == 0:
+                assert helpers.product_rows_text(res.rows, names) == txt
+                assert [s for _, s in res.seqs] == out
+                assert res.tallies == tallies
+            reruns += res.counters["segment_reruns"]
+    finally:
+        qf.close()
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_polish_fuzz_matches_oracle(tmp_path, seed):
     k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]

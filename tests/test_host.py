@@ -98,7 +98,7 @@ def test_alignment_matches_shim(hostsim_lib):
 
 
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
-@pytest.mark.parametrize("use_events", [0, 1])
+@pytest.mark.parametrize("use_events", [0, 1, 64, 300, 2048])
 def test_walker_source_matches_golden(golden_cases, hostsim_lib, name, use_events):
     case = golden_cases[name]
     odb = helpers.OracleDB(case["db"])
@@ -123,7 +123,7 @@ def test_walker_source_fuzz(tmp_path, hostsim_lib, seed):
     recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k)
     odb = helpers.OracleDB(path)
     res, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
-    for use_events in (0, 1):
+    for use_events in (0, 1, 64, 512):       # >= 64: split into segments at anchors, one per that many positions
         st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, use_events)
         if res is None:
             assert st == -7          # JB_E_REFERENCE_CRASH
@@ -132,3 +132,33 @@ def test_walker_source_fuzz(tmp_path, hostsim_lib, seed):
         assert txt == helpers.rows_text(res.passes, [n for n, _ in recs])
         assert out == [s for _, s in res.seqs]
         assert tallies == [(p.wrong, p.total) for p in res.passes]
+
+
+@pytest.mark.parametrize("seed", range(100, 110))
+def test_segment_seams_are_exact(tmp_path, hostsim_lib, seed, monkeypatch):
+    """Splitting a contig at anchors and walking the segments independently must not change a byte:
+    compare against the same walker run sequentially over bigger fuzz genomes (many seams), with the
+    default anchor margin and with margin 0, where neighbouring fixes do collide with seams and the
+    walkers' run-time seam checks must catch every collision (the contig is then re-walked whole)."""
+    k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
+    recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k, big=True)
+    odb = helpers.OracleDB(path)
+    base = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, 1)
+    if seed < 103:                               # and the sequential walker against the oracle itself
+        res, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
+        if res is not None:
+            assert base[0] == 0 and base[2] == [s for _, s in res.seqs]
+            assert base[1] == helpers.rows_text(res.passes, [n for n, _ in recs])
+    total = {"segments": 0, "reruns": 0}
+    for margin in (None, "0"):
+        if margin is None:
+            monkeypatch.delenv("JB_ANCHOR_MARGIN", raising=False)
+        else:
+            monkeypatch.setenv("JB_ANCHOR_MARGIN", margin)
+        for block in (64, 1024):
+            st = {}
+            got = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, block, stats=st)
+            assert got == base, (margin, block)
+            for key in total:
+                total[key] += st[key]
+    assert total["segments"] > 3 * len(recs) * 4          # the contigs really were split
