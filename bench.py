@@ -228,7 +228,9 @@ def main():
                  "scan_lookups": capi.counter("scan_lookups"), "walk_lookups": capi.counter("walk_lookups"),
                  "launches": capi.counter("kernel_launches"), "probe_steps": capi.counter("probe_steps"), "events": capi.counter("events"),
                  "plan_ms": capi.timing_ms("polish_plan"), "segments": capi.counter("segments"), "reruns": capi.counter("segment_reruns"),
-                 "seg_block": capi.counter("seg_block")}
+                 "seg_block": capi.counter("seg_block"), "kwalk_ms": capi.timing_ms("polish_kwalk"),
+                 "max_seg_events": capi.counter("max_seg_events"), "max_seg_lookups": capi.counter("max_seg_lookups"),
+                 "max_seg_span": capi.counter("max_seg_span")}
         return b, ms, stats
 
     for _ in range(args.warmup):
@@ -329,7 +331,8 @@ def main():
         "cpu_baseline": cpu,
         "lookups_per_s": (last_stats["scan_lookups"] + last_stats["walk_lookups"]) / (ms_per_step * 1e-3) * world,
         "detail": {"scan_ms": last_stats["scan_ms"], "plan_ms": last_stats["plan_ms"], "walk_ms": last_stats["walk_ms"], "events": last_stats["events"],
-                   "segments": last_stats["segments"], "segment_reruns": last_stats["reruns"], "seg_block": last_stats["seg_block"],
+                   "kwalk_ms": last_stats["kwalk_ms"], "max_seg_events": last_stats["max_seg_events"], "max_seg_lookups": last_stats["max_seg_lookups"],
+                   "max_seg_span": last_stats["max_seg_span"], "segments": last_stats["segments"], "segment_reruns": last_stats["reruns"], "seg_block": last_stats["seg_block"],
                    "walk_lookups": last_stats["walk_lookups"], "db_open_s": open_s, "table_gb": qf.info["table_bytes"] / 1e9,
                    "workload_gen_s": meta["gen_seconds"], "qv_tallies_all_ranks": list(tallies),
                    "fix_rows_pass0": len(res.rows[0]), "fix_rows_pass1": len(res.rows[1]) if len(res.rows) > 1 else 0},

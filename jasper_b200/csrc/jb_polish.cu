@@ -34,7 +34,7 @@ struct WalkCfg { int k, step; uint32_t solid; int fix; };
 
 __global__ void __launch_bounds__(kWalkWarps * 32)
 k_walk(TableView t, UnitIO* segs, const uint32_t* order, uint32_t n_segs, WalkCfg cfg, BridgePool pool, RowSink sink,
-       unsigned int* next_seg) {
+       JobSink jobs, unsigned int* next_seg) {
   __shared__ WarpScratch scratch[kWalkWarps];
   const int warp = threadIdx.x >> 5;
   DevDB db{t};
@@ -44,7 +44,7 @@ k_walk(TableView t, UnitIO* segs, const uint32_t* order, uint32_t n_segs, WalkCf
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= n_segs) break;
     UnitIO& u = segs[order[slot]];
-    Walker<DevDB> w(db, cfg.k, cfg.step, cfg.solid, cfg.fix != 0, u, scratch[warp], pool, sink);
+    Walker<DevDB> w(db, cfg.k, cfg.step, cfg.solid, cfg.fix != 0, u, scratch[warp], pool, sink, jobs);
     w.run();
     __syncwarp();
   }
@@ -79,13 +79,14 @@ __device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int6
   for (int64_t q = head + nvec * 16 + tid; q < n; q += nth) dst[q] = src[q];
 }
 
-// new bases of segment s = out[0:fin_olen) ++ in[fin_ipos:end_old)  ->  outb + dst_off[s]
-__global__ void k_concat(const UnitIO* segs, const int64_t* dst_off, uint32_t n_segs, uint8_t* outb) {
-  for (uint32_t si = blockIdx.y; si < n_segs; si += gridDim.y) {
-    const UnitIO u = segs[si];
-    uint8_t* dst = outb + dst_off[si];
-    copy_span(u.out, dst, u.fin_olen);
-    copy_span(u.in + u.fin_ipos, dst + u.fin_olen, u.end_old - u.fin_ipos);
+// every copy job of an accepted segment: outb[dst_off[slot] + rel ...) = src[0:len); superseded slots have dst_off < 0
+__global__ void k_concat(const CopyJob* jobs, const unsigned long long* n_jobs, const int64_t* dst_off, uint8_t* outb) {
+  const unsigned long long n = *n_jobs;
+  for (unsigned long long j = blockIdx.y; j < n; j += gridDim.y) {
+    const CopyJob job = jobs[j];
+    const int64_t off = dst_off[job.slot];
+    if (off < 0) continue;
+    copy_span(job.src, outb + off + job.rel, job.len);
   }
 }
 
@@ -122,7 +123,8 @@ struct jb_batch {
   unsigned int* d_next = nullptr;
   DevRow* d_rows = nullptr; unsigned long long rows_cap = 0;
   uint8_t* d_aux = nullptr; unsigned long long aux_cap = 0;
-  unsigned long long* d_used = nullptr;   // [0] rows, [1] aux, [2] probe steps
+  unsigned long long* d_used = nullptr;   // [0] rows, [1] aux, [2] probe steps, [3] copy jobs
+  CopyJob* d_jobs = nullptr; unsigned long long jobs_cap = 0;
   BridgeScratch* d_pool = nullptr; uint32_t* d_trie = nullptr; uint8_t* d_patch = nullptr; uint32_t* d_busy = nullptr;
   uint8_t* pinned_in = nullptr;
   int sms = 148;
@@ -134,7 +136,7 @@ struct jb_batch {
     cudaSetDevice(db->device);
     cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(stage); cudaFree(events); cudaFree(weak); cudaFree(events_l1);
     cudaFree(d_segs); cudaFree(d_order); cudaFree(d_dst_off); cudaFree(d_scan_units); cudaFree(d_seg_units); cudaFree(d_tiles);
-    cudaFree(d_blocks); cudaFree(d_anchors); cudaFree(d_next); cudaFree(d_rows); cudaFree(d_aux); cudaFree(d_used);
+    cudaFree(d_blocks); cudaFree(d_anchors); cudaFree(d_next); cudaFree(d_rows); cudaFree(d_aux); cudaFree(d_used); cudaFree(d_jobs);
     cudaFree(d_pool); cudaFree(d_trie); cudaFree(d_patch); cudaFree(d_busy);
     if (pinned_in) cudaFreeHost(pinned_in);
   }
@@ -177,6 +179,8 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   JB_CUDA(cudaMalloc(&b->d_rows, b->rows_cap * sizeof(DevRow)));
   JB_CUDA(cudaMalloc(&b->d_aux, b->aux_cap));
   JB_CUDA(cudaMalloc(&b->d_used, 32));
+  b->jobs_cap = total_len / 8 + 4 * n + 65536;
+  JB_CUDA(cudaMalloc(&b->d_jobs, b->jobs_cap * sizeof(CopyJob)));
   cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, db->device);
   JB_CUDA(cudaMalloc(&b->d_pool, (size_t)kPoolSlots * sizeof(BridgeScratch)));
   JB_CUDA(cudaMalloc(&b->d_trie, (size_t)kPoolSlots * kTrieCap * 4));
@@ -211,15 +215,16 @@ extern "C" void jb_batch_free(jb_batch* b) { delete b; }
 namespace {
 
 int64_t pick_seg_block(int64_t total_len, int sms) {
-  if (const char* e = getenv("JB_SEG_BLOCK")) { long v = atol(e); if (v >= 64) return v; if (v == 0) return 0; }
+  // (multiples of 32: k_find_anchors walks whole bitmask words)
+  if (const char* e = getenv("JB_SEG_BLOCK")) { long v = atol(e); if (v >= 64) return (v + 31) / 32 * 32; if (v == 0) return 0; }
   // enough segments to fill the resident walkers a few times over, but not so short that seams dominate
   const int64_t resident = (int64_t)sms * kWalkCtasPerSm * kWalkWarps;
   int64_t blk = total_len / (4 * resident);
   blk = std::max<int64_t>(1024, std::min<int64_t>(8192, blk));
-  return blk;
+  return (blk + 31) / 32 * 32;
 }
 
-UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen) {
+UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, uint32_t slot, int keep_margin) {
   UnitIO u;
   std::memset(&u, 0, sizeof u);
   const size_t i = p.unit;
@@ -227,7 +232,9 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen) 
   u.out = b->stage + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
   u.ev = b->events + b->off[i] / 32; u.ev_l1 = b->events_l1; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
-  u.unit = p.unit; u.seg = p.seg; u.gen = gen;
+  u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
+  u.materialize_all = gen ? 1u : 0u;               // re-runs take the conservative path
+  u.keep_margin = keep_margin;
   return u;
 }
 
@@ -245,11 +252,14 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
   const size_t n = b->n;
-  cudaEvent_t ev_begin, ev_end, ev_a, ev_b, ev_c, ev_d;
+  cudaEvent_t ev_begin, ev_end, ev_a, ev_b, ev_c, ev_d, ev_e;
+  JB_CUDA(cudaEventCreate(&ev_e));
   JB_CUDA(cudaEventCreate(&ev_begin)); JB_CUDA(cudaEventCreate(&ev_end));
   JB_CUDA(cudaEventCreate(&ev_a)); JB_CUDA(cudaEventCreate(&ev_b)); JB_CUDA(cudaEventCreate(&ev_c)); JB_CUDA(cudaEventCreate(&ev_d));
   double scan_ms = 0, walk_ms = 0, plan_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
+  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0;
+  double kwalk_ms = 0;
   std::vector<ScanUnit> sunits(n);
   std::vector<SegUnit> gunits(n);
   std::vector<int64_t> caps(n);
@@ -264,6 +274,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   const int64_t seg_block = pick_seg_block(total_len, b->sms);
   int64_t margin = anchor_margin(k);
   if (const char* e = getenv("JB_ANCHOR_MARGIN")) margin = std::max<long>(0, atol(e));   // tests: provoke seam re-runs
+  int keep_margin = default_keep_margin(k);
+  if (const char* e = getenv("JB_KEEP_MARGIN")) keep_margin = (int)std::max<long>(0, atol(e));   // tests: provoke far-back re-runs
   b->passes.clear();
   JB_CUDA(cudaEventRecord(ev_begin, s));
   for (int ite = 0; ite <= passes && n > 0; ++ite) {
@@ -320,7 +332,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     }
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, anchors.data());
     std::vector<UnitIO> segs(plan.size());
-    for (size_t q = 0; q < plan.size(); ++q) segs[q] = make_seg(b, plan[q], in, 0);
+    for (size_t q = 0; q < plan.size(); ++q) segs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin);
     const size_t need = segs.size() + n;                  // room for whole-contig re-runs behind the plan
     if (need > b->segs_cap) {
       cudaFree(b->d_segs); cudaFree(b->d_order); cudaFree(b->d_dst_off);
@@ -338,34 +350,37 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     // ---- walk
     WalkCfg c2 = cfg; c2.fix = do_fix ? 1 : 0;
     RowSink sink{b->d_rows, b->rows_cap, b->d_used, b->d_aux, b->aux_cap, b->d_used + 1};
+    JobSink jobs{b->d_jobs, b->jobs_cap, b->d_used + 3};
     auto walk_grid = [&](size_t cnt) { return (unsigned)std::min<size_t>((cnt + kWalkWarps - 1) / kWalkWarps, (size_t)b->sms * kWalkCtasPerSm); };
     JB_CUDA(cudaEventRecord(ev_c, s));
-    k_walk<<<walk_grid(segs.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)segs.size(), c2, pool, sink, b->d_next);
+    k_walk<<<walk_grid(segs.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)segs.size(), c2, pool, sink, jobs, b->d_next);
     JB_CUDA(cudaGetLastError());
     ++launches;
+    JB_CUDA(cudaEventRecord(ev_e, s));
     JB_CUDA(cudaMemcpyAsync(segs.data(), b->d_segs, segs.size() * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
     JB_CUDA(cudaStreamSynchronize(s));
+    { float m2 = 0; cudaEventElapsedTime(&m2, ev_c, ev_e); kwalk_ms += m2; }
     n_segments += (int64_t)segs.size();
     // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment
     std::vector<uint8_t> redo(n, 0);
-    size_t n_redo = 0;
+    size_t n_redo = 0, n_slots = segs.size();
     for (const UnitIO& u : segs) {
       if (!u.status) continue;
       const bool split = plan[&u - segs.data()].n_segs > 1;
-      if (split && (u.status == kSeamViolation || u.status == JB_E_SCRATCH)) { if (!redo[u.unit]) { redo[u.unit] = 1; ++n_redo; } continue; }
+      if (u.status == kFarBack || (split && (u.status == kSeamViolation || u.status == JB_E_SCRATCH))) { if (!redo[u.unit]) { redo[u.unit] = 1; ++n_redo; } continue; }
       b->status = u.status;
       return fail(JB_E_SCRATCH, "contig " + std::to_string(u.unit) + ": a device work pool overflowed during polishing "
                                 "(output slack, fix-row arena, or de-Bruijn path pool; status " + std::to_string(u.status) + ")");
     }
     if (n_redo) {
       std::vector<UnitIO> again;
-      for (size_t i = 0; i < n; ++i) if (redo[i]) again.push_back(make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1));
+      for (size_t i = 0; i < n; ++i) if (redo[i]) again.push_back(make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(segs.size() + again.size()), keep_margin));
       std::vector<uint32_t> ord2(again.size());
       for (size_t q = 0; q < again.size(); ++q) ord2[q] = (uint32_t)(segs.size() + q);
       JB_CUDA(cudaMemcpyAsync(b->d_segs + segs.size(), again.data(), again.size() * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
       JB_CUDA(cudaMemcpyAsync(b->d_order, ord2.data(), ord2.size() * 4, cudaMemcpyHostToDevice, s));
       JB_CUDA(cudaMemsetAsync(b->d_next, 0, 4, s));
-      k_walk<<<walk_grid(again.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)again.size(), c2, pool, sink, b->d_next);
+      k_walk<<<walk_grid(again.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)again.size(), c2, pool, sink, jobs, b->d_next);
       JB_CUDA(cudaGetLastError());
       ++launches;
       JB_CUDA(cudaMemcpyAsync(again.data(), b->d_segs + segs.size(), again.size() * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
@@ -385,27 +400,34 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
           while (q < segs.size() && segs[q].unit == unit) ++q;
         } else merged.push_back(segs[q++]);
       }
+      n_slots = segs.size() + again.size();
       segs.swap(merged);
-      JB_CUDA(cudaMemcpyAsync(b->d_segs, segs.data(), segs.size() * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
     }
-    for (const UnitIO& u : segs) { po.wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events; }
+    for (const UnitIO& u : segs) {
+      po.wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events;
+      max_seg_events = std::max<int64_t>(max_seg_events, (int64_t)u.events);
+      max_seg_lookups = std::max<int64_t>(max_seg_lookups, (int64_t)u.lookups);
+      max_seg_span = std::max<int64_t>(max_seg_span, u.end_old - u.base);
+    }
     unsigned long long used[4] = {0, 0, 0, 0};
     JB_CUDA(cudaMemcpyAsync(used, b->d_used, 32, cudaMemcpyDeviceToHost, s));
+    JB_CUDA(cudaStreamSynchronize(s));
     if (do_fix) {
       // ---- stitch the segments into the other buffer
       std::vector<int64_t> new_lens(b->len);
       std::vector<SegPlace> place = place_segments(segs, &new_lens);
-      std::vector<int64_t> dst_off(segs.size());
+      std::vector<int64_t> dst_off(n_slots, -1);       // by launch slot; superseded attempts stay at -1
       std::vector<size_t> first_seg(n, 0);
       for (size_t q = 0; q < segs.size(); ++q) {
-        dst_off[q] = (int64_t)b->off[segs[q].unit] + place[q].new_off;
+        dst_off[segs[q].slot] = (int64_t)b->off[segs[q].unit] + place[q].new_off;
         if (segs[q].seg == 0) first_seg[segs[q].unit] = q;
       }
+      if (used[3] > b->jobs_cap) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "copy-job arena overflow"); }
       for (size_t i = 0; i < n; ++i)
         if (new_lens[i] > caps[i]) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "contig " + std::to_string(i) + " outgrew its output slack"); }
       JB_CUDA(cudaMemcpyAsync(b->d_dst_off, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
-      dim3 g(segs.size() > 4 * n ? 2 : 64, (unsigned)std::min<size_t>(segs.size(), 32768));
-      k_concat<<<g, 256, 0, s>>>(b->d_segs, b->d_dst_off, (uint32_t)segs.size(), outb);
+      dim3 g(4, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(used[3], 1), 16384));
+      k_concat<<<g, 256, 0, s>>>(b->d_jobs, b->d_used + 3, b->d_dst_off, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;
       JB_CUDA(cudaEventRecord(ev_d, s));
@@ -438,8 +460,10 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   note_timing("polish", ms); note_timing("polish_scan", scan_ms); note_timing("polish_walk", walk_ms); note_timing("polish_plan", plan_ms);
   note_counter("scan_lookups", scan_lookups); note_counter("walk_lookups", walk_lookups);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
+  note_timing("polish_kwalk", kwalk_ms);
+  note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
   note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
-  cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d);
+  cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
   if (n == 0) for (int ite = 0; ite <= passes; ++ite) b->passes.push_back(PassOut{});
   return JB_OK;

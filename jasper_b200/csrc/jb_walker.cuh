@@ -74,6 +74,16 @@ struct BridgeScratch {       // global memory, one per resident walker
   uint32_t patch_cap;
 };
 
+// The new bases of a segment are described as copy jobs: materialised windows around edits (src = the
+// segment's staging region) and untouched stretches (src = the pass-start contig).  `rel` = offset inside
+// the segment's new bases; k_concat adds the segment's offset in the new contig.
+struct CopyJob { const uint8_t* src; int64_t rel; int64_t len; uint32_t slot; uint32_t pad; };
+struct JobSink { CopyJob* jobs; unsigned long long cap; unsigned long long* used; };
+
+constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
+constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
+JB_HD int default_keep_margin(int k) { return 3 * k + 64; }
+
 struct BridgePool {          // bridging scratch is borrowed only while a multi-error patch is being searched
   BridgeScratch* slots;
   uint32_t n;
@@ -94,7 +104,7 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
 struct UnitIO {               // one SEGMENT of one contig (a whole contig is the one-segment case)
   const uint8_t* in;         // the contig at the start of the pass
   int64_t in_len;
-  uint8_t* out;              // new bases of old range [base, ...): materialised part
+  uint8_t* out;              // staging: out[r] = new base r of this segment, valid inside materialised windows
   int64_t out_cap;
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
@@ -104,8 +114,11 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   uint32_t unit;             // contig index
   uint32_t seg;              // segment index inside the contig
   uint32_t gen;
-  // results: new bases of old [base, end_old) = out[0:fin_olen] ++ in[fin_ipos:end_old]
-  int64_t fin_olen, fin_ipos, end_old;
+  uint32_t slot;             // index of this descriptor in the launch's array (copy jobs refer to it)
+  uint32_t materialize_all;  // 1: never skip clean stretches (the conservative mode of re-runs)
+  int32_t keep_margin;       // bases kept materialised in front of an edit (default_keep_margin(k); tests shrink it)
+  // results: old [base, end_old) became new_len bases, described by this segment's copy jobs
+  int64_t end_old;
   int64_t new_len;
   int64_t wrong;
   int32_t status;
@@ -128,8 +141,12 @@ struct Walker {
   BridgeScratch* bs = nullptr;
   int bs_slot = -1;
   RowSink sink;
+  JobSink jobs;
 
   int64_t i = 0, olen = 0, ipos = 0, L = 0, clean_from = 0;
+  int64_t wstart = 0;                  // out[wstart:olen) is the materialised window; [0, wstart) is closed (copy jobs)
+  int64_t keep_margin = 0;             // bases kept materialised in front of an edit
+  bool far_back = false;
   int64_t base = 0, seam_margin = 0;   // seam_margin: how far before `base` this walker may read / how far before the
                                        // next anchor the previous walker must have stopped editing
   int64_t wrong = 0;
@@ -144,8 +161,8 @@ struct Walker {
   unsigned long long lookups = 0, events = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
-               BridgePool pool_, RowSink sink_)
-      : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), pool(pool_), sink(sink_) {}
+               BridgePool pool_, RowSink sink_, JobSink jobs_)
+      : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), pool(pool_), sink(sink_), jobs(jobs_) {}
 
   // ---------------------------------------------------------------------------- bridging scratch
   JB_W bool acquire_bridge() {
@@ -188,7 +205,10 @@ struct Walker {
       return u.in[x];
     }
     const int64_t y = x - base;
-    return y < olen ? u.out[y] : u.in[ipos + (y - olen)];
+    if (y >= olen) return u.in[ipos + (y - olen)];
+    if (y >= wstart) return u.out[y];
+    far_back = true;                                  // behind the window: the contig is re-walked fully materialised
+    return (uint8_t)'A';
   }
 
   // dst[0:n] = seq[a:b] clamped to [0, L); returns n
@@ -284,13 +304,48 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- edits
-  JB_W bool ensure_out(int64_t upto_abs) {           // materialise seq[base+olen : upto_abs) into out
+  JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
+    if (len <= 0) return true;
+    JB_SYNC();
+    unsigned long long slot = 0;
+#if defined(__CUDA_ARCH__)
+    if ((threadIdx.x & 31) == 0) slot = atomicAdd(jobs.used, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+#else
+    slot = (*jobs.used)++;
+#endif
+    if (slot >= jobs.cap) { status = JB_E_SCRATCH; return false; }
+    JB_LANES(l) { if (l == 0) { CopyJob j; j.src = src; j.rel = rel; j.len = len; j.slot = u.slot; j.pad = 0; jobs.jobs[slot] = j; } }
+    JB_SYNC();
+    return true;
+  }
+
+  // materialise the new sequence up to upto_abs for an edit that starts at a_abs; a long clean stretch
+  // in front of the edit is handed to k_concat as a copy job instead of being copied here
+  JB_W bool ensure_out(int64_t a_abs, int64_t upto_abs) {
     const int64_t upto = upto_abs - base;
     if (upto <= olen) return true;
     if (upto > u.out_cap) { status = JB_E_SCRATCH; return false; }
-    int64_t n = upto - olen;
+    if (!u.materialize_all) {
+      const int64_t keep_from = (a_abs - base) - keep_margin;
+      if (keep_from > olen + kMinGap) {
+        if (!emit_job(u.out + wstart, wstart, olen - wstart)) return false;
+        const int64_t gap = keep_from - olen;
+        if (!emit_job(u.in + ipos, olen, gap)) return false;
+        ipos += gap; olen += gap; wstart = olen;
+      }
+    }
+    const int64_t n = upto - olen;
     JB_SYNC();
-    JB_LANES(l) { for (int64_t q = l; q < n; q += 32) u.out[olen + q] = u.in[ipos + q]; }
+    for (int64_t q0 = 0; q0 < n; q0 += 256) {           // 8 independent loads per lane before the stores
+      uint8_t v[8];
+      JB_LANES(l) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; v[j] = q < n ? u.in[ipos + q] : (uint8_t)0; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; if (q < n) u.out[olen + q] = v[j]; }
+      }
+    }
     JB_SYNC();
     ipos += n; olen = upto;
     return true;
@@ -299,7 +354,8 @@ struct Walker {
   // seq = seq[:a] + repl + seq[e:]
   JB_W bool apply_edit(int64_t a_abs, int64_t e_abs, const uint8_t* repl, int64_t rlen) {
     if (a_abs < base) { status = kSeamViolation; return false; }
-    if (!ensure_out(e_abs)) return false;
+    if (a_abs - base < wstart) { status = kFarBack; return false; }
+    if (!ensure_out(a_abs, e_abs)) return false;
     const int64_t a = a_abs - base, e = e_abs - base;   // offsets into out
     const int64_t delta = rlen - (e - a);
     const int64_t tail = olen - e;
@@ -844,10 +900,15 @@ struct Walker {
   }
 
   JB_W void run() {
-    base = u.base; seam_margin = seam_read_margin(k);
+    base = u.base; seam_margin = seam_read_margin(k); keep_margin = u.keep_margin; wstart = 0; far_back = false;
     i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; wc_n = 0;
     bool reached = false;
     while (i < L - k + 1 && !brk && !status) {
+#if defined(__CUDA_ARCH__)
+      if (__any_sync(0xffffffffu, far_back || seam_bad)) break;   // the result is void already: stop early
+#else
+      if (far_back || seam_bad) break;
+#endif
       if (u.next_anchor >= 0) {
         const int64_t i_old = i - (L - u.in_len);
         if (i_old >= u.next_anchor) {
@@ -902,14 +963,20 @@ struct Walker {
       }
     }
 #if defined(__CUDA_ARCH__)
-    seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdict warp-uniform
+    seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdicts warp-uniform
+    far_back = __any_sync(0xffffffffu, far_back);
 #endif
     if (!status && seam_bad) status = kSeamViolation;
+    if (!status && far_back) status = kFarBack;
     if (!status && u.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
     const int64_t end_old = u.next_anchor >= 0 ? u.next_anchor : u.in_len;
     if (!status && ipos > end_old) status = kSeamViolation;
-    // new bases of old [base, end_old) = out[0:olen) ++ in[ipos:end_old); k_concat streams both parts
-    u.fin_olen = olen; u.fin_ipos = ipos; u.end_old = end_old;
+    // new bases of old [base, end_old) = closed jobs ++ out[wstart:olen) ++ in[ipos:end_old)
+    if (fix && !status) {
+      emit_job(u.out + wstart, wstart, olen - wstart);
+      emit_job(u.in + ipos, olen, end_old - ipos);
+    }
+    u.end_old = end_old;
     u.new_len = status ? 0 : olen + (end_old - ipos);
     u.wrong = wrong;
     u.status = status;

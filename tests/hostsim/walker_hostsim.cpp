@@ -26,7 +26,7 @@ struct SimResult {
   std::vector<PassOut> passes;
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
-  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0;
+  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0;
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
@@ -72,6 +72,8 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
   const int64_t seg_block = use_events >= 64 ? use_events : 0;
   int64_t margin = anchor_margin(k);
   if (const char* e = getenv("JB_ANCHOR_MARGIN")) margin = atol(e);   // tests shrink it to provoke seam re-runs
+  int keep_margin = default_keep_margin(k);
+  if (const char* e = getenv("JB_KEEP_MARGIN")) keep_margin = atoi(e);
   std::vector<int64_t> caps(n);
   for (size_t i = 0; i < n; ++i) { int64_t L = (int64_t)cur[i].size(); caps[i] = L + L / 8 + 4096; }
   for (int ite = 0; ite <= passes; ++ite) {
@@ -79,6 +81,9 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
     PassOut po;
     unsigned long long used = 0, aux_used = 0;
     RowSink sink{rows.data(), rows.size(), &used, aux.data(), aux.size(), &aux_used};
+    unsigned long long jobs_used = 0;
+    std::vector<CopyJob> jobv(1 << 18);
+    JobSink jobs{jobv.data(), jobv.size(), &jobs_used};
     std::vector<int64_t> len(n);
     std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n);
     std::vector<std::vector<uint8_t>> stage(n);
@@ -102,7 +107,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       anchors[q] = first_anchor(ev[u].data(), weak[u].data(), lo, hi, k, len[u], margin);
     }
     std::vector<SegPlan> plan = plan_segments(len, caps, blocks, anchors.data());
-    auto make_seg = [&](const SegPlan& p, uint32_t gen) {
+    auto make_seg = [&](const SegPlan& p, uint32_t gen, uint32_t slot) {
       UnitIO u;
       memset(&u, 0, sizeof u);
       const size_t i = p.unit;
@@ -110,28 +115,34 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       u.out = stage[i].data() + p.stage_off; u.out_cap = p.stage_cap;
       u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
+      u.slot = slot; u.materialize_all = gen ? 1u : 0u;
+  u.keep_margin = keep_margin;
       return u;
     };
     std::vector<UnitIO> segs(plan.size());
     std::vector<uint8_t> redo(n, 0);
     bool any_redo = false;
     for (size_t q = 0; q < plan.size(); ++q) {
-      segs[q] = make_seg(plan[q], 0);
-      Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, segs[q], ws, pool, sink);
+      segs[q] = make_seg(plan[q], 0, (uint32_t)q);
+      Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, segs[q], ws, pool, sink, jobs);
       w.run();
       if (segs[q].status) {
-        if (plan[q].n_segs > 1 && (segs[q].status == kSeamViolation || segs[q].status == JB_E_SCRATCH)) { redo[plan[q].unit] = 1; any_redo = true; }
+        if (segs[q].status == kFarBack || (plan[q].n_segs > 1 && (segs[q].status == kSeamViolation || segs[q].status == JB_E_SCRATCH))) {
+          redo[plan[q].unit] = 1; any_redo = true;
+          if (segs[q].status == kFarBack) ++res->far_backs;
+        }
         else { res->status = segs[q].status; return res; }
       }
     }
     res->segments += plan.size();
+    size_t n_slots = plan.size();
     if (any_redo) {
       std::vector<UnitIO> merged;
       for (size_t q = 0; q < segs.size();) {
         const uint32_t unit = segs[q].unit;
         if (!redo[unit]) { merged.push_back(segs[q++]); continue; }
-        UnitIO u = make_seg(whole_contig(unit, caps[unit]), 1);
-        Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink);
+        UnitIO u = make_seg(whole_contig(unit, caps[unit]), 1, (uint32_t)n_slots++);
+        Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink, jobs);
         w.run();
         if (u.status) { res->status = u.status; return res; }
         merged.push_back(u);
@@ -146,16 +157,30 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       std::vector<SegPlace> place = place_segments(segs, &new_lens);
       std::vector<size_t> first_seg(n, 0);
       std::vector<std::string> next(n);
+      std::vector<std::vector<uint8_t>> covered(n);
+      for (size_t i = 0; i < n; ++i) { next[i].assign((size_t)new_lens[i], '?'); covered[i].assign((size_t)new_lens[i], 0); }
+      std::vector<int64_t> dst_off(n_slots, -1);
+      std::vector<uint32_t> slot_unit(n_slots, 0);
       for (size_t q = 0; q < segs.size(); ++q) {
         const UnitIO& u = segs[q];
         if (u.seg == 0) first_seg[u.unit] = q;
-        std::string& dst = next[u.unit];
-        if ((int64_t)dst.size() != place[q].new_off) { res->status = -100; return res; }
-        dst.append((const char*)u.out, (size_t)u.fin_olen);
-        dst.append((const char*)u.in + u.fin_ipos, (size_t)(u.end_old - u.fin_ipos));
+        dst_off[u.slot] = place[q].new_off; slot_unit[u.slot] = u.unit;
+      }
+      // what k_concat does: every copy job of an accepted segment; the jobs must tile the new contig exactly
+      for (unsigned long long j = 0; j < jobs_used; ++j) {
+        const CopyJob& job = jobv[j];
+        if (dst_off[job.slot] < 0) continue;
+        const uint32_t unit = slot_unit[job.slot];
+        const int64_t at = dst_off[job.slot] + job.rel;
+        if (at < 0 || at + job.len > new_lens[unit]) { res->status = -100; return res; }
+        for (int64_t q = 0; q < job.len; ++q) {
+          if (covered[unit][at + q]) { res->status = -100; return res; }
+          covered[unit][at + q] = 1; next[unit][at + q] = (char)job.src[q];
+        }
       }
       for (size_t i = 0; i < n; ++i) {
-        if ((int64_t)next[i].size() != new_lens[i] || new_lens[i] > caps[i]) { res->status = -100; return res; }
+        if (new_lens[i] > caps[i]) { res->status = -100; return res; }
+        for (int64_t q = 0; q < new_lens[i]; ++q) if (!covered[i][q]) { res->status = -100; return res; }
         cur[i].swap(next[i]);
       }
       std::vector<DevRow> got(rows.begin(), rows.begin() + used);
@@ -183,6 +208,7 @@ extern "C" const char* hostsim_seq(const SimResult* r, int i, uint64_t* len) { *
 extern "C" unsigned long long hostsim_lookups(const SimResult* r) { return r->lookups; }
 extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->segments; }
 extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
+extern "C" unsigned long long hostsim_far_backs(const SimResult* r) { return r->far_backs; }
 extern "C" void hostsim_free(SimResult* r) { delete r; }
 
 // also expose the shared k-mer arithmetic for unit tests

@@ -118,12 +118,13 @@ def test_polish_big_fuzz_segmented_matches_hostsim_and_oracle(tmp_path, hostsim_
     qf = capi.QueryMerFile(path)
     try:
         reruns = 0
-        for seg_block, margin in (("128", None), ("128", "0"), ("1024", "0")):
+        for seg_block, margin, keep in (("128", None, None), ("128", "0", None), ("1024", "0", "0"), ("100", None, "0")):
             monkeypatch.setenv("JB_SEG_BLOCK", seg_block)
-            if margin is None:
-                monkeypatch.delenv("JB_ANCHOR_MARGIN", raising=False)
-            else:
-                monkeypatch.setenv("JB_ANCHOR_MARGIN", margin)
+            for var, val in (("JB_ANCHOR_MARGIN", margin), ("JB_KEEP_MARGIN", keep)):
+                if val is None:
+                    monkeypatch.delenv(var, raising=False)
+                else:
+                    monkeypatch.setenv(var, val)
             res = qf.polish(recs, k, thr, 2)
             assert res.status == (0 if st == 0 else st)
             if st == 0:
@@ -240,3 +241,23 @@ def test_errors_mirror_the_binding(tmp_path, golden_cases):
 def test_gather_roofline_probe(dbs):
     gbps, gps = dbs["k37_mix"].gather_bench(n_probes=1 << 24, sector_bytes=32, iters=2)
     assert gbps > 0 and gps > 0
+
+
+@pytest.mark.parametrize("name", ["k37_mix", "k31_dirty"])
+def test_jasper_py_cli_is_drop_in(golden_cases, name, tmp_path):
+    """jasper_b200/jasper.py run exactly as src/jasper.sh:207 runs src/jasper.py writes the reference's bytes."""
+    import shutil
+    import subprocess
+    import sys
+    case = golden_cases[name]
+    shutil.copy(case["fasta"], tmp_path / "asm.fa")
+    script = os.path.join(helpers.ROOT, "jasper_b200", "jasper.py")
+    cmd = [sys.executable, script, "--db", case["db"], "--query", "asm.fa", "--ksize", str(case["k"]), "-p", str(case["passes"]),
+           "--fix", "--fout", "asm.fa.fix.csv", "-ff", "asm.fa.fixed.fa.tmp", "--test", "-thre", str(case["threshold"])]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for fn in os.listdir(os.path.join(case["dir"], "expected")):
+        assert (tmp_path / fn).read_bytes() == helpers.expected_file(case, fn), fn
+    # a wrong k is refused with exit 1 (the reference would silently mis-read k-mers)
+    bad = subprocess.run([c if c != str(case["k"]) else str(case["k"] - 2) for c in cmd], cwd=tmp_path, capture_output=True, text=True)
+    assert bad.returncode == 1

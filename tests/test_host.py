@@ -150,11 +150,12 @@ def test_segment_seams_are_exact(tmp_path, hostsim_lib, seed, monkeypatch):
             assert base[0] == 0 and base[2] == [s for _, s in res.seqs]
             assert base[1] == helpers.rows_text(res.passes, [n for n, _ in recs])
     total = {"segments": 0, "reruns": 0}
-    for margin in (None, "0"):
-        if margin is None:
-            monkeypatch.delenv("JB_ANCHOR_MARGIN", raising=False)
-        else:
-            monkeypatch.setenv("JB_ANCHOR_MARGIN", margin)
+    for margin, keep in ((None, None), ("0", None), (None, "0")):
+        for var, val in (("JB_ANCHOR_MARGIN", margin), ("JB_KEEP_MARGIN", keep)):
+            if val is None:
+                monkeypatch.delenv(var, raising=False)
+            else:
+                monkeypatch.setenv(var, val)      # 0: seams collide with fixes / walkers need bases behind their window
         for block in (64, 1024):
             st = {}
             got = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, block, stats=st)
@@ -162,3 +163,31 @@ def test_segment_seams_are_exact(tmp_path, hostsim_lib, seed, monkeypatch):
             for key in total:
                 total[key] += st[key]
     assert total["segments"] > 3 * len(recs) * 4          # the contigs really were split
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_jasper_py_host_side_writes_reference_bytes(golden_cases, name, tmp_path):
+    """The host half of the drop-in jasper.py (FASTA parse, csv / FASTA writers) against the golden files,
+    fed with the oracle's result in place of the GPU's."""
+    from jasper_b200 import jasper as host
+    case = golden_cases[name]
+    seq_dict = host.parse_fasta(case["fasta"])
+    assert list(seq_dict.items()) == jo.read_fasta(case["fasta"])
+    odb = helpers.OracleDB(case["db"])
+    res, _ = helpers.oracle_polish(odb, list(seq_dict.items()), case["k"], case["threshold"], case["passes"])
+    for ite in range(case["passes"]):
+        out = str(tmp_path / host._prefixed("asm.fa.fix.csv", ite))
+        host.write_fix_csv(out, res.passes[ite].rows)
+        assert open(out, "rb").read() == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+    fa = str(tmp_path / "x.fa")
+    host.write_fasta(fa, res.seqs)
+    assert open(fa, "rb").read() == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+
+
+def test_jasper_py_parse_fasta_quirks(tmp_path):
+    from jasper_b200 import jasper as host
+    p = tmp_path / "q.fa"
+    p.write_text("ACGT\n>a desc here\nAC GT\r\nTT\n>b\n\n>a\nGG\n>\nCC\n")
+    d = host.parse_fasta(str(p))
+    assert list(d.items()) == [("a", "GG"), ("b", ""), ("", "CC")]       # dict semantics: first position, last value
+    assert host._prefixed("x.csv", 3) == "_iter3_x.csv" and host._prefixed("d/x.csv", 0) == "d_iter0_x.csv"
