@@ -43,6 +43,19 @@ class _FixRow(C.Structure):
     _fields_ = [("seq_index", C.c_uint32), ("coord", C.c_int64), ("mutation", C.c_char * 64), ("original", C.c_char * 64)]
 
 
+def _fixrow_dtype():
+    import numpy as np
+    return np.dtype({"names": ["seq_index", "coord", "mutation", "original"], "formats": ["<u4", "<i8", "S64", "S64"],
+                     "offsets": [_FixRow.seq_index.offset, _FixRow.coord.offset, _FixRow.mutation.offset, _FixRow.original.offset],
+                     "itemsize": C.sizeof(_FixRow)})
+
+
+try:
+    _FIXROW_DTYPE = _fixrow_dtype()
+except Exception:                                  # numpy is optional: the slow path needs nothing
+    _FIXROW_DTYPE = None
+
+
 # every symbol include/jasper_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "jb_init", "jb_device_count", "jb_last_error", "jb_version",
@@ -254,8 +267,16 @@ class QueryMerFile(object):
             nr = lib.jb_result_num_rows(res, ite)
             buf = (_FixRow * max(1, nr))()
             _check(lib.jb_result_rows(res, ite, buf, nr))
-            rows.append([[names[buf[i].seq_index], buf[i].coord, buf[i].mutation.decode("latin-1"), buf[i].original.decode("latin-1")]
-                         for i in range(nr)])
+            if nr > 256 and _FIXROW_DTYPE is not None:                           # bulk conversion through numpy: per-field ctypes access costs ~2 us each
+                import numpy as np
+                a = np.frombuffer(buf, dtype=_FIXROW_DTYPE, count=nr)
+                idx, coord = a["seq_index"].tolist(), a["coord"].tolist()
+                mut = [m.decode("latin-1") for m in a["mutation"].tolist()]
+                org = [o.decode("latin-1") for o in a["original"].tolist()]
+                rows.append([[names[i], c, m, o] for i, c, m, o in zip(idx, coord, mut, org)])
+            else:
+                rows.append([[names[buf[i].seq_index], buf[i].coord, buf[i].mutation.decode("latin-1"), buf[i].original.decode("latin-1")]
+                             for i in range(nr)])
         seqs = []
         for i in range(lib.jb_result_num_seqs(res)):
             p, ln = C.c_void_p(), C.c_uint64()

@@ -48,11 +48,10 @@ __global__ void k_gather(const uint8_t* __restrict__ base, uint64_t n_sectors, u
   if (acc == 0x1234567ull) *sink = acc;
 }
 
-std::vector<ScanTile> make_tiles(const std::vector<ScanUnit>& units) {
-  std::vector<ScanTile> tiles;
-  for (size_t u = 0; u < units.size(); ++u)
-    for (uint64_t s = 0; s < units[u].len + 1; s += kTile) tiles.push_back(ScanTile{(uint32_t)u, 0, s});
-  return tiles;
+std::vector<uint32_t> make_tile_prefix(const std::vector<ScanUnit>& units) {
+  std::vector<uint32_t> first(units.size() + 1, 0);
+  for (size_t u = 0; u < units.size(); ++u) first[u + 1] = first[u] + tiles_of(units[u].len);
+  return first;
 }
 
 int scan_grid(uint32_t n_tiles) {
@@ -105,20 +104,20 @@ extern "C" int jb_count_positions(const jb_db* db, const char* seq, size_t len, 
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
   std::vector<ScanUnit> units{ScanUnit{0, (uint64_t)len, 0}};
-  std::vector<ScanTile> tiles = make_tiles(units);
-  uint8_t* d_seq = nullptr; uint32_t* d_cnt = nullptr; ScanUnit* d_units = nullptr; ScanTile* d_tiles = nullptr;
+  std::vector<uint32_t> tiles = make_tile_prefix(units);
+  uint8_t* d_seq = nullptr; uint32_t* d_cnt = nullptr; ScanUnit* d_units = nullptr; uint32_t* d_tiles = nullptr;
   cudaEvent_t e0, e1, e2, e3;
   JB_CUDA(cudaEventCreate(&e0)); JB_CUDA(cudaEventCreate(&e1)); JB_CUDA(cudaEventCreate(&e2)); JB_CUDA(cudaEventCreate(&e3));
   JB_CUDA(cudaMalloc(&d_seq, len + 16));
   JB_CUDA(cudaMalloc(&d_cnt, (len + 1) * 4));
   JB_CUDA(cudaMalloc(&d_units, sizeof(ScanUnit)));
-  JB_CUDA(cudaMalloc(&d_tiles, tiles.size() * sizeof(ScanTile)));
+  JB_CUDA(cudaMalloc(&d_tiles, tiles.size() * sizeof(uint32_t)));
   JB_CUDA(cudaEventRecord(e0, s));
   if (len) JB_CUDA(cudaMemcpyAsync(d_seq, seq, len, cudaMemcpyHostToDevice, s));
   JB_CUDA(cudaMemcpyAsync(d_units, units.data(), sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-  JB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(ScanTile), cudaMemcpyHostToDevice, s));
+  JB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   ScanArgs a{};
-  a.bases = d_seq; a.units = d_units; a.tiles = d_tiles; a.n_tiles = (uint32_t)tiles.size(); a.counts = d_cnt;
+  a.bases = d_seq; a.units = d_units; a.tile_first = d_tiles; a.n_units = 1; a.n_tiles = tiles.back(); a.counts = d_cnt;
   JB_CUDA(cudaEventRecord(e1, s));
   k_scan<true, false><<<scan_grid(a.n_tiles), kScanThreads, 0, s>>>(db->view(), a);
   JB_CUDA(cudaGetLastError());

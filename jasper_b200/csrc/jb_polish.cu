@@ -9,6 +9,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <numeric>
 
 #include "jb_plan.hpp"
@@ -16,7 +18,6 @@
 
 namespace jb {
 
-std::vector<ScanTile> make_tiles(const std::vector<ScanUnit>& units);
 int scan_grid(uint32_t n_tiles);
 
 struct DevDB {
@@ -101,60 +102,166 @@ __global__ void k_init_pool(BridgeScratch* pool, int n, uint32_t* trie, uint32_t
 
 using namespace jb;
 
+// ---------------------------------------------------------------------------------------------
+// Work buffers.  Device allocations and pinned host staging are expensive to create (a pinned
+// 64 MB buffer alone costs tens of milliseconds), so a finished batch parks its workspace in a
+// process-wide cache and the next batch on the same device picks it up (grow-only).
+namespace {
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {                         // capacity in elements, grow-only, contents not preserved
+    if (n <= cap) return JB_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return JB_E_NOMEM; }
+    cap = want;
+    return JB_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return JB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    if (cudaMallocHost(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return JB_E_NOMEM; }
+    cap = want;
+    return JB_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Workspace {
+  int device = -1;
+  DevBuf<uint8_t> buf[2], stage;
+  DevBuf<uint32_t> events, weak, events_l1, order, tile_first, block_first;
+  DevBuf<UnitIO> segs;
+  DevBuf<int64_t> dst_off;
+  DevBuf<long long> anchors;
+  DevBuf<ScanUnit> scan_units;
+  DevBuf<SegUnit> seg_units;
+  DevBuf<DevRow> rows;
+  DevBuf<uint8_t> aux;
+  DevBuf<CopyJob> jobs;
+  DevBuf<unsigned long long> used;          // [0] rows, [1] aux, [2] probe steps, [3] copy jobs
+  DevBuf<unsigned int> next;
+  DevBuf<BridgeScratch> pool; DevBuf<uint32_t> trie; DevBuf<uint8_t> patch; DevBuf<uint32_t> busy;
+  bool pool_ready = false;
+  PinBuf<uint8_t> h_in;                     // staged input bases
+  PinBuf<UnitIO> h_segs;
+  PinBuf<long long> h_anchors;
+  PinBuf<DevRow> h_rows;
+  PinBuf<uint8_t> h_aux;
+  PinBuf<unsigned long long> h_used;
+  cudaStream_t s2 = nullptr;                // side stream: fix rows travel while the next pass scans
+  cudaEvent_t ev_walk = nullptr, ev_rows = nullptr;
+  ~Workspace() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    buf[0].release(); buf[1].release(); stage.release(); events.release(); weak.release(); events_l1.release(); order.release();
+    tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
+    seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
+    trie.release(); patch.release(); busy.release();
+    h_in.release(); h_segs.release(); h_anchors.release(); h_rows.release(); h_aux.release(); h_used.release();
+    if (s2) cudaStreamDestroy(s2);
+    if (ev_walk) cudaEventDestroy(ev_walk);
+    if (ev_rows) cudaEventDestroy(ev_rows);
+  }
+};
+
+std::mutex g_ws_mutex;
+std::vector<Workspace*> g_ws_cache;          // at most one parked workspace per device
+
+Workspace* take_workspace(int device) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (size_t i = 0; i < g_ws_cache.size(); ++i)
+    if (g_ws_cache[i]->device == device) { Workspace* w = g_ws_cache[i]; g_ws_cache.erase(g_ws_cache.begin() + i); return w; }
+  auto w = new Workspace();
+  w->device = device;
+  return w;
+}
+void park_workspace(Workspace* w) {
+  if (!w) return;
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    bool have = false;
+    for (Workspace* c : g_ws_cache) have |= c->device == w->device;
+    if (!have) { g_ws_cache.push_back(w); return; }
+  }
+  delete w;
+}
+
+// pinned buffers that carry polished sequences back; results own one until jb_result_free
+std::vector<std::pair<uint8_t*, size_t>> g_out_pool;
+uint8_t* take_out_buffer(size_t n, size_t* cap) {
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (size_t i = 0; i < g_out_pool.size(); ++i)
+      if (g_out_pool[i].second >= n) { uint8_t* p = g_out_pool[i].first; *cap = g_out_pool[i].second; g_out_pool.erase(g_out_pool.begin() + i); return p; }
+    for (auto& e : g_out_pool) cudaFreeHost(e.first);     // too small: drop them
+    g_out_pool.clear();
+  }
+  uint8_t* p = nullptr;
+  size_t want = n + n / 8 + 4096;
+  if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *cap = want;
+  return p;
+}
+void park_out_buffer(uint8_t* p, size_t cap) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  if (g_out_pool.size() < 2) g_out_pool.push_back({p, cap}); else cudaFreeHost(p);
+}
+
+}  // namespace
+
+void jb_release_cached_workspaces(int device) {           // jb_db_close: nothing may outlive the context's owner
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (size_t i = 0; i < g_ws_cache.size();)
+    if (g_ws_cache[i]->device == device) { delete g_ws_cache[i]; g_ws_cache.erase(g_ws_cache.begin() + i); } else ++i;
+}
+
 struct jb_batch {
   const jb_db* db = nullptr;
+  Workspace* ws = nullptr;
   size_t n = 0;
   std::vector<uint64_t> off, cap;      // per-contig region in the flat buffers (bytes; multiples of 32)
   std::vector<int64_t> len;            // current lengths
   uint64_t flat_bytes = 0;
-  uint8_t* buf[2] = {nullptr, nullptr};
-  uint8_t* stage = nullptr;            // where segment walkers materialise edited bases
   int cur = 0;                         // buffer holding the current sequences
-  uint32_t* events = nullptr;          // flat_bytes / 32 words
-  uint32_t* weak = nullptr;
-  uint32_t* events_l1 = nullptr; size_t l1_words = 0;
-  UnitIO* d_segs = nullptr; size_t segs_cap = 0;
-  uint32_t* d_order = nullptr;
-  int64_t* d_dst_off = nullptr;
-  ScanUnit* d_scan_units = nullptr;
-  SegUnit* d_seg_units = nullptr;
-  ScanTile* d_tiles = nullptr; size_t tiles_cap = 0;
-  SegBlock* d_blocks = nullptr; long long* d_anchors = nullptr; size_t blocks_cap = 0;
-  unsigned int* d_next = nullptr;
-  DevRow* d_rows = nullptr; unsigned long long rows_cap = 0;
-  uint8_t* d_aux = nullptr; unsigned long long aux_cap = 0;
-  unsigned long long* d_used = nullptr;   // [0] rows, [1] aux, [2] probe steps, [3] copy jobs
-  CopyJob* d_jobs = nullptr; unsigned long long jobs_cap = 0;
-  BridgeScratch* d_pool = nullptr; uint32_t* d_trie = nullptr; uint8_t* d_patch = nullptr; uint32_t* d_busy = nullptr;
-  uint8_t* pinned_in = nullptr;
   int sms = 148;
   std::vector<PassOut> passes;
   int status = JB_OK;
   bool polished = false;
-  ~jb_batch() {
-    if (!db) return;
-    cudaSetDevice(db->device);
-    cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(stage); cudaFree(events); cudaFree(weak); cudaFree(events_l1);
-    cudaFree(d_segs); cudaFree(d_order); cudaFree(d_dst_off); cudaFree(d_scan_units); cudaFree(d_seg_units); cudaFree(d_tiles);
-    cudaFree(d_blocks); cudaFree(d_anchors); cudaFree(d_next); cudaFree(d_rows); cudaFree(d_aux); cudaFree(d_used); cudaFree(d_jobs);
-    cudaFree(d_pool); cudaFree(d_trie); cudaFree(d_patch); cudaFree(d_busy);
-    if (pinned_in) cudaFreeHost(pinned_in);
-  }
+  ~jb_batch() { park_workspace(ws); }
 };
 
 struct jb_result {
   int status = JB_OK;
   std::vector<PassOut> passes;
-  std::vector<std::string> seqs;
+  uint8_t* data = nullptr; size_t data_cap = 0;      // pinned: all sequences back to back
+  std::vector<uint64_t> seq_off, seq_len;
+  ~jb_result() { park_out_buffer(data, data_cap); }
 };
+
+#define JB_TRY(expr) do { int rc_ = (expr); if (rc_ != JB_OK) return fail(rc_, "out of memory for polishing work buffers"); } while (0)
 
 extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out) {
   if (!db || (!seqs && n) || !out) return fail(JB_E_ARG, "jb_batch_upload: null argument");
   *out = nullptr;
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
-  auto b = new jb_batch();
+  std::unique_ptr<jb_batch> b(new jb_batch());
   b->db = db; b->n = n;
+  b->ws = take_workspace(db->device);
+  Workspace& w = *b->ws;
   b->off.resize(n); b->cap.resize(n); b->len.resize(n);
   uint64_t total = 0, total_len = 0;
   for (size_t i = 0; i < n; ++i) {
@@ -164,40 +271,41 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
     total += c; total_len += L;
   }
   b->flat_bytes = total;
+  cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, db->device);
+  if (!w.s2) {
+    JB_CUDA(cudaStreamCreateWithFlags(&w.s2, cudaStreamNonBlocking));
+    JB_CUDA(cudaEventCreateWithFlags(&w.ev_walk, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&w.ev_rows, cudaEventDisableTiming));
+  }
+  JB_TRY(w.buf[0].ensure(total + 64)); JB_TRY(w.buf[1].ensure(total + 64)); JB_TRY(w.stage.ensure(total + 64));
+  JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
+  JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
+  JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
+  JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.h_rows.ensure(total_len / 32 + 4096));
+  JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20))); JB_TRY(w.h_aux.ensure(total_len / 4 + (1u << 20)));
+  JB_TRY(w.jobs.ensure(total_len / 16 + 4 * n + 65536));
+  if (!w.pool_ready) {
+    JB_TRY(w.pool.ensure(kPoolSlots)); JB_TRY(w.trie.ensure((size_t)kPoolSlots * kTrieCap)); JB_TRY(w.patch.ensure((size_t)kPoolSlots * kPatchCap));
+    JB_TRY(w.busy.ensure(kPoolSlots));
+    JB_CUDA(cudaMemsetAsync(w.busy.p, 0, (size_t)kPoolSlots * 4, s));
+    k_init_pool<<<(kPoolSlots + 127) / 128, 128, 0, s>>>(w.pool.p, (int)kPoolSlots, w.trie.p, kTrieCap, w.patch.p, kPatchCap);
+    JB_CUDA(cudaGetLastError());
+    w.pool_ready = true;
+  }
+  JB_TRY(w.h_in.ensure(std::max<uint64_t>(total_len, 1)));
   cudaEvent_t e0, e1;
   JB_CUDA(cudaEventCreate(&e0)); JB_CUDA(cudaEventCreate(&e1));
-  JB_CUDA(cudaMalloc(&b->buf[0], total + 64)); JB_CUDA(cudaMalloc(&b->buf[1], total + 64)); JB_CUDA(cudaMalloc(&b->stage, total + 64));
-  JB_CUDA(cudaMalloc(&b->events, (total / 32 + 64) * 4));
-  JB_CUDA(cudaMalloc(&b->weak, (total / 32 + 64) * 4));
-  b->l1_words = total / 32768 + 64;
-  JB_CUDA(cudaMalloc(&b->events_l1, b->l1_words * 4));
-  JB_CUDA(cudaMalloc(&b->d_scan_units, std::max<size_t>(1, n) * sizeof(ScanUnit)));
-  JB_CUDA(cudaMalloc(&b->d_seg_units, std::max<size_t>(1, n) * sizeof(SegUnit)));
-  JB_CUDA(cudaMalloc(&b->d_next, 4));
-  b->rows_cap = total_len / 16 + 4096;
-  b->aux_cap = total_len / 4 + (1u << 20);
-  JB_CUDA(cudaMalloc(&b->d_rows, b->rows_cap * sizeof(DevRow)));
-  JB_CUDA(cudaMalloc(&b->d_aux, b->aux_cap));
-  JB_CUDA(cudaMalloc(&b->d_used, 32));
-  b->jobs_cap = total_len / 8 + 4 * n + 65536;
-  JB_CUDA(cudaMalloc(&b->d_jobs, b->jobs_cap * sizeof(CopyJob)));
-  cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, db->device);
-  JB_CUDA(cudaMalloc(&b->d_pool, (size_t)kPoolSlots * sizeof(BridgeScratch)));
-  JB_CUDA(cudaMalloc(&b->d_trie, (size_t)kPoolSlots * kTrieCap * 4));
-  JB_CUDA(cudaMalloc(&b->d_patch, (size_t)kPoolSlots * kPatchCap));
-  JB_CUDA(cudaMalloc(&b->d_busy, (size_t)kPoolSlots * 4));
-  JB_CUDA(cudaMemsetAsync(b->d_busy, 0, (size_t)kPoolSlots * 4, s));
-  k_init_pool<<<(kPoolSlots + 127) / 128, 128, 0, s>>>(b->d_pool, (int)kPoolSlots, b->d_trie, kTrieCap, b->d_patch, kPatchCap);
-  JB_CUDA(cudaGetLastError());
-  // stage through pinned memory so the H2D copy runs at full PCIe rate
-  JB_CUDA(cudaMallocHost(&b->pinned_in, std::max<uint64_t>(total_len, 1)));
-  uint64_t p = 0;
-  for (size_t i = 0; i < n; ++i) { if (seqs[i].len) std::memcpy(b->pinned_in + p, seqs[i].seq, seqs[i].len); p += seqs[i].len; }
   JB_CUDA(cudaEventRecord(e0, s));
-  p = 0;
+  // stage through pinned memory in slices so the host copy of slice i+1 overlaps the DMA of slice i
+  uint64_t p = 0;
+  constexpr uint64_t kSlice = 8ull << 20;
   for (size_t i = 0; i < n; ++i) {
-    if (seqs[i].len) JB_CUDA(cudaMemcpyAsync(b->buf[0] + b->off[i], b->pinned_in + p, seqs[i].len, cudaMemcpyHostToDevice, s));
-    p += seqs[i].len;
+    for (uint64_t at = 0; at < seqs[i].len; at += kSlice) {
+      const uint64_t m = std::min<uint64_t>(kSlice, seqs[i].len - at);
+      std::memcpy(w.h_in.p + p, seqs[i].seq + at, m);
+      JB_CUDA(cudaMemcpyAsync(w.buf[0].p + b->off[i] + at, w.h_in.p + p, m, cudaMemcpyHostToDevice, s));
+      p += m;
+    }
   }
   JB_CUDA(cudaEventRecord(e1, s));
   JB_CUDA(cudaStreamSynchronize(s));
@@ -206,7 +314,7 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   note_timing("h2d", ms);
   note_counter("h2d_bytes", (int64_t)total_len);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  *out = b;
+  *out = b.release();
   return JB_OK;
 }
 
@@ -228,14 +336,37 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   UnitIO u;
   std::memset(&u, 0, sizeof u);
   const size_t i = p.unit;
+  const Workspace& w = *b->ws;
   u.in = in + b->off[i]; u.in_len = b->len[i];
-  u.out = b->stage + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
-  u.ev = b->events + b->off[i] / 32; u.ev_l1 = b->events_l1; u.ev_bit_base = b->off[i];
+  u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
+  u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
   u.materialize_all = gen ? 1u : 0u;               // re-runs take the conservative path
   u.keep_margin = keep_margin;
   return u;
+}
+
+// rows of one pass wait in pinned memory until the host has time for them (while the next pass scans)
+struct PendingRows {
+  bool live = false;
+  size_t pass = 0;
+  unsigned long long n_rows = 0, n_aux = 0;
+  std::vector<UnitIO> segs;
+  std::vector<SegPlace> place;
+  std::vector<size_t> first_seg;
+};
+
+int finish_rows(jb_batch* b, PendingRows* pr) {
+  if (!pr->live) return JB_OK;
+  Workspace& w = *b->ws;
+  JB_CUDA(cudaEventSynchronize(w.ev_rows));
+  std::vector<DevRow> rows(w.h_rows.p, w.h_rows.p + pr->n_rows);
+  std::vector<uint8_t> aux(w.h_aux.p, w.h_aux.p + pr->n_aux);
+  settle_rows(&rows, pr->segs, pr->place, pr->first_seg);
+  if (!rows_from_log(rows, aux, &b->passes[pr->pass].rows)) b->status = JB_E_REFERENCE_CRASH;   // exit 1 in the reference
+  pr->live = false;
+  return JB_OK;
 }
 
 }  // namespace
@@ -251,24 +382,20 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   if (b->polished) return fail(JB_E_ARG, "batch already polished");
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
+  Workspace& w = *b->ws;
   const size_t n = b->n;
   cudaEvent_t ev_begin, ev_end, ev_a, ev_b, ev_c, ev_d, ev_e;
-  JB_CUDA(cudaEventCreate(&ev_e));
-  JB_CUDA(cudaEventCreate(&ev_begin)); JB_CUDA(cudaEventCreate(&ev_end));
+  JB_CUDA(cudaEventCreate(&ev_begin)); JB_CUDA(cudaEventCreate(&ev_end)); JB_CUDA(cudaEventCreate(&ev_e));
   JB_CUDA(cudaEventCreate(&ev_a)); JB_CUDA(cudaEventCreate(&ev_b)); JB_CUDA(cudaEventCreate(&ev_c)); JB_CUDA(cudaEventCreate(&ev_d));
-  double scan_ms = 0, walk_ms = 0, plan_ms = 0;
+  double scan_ms = 0, walk_ms = 0, plan_ms = 0, kwalk_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
   int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0;
-  double kwalk_ms = 0;
   std::vector<ScanUnit> sunits(n);
   std::vector<SegUnit> gunits(n);
   std::vector<int64_t> caps(n);
-  std::vector<DevRow> rows;
-  std::vector<uint8_t> aux;
-  std::vector<long long> anchors;
   const WalkCfg cfg{k, sampling_step(k), solid_thre, 0};
   const TableView view = db->view();
-  const BridgePool pool{b->d_pool, kPoolSlots, b->d_busy};
+  const BridgePool pool{w.pool.p, kPoolSlots, w.busy.p};
   int64_t total_len = 0;
   for (size_t i = 0; i < n; ++i) { caps[i] = (int64_t)b->cap[i]; total_len += b->len[i]; }
   const int64_t seg_block = pick_seg_block(total_len, b->sms);
@@ -277,195 +404,189 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   int keep_margin = default_keep_margin(k);
   if (const char* e = getenv("JB_KEEP_MARGIN")) keep_margin = (int)std::max<long>(0, atol(e));   // tests: provoke far-back re-runs
   b->passes.clear();
+  b->passes.reserve((size_t)passes + 1);
+  PendingRows pending;
+  unsigned long long* used = w.h_used.p;
   JB_CUDA(cudaEventRecord(ev_begin, s));
   for (int ite = 0; ite <= passes && n > 0; ++ite) {
     const bool do_fix = fix && ite != passes;
-    PassOut po;
-    uint8_t* in = b->buf[b->cur];
-    uint8_t* outb = b->buf[b->cur ^ 1];
+    b->passes.push_back(PassOut{});
+    uint8_t* in = w.buf[b->cur].p;
+    uint8_t* outb = w.buf[b->cur ^ 1].p;
+    std::vector<uint32_t> tile_first(n + 1, 0), block_first(n + 1, 0);
+    int64_t pass_total = 0;
     for (size_t i = 0; i < n; ++i) {
-      po.total += b->len[i] - k + 1;                                    // may be negative (src/jasper.py:51)
+      pass_total += b->len[i] - k + 1;                                  // may be negative (src/jasper.py:51)
       sunits[i] = ScanUnit{b->off[i], (uint64_t)b->len[i], b->off[i]};
       gunits[i] = SegUnit{b->off[i], (uint64_t)b->len[i]};
       scan_lookups += b->len[i] + 1 + (b->len[i] > 0 ? k : 0);
+      tile_first[i + 1] = tile_first[i] + tiles_of((uint64_t)b->len[i]);
+      block_first[i + 1] = block_first[i] + (uint32_t)(seg_block > 0 && b->len[i] > 0 ? (b->len[i] - 1) / seg_block : 0);
     }
+    b->passes[ite].total = pass_total;
     // ---- scan: counts -> event / weak bits
-    std::vector<ScanTile> tiles = make_tiles(sunits);
-    if (tiles.size() > b->tiles_cap) {
-      cudaFree(b->d_tiles);
-      b->tiles_cap = tiles.size() + tiles.size() / 4 + 64;
-      JB_CUDA(cudaMalloc(&b->d_tiles, b->tiles_cap * sizeof(ScanTile)));
-    }
     std::vector<BlockRef> blocks;
     if (seg_block > 0) blocks = make_blocks(b->len, seg_block);
-    if (blocks.size() > b->blocks_cap) {
-      cudaFree(b->d_blocks); cudaFree(b->d_anchors);
-      b->blocks_cap = blocks.size() + blocks.size() / 4 + 64;
-      JB_CUDA(cudaMalloc(&b->d_blocks, b->blocks_cap * sizeof(SegBlock)));
-      JB_CUDA(cudaMalloc(&b->d_anchors, b->blocks_cap * sizeof(long long)));
-    }
-    static_assert(sizeof(BlockRef) == sizeof(SegBlock), "host and device block descriptors must match");
-    JB_CUDA(cudaMemcpyAsync(b->d_tiles, tiles.data(), tiles.size() * sizeof(ScanTile), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(b->d_scan_units, sunits.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(b->d_seg_units, gunits.data(), n * sizeof(SegUnit), cudaMemcpyHostToDevice, s));
-    if (!blocks.empty()) JB_CUDA(cudaMemcpyAsync(b->d_blocks, blocks.data(), blocks.size() * sizeof(SegBlock), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemsetAsync(b->d_next, 0, 4, s));
-    JB_CUDA(cudaMemsetAsync(b->d_used, 0, 32, s));
-    JB_CUDA(cudaMemsetAsync(b->events_l1, 0, b->l1_words * 4, s));
+    JB_TRY(w.anchors.ensure(blocks.size() + 1)); JB_TRY(w.h_anchors.ensure(blocks.size() + 1));
+    JB_CUDA(cudaMemcpyAsync(w.tile_first.p, tile_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.block_first.p, block_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.scan_units.p, sunits.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.seg_units.p, gunits.data(), n * sizeof(SegUnit), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
+    JB_CUDA(cudaMemsetAsync(w.used.p, 0, 64, s));        // (the previous pass's counters are on the host already)
+    JB_CUDA(cudaMemsetAsync(w.events_l1.p, 0, (b->flat_bytes / 32768 + 64) * 4, s));
     ScanArgs a{};
-    a.bases = in; a.units = b->d_scan_units; a.tiles = b->d_tiles; a.n_tiles = (uint32_t)tiles.size();
-    a.events = b->events; a.weak = b->weak; a.events_l1 = b->events_l1; a.solid_thre = solid_thre; a.probe_steps = b->d_used + 2;
+    a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
+    a.events = w.events.p; a.weak = w.weak.p; a.events_l1 = w.events_l1.p; a.solid_thre = solid_thre; a.probe_steps = w.used.p + 2;
     JB_CUDA(cudaEventRecord(ev_a, s));
     k_scan<false, true><<<scan_grid(a.n_tiles), kScanThreads, 0, s>>>(view, a);
     JB_CUDA(cudaGetLastError());
     ++launches;
     JB_CUDA(cudaEventRecord(ev_b, s));
     // ---- anchors -> segments
-    anchors.assign(blocks.size(), -1);
+    long long* anchors = w.h_anchors.p;
     if (!blocks.empty()) {
       const uint32_t nb = (uint32_t)blocks.size();
-      k_find_anchors<<<(nb + 7) / 8, 256, 0, s>>>(b->events, b->weak, b->d_seg_units, b->d_blocks, nb, k, (int)seg_block, (int)margin, b->d_anchors);
+      k_find_anchors<<<(nb + 7) / 8, 256, 0, s>>>(w.events.p, w.weak.p, w.seg_units.p, w.block_first.p, (uint32_t)n, nb, k, (int)seg_block,
+                                                   (int)margin, w.anchors.p);
       JB_CUDA(cudaGetLastError());
       ++launches;
-      JB_CUDA(cudaMemcpyAsync(anchors.data(), b->d_anchors, nb * sizeof(long long), cudaMemcpyDeviceToHost, s));
-      JB_CUDA(cudaStreamSynchronize(s));
+      JB_CUDA(cudaMemcpyAsync(anchors, w.anchors.p, nb * sizeof(long long), cudaMemcpyDeviceToHost, s));
     }
-    std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, anchors.data());
-    std::vector<UnitIO> segs(plan.size());
-    for (size_t q = 0; q < plan.size(); ++q) segs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin);
-    const size_t need = segs.size() + n;                  // room for whole-contig re-runs behind the plan
-    if (need > b->segs_cap) {
-      cudaFree(b->d_segs); cudaFree(b->d_order); cudaFree(b->d_dst_off);
-      b->segs_cap = need + need / 4 + 64;
-      JB_CUDA(cudaMalloc(&b->d_segs, b->segs_cap * sizeof(UnitIO)));
-      JB_CUDA(cudaMalloc(&b->d_order, b->segs_cap * 4));
-      JB_CUDA(cudaMalloc(&b->d_dst_off, b->segs_cap * 8));
-    }
-    std::vector<uint32_t> order(segs.size());
+    // while the scan runs: turn the previous pass's fix log into csv rows
+    if (int rc = finish_rows(b, &pending)) return rc;
+    if (b->status == JB_E_REFERENCE_CRASH) break;
+    JB_CUDA(cudaStreamSynchronize(s));
+    std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
+    const size_t n_first = plan.size();
+    JB_TRY(w.segs.ensure(n_first + n)); JB_TRY(w.h_segs.ensure(n_first + n));     // room for whole-contig re-runs behind the plan
+    JB_TRY(w.order.ensure(n_first + n)); JB_TRY(w.dst_off.ensure(n_first + n));
+    UnitIO* hs = w.h_segs.p;
+    for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin);
+    std::vector<uint32_t> order(n_first);
     std::iota(order.begin(), order.end(), 0u);
-    auto seg_span = [&](uint32_t q) { return (segs[q].next_anchor >= 0 ? segs[q].next_anchor : segs[q].in_len) - segs[q].base; };
+    auto seg_span = [&](uint32_t q) { return (hs[q].next_anchor >= 0 ? hs[q].next_anchor : hs[q].in_len) - hs[q].base; };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return seg_span(x) > seg_span(y); });
-    JB_CUDA(cudaMemcpyAsync(b->d_segs, segs.data(), segs.size() * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(b->d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
-    // ---- walk
+    JB_CUDA(cudaMemcpyAsync(w.segs.p, hs, n_first * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.order.p, order.data(), n_first * 4, cudaMemcpyHostToDevice, s));
+    // ---- walk (the previous pass's rows have left the arena: the stream waited for ev_rows)
     WalkCfg c2 = cfg; c2.fix = do_fix ? 1 : 0;
-    RowSink sink{b->d_rows, b->rows_cap, b->d_used, b->d_aux, b->aux_cap, b->d_used + 1};
-    JobSink jobs{b->d_jobs, b->jobs_cap, b->d_used + 3};
+    RowSink sink{w.rows.p, w.rows.cap, w.used.p, w.aux.p, w.aux.cap, w.used.p + 1};
+    JobSink jobs{w.jobs.p, w.jobs.cap, w.used.p + 3};
     auto walk_grid = [&](size_t cnt) { return (unsigned)std::min<size_t>((cnt + kWalkWarps - 1) / kWalkWarps, (size_t)b->sms * kWalkCtasPerSm); };
     JB_CUDA(cudaEventRecord(ev_c, s));
-    k_walk<<<walk_grid(segs.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)segs.size(), c2, pool, sink, jobs, b->d_next);
+    k_walk<<<walk_grid(n_first), kWalkWarps * 32, 0, s>>>(view, w.segs.p, w.order.p, (uint32_t)n_first, c2, pool, sink, jobs, w.next.p);
     JB_CUDA(cudaGetLastError());
     ++launches;
     JB_CUDA(cudaEventRecord(ev_e, s));
-    JB_CUDA(cudaMemcpyAsync(segs.data(), b->d_segs, segs.size() * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
+    JB_CUDA(cudaMemcpyAsync(hs, w.segs.p, n_first * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
+    JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
     JB_CUDA(cudaStreamSynchronize(s));
     { float m2 = 0; cudaEventElapsedTime(&m2, ev_c, ev_e); kwalk_ms += m2; }
-    n_segments += (int64_t)segs.size();
+    n_segments += (int64_t)n_first;
     // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment
     std::vector<uint8_t> redo(n, 0);
-    size_t n_redo = 0, n_slots = segs.size();
-    for (const UnitIO& u : segs) {
+    size_t n_redo = 0, n_slots = n_first;
+    for (size_t q = 0; q < n_first; ++q) {
+      const UnitIO& u = hs[q];
       if (!u.status) continue;
-      const bool split = plan[&u - segs.data()].n_segs > 1;
+      const bool split = plan[q].n_segs > 1;
       if (u.status == kFarBack || (split && (u.status == kSeamViolation || u.status == JB_E_SCRATCH))) { if (!redo[u.unit]) { redo[u.unit] = 1; ++n_redo; } continue; }
       b->status = u.status;
       return fail(JB_E_SCRATCH, "contig " + std::to_string(u.unit) + ": a device work pool overflowed during polishing "
                                 "(output slack, fix-row arena, or de-Bruijn path pool; status " + std::to_string(u.status) + ")");
     }
+    std::vector<UnitIO> segs;                            // accepted segments in (contig, segment) order
     if (n_redo) {
-      std::vector<UnitIO> again;
-      for (size_t i = 0; i < n; ++i) if (redo[i]) again.push_back(make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(segs.size() + again.size()), keep_margin));
-      std::vector<uint32_t> ord2(again.size());
-      for (size_t q = 0; q < again.size(); ++q) ord2[q] = (uint32_t)(segs.size() + q);
-      JB_CUDA(cudaMemcpyAsync(b->d_segs + segs.size(), again.data(), again.size() * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
-      JB_CUDA(cudaMemcpyAsync(b->d_order, ord2.data(), ord2.size() * 4, cudaMemcpyHostToDevice, s));
-      JB_CUDA(cudaMemsetAsync(b->d_next, 0, 4, s));
-      k_walk<<<walk_grid(again.size()), kWalkWarps * 32, 0, s>>>(view, b->d_segs, b->d_order, (uint32_t)again.size(), c2, pool, sink, jobs, b->d_next);
+      size_t na = 0;
+      UnitIO* again = hs + n_first;
+      for (size_t i = 0; i < n; ++i) if (redo[i]) { again[na] = make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(n_first + na), keep_margin); ++na; }
+      std::vector<uint32_t> ord2(na);
+      for (size_t q = 0; q < na; ++q) ord2[q] = (uint32_t)(n_first + q);
+      JB_CUDA(cudaMemcpyAsync(w.segs.p + n_first, again, na * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
+      JB_CUDA(cudaMemcpyAsync(w.order.p, ord2.data(), na * 4, cudaMemcpyHostToDevice, s));
+      JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
+      k_walk<<<walk_grid(na), kWalkWarps * 32, 0, s>>>(view, w.segs.p, w.order.p, (uint32_t)na, c2, pool, sink, jobs, w.next.p);
       JB_CUDA(cudaGetLastError());
       ++launches;
-      JB_CUDA(cudaMemcpyAsync(again.data(), b->d_segs + segs.size(), again.size() * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
+      JB_CUDA(cudaMemcpyAsync(again, w.segs.p + n_first, na * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
+      JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
       JB_CUDA(cudaStreamSynchronize(s));
-      n_reruns += (int64_t)again.size();
-      std::vector<UnitIO> merged;
+      n_reruns += (int64_t)na;
       size_t ai = 0;
-      for (size_t q = 0; q < segs.size();) {
-        const uint32_t unit = segs[q].unit;
+      for (size_t q = 0; q < n_first;) {
+        const uint32_t unit = hs[q].unit;
         if (redo[unit]) {
           const UnitIO& u = again[ai++];
           if (u.status) {
             b->status = u.status;
             return fail(JB_E_SCRATCH, "contig " + std::to_string(unit) + ": a device work pool overflowed during polishing (status " + std::to_string(u.status) + ")");
           }
-          merged.push_back(u);
-          while (q < segs.size() && segs[q].unit == unit) ++q;
-        } else merged.push_back(segs[q++]);
+          segs.push_back(u);
+          while (q < n_first && hs[q].unit == unit) ++q;
+        } else segs.push_back(hs[q++]);
       }
-      n_slots = segs.size() + again.size();
-      segs.swap(merged);
+      n_slots = n_first + na;
+    } else {
+      segs.assign(hs, hs + n_first);
     }
     for (const UnitIO& u : segs) {
-      po.wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events;
+      b->passes[ite].wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events;
       max_seg_events = std::max<int64_t>(max_seg_events, (int64_t)u.events);
       max_seg_lookups = std::max<int64_t>(max_seg_lookups, (int64_t)u.lookups);
       max_seg_span = std::max<int64_t>(max_seg_span, u.end_old - u.base);
     }
-    unsigned long long used[4] = {0, 0, 0, 0};
-    JB_CUDA(cudaMemcpyAsync(used, b->d_used, 32, cudaMemcpyDeviceToHost, s));
-    JB_CUDA(cudaStreamSynchronize(s));
+    probe_steps += (int64_t)used[2];
     if (do_fix) {
-      // ---- stitch the segments into the other buffer
+      // ---- stitch the segments into the other buffer; the fix log follows on the side stream
+      if (used[0] > w.rows.cap || used[1] > w.aux.cap || used[3] > w.jobs.cap) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "fix-row / copy-job arena overflow"); }
       std::vector<int64_t> new_lens(b->len);
-      std::vector<SegPlace> place = place_segments(segs, &new_lens);
-      std::vector<int64_t> dst_off(n_slots, -1);       // by launch slot; superseded attempts stay at -1
-      std::vector<size_t> first_seg(n, 0);
+      pending.place = place_segments(segs, &new_lens);
+      std::vector<int64_t> dst_off(n_slots, -1);        // by launch slot; superseded attempts stay at -1
+      pending.first_seg.assign(n, 0);
       for (size_t q = 0; q < segs.size(); ++q) {
-        dst_off[segs[q].slot] = (int64_t)b->off[segs[q].unit] + place[q].new_off;
-        if (segs[q].seg == 0) first_seg[segs[q].unit] = q;
+        dst_off[segs[q].slot] = (int64_t)b->off[segs[q].unit] + pending.place[q].new_off;
+        if (segs[q].seg == 0) pending.first_seg[segs[q].unit] = q;
       }
-      if (used[3] > b->jobs_cap) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "copy-job arena overflow"); }
       for (size_t i = 0; i < n; ++i)
         if (new_lens[i] > caps[i]) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "contig " + std::to_string(i) + " outgrew its output slack"); }
-      JB_CUDA(cudaMemcpyAsync(b->d_dst_off, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
+      JB_CUDA(cudaEventRecord(w.ev_walk, s));
+      JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
+      if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows.p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
+      if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux.p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
+      JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
+      JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
       dim3 g(4, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(used[3], 1), 16384));
-      k_concat<<<g, 256, 0, s>>>(b->d_jobs, b->d_used + 3, b->d_dst_off, outb);
+      k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;
-      JB_CUDA(cudaEventRecord(ev_d, s));
-      JB_CUDA(cudaStreamSynchronize(s));
-      if (used[0] > b->rows_cap || used[1] > b->aux_cap) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "fix-row arena overflow"); }
-      rows.resize(used[0]); aux.resize(used[1]);
-      if (used[0]) JB_CUDA(cudaMemcpyAsync(rows.data(), b->d_rows, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, s));
-      if (used[1]) JB_CUDA(cudaMemcpyAsync(aux.data(), b->d_aux, used[1], cudaMemcpyDeviceToHost, s));
-      JB_CUDA(cudaStreamSynchronize(s));
-      settle_rows(&rows, segs, place, first_seg);
-      if (!rows_from_log(rows, aux, &po.rows)) b->status = JB_E_REFERENCE_CRASH;   // exit 1 in the reference
+      JB_CUDA(cudaStreamWaitEvent(s, w.ev_rows, 0));     // the next walk reuses the row arena
+      pending.live = true; pending.pass = (size_t)ite; pending.n_rows = used[0]; pending.n_aux = used[1];
+      pending.segs.swap(segs);
       b->len = new_lens;
       b->cur ^= 1;
-    } else {
-      JB_CUDA(cudaEventRecord(ev_d, s));
-      JB_CUDA(cudaStreamSynchronize(s));
     }
+    JB_CUDA(cudaEventRecord(ev_d, s));
+    JB_CUDA(cudaStreamSynchronize(s));                   // dst_off (a host vector) must stay alive until k_concat has read it
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_a, ev_b); scan_ms += ms;
     cudaEventElapsedTime(&ms, ev_b, ev_c); plan_ms += ms;
     cudaEventElapsedTime(&ms, ev_c, ev_d); walk_ms += ms;
-    probe_steps += (int64_t)used[2];
-    b->passes.push_back(std::move(po));
-    if (b->status == JB_E_REFERENCE_CRASH) break;
   }
+  if (int rc = finish_rows(b, &pending)) return rc;
   JB_CUDA(cudaEventRecord(ev_end, s));
   JB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
   note_timing("polish", ms); note_timing("polish_scan", scan_ms); note_timing("polish_walk", walk_ms); note_timing("polish_plan", plan_ms);
+  note_timing("polish_kwalk", kwalk_ms);
   note_counter("scan_lookups", scan_lookups); note_counter("walk_lookups", walk_lookups);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
-  note_timing("polish_kwalk", kwalk_ms);
   note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
   note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
-  if (n == 0) for (int ite = 0; ite <= passes; ++ite) b->passes.push_back(PassOut{});
+  while ((int)b->passes.size() <= passes && b->status != JB_E_REFERENCE_CRASH) b->passes.push_back(PassOut{});
   return JB_OK;
 }
 
@@ -473,26 +594,26 @@ extern "C" int jb_batch_fetch(jb_batch* b, jb_result** out) {
   if (!b || !out) return fail(JB_E_ARG, "jb_batch_fetch: null argument");
   JB_CUDA(cudaSetDevice(b->db->device));
   cudaStream_t s = b->db->stream;
-  auto r = new jb_result();
+  std::unique_ptr<jb_result> r(new jb_result());
   r->status = b->status;
   r->passes = b->passes;
-  r->seqs.resize(b->n);
+  r->seq_off.resize(b->n); r->seq_len.resize(b->n);
+  uint64_t total = 0;
+  for (size_t i = 0; i < b->n; ++i) { r->seq_off[i] = total; r->seq_len[i] = (uint64_t)b->len[i]; total += (uint64_t)b->len[i]; }
+  r->data = take_out_buffer(std::max<uint64_t>(total, 1), &r->data_cap);
+  if (!r->data) return fail(JB_E_NOMEM, "cannot allocate the pinned result buffer");
   cudaEvent_t e0, e1;
   JB_CUDA(cudaEventCreate(&e0)); JB_CUDA(cudaEventCreate(&e1));
   JB_CUDA(cudaEventRecord(e0, s));
-  int64_t bytes = 0;
-  for (size_t i = 0; i < b->n; ++i) {
-    r->seqs[i].resize((size_t)b->len[i]);
-    if (b->len[i]) JB_CUDA(cudaMemcpyAsync(&r->seqs[i][0], b->buf[b->cur] + b->off[i], (size_t)b->len[i], cudaMemcpyDeviceToHost, s));
-    bytes += b->len[i];
-  }
+  for (size_t i = 0; i < b->n; ++i)
+    if (b->len[i]) JB_CUDA(cudaMemcpyAsync(r->data + r->seq_off[i], b->ws->buf[b->cur].p + b->off[i], (size_t)b->len[i], cudaMemcpyDeviceToHost, s));
   JB_CUDA(cudaEventRecord(e1, s));
   JB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
-  note_timing("d2h", ms); note_counter("d2h_bytes", bytes);
+  note_timing("d2h", ms); note_counter("d2h_bytes", (int64_t)total);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  *out = r;
+  *out = r.release();
   return JB_OK;
 }
 
@@ -501,11 +622,17 @@ extern "C" int jb_polish(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, i
   if (!out) return fail(JB_E_ARG, "jb_polish: null out");
   *out = nullptr;
   jb_batch* b = nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   int rc = jb_batch_upload(db, seqs, n_seqs, &b);
   if (rc) return rc;
+  auto t1 = std::chrono::steady_clock::now();
   rc = jb_batch_polish(b, k, solid_thre, passes, fix);
+  auto t2 = std::chrono::steady_clock::now();
   if (!rc) rc = jb_batch_fetch(b, out);
   jb_batch_free(b);
+  auto t3 = std::chrono::steady_clock::now();
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+  note_timing("wall_upload", ms(t0, t1)); note_timing("wall_polish", ms(t1, t2)); note_timing("wall_fetch", ms(t2, t3));
   return rc;
 }
 
@@ -532,10 +659,10 @@ extern "C" int jb_result_rows(const jb_result* r, int ite, jb_fix_row_t* rows, s
   }
   return JB_OK;
 }
-extern "C" int64_t jb_result_num_seqs(const jb_result* r) { return r ? (int64_t)r->seqs.size() : JB_E_ARG; }
+extern "C" int64_t jb_result_num_seqs(const jb_result* r) { return r ? (int64_t)r->seq_len.size() : JB_E_ARG; }
 extern "C" int jb_result_seq(const jb_result* r, size_t i, const char** data, uint64_t* len) {
-  if (!r || i >= r->seqs.size() || !data || !len) return fail(JB_E_ARG, "jb_result_seq: bad argument");
-  *data = r->seqs[i].data(); *len = r->seqs[i].size();
+  if (!r || i >= r->seq_len.size() || !data || !len) return fail(JB_E_ARG, "jb_result_seq: bad argument");
+  *data = (const char*)r->data + r->seq_off[i]; *len = r->seq_len[i];
   return JB_OK;
 }
 extern "C" void jb_result_free(jb_result* r) { delete r; }

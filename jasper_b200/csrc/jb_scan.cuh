@@ -36,10 +36,21 @@ struct ScanTile {
   uint64_t start;          // first position of the tile inside the unit (multiple of kTile)
 };
 
+// tiles are numbered contig by contig: contig u owns tiles [tile_first[u], tile_first[u+1]),
+// tile_first[u+1] - tile_first[u] = ceil((len_u + 1) / kTile)
+__host__ __device__ inline uint32_t tiles_of(uint64_t len) { return (uint32_t)((len + 1 + kTile - 1) / kTile); }
+
+__device__ __forceinline__ ScanTile decode_tile(const uint32_t* __restrict__ tile_first, uint32_t n_units, uint32_t ti) {
+  uint32_t lo = 0, hi = n_units;                    // last u with tile_first[u] <= ti
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (tile_first[mid] <= ti) lo = mid; else hi = mid; }
+  return ScanTile{lo, 0, (uint64_t)(ti - tile_first[lo]) * kTile};
+}
+
 struct ScanArgs {
   const uint8_t* bases;
   const ScanUnit* units;
-  const ScanTile* tiles;
+  const uint32_t* tile_first;   // n_units + 1 entries
+  uint32_t n_units;
   uint32_t n_tiles;
   uint32_t* counts;        // may be null
   uint32_t* events;        // may be null (bit words)
@@ -64,7 +75,7 @@ k_scan(TableView t, ScanArgs a) {
   unsigned long long steps_total = 0;
 
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
-    const ScanTile tile = a.tiles[ti];
+    const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
     const ScanUnit u = a.units[tile.unit];
     // positions [tile.start, min(start + kTile, len + 1)) are produced (len + 1: the walker also
     // queries the empty tail window); the region additionally covers `back` positions before.

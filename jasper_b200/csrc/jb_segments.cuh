@@ -46,18 +46,21 @@ JB_HD int64_t first_anchor(const uint32_t* ev, const uint32_t* weak, int64_t lo,
 }
 
 #if defined(__CUDACC__)
-struct SegBlock { uint32_t unit; uint32_t pad; uint64_t start; };
 struct SegUnit { uint64_t bit_off; uint64_t len; };
 
 // one warp per block of seg_block positions: anchors[blk] = first anchor in the block or -1
 __global__ void k_find_anchors(const uint32_t* __restrict__ events, const uint32_t* __restrict__ weak,
-                               const SegUnit* __restrict__ units, const SegBlock* __restrict__ blocks, uint32_t n_blocks,
-                               int k, int seg_block, int margin, long long* __restrict__ anchors) {
+                               const SegUnit* __restrict__ units, const uint32_t* __restrict__ block_first, uint32_t n_units,
+                               uint32_t n_blocks, int k, int seg_block, int margin, long long* __restrict__ anchors) {
   const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (blk >= n_blocks) return;
-  const SegBlock b = blocks[blk];
-  const SegUnit u = units[b.unit];
+  // blocks are numbered contig by contig (make_blocks): contig u owns [block_first[u], block_first[u+1]),
+  // its j-th block starts at (j + 1) * seg_block
+  uint32_t ulo = 0, uhi = n_units;
+  while (uhi - ulo > 1) { uint32_t mid = (ulo + uhi) >> 1; if (block_first[mid] <= blk) ulo = mid; else uhi = mid; }
+  struct { uint64_t start; } b{(uint64_t)(blk - block_first[ulo] + 1) * (uint64_t)seg_block};
+  const SegUnit u = units[ulo];
   const uint32_t* ev = events + (u.bit_off >> 5);
   const uint32_t* wk = weak + (u.bit_off >> 5);
   const int64_t len = (int64_t)u.len;

@@ -332,9 +332,12 @@ extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
   return JB_OK;
 }
 
+void jb_release_cached_workspaces(int device);      // jb_polish.cu
+
 extern "C" void jb_db_close(jb_db* db) {
   if (!db) return;
   cudaSetDevice(db->device);
+  jb_release_cached_workspaces(db->device);
   if (db->slots) cudaFree(db->slots);
   if (db->lut) cudaFree(db->lut);
   if (db->stream) cudaStreamDestroy(db->stream);

@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define JB_W __device__
-#else
+#define JB_WN __device__ __noinline__   // the big helpers stay out of line: inlined everywhere the kernel was 860 KB of
+#else                                    // SASS and the warps starved on instruction fetch (ncu: 60 % stall_no_inst)
 #define JB_W
+#define JB_WN
 #endif
 #if defined(__CUDA_ARCH__)
 #define JB_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
@@ -165,7 +167,7 @@ struct Walker {
       : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), pool(pool_), sink(sink_), jobs(jobs_) {}
 
   // ---------------------------------------------------------------------------- bridging scratch
-  JB_W bool acquire_bridge() {
+  JB_WN bool acquire_bridge() {
     if (!pool.slots || !pool.n) { status = JB_E_SCRATCH; return false; }
 #if defined(__CUDA_ARCH__)
     int got = -1;
@@ -188,7 +190,7 @@ struct Walker {
     bs = pool.slots + bs_slot;
     return true;
   }
-  JB_W void release_bridge() {
+  JB_WN void release_bridge() {
     if (bs_slot < 0) return;
 #if defined(__CUDA_ARCH__)
     __syncwarp();
@@ -212,7 +214,7 @@ struct Walker {
   }
 
   // dst[0:n] = seq[a:b] clamped to [0, L); returns n
-  JB_W int load(uint8_t* dst, int64_t a, int64_t b) {
+  JB_WN int load(uint8_t* dst, int64_t a, int64_t b) {
     if (a < 0) a = 0;
     if (b > L) b = L;
     int n = b > a ? (int)(b - a) : 0;
@@ -222,7 +224,7 @@ struct Walker {
     return n;
   }
 
-  JB_W uint32_t count_in(const uint8_t* buf, int len, int m) const {
+  JB_WN uint32_t count_in(const uint8_t* buf, int len, int m) const {
     Key key = key_from_chars(buf + m, (int64_t)len - m, k, mask);
     return db.count(key_canonical(key, k));
   }
@@ -234,7 +236,7 @@ struct Walker {
   }
 
   // C(seq[x:x+k]); a miss refills the cache with 32 consecutive windows in direction `dir`.
-  JB_W uint32_t Cw(int64_t x, int dir) {
+  JB_WN uint32_t Cw(int64_t x, int dir) {
     if (x < 0) return C_empty();                     // the slices with negative starts are empty (L >= k)
     if (x >= wc_base && x < wc_base + wc_n) return s.wc[x - wc_base];
     int64_t base = dir > 0 ? x : (x - 31 > 0 ? x - 31 : 0);
@@ -247,7 +249,7 @@ struct Walker {
   }
 
   // n <= 32 windows at arbitrary starts s.px[0..n) (non-negative, within a span that fits s.c)
-  JB_W void Cpts(int n) {
+  JB_WN void Cpts(int n) {
     int64_t lo = s.px[0], hi = s.px[0];
     for (int q = 1; q < n; ++q) { lo = s.px[q] < lo ? s.px[q] : lo; hi = s.px[q] > hi ? s.px[q] : hi; }
     if (hi + k - lo > kStrCap - 8) {                 // cannot happen for the call sites below; stay exact anyway
@@ -261,7 +263,7 @@ struct Walker {
   }
 
   // src/jasper.py:585-599 on a string in scratch memory
-  JB_W bool check_sequence(const uint8_t* buf, int len, int64_t thr) {
+  JB_WN bool check_sequence(const uint8_t* buf, int len, int64_t thr) {
     // sample starts: 0, max(0,len-k), then step, 2*step, ... < len-k
     int n_mid = 0;
     for (int m = step; m < len - k; m += step) ++n_mid;
@@ -287,7 +289,7 @@ struct Walker {
   }
 
   // number of windows of buf (all of them) below thr
-  JB_W int count_weak(const uint8_t* buf, int len, int64_t thr) {
+  JB_WN int count_weak(const uint8_t* buf, int len, int64_t thr) {
     int total = len - k + 1, bad = 0;
     for (int w0 = 0; w0 < total; w0 += 32) {
       JB_SYNC();
@@ -304,7 +306,7 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- edits
-  JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
+  JB_WN bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
     if (len <= 0) return true;
     JB_SYNC();
     unsigned long long slot = 0;
@@ -322,7 +324,7 @@ struct Walker {
 
   // materialise the new sequence up to upto_abs for an edit that starts at a_abs; a long clean stretch
   // in front of the edit is handed to k_concat as a copy job instead of being copied here
-  JB_W bool ensure_out(int64_t a_abs, int64_t upto_abs) {
+  JB_WN bool ensure_out(int64_t a_abs, int64_t upto_abs) {
     const int64_t upto = upto_abs - base;
     if (upto <= olen) return true;
     if (upto > u.out_cap) { status = JB_E_SCRATCH; return false; }
@@ -352,7 +354,7 @@ struct Walker {
   }
 
   // seq = seq[:a] + repl + seq[e:]
-  JB_W bool apply_edit(int64_t a_abs, int64_t e_abs, const uint8_t* repl, int64_t rlen) {
+  JB_WN bool apply_edit(int64_t a_abs, int64_t e_abs, const uint8_t* repl, int64_t rlen) {
     if (a_abs < base) { status = kSeamViolation; return false; }
     if (a_abs - base < wstart) { status = kFarBack; return false; }
     if (!ensure_out(a_abs, e_abs)) return false;
@@ -398,7 +400,7 @@ struct Walker {
     return true;
   }
 
-  JB_W void emit_row(int64_t coord, const uint8_t* fb, int fb_len, uint8_t tag, const uint8_t* orig, int orig_len) {
+  JB_WN void emit_row(int64_t coord, const uint8_t* fb, int fb_len, uint8_t tag, const uint8_t* orig, int orig_len) {
     JB_SYNC();
     unsigned long long slot = 0;
 #if defined(__CUDA_ARCH__)
@@ -426,23 +428,23 @@ struct Walker {
   // ---------------------------------------------------------------------------- fix_* family
   // All take the to_be_fixed string in s.t (length n) that starts at sequence position s0.
 
-  JB_W void copy_t_to_b(int n) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < n; q += 32) s.b[q] = s.t[q]; } JB_SYNC(); }
+  JB_WN void copy_t_to_b(int n) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < n; q += 32) s.b[q] = s.t[q]; } JB_SYNC(); }
   JB_W void set_b(int at, uint8_t v) { JB_SYNC(); JB_LANES(l) { if (l == 0) s.b[at] = v; } JB_SYNC(); }
   // b = t[:at] + ins(len m, same char v) + t[at:]
-  JB_W void b_from_t_insert(int n, int at, uint8_t v, int m) {
+  JB_WN void b_from_t_insert(int n, int at, uint8_t v, int m) {
     JB_SYNC();
     JB_LANES(l) { for (int q = l; q < n + m; q += 32) s.b[q] = q < at ? s.t[q] : (q < at + m ? v : s.t[q - m]); }
     JB_SYNC();
   }
   // b = t[:at] + t[at+m:]
-  JB_W void b_from_t_delete(int n, int at, int m) {
+  JB_WN void b_from_t_delete(int n, int at, int m) {
     JB_SYNC();
     JB_LANES(l) { for (int q = l; q < n - m; q += 32) s.b[q] = q < at ? s.t[q] : s.t[q + m]; }
     JB_SYNC();
   }
 
   // src/jasper.py:392-406 then :409-419
-  JB_W bool fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
+  JB_WN bool fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
     const uint8_t bad = s.t[k - 1];
     const uint8_t before = get(ga - 1);
     const char order[4] = {'A', 'C', 'T', 'G'};
@@ -468,7 +470,7 @@ struct Walker {
   }
 
   // src/jasper.py:422-431
-  JB_W bool fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
+  JB_WN bool fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
     const char order[4] = {'A', 'T', 'C', 'G'};
     for (int o = 0; o < 4; ++o) {
       uint8_t bb = (uint8_t)order[o];
@@ -484,7 +486,7 @@ struct Walker {
   }
 
   // src/jasper.py:340-388
-  JB_W bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
+  JB_WN bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
     const uint8_t left_bad = s.t[n - k], right_bad = s.t[k - 1];
     const int64_t g0 = gb - k + 1 > 0 ? gb - k + 1 : 0;
     const int na = (2 * k - 1 - n) / 2;
@@ -528,7 +530,7 @@ struct Walker {
   }
 
   // src/jasper.py:434-477
-  JB_W bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
+  JB_WN bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
     if (thr > solid) return false;
     const uint8_t sb = s.t[k - 2];
     const int start_bad = n - k + 1;
@@ -561,7 +563,7 @@ struct Walker {
   }
 
   // src/jasper.py:479-524
-  JB_W bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
+  JB_WN bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
     if (thr > solid) return false;
     const uint8_t sb = s.t[k - 1];
     const int start_bad = n - k + 1;
@@ -607,7 +609,7 @@ struct Walker {
     return id;
   }
 
-  JB_W int64_t base_extension(int len_tbf, int64_t thr) {
+  JB_WN int64_t base_extension(int len_tbf, int64_t thr) {
     if (thr > solid) return 0;
     const uint8_t* G = s.t;          // good_kmer_before
     const uint8_t* A = s.b;          // good_k_mer_after
@@ -763,7 +765,7 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- fixing_sid
-  JB_W void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
+  JB_WN void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
     if (nbad == k) {
       int n = load(s.t, s0, ga + k - 1);
@@ -814,7 +816,7 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- handle_bad_kmers
-  JB_W void handle_bad_kmers(int64_t rolling_thre) {
+  JB_WN void handle_bad_kmers(int64_t rolling_thre) {
     ++events;
     const int64_t thre = rolling_thre > 0 ? rolling_thre : solid;
     int64_t j = i - 1;
@@ -861,7 +863,7 @@ struct Walker {
   // ---------------------------------------------------------------------------- scan loop
   // Fast hop: while the walker is in untouched territory, 32 strided event bits decide in one step
   // how far the plain `i += k-1` branch carries it.
-  JB_W bool fast_hop() {
+  JB_WN bool fast_hop() {
     if (!u.ev || i - k < clean_from) return false;
     const int64_t shift = base + olen - ipos;          // new = old + shift for everything >= clean_from
     const int64_t p = i - shift;
