@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjasper_b200.so")
-SOURCES = ["jb_api.cu", "jb_table.cu", "jb_lookup.cu", "jb_polish.cu", "jb_header.cpp", "jb_align.cpp"]
+SOURCES = ["jb_api.cu", "jb_table.cu", "jb_lookup.cu", "jb_scan.cu", "jb_polish.cu", "jb_header.cpp", "jb_align.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 
@@ -20,18 +20,19 @@ def newest_source_mtime():
     return m
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest_source_mtime():
-        return LIB
+def build(force: bool = False, verbose: bool = False, defines=(), lib: str = LIB, objdir_name: str = "build") -> str:
+    """defines / lib / objdir_name: experiment variants (e.g. -DJB_NOINLINE_LEVEL=0 into another .so)."""
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest_source_mtime():
+        return lib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
@@ -44,9 +45,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-lcudart", "-ldl", "-lpthread"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -48,19 +48,6 @@ __global__ void k_gather(const uint8_t* __restrict__ base, uint64_t n_sectors, u
   if (acc == 0x1234567ull) *sink = acc;
 }
 
-std::vector<uint32_t> make_tile_prefix(const std::vector<ScanUnit>& units) {
-  std::vector<uint32_t> first(units.size() + 1, 0);
-  for (size_t u = 0; u < units.size(); ++u) first[u + 1] = first[u] + tiles_of(units[u].len);
-  return first;
-}
-
-int scan_grid(uint32_t n_tiles) {
-  int dev = 0, sms = 148, per_sm = 2;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (int)std::min<uint64_t>(n_tiles, (uint64_t)sms * per_sm);
-}
-
 }  // namespace jb
 
 using namespace jb;
@@ -119,8 +106,7 @@ extern "C" int jb_count_positions(const jb_db* db, const char* seq, size_t len, 
   ScanArgs a{};
   a.bases = d_seq; a.units = d_units; a.tile_first = d_tiles; a.n_units = 1; a.n_tiles = tiles.back(); a.counts = d_cnt;
   JB_CUDA(cudaEventRecord(e1, s));
-  k_scan<true, false><<<scan_grid(a.n_tiles), kScanThreads, 0, s>>>(db->view(), a);
-  JB_CUDA(cudaGetLastError());
+  if (int rc = launch_scan(db->view(), a, s)) return rc;
   JB_CUDA(cudaEventRecord(e2, s));
   JB_CUDA(cudaMemcpyAsync(counts, d_cnt, (len + 1) * 4, cudaMemcpyDeviceToHost, s));
   JB_CUDA(cudaEventRecord(e3, s));

@@ -81,19 +81,30 @@ inline std::vector<SegPlace> place_segments(const std::vector<UnitIO>& segs, std
   return out;
 }
 
-// Keep the rows of the accepted launch of every contig and move them into contig coordinates.
+// Keep the rows of the accepted launch of every contig, move them into contig coordinates and put them in
+// (contig, segment, emission) order WITHOUT sorting: a segment's rows carry distinct increasing sequence
+// numbers below its n_rows, so each row has a fixed slot behind the rows of the segments before it.
 // first_seg[u] = index of contig u's first accepted segment in segs / place.
 inline void settle_rows(std::vector<DevRow>* rows, const std::vector<UnitIO>& segs, const std::vector<SegPlace>& place,
                         const std::vector<size_t>& first_seg) {
-  size_t w = 0;
-  for (size_t i = 0; i < rows->size(); ++i) {
-    DevRow r = (*rows)[i];
-    const size_t s0 = first_seg[r.unit];
-    if (segs[s0].gen != r.gen) continue;             // superseded attempt
-    r.coord += place[s0 + r.seg].row_shift;
-    (*rows)[w++] = r;
+  std::vector<uint64_t> slot0(segs.size() + 1, 0);
+  for (size_t q = 0; q < segs.size(); ++q) slot0[q + 1] = slot0[q] + segs[q].n_rows;
+  std::vector<DevRow> placed((size_t)slot0[segs.size()]);
+  std::vector<uint8_t> filled(placed.size(), 0);
+  for (const DevRow& r0 : *rows) {
+    const size_t s0 = first_seg[r0.unit];
+    if (segs[s0].gen != r0.gen) continue;             // superseded attempt
+    const size_t q = s0 + r0.seg;
+    if (r0.seqno >= segs[q].n_rows) continue;         // cannot happen; stay in bounds regardless
+    const size_t at = (size_t)slot0[q] + r0.seqno;
+    placed[at] = r0;
+    placed[at].coord += place[q].row_shift;
+    filled[at] = 1;
   }
-  rows->resize(w);
+  size_t w = 0;
+  for (size_t i = 0; i < placed.size(); ++i) if (filled[i]) placed[w++] = placed[i];
+  placed.resize(w);
+  rows->swap(placed);
 }
 
 }  // namespace jb

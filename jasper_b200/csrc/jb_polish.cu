@@ -1,24 +1,28 @@
 // jb_polish.cu -- the per-batch loop of src/jasper.py main() (lines 12-32) on the GPU.  Per pass:
-//   k_scan          every window's count -> event / weak bitmasks (+ 1-per-1024 event summary)
+//   k_scan          every window's count (one random 128-byte line of the table per window)
+//   k_events        counts -> event / weak bitmasks (+ 1-per-1024 event summary)
 //   k_find_anchors  first phase-independent restart point in every seg_block positions (jb_segments.cuh)
 //   k_walk          one warp per SEGMENT runs the reference's sequential state machine
 //   k_concat        stitches the segments' new bases into the other ping-pong buffer
 // Contigs stay resident in HBM between passes in flat ping-pong buffers (per-contig regions with
 // slack for insertions); per pass only segment summaries, tallies and fix rows come back.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "jb_plan.hpp"
 #include "jb_scan.cuh"
 
 namespace jb {
 
-int scan_grid(uint32_t n_tiles);
+
 
 struct DevDB {
   TableView t;
@@ -33,7 +37,10 @@ constexpr uint32_t kPoolSlots = 256;        // bridging scratch slots shared by 
 
 struct WalkCfg { int k, step; uint32_t solid; int fix; };
 
-__global__ void __launch_bounds__(kWalkWarps * 32)
+#ifndef JB_WALK_MINBLOCKS
+#define JB_WALK_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kWalkWarps * 32, JB_WALK_MINBLOCKS)
 k_walk(TableView t, UnitIO* segs, const uint32_t* order, uint32_t n_segs, WalkCfg cfg, BridgePool pool, RowSink sink,
        JobSink jobs, unsigned int* next_seg) {
   __shared__ WarpScratch scratch[kWalkWarps];
@@ -141,7 +148,7 @@ struct PinBuf {
 struct Workspace {
   int device = -1;
   DevBuf<uint8_t> buf[2], stage;
-  DevBuf<uint32_t> events, weak, events_l1, order, tile_first, block_first;
+  DevBuf<uint32_t> counts, okbits, events, weak, events_l1, order, tile_first, block_first;
   DevBuf<UnitIO> segs;
   DevBuf<int64_t> dst_off;
   DevBuf<long long> anchors;
@@ -165,7 +172,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); events.release(); weak.release(); events_l1.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts.release(); okbits.release(); events.release(); weak.release(); events_l1.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -278,6 +285,7 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
     JB_CUDA(cudaEventCreateWithFlags(&w.ev_rows, cudaEventDisableTiming));
   }
   JB_TRY(w.buf[0].ensure(total + 64)); JB_TRY(w.buf[1].ensure(total + 64)); JB_TRY(w.stage.ensure(total + 64));
+  JB_TRY(w.counts.ensure(total + 64)); JB_TRY(w.okbits.ensure(total / 32 + 64));
   JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
   JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
@@ -347,7 +355,9 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   return u;
 }
 
-// rows of one pass wait in pinned memory until the host has time for them (while the next pass scans)
+// The fix log of one pass waits in pinned memory until its copy has landed (while the next pass scans);
+// turning it into csv rows (sort, alignment of multi-error patches, text) then runs on a host thread
+// beside the GPU work of the following passes.
 struct PendingRows {
   bool live = false;
   size_t pass = 0;
@@ -357,16 +367,49 @@ struct PendingRows {
   std::vector<size_t> first_seg;
 };
 
-int finish_rows(jb_batch* b, PendingRows* pr) {
+struct RowJob {
+  std::thread th;
+  std::vector<DevRow> rows;
+  std::vector<uint8_t> aux;
+  std::vector<UnitIO> segs;
+  std::vector<SegPlace> place;
+  std::vector<size_t> first_seg;
+  std::vector<HostRow> out;
+  bool ok = true;
+  size_t pass = 0;
+  std::atomic<bool> copied{true};
+};
+
+int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob>>* jobs) {
   if (!pr->live) return JB_OK;
   Workspace& w = *b->ws;
   JB_CUDA(cudaEventSynchronize(w.ev_rows));
-  std::vector<DevRow> rows(w.h_rows.p, w.h_rows.p + pr->n_rows);
-  std::vector<uint8_t> aux(w.h_aux.p, w.h_aux.p + pr->n_aux);
-  settle_rows(&rows, pr->segs, pr->place, pr->first_seg);
-  if (!rows_from_log(rows, aux, &b->passes[pr->pass].rows)) b->status = JB_E_REFERENCE_CRASH;   // exit 1 in the reference
+  std::unique_ptr<RowJob> j(new RowJob());
+  j->segs.swap(pr->segs); j->place.swap(pr->place); j->first_seg.swap(pr->first_seg);
+  j->pass = pr->pass;
+  RowJob* raw = j.get();
+  const DevRow* src_rows = w.h_rows.p; const uint8_t* src_aux = w.h_aux.p;
+  const size_t n_rows = pr->n_rows, n_aux = pr->n_aux;
+  raw->copied.store(false);
+  j->th = std::thread([raw, src_rows, src_aux, n_rows, n_aux]() {
+    raw->rows.assign(src_rows, src_rows + n_rows);          // out of the pinned buffer first: the next pass reuses it
+    raw->aux.assign(src_aux, src_aux + n_aux);
+    raw->copied.store(true, std::memory_order_release);
+    settle_rows(&raw->rows, raw->segs, raw->place, raw->first_seg);
+    raw->ok = rows_to_csv(raw->rows, raw->aux, &raw->out);
+  });
+  jobs->push_back(std::move(j));
   pr->live = false;
   return JB_OK;
+}
+
+void join_rows(jb_batch* b, std::vector<std::unique_ptr<RowJob>>* jobs) {
+  for (auto& j : *jobs) {
+    if (j->th.joinable()) j->th.join();
+    if (j->pass < b->passes.size()) b->passes[j->pass].rows.swap(j->out);
+    if (!j->ok) b->status = JB_E_REFERENCE_CRASH;          // exit 1 in the reference
+  }
+  jobs->clear();
 }
 
 }  // namespace
@@ -405,7 +448,14 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   if (const char* e = getenv("JB_KEEP_MARGIN")) keep_margin = (int)std::max<long>(0, atol(e));   // tests: provoke far-back re-runs
   b->passes.clear();
   b->passes.reserve((size_t)passes + 1);
+  const bool trace = getenv("JB_TRACE") != nullptr;
+  const auto t_origin = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what, int ite) {
+    if (trace) fprintf(stderr, "[jb trace] pass %d %-18s %9.3f ms\n", ite, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count());
+  };
   PendingRows pending;
+  std::vector<std::unique_ptr<RowJob>> row_jobs;
+  struct Joiner { jb_batch* b; std::vector<std::unique_ptr<RowJob>>* j; ~Joiner() { join_rows(b, j); } } joiner{b, &row_jobs};   // also on error returns
   unsigned long long* used = w.h_used.p;
   JB_CUDA(cudaEventRecord(ev_begin, s));
   for (int ite = 0; ite <= passes && n > 0; ++ite) {
@@ -437,12 +487,17 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaMemsetAsync(w.events_l1.p, 0, (b->flat_bytes / 32768 + 64) * 4, s));
     ScanArgs a{};
     a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
-    a.events = w.events.p; a.weak = w.weak.p; a.events_l1 = w.events_l1.p; a.solid_thre = solid_thre; a.probe_steps = w.used.p + 2;
+    a.counts = w.counts.p; a.okbits = w.okbits.p; a.probe_steps = w.used.p + 2;
     JB_CUDA(cudaEventRecord(ev_a, s));
-    k_scan<false, true><<<scan_grid(a.n_tiles), kScanThreads, 0, s>>>(view, a);
-    JB_CUDA(cudaGetLastError());
+    if (int rc = launch_scan(view, a, s)) return rc;
     ++launches;
     JB_CUDA(cudaEventRecord(ev_b, s));
+    EventArgs ea{};
+    ea.units = w.scan_units.p; ea.tile_first = w.tile_first.p; ea.n_units = (uint32_t)n; ea.n_tiles = tile_first[n];
+    ea.counts = w.counts.p; ea.okbits = w.okbits.p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p;
+    ea.solid_thre = solid_thre; ea.k = k;
+    if (int rc = launch_events(ea, s)) return rc;
+    ++launches;
     // ---- anchors -> segments
     long long* anchors = w.h_anchors.p;
     if (!blocks.empty()) {
@@ -454,9 +509,11 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       JB_CUDA(cudaMemcpyAsync(anchors, w.anchors.p, nb * sizeof(long long), cudaMemcpyDeviceToHost, s));
     }
     // while the scan runs: turn the previous pass's fix log into csv rows
-    if (int rc = finish_rows(b, &pending)) return rc;
-    if (b->status == JB_E_REFERENCE_CRASH) break;
+    mark("scan launched", ite);
+    if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
+    mark("rows handed off", ite);
     JB_CUDA(cudaStreamSynchronize(s));
+    mark("scan+anchors done", ite);
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
     const size_t n_first = plan.size();
     JB_TRY(w.segs.ensure(n_first + n)); JB_TRY(w.h_segs.ensure(n_first + n));     // room for whole-contig re-runs behind the plan
@@ -481,7 +538,9 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaEventRecord(ev_e, s));
     JB_CUDA(cudaMemcpyAsync(hs, w.segs.p, n_first * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
     JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
+    mark("walk launched", ite);
     JB_CUDA(cudaStreamSynchronize(s));
+    mark("walk done", ite);
     { float m2 = 0; cudaEventElapsedTime(&m2, ev_c, ev_e); kwalk_ms += m2; }
     n_segments += (int64_t)n_first;
     // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment
@@ -550,6 +609,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       }
       for (size_t i = 0; i < n; ++i)
         if (new_lens[i] > caps[i]) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "contig " + std::to_string(i) + " outgrew its output slack"); }
+      for (auto& rj : row_jobs) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
       JB_CUDA(cudaEventRecord(w.ev_walk, s));
       JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
       if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows.p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
@@ -567,13 +627,17 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       b->cur ^= 1;
     }
     JB_CUDA(cudaEventRecord(ev_d, s));
+    mark("concat launched", ite);
     JB_CUDA(cudaStreamSynchronize(s));                   // dst_off (a host vector) must stay alive until k_concat has read it
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_a, ev_b); scan_ms += ms;
     cudaEventElapsedTime(&ms, ev_b, ev_c); plan_ms += ms;
     cudaEventElapsedTime(&ms, ev_c, ev_d); walk_ms += ms;
+    mark("pass done", ite);
   }
-  if (int rc = finish_rows(b, &pending)) return rc;
+  if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
+  join_rows(b, &row_jobs);
+  mark("rows joined", passes);
   JB_CUDA(cudaEventRecord(ev_end, s));
   JB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
@@ -586,7 +650,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
-  while ((int)b->passes.size() <= passes && b->status != JB_E_REFERENCE_CRASH) b->passes.push_back(PassOut{});
+  while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});
   return JB_OK;
 }
 

@@ -13,15 +13,11 @@ namespace jb {
 struct HostRow { uint32_t seq_index; int64_t coord; std::string mutation, original; };
 struct PassOut { int64_t wrong = 0, total = 0; std::vector<HostRow> rows; };
 
-// Sorts `rows` by (contig, segment, emission order) and appends the csv rows to out.  Returns false when the
-// reference would have crashed (IndexError at src/jasper.py:221 / :309 -> exit 1).
-inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
+// Appends the csv rows of `rows` (already in (contig, segment, emission) order) to out.  Returns false when
+// the reference would have crashed (IndexError at src/jasper.py:221 / :309 -> exit 1).
+inline bool rows_to_csv(const std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
   bool ok = true;
-  std::sort(rows.begin(), rows.end(), [](const DevRow& x, const DevRow& y) {
-    if (x.unit != y.unit) return x.unit < y.unit;
-    if (x.seg != y.seg) return x.seg < y.seg;
-    return x.seqno < y.seqno;
-  });
+  out->reserve(out->size() + rows.size() + 16);
   for (const DevRow& r : rows) {
     if (r.kind == kRowPlain) {
       out->push_back(HostRow{r.unit, r.coord, std::string(r.fb, r.fb_len), std::string(r.orig, r.orig_len)});
@@ -53,6 +49,16 @@ inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>&
     }
   }
   return ok;
+}
+
+// Sorts `rows` by (contig, segment, emission order) first (callers without a segment table).
+inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
+  std::sort(rows.begin(), rows.end(), [](const DevRow& x, const DevRow& y) {
+    if (x.unit != y.unit) return x.unit < y.unit;
+    if (x.seg != y.seg) return x.seg < y.seg;
+    return x.seqno < y.seqno;
+  });
+  return rows_to_csv(rows, aux, out);
 }
 
 inline int sampling_step(int k) {                  // max(2, round(k/8)), Python's half-to-even round (src/jasper.py:20)

@@ -1,0 +1,207 @@
+// jb_scan.cu -- the bulk scan kernels (design notes in jb_scan.cuh).
+#include <algorithm>
+
+#include "jb_scan.cuh"
+
+namespace jb {
+
+// (rc >> 2) | (3 - code) << (2k - 2): the reverse complement of the window after pushing `code` on the right
+__device__ __forceinline__ Key rc_push(Key rc, uint32_t code, int top_shift) {
+  Key r;
+  r.lo = (rc.lo >> 2) | (rc.hi << 62);
+  r.hi = rc.hi >> 2;
+  const uint64_t c = (uint64_t)(3u - code);
+  if (top_shift >= 64) r.hi |= c << (top_shift - 64); else r.lo |= c << top_shift;
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
+k_scan(TableView t, ScanArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int k = t.g.k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(smem);
+  const int lut_n = t.g.key_bytes * 256;
+  uint8_t* s_seq = smem + (size_t)lut_n * 8 + (size_t)warp * kScanSmemPerWarp;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_seq + kSeqSlice);
+  for (int i = threadIdx.x; i < lut_n; i += kScanThreads) s_lut[i] = t.lut[i];
+  __syncthreads();                                   // the only block-wide barrier
+  unsigned long long steps_total = 0;
+  const int top_shift = 2 * k - 2;
+  const uint32_t warps_total = gridDim.x * kScanWarps;
+
+  for (uint32_t ti = blockIdx.x * kScanWarps + warp; ti < a.n_tiles; ti += warps_total) {
+    const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
+    const ScanUnit u = a.units[tile.unit];
+    const int64_t n_out = (int64_t)min((uint64_t)kTile, u.len + 1 - tile.start);   // positions produced
+    const int n_chars = (int)n_out + k - 1;
+    const uint8_t* src = a.bases + u.seq_off + tile.start;
+    const int64_t avail = (int64_t)u.len - (int64_t)tile.start;                    // real bases from tile.start on
+    __syncwarp();                                                                  // previous tile's smem reads are done
+    // ---- stage bases: 16-byte loads where the source is aligned, zero-fill past the contig end
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      for (int v = lane; v * 16 < n_chars + 1; v += 32) {
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if ((int64_t)v * 16 + 16 <= avail) w = *reinterpret_cast<const uint4*>(src + v * 16);
+        else {
+          uint8_t tmp[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) tmp[q] = ((int64_t)v * 16 + q < avail) ? src[v * 16 + q] : (uint8_t)0;
+          w = *reinterpret_cast<uint4*>(tmp);
+        }
+        *reinterpret_cast<uint4*>(s_seq + v * 16) = w;
+      }
+    } else {
+      for (int i = lane; i < n_chars + 1; i += 32) s_seq[i] = (i < avail) ? src[i] : (uint8_t)0;
+    }
+    __syncwarp();
+
+    // ---- each lane: 32 consecutive windows starting at r0
+    const int r0 = lane * kLanePos;
+    const int nr = (int)min((int64_t)kLanePos, n_out - r0);      // may be <= 0
+    uint32_t okmask = 0;
+    if (nr > 0) {
+      Key fwd = {0, 0}, rc = {0, 0};
+      int nv = 0;
+      for (int j = 0; j < k - 1; ++j) {                           // the first k-1 bases of the first window
+        const uint8_t c = s_seq[r0 + j];
+        const bool v = base_valid(c);
+        const uint32_t code = v ? base_code(c) : 0u;
+        nv = v ? nv + 1 : 0;
+        fwd = key_push(fwd, code, t.mask);
+        rc = rc_push(rc, code, top_shift);
+      }
+      for (int q0 = 0; q0 < nr; q0 += kGroup) {
+        Key keys[kGroup];
+        const ulonglong4* sec[kGroup];
+        unsigned long long w[kGroup][4];
+#pragma unroll
+        for (int b = 0; b < kGroup; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            const uint8_t c = s_seq[r0 + q + k - 1];
+            const bool v = base_valid(c);
+            const uint32_t code = v ? base_code(c) : 0u;
+            nv = v ? nv + 1 : 0;
+            fwd = key_push(fwd, code, t.mask);
+            rc = rc_push(rc, code, top_shift);
+            Key m;
+            if (nv >= k) { okmask |= 1u << q; m = key_less(rc, fwd) ? rc : fwd; }
+            else m = key_canonical(key_from_chars(s_seq + r0 + q, k, k, t.mask), k);   // rare: N / IUPAC / contig tail
+            keys[b] = m;
+            const uint64_t pos = hash_lut(s_lut, t.g.key_bytes, m);
+            sec[b] = reinterpret_cast<const ulonglong4*>(t.slots) + (home_slot(t.g, pos, m) >> 1);
+            asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < kGroup; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            const Key key = keys[b];
+            uint32_t r = 0;
+            ++steps_total;
+            while (true) {
+              const uint32_t c0 = (uint32_t)(w[b][1] >> 32), c1 = (uint32_t)(w[b][3] >> 32);
+              if (c0 == 0) { r = 0; break; }
+              if (w[b][0] == key.lo && (uint32_t)w[b][1] == (uint32_t)key.hi) { r = c0; break; }
+              if (c1 == 0) { r = 0; break; }
+              if (w[b][2] == key.lo && (uint32_t)w[b][3] == (uint32_t)key.hi) { r = c1; break; }
+              ++sec[b];
+              ++steps_total;
+              asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                           : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
+            }
+            s_cnt[lane * 33 + q] = r;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- stream the counts out coalesced; one validity word per lane
+    uint32_t* dst = a.counts + u.out_off + tile.start;
+    for (int row = 0; row < 32; ++row) {
+      const int i = row * 32 + lane;
+      if (i < n_out) dst[i] = s_cnt[row * 33 + lane];
+    }
+    if (a.okbits && r0 < n_out) a.okbits[((u.out_off + tile.start) >> 5) + lane] = okmask;
+  }
+  if (a.probe_steps) {
+    for (int o = 16; o; o >>= 1) steps_total += __shfl_xor_sync(0xffffffffu, steps_total, o);
+    if (lane == 0 && steps_total) atomicAdd(a.probe_steps, steps_total);
+  }
+}
+
+// one warp per 1024-position tile, one position per lane and step
+__global__ void __launch_bounds__(256)
+k_events(EventArgs a) {
+  const uint32_t ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ti >= a.n_tiles) return;
+  const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
+  const ScanUnit u = a.units[tile.unit];
+  const int64_t n_out = (int64_t)min((uint64_t)kTile, u.len + 1 - tile.start);
+  const uint32_t* cnt = a.counts + u.out_off;
+  const uint64_t f0 = u.out_off + tile.start;                       // flat bit index of the tile, multiple of 1024
+  for (int w0 = 0; w0 < n_out; w0 += 32) {
+    const int64_t p = (int64_t)tile.start + w0 + lane;
+    bool ev = false, wk = false;
+    if (w0 + lane < n_out) {
+      const bool ok = (a.okbits[(f0 + w0) >> 5] >> lane) & 1u;
+      const uint32_t c = cnt[p];
+      wk = ok && c < a.solid_thre;
+      ev = !ok || p < (int64_t)a.k || c < a.solid_thre;
+      if (!ev) ev = (unsigned long long)c * JB_DIVISOR < (unsigned long long)cnt[p - a.k];
+    }
+    const unsigned int word = __ballot_sync(0xffffffffu, ev);
+    const unsigned int wword = __ballot_sync(0xffffffffu, wk);
+    if (lane == 0) {
+      const uint64_t f = f0 + w0;                                   // contig offsets are multiples of 32, not of 1024:
+      a.events[f >> 5] = word; a.weak[f >> 5] = wword;              // a tile can straddle two summary blocks
+      if (word) atomicOr(&a.events_l1[f >> 15], 1u << ((f >> 10) & 31));
+    }
+  }
+}
+
+
+std::vector<uint32_t> make_tile_prefix(const std::vector<ScanUnit>& units) {
+  std::vector<uint32_t> first(units.size() + 1, 0);
+  for (size_t u = 0; u < units.size(); ++u) first[u + 1] = first[u] + tiles_of(units[u].len);
+  return first;
+}
+
+int scan_grid(uint32_t n_tiles) {
+  int dev = 0, sms = 148, per_sm = kScanCtasPerSm;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + kScanWarps - 1) / kScanWarps, (uint64_t)sms * per_sm));
+}
+
+// k_scan needs more than the default 48 KB of dynamic shared memory (hash LUT + 8 warp slices)
+int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s) {
+  const size_t smem = scan_smem_bytes(view.g.key_bytes);
+  static thread_local int configured_device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_device != dev) {
+    cudaError_t e = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
+    if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("cudaFuncSetAttribute(k_scan): ") + cudaGetErrorString(e));
+    configured_device = dev;
+  }
+  if (a.n_tiles == 0) return JB_OK;
+  k_scan<<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_scan launch: ") + cudaGetErrorString(e));
+  return JB_OK;
+}
+
+int launch_events(const EventArgs& a, cudaStream_t s) {
+  if (a.n_tiles == 0) return JB_OK;
+  k_events<<<(a.n_tiles + 7) / 8, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_events launch: ") + cudaGetErrorString(e));
+  return JB_OK;
+}
+
+}  // namespace jb

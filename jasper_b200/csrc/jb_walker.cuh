@@ -21,12 +21,28 @@
 #include "jb_kmer.cuh"
 #include "jb_segments.cuh"
 
+// Inlined everywhere the kernel is 860 KB of SASS and the warps starve on instruction fetch (ncu: 60 %
+// stall_no_inst); everything out of line costs registers and call overhead.  JB_WC marks the cold, bulky
+// helpers (bridging, diploid, homopolymer repairs), JB_WN the hot ones; JB_NOINLINE_LEVEL picks who stays out.
+#ifndef JB_NOINLINE_LEVEL
+#define JB_NOINLINE_LEVEL 1
+#endif
 #if defined(__CUDACC__)
 #define JB_W __device__
-#define JB_WN __device__ __noinline__   // the big helpers stay out of line: inlined everywhere the kernel was 860 KB of
-#else                                    // SASS and the warps starved on instruction fetch (ncu: 60 % stall_no_inst)
+#if JB_NOINLINE_LEVEL >= 2
+#define JB_WN __device__ __noinline__
+#else
+#define JB_WN __device__
+#endif
+#if JB_NOINLINE_LEVEL >= 1
+#define JB_WC __device__ __noinline__
+#else
+#define JB_WC __device__
+#endif
+#else
 #define JB_W
 #define JB_WN
+#define JB_WC
 #endif
 #if defined(__CUDA_ARCH__)
 #define JB_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
@@ -167,7 +183,7 @@ struct Walker {
       : db(db_), k(k_), step(step_), solid((int64_t)solid_), fix(fix_), mask(key_mask(k_)), u(u_), s(s_), pool(pool_), sink(sink_), jobs(jobs_) {}
 
   // ---------------------------------------------------------------------------- bridging scratch
-  JB_WN bool acquire_bridge() {
+  JB_WC bool acquire_bridge() {
     if (!pool.slots || !pool.n) { status = JB_E_SCRATCH; return false; }
 #if defined(__CUDA_ARCH__)
     int got = -1;
@@ -190,7 +206,7 @@ struct Walker {
     bs = pool.slots + bs_slot;
     return true;
   }
-  JB_WN void release_bridge() {
+  JB_WC void release_bridge() {
     if (bs_slot < 0) return;
 #if defined(__CUDA_ARCH__)
     __syncwarp();
@@ -486,7 +502,7 @@ struct Walker {
   }
 
   // src/jasper.py:340-388
-  JB_WN bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
+  JB_WC bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
     const uint8_t left_bad = s.t[n - k], right_bad = s.t[k - 1];
     const int64_t g0 = gb - k + 1 > 0 ? gb - k + 1 : 0;
     const int na = (2 * k - 1 - n) / 2;
@@ -530,7 +546,7 @@ struct Walker {
   }
 
   // src/jasper.py:434-477
-  JB_WN bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
+  JB_WC bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
     if (thr > solid) return false;
     const uint8_t sb = s.t[k - 2];
     const int start_bad = n - k + 1;
@@ -563,7 +579,7 @@ struct Walker {
   }
 
   // src/jasper.py:479-524
-  JB_WN bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
+  JB_WC bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
     if (thr > solid) return false;
     const uint8_t sb = s.t[k - 1];
     const int start_bad = n - k + 1;
@@ -609,7 +625,7 @@ struct Walker {
     return id;
   }
 
-  JB_WN int64_t base_extension(int len_tbf, int64_t thr) {
+  JB_WC int64_t base_extension(int len_tbf, int64_t thr) {
     if (thr > solid) return 0;
     const uint8_t* G = s.t;          // good_kmer_before
     const uint8_t* A = s.b;          // good_k_mer_after
