@@ -173,6 +173,26 @@ def cpu_baseline(db_path, chunks, sample_bp: int, procs: int):
     return {"wall": wall, "bp": bp, "lookups": lookups, "kind": outs[0][4], "procs": len(jobs), "jobs": jobs, "outs": outs}
 
 
+def workload_text(genome_mb, meta, n_chunks):
+    return ("synthetic %.0f Mb chr20-scale assembly, 0.1%% injected errors, simulated 30x Illumina .jf (%d records), k=%d, p=%d, "
+            "chunked as jasper.sh -t %d (%d chunks of <= %d bp), solid_thre=%d; one assembly per GPU against a replicated table"
+            % (genome_mb, meta["n_records"], K, PASSES, CHUNK_THREADS, n_chunks, meta["batch_size"], SOLID_THRE))
+
+
+def ncu_traffic_gb():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch on this workload, from the committed
+    ncu --set full summary (profiles/); None when the summary is missing."""
+    try:
+        vals = {}
+        for line in open(os.path.join(ROOT, "profiles", "r1_k_scan_ncu_full_keymetrics.csv")):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0].startswith("dram__bytes_"):
+                vals[f[0]] = float(f[2]) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[f[1]]
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse_args()
@@ -321,9 +341,10 @@ def main():
     scan_ms_per_launch = last_stats["scan_ms"] / (PASSES + 1)
     lookups_per_launch = last_stats["scan_lookups"] / (PASSES + 1)
     achieved = lookups_per_launch * 32 / (scan_ms_per_launch * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_scan<events>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback 6650",
-                "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy), of measured" if peaks else "fallback 6650, of fallback",
+                "traffic": ncu_traffic_gb(), "traffic_unit": "GB per launch (dram read+write, profiles/ ncu --set full capture of this workload)",
+                "algorithmic_gb_per_launch": lookups_per_launch * 32 / 1e9,
                 "lookups_per_s": lookups_per_launch / (scan_ms_per_launch * 1e-3),
                 "random_sector_peak_GBps": gather_gbps, "frac_of_random_sector_peak": achieved / gather_gbps if gather_gbps else None,
                 "ms_per_launch": scan_ms_per_launch, "share_of_step": last_stats["scan_ms"] / (dev_ms / args.steps),
@@ -346,8 +367,7 @@ def main():
         "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64/u8 (2-bit packed k-mers, 32-bit counts)", "data": "synthetic",
-        "config": {"workload": "synthetic %.0f Mb chr20-scale assembly, 0.1%% injected errors, simulated 30x Illumina .jf (%d records), k=%d, p=%d, chunked as jasper.sh -t %d (%d chunks of <= %d bp), solid_thre=%d; one assembly per GPU against a replicated table"
-                   % (args.genome_mb, meta["n_records"], K, PASSES, CHUNK_THREADS, len(chunks), meta["batch_size"], SOLID_THRE),
+        "config": {"workload": workload_text(args.genome_mb, meta, len(chunks)),
                    "l2_policy": "inputs larger than L2: %.1f GB table probed at random, fresh upload every step" % (qf.info["table_bytes"] / 1e9)},
         "e2e": {"value": e2e_value, "unit": "bp polished/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "call": "jb_polish (C ABI, host buffers in / host results out)",
@@ -394,8 +414,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "python int / uint64", "data": "synthetic",
-        "config": {"workload": "bounded sample of: synthetic %.0f Mb chr20-scale assembly, 0.1%% injected errors, simulated 30x Illumina .jf (%d records), k=%d, p=%d, solid_thre=%d"
-                   % (args.genome_mb, meta["n_records"], K, PASSES, SOLID_THRE)},
+        "config": {"workload": workload_text(args.genome_mb, meta, len(chunks)),
+                   "l2_policy": "CPU path: a bounded sample of the workload per step (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "bp polished/s", "cores": procs, "kind": "reference" if kind == "reference-binding" else "port",
                          "sample": "each step: %d worker processes x %d bp slices of the workload's chunks (python restatement of src/jasper.py over %s)"
                                    % (procs, bps[-1] // max(1, procs), "the reference's compiled Jellyfish binding" if kind == "reference-binding" else "oracle/libjf_oracle.so")},
