@@ -107,4 +107,33 @@ inline void settle_rows(std::vector<DevRow>* rows, const std::vector<UnitIO>& se
   rows->swap(placed);
 }
 
+// The same without copying or sorting the log: walk the rows in (contig, segment, emission) order through
+// an index and emit csv rows straight from the (pinned) log.
+inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux, const std::vector<UnitIO>& segs,
+                          const std::vector<SegPlace>& place, const std::vector<size_t>& first_seg, PassOut* out) {
+  std::vector<uint64_t> slot0(segs.size() + 1, 0);
+  for (size_t q = 0; q < segs.size(); ++q) slot0[q + 1] = slot0[q] + segs[q].n_rows;
+  std::vector<uint32_t> at((size_t)slot0[segs.size()], 0xFFFFFFFFu);
+  size_t live = 0;
+  for (size_t i = 0; i < n_rows; ++i) {
+    const DevRow& r = rows[i];
+    const size_t s0 = first_seg[r.unit];
+    if (segs[s0].gen != r.gen) continue;             // superseded attempt
+    const size_t q = s0 + r.seg;
+    if (r.seqno >= segs[q].n_rows) continue;
+    at[(size_t)slot0[q] + r.seqno] = (uint32_t)i;
+    ++live;
+  }
+  out->rows.reserve(out->rows.size() + live + 16);
+  bool ok = true;
+  size_t q = 0;
+  for (size_t sl = 0; sl < at.size(); ++sl) {
+    while (sl >= slot0[q + 1]) ++q;
+    if (at[sl] == 0xFFFFFFFFu) continue;
+    const DevRow& r = rows[at[sl]];
+    ok = row_to_csv(r, r.coord + place[q].row_shift, aux, out) && ok;
+  }
+  return ok;
+}
+
 }  // namespace jb

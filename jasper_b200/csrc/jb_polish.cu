@@ -33,7 +33,7 @@ constexpr int kWalkWarps = 4;               // walkers per CTA
 constexpr int kWalkCtasPerSm = 5;
 constexpr uint32_t kTrieCap = 1u << 20;     // de-Bruijn trie nodes per bridging slot
 constexpr uint32_t kPatchCap = 1u << 18;    // longest recoverable patch
-constexpr uint32_t kPoolSlots = 256;        // bridging scratch slots shared by all walkers
+constexpr uint32_t kPoolSlots = 512;        // bridging scratch slots shared by all walkers
 
 struct WalkCfg { int k, step; uint32_t solid; int fix; };
 
@@ -304,17 +304,39 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   cudaEvent_t e0, e1;
   JB_CUDA(cudaEventCreate(&e0)); JB_CUDA(cudaEventCreate(&e1));
   JB_CUDA(cudaEventRecord(e0, s));
-  // stage through pinned memory in slices so the host copy of slice i+1 overlaps the DMA of slice i
+  // stage through pinned memory in slices: a few host threads copy slices while the DMA engine drains the
+  // ones already staged (one thread saturates at ~9 GB/s, the link takes 3x that)
+  struct Slice { const char* src; uint64_t dev_off, pin_off, len; };
+  std::vector<Slice> slices;
+  constexpr uint64_t kSlice = 4ull << 20;
   uint64_t p = 0;
-  constexpr uint64_t kSlice = 8ull << 20;
-  for (size_t i = 0; i < n; ++i) {
+  for (size_t i = 0; i < n; ++i)
     for (uint64_t at = 0; at < seqs[i].len; at += kSlice) {
       const uint64_t m = std::min<uint64_t>(kSlice, seqs[i].len - at);
-      std::memcpy(w.h_in.p + p, seqs[i].seq + at, m);
-      JB_CUDA(cudaMemcpyAsync(w.buf[0].p + b->off[i] + at, w.h_in.p + p, m, cudaMemcpyHostToDevice, s));
+      slices.push_back(Slice{seqs[i].seq + at, b->off[i] + at, p, m});
       p += m;
     }
+  const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, slices.size() / 2));
+  std::vector<std::atomic<int>> ready(slices.size());
+  for (auto& r : ready) r.store(0);
+  std::vector<std::thread> copiers;
+  uint8_t* pin = w.h_in.p;
+  for (int t = 1; t < n_thr; ++t)
+    copiers.emplace_back([&, t]() {
+      for (size_t j = (size_t)t; j < slices.size(); j += (size_t)n_thr) {
+        std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
+        ready[j].store(1, std::memory_order_release);
+      }
+    });
+  cudaError_t copy_err = cudaSuccess;
+  for (size_t j = 0; j < slices.size(); ++j) {
+    if (j % (size_t)n_thr == 0) std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
+    else while (!ready[j].load(std::memory_order_acquire)) std::this_thread::yield();
+    if (copy_err == cudaSuccess)
+      copy_err = cudaMemcpyAsync(w.buf[0].p + slices[j].dev_off, pin + slices[j].pin_off, slices[j].len, cudaMemcpyHostToDevice, s);
   }
+  for (auto& t : copiers) t.join();
+  JB_CUDA(copy_err);
   JB_CUDA(cudaEventRecord(e1, s));
   JB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
@@ -341,12 +363,13 @@ int64_t pick_seg_block(int64_t total_len, int sms) {
 }
 
 UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, uint32_t slot, int keep_margin) {
-  UnitIO u;
-  std::memset(&u, 0, sizeof u);
+  UnitIO u;                                        // (result fields are written by the walker)
   const size_t i = p.unit;
   const Workspace& w = *b->ws;
+  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0;
   u.in = in + b->off[i]; u.in_len = b->len[i];
   u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
+  u.cnt = w.counts.p + b->off[i];
   u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
@@ -369,12 +392,10 @@ struct PendingRows {
 
 struct RowJob {
   std::thread th;
-  std::vector<DevRow> rows;
-  std::vector<uint8_t> aux;
   std::vector<UnitIO> segs;
   std::vector<SegPlace> place;
   std::vector<size_t> first_seg;
-  std::vector<HostRow> out;
+  PassOut out;
   bool ok = true;
   size_t pass = 0;
   std::atomic<bool> copied{true};
@@ -391,12 +412,11 @@ int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob
   const DevRow* src_rows = w.h_rows.p; const uint8_t* src_aux = w.h_aux.p;
   const size_t n_rows = pr->n_rows, n_aux = pr->n_aux;
   raw->copied.store(false);
-  j->th = std::thread([raw, src_rows, src_aux, n_rows, n_aux]() {
-    raw->rows.assign(src_rows, src_rows + n_rows);          // out of the pinned buffer first: the next pass reuses it
-    raw->aux.assign(src_aux, src_aux + n_aux);
+  (void)n_aux;
+  j->th = std::thread([raw, src_rows, src_aux, n_rows]() {
+    // straight from the pinned log (the next pass's log is not copied into it before `copied` is set)
+    raw->ok = rows_in_order(src_rows, n_rows, src_aux, raw->segs, raw->place, raw->first_seg, &raw->out);
     raw->copied.store(true, std::memory_order_release);
-    settle_rows(&raw->rows, raw->segs, raw->place, raw->first_seg);
-    raw->ok = rows_to_csv(raw->rows, raw->aux, &raw->out);
   });
   jobs->push_back(std::move(j));
   pr->live = false;
@@ -406,7 +426,7 @@ int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob
 void join_rows(jb_batch* b, std::vector<std::unique_ptr<RowJob>>* jobs) {
   for (auto& j : *jobs) {
     if (j->th.joinable()) j->th.join();
-    if (j->pass < b->passes.size()) b->passes[j->pass].rows.swap(j->out);
+    if (j->pass < b->passes.size()) { b->passes[j->pass].rows.swap(j->out.rows); b->passes[j->pass].spill.swap(j->out.spill); }
     if (!j->ok) b->status = JB_E_REFERENCE_CRASH;          // exit 1 in the reference
   }
   jobs->clear();
@@ -520,10 +540,16 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_TRY(w.order.ensure(n_first + n)); JB_TRY(w.dst_off.ensure(n_first + n));
     UnitIO* hs = w.h_segs.p;
     for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin);
-    std::vector<uint32_t> order(n_first);
-    std::iota(order.begin(), order.end(), 0u);
-    auto seg_span = [&](uint32_t q) { return (hs[q].next_anchor >= 0 ? hs[q].next_anchor : hs[q].in_len) - hs[q].base; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return seg_span(x) > seg_span(y); });
+    // queue order: the few long segments (stretches without an anchor) first, the rest as planned
+    std::vector<uint32_t> order;
+    order.reserve(n_first);
+    auto seg_span = [&](size_t q) { return (hs[q].next_anchor >= 0 ? hs[q].next_anchor : hs[q].in_len) - hs[q].base; };
+    const int64_t long_span = 4 * std::max<int64_t>(seg_block, 1024);
+    std::vector<uint32_t> longs;
+    for (size_t q = 0; q < n_first; ++q) if (seg_span(q) > long_span) longs.push_back((uint32_t)q);
+    std::sort(longs.begin(), longs.end(), [&](uint32_t x, uint32_t y) { return seg_span(x) > seg_span(y); });
+    order = longs;
+    for (size_t q = 0; q < n_first; ++q) if (seg_span(q) <= long_span) order.push_back((uint32_t)q);
     JB_CUDA(cudaMemcpyAsync(w.segs.p, hs, n_first * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
     JB_CUDA(cudaMemcpyAsync(w.order.p, order.data(), n_first * 4, cudaMemcpyHostToDevice, s));
     // ---- walk (the previous pass's rows have left the arena: the stream waited for ev_rows)
@@ -714,13 +740,9 @@ extern "C" int64_t jb_result_num_rows(const jb_result* r, int ite) {
 }
 extern "C" int jb_result_rows(const jb_result* r, int ite, jb_fix_row_t* rows, size_t cap) {
   if (!r || ite < 0 || ite >= (int)r->passes.size() || (!rows && cap)) return fail(JB_E_ARG, "jb_result_rows: bad argument");
-  const auto& v = r->passes[ite].rows;
-  for (size_t i = 0; i < v.size() && i < cap; ++i) {
-    std::memset(&rows[i], 0, sizeof rows[i]);
-    rows[i].seq_index = v[i].seq_index; rows[i].coord = v[i].coord;
-    std::strncpy(rows[i].mutation, v[i].mutation.c_str(), sizeof rows[i].mutation - 1);
-    std::strncpy(rows[i].original, v[i].original.c_str(), sizeof rows[i].original - 1);
-  }
+  const PassOut& po = r->passes[ite];
+  const size_t m = std::min(cap, po.rows.size());
+  for (size_t i = 0; i < m; ++i) po.expand(po.rows[i], &rows[i]);
   return JB_OK;
 }
 extern "C" int64_t jb_result_num_seqs(const jb_result* r) { return r ? (int64_t)r->seq_len.size() : JB_E_ARG; }

@@ -2,6 +2,7 @@
 // (src/jasper.py:214-222 and, for multi-error patches, :305-329).
 #pragma once
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -10,27 +11,59 @@
 
 namespace jb {
 
-struct HostRow { uint32_t seq_index; int64_t coord; std::string mutation, original; };
-struct PassOut { int64_t wrong = 0, total = 0; std::vector<HostRow> rows; };
+// One csv row, compact: almost every row carries 1-3 characters of text, and the rows of a 64 Mb pass are
+// built beside the GPU work, so they must not cost 144 bytes (and a page fault per 28 rows) each.
+struct HostRow {
+  int64_t coord;
+  uint32_t seq_index;
+  uint32_t spill;            // offset of the text in PassOut::spill when it does not fit inline
+  uint8_t mut_len, orig_len;
+  char text[14];             // mutation then original
+};
+static_assert(sizeof(HostRow) == 32, "HostRow is meant to be 32 bytes");
+
+struct PassOut {
+  int64_t wrong = 0, total = 0;
+  std::vector<HostRow> rows;
+  std::string spill;
+  const char* mutation(const HostRow& r) const { return (r.mut_len + r.orig_len <= (int)sizeof r.text) ? r.text : spill.data() + r.spill; }
+  const char* original(const HostRow& r) const { return mutation(r) + r.mut_len; }
+  void add(uint32_t seq_index, int64_t coord, const char* mut, size_t mut_len, const char* orig, size_t orig_len) {
+    HostRow h;
+    if (mut_len > 63) mut_len = 63;
+    if (orig_len > 63) orig_len = 63;
+    h.coord = coord; h.seq_index = seq_index; h.spill = 0; h.mut_len = (uint8_t)mut_len; h.orig_len = (uint8_t)orig_len;
+    if (mut_len + orig_len <= sizeof h.text) { std::memcpy(h.text, mut, mut_len); std::memcpy(h.text + mut_len, orig, orig_len); }
+    else { h.spill = (uint32_t)spill.size(); spill.append(mut, mut_len); spill.append(orig, orig_len); }
+    rows.push_back(h);
+  }
+  void expand(const HostRow& r, jb_fix_row_t* o) const {
+    std::memset(o, 0, sizeof *o);                  // consumers read the char arrays as fixed-width fields
+    o->seq_index = r.seq_index; o->coord = r.coord;
+    std::memcpy(o->mutation, mutation(r), r.mut_len);
+    std::memcpy(o->original, original(r), r.orig_len);
+  }
+};
 
 // Appends the csv rows of `rows` (already in (contig, segment, emission) order) to out.  Returns false when
 // the reference would have crashed (IndexError at src/jasper.py:221 / :309 -> exit 1).
-inline bool rows_to_csv(const std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
+// One logged row -> zero, one or two csv rows.
+inline bool row_to_csv(const DevRow& r, int64_t coord, const uint8_t* aux, PassOut* out) {
   bool ok = true;
-  out->reserve(out->size() + rows.size() + 16);
-  for (const DevRow& r : rows) {
+  {
     if (r.kind == kRowPlain) {
-      out->push_back(HostRow{r.unit, r.coord, std::string(r.fb, r.fb_len), std::string(r.orig, r.orig_len)});
-      continue;
+      out->add(r.unit, coord, r.fb, r.fb_len, r.orig, r.orig_len);
+      return true;
     }
-    std::string patch((const char*)aux.data() + r.aux_off, r.aux_patch_len);
-    std::string orig((const char*)aux.data() + r.aux_off + r.aux_patch_len, r.aux_orig_len);
+    std::string patch((const char*)aux + r.aux_off, r.aux_patch_len);
+    std::string orig((const char*)aux + r.aux_off + r.aux_patch_len, r.aux_orig_len);
     std::string pa, oa;
-    std::vector<HostRow> diffs;
+    struct Diff { int64_t coord; std::string mutation, original; };
+    std::vector<Diff> diffs;
     if (first_global_alignment(patch, orig, &pa, &oa)) {
-      for (size_t c = 0; c < pa.size(); ++c) {
+      for (size_t c = 0; c < pa.size() && diffs.size() < 2; ++c) {     // only the first two are ever written (src/jasper.py:218-222)
         if (pa[c] == oa[c]) continue;
-        HostRow h{r.unit, r.coord + (int64_t)c, "", ""};
+        Diff h{coord + (int64_t)c, "", ""};
         if (pa[c] == '-') { h.mutation = "-"; h.original = std::string("i") + oa[c]; }
         else if (oa[c] == '-') { h.mutation = std::string(1, pa[c]); h.original = "d-"; }
         else { h.mutation = std::string(1, pa[c]); h.original = std::string("s") + oa[c]; }
@@ -42,17 +75,21 @@ inline bool rows_to_csv(const std::vector<DevRow>& rows, const std::vector<uint8
     } else if (diffs.size() == 1) {                // csv.writer prints the one-element lists' repr
       diffs[0].mutation = "['" + diffs[0].mutation + "']";
       diffs[0].original = "['" + diffs[0].original + "']";
-      out->push_back(diffs[0]);
-    } else {
-      out->push_back(diffs[0]);
-      out->push_back(diffs[1]);
     }
+    for (const Diff& h : diffs) out->add(r.unit, h.coord, h.mutation.data(), h.mutation.size(), h.original.data(), h.original.size());
   }
   return ok;
 }
 
+inline bool rows_to_csv(const std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, PassOut* out) {
+  bool ok = true;
+  out->rows.reserve(out->rows.size() + rows.size() + 16);
+  for (const DevRow& r : rows) ok = row_to_csv(r, r.coord, aux.data(), out) && ok;
+  return ok;
+}
+
 // Sorts `rows` by (contig, segment, emission order) first (callers without a segment table).
-inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, std::vector<HostRow>* out) {
+inline bool rows_from_log(std::vector<DevRow>& rows, const std::vector<uint8_t>& aux, PassOut* out) {
   std::sort(rows.begin(), rows.end(), [](const DevRow& x, const DevRow& y) {
     if (x.unit != y.unit) return x.unit < y.unit;
     if (x.seg != y.seg) return x.seg < y.seg;

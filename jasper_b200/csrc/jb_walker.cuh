@@ -124,6 +124,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   int64_t in_len;
   uint8_t* out;              // staging: out[r] = new base r of this segment, valid inside materialised windows
   int64_t out_cap;
+  const uint32_t* cnt;       // C(window) for every position of the pass-start contig, [0, in_len]; may be null
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
   uint64_t ev_bit_base;      // flat bit index of contig position 0
@@ -189,12 +190,13 @@ struct Walker {
     int got = -1;
     if ((threadIdx.x & 31) == 0) {
       uint32_t at = (uint32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % pool.n;
+      unsigned int backoff = 200;
       while (got < 0) {                                  // holders never wait on anything, so this terminates
-        for (uint32_t tries = 0; tries < pool.n && got < 0; ++tries) {
-          if (atomicCAS(&pool.busy[at], 0u, 1u) == 0u) got = (int)at;
+        for (uint32_t tries = 0; tries < 16 && got < 0; ++tries) {
+          if (*(volatile uint32_t*)&pool.busy[at] == 0u && atomicCAS(&pool.busy[at], 0u, 1u) == 0u) got = (int)at;
           else at = at + 1 == pool.n ? 0 : at + 1;
         }
-        if (got < 0) __nanosleep(500);
+        if (got < 0) { __nanosleep(backoff); if (backoff < 20000) backoff *= 2; }   // all busy: stay off the issue slots
       }
       __threadfence();
     }
@@ -255,19 +257,37 @@ struct Walker {
   JB_WN uint32_t Cw(int64_t x, int dir) {
     if (x < 0) return C_empty();                     // the slices with negative starts are empty (L >= k)
     if (x >= wc_base && x < wc_base + wc_n) return s.wc[x - wc_base];
-    int64_t base = dir > 0 ? x : (x - 31 > 0 ? x - 31 : 0);
-    int len = load(s.c, base, base + 32 + k - 1);
+    int64_t b0 = dir > 0 ? x : (x - 31 > 0 ? x - 31 : 0);
+    if (u.cnt && b0 >= clean_from) {
+      // untouched territory: the bulk scan of this pass already counted these windows
+      const int64_t p0 = b0 - (base + olen - ipos);            // pass-start coordinate of window b0
+      if (p0 < base - seam_margin) seam_bad = true;             // (the previous segment's walker may have changed them)
+      JB_SYNC();
+      JB_LANES(l) { int64_t p = p0 + l; s.wc[l] = u.cnt[p < u.in_len ? p : u.in_len]; }
+      JB_SYNC();
+      wc_base = b0; wc_n = 32;
+      return s.wc[x - b0];
+    }
+    int len = load(s.c, b0, b0 + 32 + k - 1);
     JB_LANES(l) { s.wc[l] = count_in(s.c, len, l < len ? l : len); }
     JB_SYNC();
     lookups += 32;
-    wc_base = base; wc_n = 32;
-    return s.wc[x - base];
+    wc_base = b0; wc_n = 32;
+    return s.wc[x - b0];
   }
 
   // n <= 32 windows at arbitrary starts s.px[0..n) (non-negative, within a span that fits s.c)
   JB_WN void Cpts(int n) {
     int64_t lo = s.px[0], hi = s.px[0];
     for (int q = 1; q < n; ++q) { lo = s.px[q] < lo ? s.px[q] : lo; hi = s.px[q] > hi ? s.px[q] : hi; }
+    if (u.cnt && lo >= clean_from) {                 // untouched territory: read the bulk scan's counts
+      const int64_t shift = base + olen - ipos;
+      if (lo - shift < base - seam_margin) seam_bad = true;
+      JB_SYNC();
+      JB_LANES(l) { if (l < n) { int64_t p = s.px[l] - shift; s.pr[l] = u.cnt[p < u.in_len ? p : u.in_len]; } }
+      JB_SYNC();
+      return;
+    }
     if (hi + k - lo > kStrCap - 8) {                 // cannot happen for the call sites below; stay exact anyway
       for (int q = 0; q < n; ++q) s.pr[q] = Cw(s.px[q], +1);
       return;

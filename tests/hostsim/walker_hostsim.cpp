@@ -30,9 +30,11 @@ struct SimResult {
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
-static void scan_bits(const HostDB& db, const std::string& seq, int k, uint32_t solid, std::vector<uint32_t>* ev, std::vector<uint32_t>* weak) {
+static void scan_bits(const HostDB& db, const std::string& seq, int k, uint32_t solid, std::vector<uint32_t>* ev, std::vector<uint32_t>* weak,
+                      std::vector<uint32_t>* cnt_out) {
   const int64_t L = (int64_t)seq.size();
-  std::vector<uint32_t> cnt(L + 1);
+  std::vector<uint32_t>& cnt = *cnt_out;
+  cnt.assign(L + 1, 0);
   std::vector<uint8_t> ok(L + 1);
   Key mask = key_mask(k);
   for (int64_t p = 0; p <= L; ++p) {
@@ -85,14 +87,14 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
     std::vector<CopyJob> jobv(1 << 18);
     JobSink jobs{jobv.data(), jobv.size(), &jobs_used};
     std::vector<int64_t> len(n);
-    std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n);
+    std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n), cnts(n);
     std::vector<std::vector<uint8_t>> stage(n);
     for (size_t i = 0; i < n; ++i) {
       len[i] = (int64_t)cur[i].size();
       po.total += len[i] - k + 1;
       stage[i].resize((size_t)caps[i] + 64);
       if (!use_events) continue;
-      scan_bits(db, cur[i], k, solid, &ev[i], &weak[i]);
+      scan_bits(db, cur[i], k, solid, &ev[i], &weak[i], &cnts[i]);
       // level-1 summary over this contig's own bit positions (ev_bit_base = 0)
       l1[i].assign((size_t)(len[i] + 1) / 32768 + 2, 0);
       for (int64_t p = 0; p <= len[i]; ++p)
@@ -113,6 +115,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       const size_t i = p.unit;
       u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
       u.out = stage[i].data() + p.stage_off; u.out_cap = p.stage_cap;
+      u.cnt = use_events ? cnts[i].data() : nullptr;
       u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
       u.slot = slot; u.materialize_all = gen ? 1u : 0u;
@@ -185,12 +188,24 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       }
       std::vector<DevRow> got(rows.begin(), rows.begin() + used);
       std::vector<uint8_t> a2(aux.begin(), aux.begin() + aux_used);
+      // the product's path (no copy, no sort) and the sorting path must agree
+      PassOut alt;
+      const bool ok1 = rows_in_order(rows.data(), used, aux.data(), segs, place, first_seg, &po);
       settle_rows(&got, segs, place, first_seg);
-      if (!rows_from_log(got, a2, &po.rows)) res->status = JB_E_REFERENCE_CRASH;
+      const bool ok2 = rows_from_log(got, a2, &alt);
+      if (ok1 != ok2 || alt.rows.size() != po.rows.size()) { res->status = -100; return res; }
+      for (size_t q = 0; q < alt.rows.size(); ++q) {
+        jb_fix_row_t x, y;
+        alt.expand(alt.rows[q], &x); po.expand(po.rows[q], &y);
+        if (memcmp(&x, &y, sizeof x)) { res->status = -100; return res; }
+      }
+      if (!ok1) res->status = JB_E_REFERENCE_CRASH;
     }
     for (const HostRow& r : po.rows) {
+      jb_fix_row_t x;
+      po.expand(r, &x);
       char line[256];
-      snprintf(line, sizeof line, "%d\t%u\t%lld\t%s\t%s\n", ite, r.seq_index, (long long)r.coord, r.mutation.c_str(), r.original.c_str());
+      snprintf(line, sizeof line, "%d\t%u\t%lld\t%s\t%s\n", ite, x.seq_index, (long long)x.coord, x.mutation, x.original);
       res->text += line;
     }
     res->passes.push_back(po);
