@@ -164,8 +164,8 @@ struct Workspace {
   PinBuf<uint8_t> h_in;                     // staged input bases
   PinBuf<UnitIO> h_segs;
   PinBuf<long long> h_anchors;
-  PinBuf<DevRow> h_rows;
-  PinBuf<uint8_t> h_aux;
+  PinBuf<DevRow> h_rows[2];                 // double-buffered: a host thread reads one log while the next lands
+  PinBuf<uint8_t> h_aux[2];
   PinBuf<unsigned long long> h_used;
   cudaStream_t s2 = nullptr;                // side stream: fix rows travel while the next pass scans
   cudaEvent_t ev_walk = nullptr, ev_rows = nullptr;
@@ -176,7 +176,7 @@ struct Workspace {
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
-    h_in.release(); h_segs.release(); h_anchors.release(); h_rows.release(); h_aux.release(); h_used.release();
+    h_in.release(); h_segs.release(); h_anchors.release(); h_rows[0].release(); h_rows[1].release(); h_aux[0].release(); h_aux[1].release(); h_used.release();
     if (s2) cudaStreamDestroy(s2);
     if (ev_walk) cudaEventDestroy(ev_walk);
     if (ev_rows) cudaEventDestroy(ev_rows);
@@ -289,8 +289,8 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
   JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
-  JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.h_rows.ensure(total_len / 32 + 4096));
-  JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20))); JB_TRY(w.h_aux.ensure(total_len / 4 + (1u << 20)));
+  JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20)));
+  for (int q = 0; q < 2; ++q) { JB_TRY(w.h_rows[q].ensure(total_len / 32 + 4096)); JB_TRY(w.h_aux[q].ensure(total_len / 4 + (1u << 20))); }
   JB_TRY(w.jobs.ensure(total_len / 16 + 4 * n + 65536));
   if (!w.pool_ready) {
     JB_TRY(w.pool.ensure(kPoolSlots)); JB_TRY(w.trie.ensure((size_t)kPoolSlots * kTrieCap)); JB_TRY(w.patch.ensure((size_t)kPoolSlots * kPatchCap));
@@ -383,6 +383,7 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
 // beside the GPU work of the following passes.
 struct PendingRows {
   bool live = false;
+  int buf = 0;               // which pinned log
   size_t pass = 0;
   unsigned long long n_rows = 0, n_aux = 0;
   std::vector<UnitIO> segs;
@@ -398,6 +399,7 @@ struct RowJob {
   PassOut out;
   bool ok = true;
   size_t pass = 0;
+  int buf = 0;
   std::atomic<bool> copied{true};
 };
 
@@ -409,7 +411,8 @@ int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob
   j->segs.swap(pr->segs); j->place.swap(pr->place); j->first_seg.swap(pr->first_seg);
   j->pass = pr->pass;
   RowJob* raw = j.get();
-  const DevRow* src_rows = w.h_rows.p; const uint8_t* src_aux = w.h_aux.p;
+  const DevRow* src_rows = w.h_rows[pr->buf].p; const uint8_t* src_aux = w.h_aux[pr->buf].p;
+  raw->buf = pr->buf;
   const size_t n_rows = pr->n_rows, n_aux = pr->n_aux;
   raw->copied.store(false);
   (void)n_aux;
@@ -635,11 +638,12 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       }
       for (size_t i = 0; i < n; ++i)
         if (new_lens[i] > caps[i]) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "contig " + std::to_string(i) + " outgrew its output slack"); }
-      for (auto& rj : row_jobs) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
+      const int hb = ite & 1;                            // the log of pass ite-2 must have been read out of this buffer
+      for (auto& rj : row_jobs) if (rj->buf == hb) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
       JB_CUDA(cudaEventRecord(w.ev_walk, s));
       JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
-      if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows.p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
-      if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux.p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
+      if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows[hb].p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
+      if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux[hb].p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
       JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
       JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
       dim3 g(4, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(used[3], 1), 16384));
@@ -647,7 +651,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       JB_CUDA(cudaGetLastError());
       ++launches;
       JB_CUDA(cudaStreamWaitEvent(s, w.ev_rows, 0));     // the next walk reuses the row arena
-      pending.live = true; pending.pass = (size_t)ite; pending.n_rows = used[0]; pending.n_aux = used[1];
+      pending.live = true; pending.buf = hb; pending.pass = (size_t)ite; pending.n_rows = used[0]; pending.n_aux = used[1];
       pending.segs.swap(segs);
       b->len = new_lens;
       b->cur ^= 1;

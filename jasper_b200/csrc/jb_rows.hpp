@@ -51,12 +51,15 @@ struct PassOut {
 inline bool row_to_csv(const DevRow& r, int64_t coord, const uint8_t* aux, PassOut* out) {
   bool ok = true;
   {
-    if (r.kind == kRowPlain) {
-      out->add(r.unit, coord, r.fb, r.fb_len, r.orig, r.orig_len);
+    if (r.kind == kRowPlain || r.kind == kRowSpill) {
+      const char* text = r.kind == kRowPlain ? r.text : (const char*)aux + r.aux_off;
+      out->add(r.unit, coord, text, r.fb_len, text + r.fb_len, r.orig_len);
       return true;
     }
-    std::string patch((const char*)aux + r.aux_off, r.aux_patch_len);
-    std::string orig((const char*)aux + r.aux_off + r.aux_patch_len, r.aux_orig_len);
+    uint32_t patch_len = 0, orig_len = 0;
+    for (int q = 0; q < 4; ++q) { patch_len |= (uint32_t)aux[r.aux_off + q] << (8 * q); orig_len |= (uint32_t)aux[r.aux_off + 4 + q] << (8 * q); }
+    std::string patch((const char*)aux + r.aux_off + 8, patch_len);
+    std::string orig((const char*)aux + r.aux_off + 8 + patch_len, orig_len);
     std::string pa, oa;
     struct Diff { int64_t coord; std::string mutation, original; };
     std::vector<Diff> diffs;

@@ -58,21 +58,25 @@ constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check st
 constexpr int kPathCap = 4 * JB_MAX_PATHS + 64;  // a round can at most quadruple the path list
 constexpr uint32_t kDeadNode = 0xFFFFFFFFu;
 
-enum RowKind : uint32_t { kRowPlain = 0, kRowBridge = 1 };
+enum RowKind : uint32_t { kRowPlain = 0, kRowBridge = 1, kRowSpill = 2 };
 
-struct DevRow {              // one fix event as logged by the walker
+// One fix event as logged by the walker, 32 bytes.  The text (mutation then original, the latter led by
+// its s/i/d tag) sits inline when it fits in 8 bytes -- nearly always -- else in the aux arena; a bridged
+// multi-error patch keeps its patch and the replaced bases in the aux arena for the host-side alignment.
+struct DevRow {
   int64_t coord;
   uint32_t unit;
   uint32_t seg;              // segment of the contig that emitted it
   uint32_t seqno;            // emission order inside the segment
-  uint32_t gen;              // which launch of the pass produced it (a re-run supersedes the first attempt)
-  uint32_t kind;
-  uint16_t fb_len, orig_len;
-  uint64_t aux_off;          // kRowBridge: patch then original bytes in the aux arena
-  uint32_t aux_patch_len, aux_orig_len;
-  char fb[48];
-  char orig[48];
+  uint8_t gen;               // which launch of the pass produced it (a re-run supersedes the first attempt)
+  uint8_t kind;              // RowKind
+  uint8_t fb_len, orig_len;  // kRowPlain / kRowSpill: lengths of mutation / original (tag included)
+  union {
+    char text[8];            // kRowPlain
+    uint64_t aux_off;        // kRowSpill: text in the aux arena; kRowBridge: {u32 patch_len, u32 orig_len, patch, original}
+  };
 };
+static_assert(sizeof(DevRow) == 32, "DevRow is meant to be 32 bytes");
 
 struct RowSink {
   DevRow* rows;
@@ -438,24 +442,34 @@ struct Walker {
 
   JB_WN void emit_row(int64_t coord, const uint8_t* fb, int fb_len, uint8_t tag, const uint8_t* orig, int orig_len) {
     JB_SYNC();
-    unsigned long long slot = 0;
+    const int total = fb_len + 1 + orig_len;
+    unsigned long long slot = 0, off = 0;
 #if defined(__CUDA_ARCH__)
-    if ((threadIdx.x & 31) == 0) slot = atomicAdd(sink.used, 1ull);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if ((threadIdx.x & 31) == 0) {
+      slot = atomicAdd(sink.used, 1ull);
+      if (total > 8) off = atomicAdd(sink.aux_used, (unsigned long long)total);
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0); off = __shfl_sync(0xffffffffu, off, 0);
 #else
     slot = (*sink.used)++;
+    if (total > 8) { off = *sink.aux_used; *sink.aux_used += (unsigned long long)total; }
 #endif
-    if (slot >= sink.cap) { status = JB_E_SCRATCH; return; }
+    if (slot >= sink.cap || (total > 8 && off + total > sink.aux_cap)) { status = JB_E_SCRATCH; return; }
     DevRow& r = sink.rows[slot];
+    char* text = total > 8 ? (char*)sink.aux + off : r.text;
     JB_LANES(l) {
       if (l == 0) {
-        r.coord = coord; r.unit = u.unit; r.seg = u.seg; r.gen = u.gen; r.seqno = seqno; r.kind = kRowPlain;
-        r.fb_len = (uint16_t)fb_len; r.orig_len = (uint16_t)(orig_len + 1);
-        r.aux_off = 0; r.aux_patch_len = 0; r.aux_orig_len = 0;
-        r.orig[0] = (char)tag;
+        r.coord = coord; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno;
+        r.kind = (uint8_t)(total > 8 ? kRowSpill : kRowPlain);
+        r.fb_len = (uint8_t)fb_len; r.orig_len = (uint8_t)(orig_len + 1);
+        if (total > 8) r.aux_off = off;
+        text[fb_len] = (char)tag;
       }
-      for (int q = l; q < fb_len; q += 32) r.fb[q] = (char)fb[q];
-      for (int q = l; q < orig_len; q += 32) r.orig[1 + q] = (char)orig[q];
+    }
+    JB_SYNC();                                       // (aux_off and inline text share storage: header first)
+    JB_LANES(l) {
+      for (int q = l; q < fb_len; q += 32) text[q] = (char)fb[q];
+      for (int q = l; q < orig_len; q += 32) text[fb_len + 1 + q] = (char)orig[q];
     }
     JB_SYNC();
     ++seqno;
@@ -829,19 +843,21 @@ struct Walker {
       unsigned long long off = 0, rslot = 0;
       JB_SYNC();
 #if defined(__CUDA_ARCH__)
-      if ((threadIdx.x & 31) == 0) { off = atomicAdd(sink.aux_used, (unsigned long long)(plen + olen_old)); rslot = atomicAdd(sink.used, 1ull); }
+      if ((threadIdx.x & 31) == 0) { off = atomicAdd(sink.aux_used, (unsigned long long)(plen + olen_old + 8)); rslot = atomicAdd(sink.used, 1ull); }
       off = __shfl_sync(0xffffffffu, off, 0); rslot = __shfl_sync(0xffffffffu, rslot, 0);
 #else
-      off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old); rslot = (*sink.used)++;
+      off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old + 8); rslot = (*sink.used)++;
 #endif
-      if (off + plen + olen_old > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; release_bridge(); return; }
+      if (off + plen + olen_old + 8 > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; release_bridge(); return; }
       JB_LANES(l) {
-        for (int64_t q = l; q < plen; q += 32) sink.aux[off + q] = bs->patch[q];
-        for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + plen + q] = get(gb + 1 + q);
+        for (int64_t q = l; q < plen; q += 32) sink.aux[off + 8 + q] = bs->patch[q];
+        for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + 8 + plen + q] = get(gb + 1 + q);
         if (l == 0) {
           DevRow& r = sink.rows[rslot];
-          r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = u.gen; r.seqno = seqno; r.kind = kRowBridge; r.fb_len = 0; r.orig_len = 0;
-          r.aux_off = off; r.aux_patch_len = (uint32_t)plen; r.aux_orig_len = (uint32_t)olen_old;
+          r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno; r.kind = (uint8_t)kRowBridge; r.fb_len = 0; r.orig_len = 0;
+          r.aux_off = off;
+          const uint32_t pl = (uint32_t)plen, ol = (uint32_t)olen_old;     // byte-wise: the arena is not aligned
+          for (int q = 0; q < 4; ++q) { sink.aux[off + q] = (uint8_t)(pl >> (8 * q)); sink.aux[off + 4 + q] = (uint8_t)(ol >> (8 * q)); }
         }
       }
       JB_SYNC();
