@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32, JB_WALK_MINBLOCKS)
 k_walk(TableView t, UnitIO* segs, const uint32_t* order, uint32_t n_segs, WalkCfg cfg, BridgePool pool, RowSink sink,
        JobSink jobs, unsigned int* next_seg) {
   __shared__ WarpScratch scratch[kWalkWarps];
+  __shared__ DevDB db;                     // shared, so the out-of-line scoring helpers take it by reference
   const int warp = threadIdx.x >> 5;
-  DevDB db{t};
+  if (threadIdx.x == 0) db.t = t;
+  __syncthreads();
   while (true) {
     unsigned int slot = 0;
     if ((threadIdx.x & 31) == 0) slot = atomicAdd(next_seg, 1u);

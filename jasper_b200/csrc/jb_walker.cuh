@@ -19,6 +19,7 @@
 
 #include "../../include/jasper_b200.h"
 #include "jb_kmer.cuh"
+#include "jb_cand.cuh"
 #include "jb_segments.cuh"
 
 // Inlined everywhere the kernel is 860 KB of SASS and the warps starve on instruction fetch (ncu: 60 %
@@ -44,17 +45,9 @@
 #define JB_WN
 #define JB_WC
 #endif
-#if defined(__CUDA_ARCH__)
-#define JB_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
-#define JB_SYNC() __syncwarp()
-#else
-#define JB_LANES(l) for (int l = 0; l < 32; ++l)
-#define JB_SYNC() ((void)0)
-#endif
 
 namespace jb {
 
-constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check string fits (<= 3k + 8)
 constexpr int kPathCap = 4 * JB_MAX_PATHS + 64;  // a round can at most quadruple the path list
 constexpr uint32_t kDeadNode = 0xFFFFFFFFu;
 
@@ -110,17 +103,6 @@ struct BridgePool {          // bridging scratch is borrowed only while a multi-
   BridgeScratch* slots;
   uint32_t n;
   uint32_t* busy;            // device: 0 = free, 1 = held
-};
-
-struct WarpScratch {         // shared memory (device) / plain struct (host)
-  uint8_t t[kStrCap];        // to_be_fixed
-  uint8_t b[kStrCap];        // trial
-  uint8_t c[kStrCap];        // check string / window staging
-  uint32_t wc[32];           // window-count cache
-  int64_t px[32];            // point queries
-  uint32_t pr[32];
-  uint32_t flag[32];
-  uint32_t ext[32];          // extension verdicts of one bridging wave (check_sequence reuses flag)
 };
 
 struct UnitIO {               // one SEGMENT of one contig (a whole contig is the one-segment case)
@@ -247,8 +229,7 @@ struct Walker {
   }
 
   JB_WN uint32_t count_in(const uint8_t* buf, int len, int m) const {
-    Key key = key_from_chars(buf + m, (int64_t)len - m, k, mask);
-    return db.count(key_canonical(key, k));
+    return count_str(db, buf, len, m, k, mask);
   }
 
   // ---------------------------------------------------------------------------- lookups
@@ -303,7 +284,7 @@ struct Walker {
   }
 
   // src/jasper.py:585-599 on a string in scratch memory
-  JB_WN bool check_sequence(const uint8_t* buf, int len, int64_t thr) {
+  JB_W bool check_sequence(const uint8_t* buf, int len, int64_t thr) {   // (bridging only; the fix_* family scores through jb_cand.cuh)
     // sample starts: 0, max(0,len-k), then step, 2*step, ... < len-k
     int n_mid = 0;
     for (int m = step; m < len - k; m += step) ++n_mid;
@@ -326,23 +307,6 @@ struct Walker {
       for (int q = 0; q < cnt; ++q) ok = ok && !s.flag[q];
     }
     return ok;
-  }
-
-  // number of windows of buf (all of them) below thr
-  JB_WN int count_weak(const uint8_t* buf, int len, int64_t thr) {
-    int total = len - k + 1, bad = 0;
-    for (int w0 = 0; w0 < total; w0 += 32) {
-      JB_SYNC();
-      JB_LANES(l) {
-        int q = w0 + l;
-        s.flag[l] = (q < total && (int64_t)count_in(buf, len, q) < thr) ? 1u : 0u;
-      }
-      JB_SYNC();
-      int cnt = total - w0 < 32 ? total - w0 : 32;
-      lookups += cnt;
-      for (int q = 0; q < cnt; ++q) bad += (int)s.flag[q];
-    }
-    return bad;
   }
 
   // ---------------------------------------------------------------------------- edits
@@ -478,61 +442,47 @@ struct Walker {
   // ---------------------------------------------------------------------------- fix_* family
   // All take the to_be_fixed string in s.t (length n) that starts at sequence position s0.
 
-  JB_WN void copy_t_to_b(int n) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < n; q += 32) s.b[q] = s.t[q]; } JB_SYNC(); }
-  JB_W void set_b(int at, uint8_t v) { JB_SYNC(); JB_LANES(l) { if (l == 0) s.b[at] = v; } JB_SYNC(); }
-  // b = t[:at] + ins(len m, same char v) + t[at:]
-  JB_WN void b_from_t_insert(int n, int at, uint8_t v, int m) {
-    JB_SYNC();
-    JB_LANES(l) { for (int q = l; q < n + m; q += 32) s.b[q] = q < at ? s.t[q] : (q < at + m ? v : s.t[q - m]); }
-    JB_SYNC();
+  JB_W void set_cand(int idx, uint8_t kind, uint8_t b1, uint8_t b2, int pos, int m) {
+    JB_LANES(l) { if (l == 0) { Cand c; c.kind = kind; c.base = b1; c.base2 = b2; c.pad = 0; c.pos = (int16_t)pos; c.m = (int16_t)m; s.cand[idx] = c; } }
   }
-  // b = t[:at] + t[at+m:]
-  JB_WN void b_from_t_delete(int n, int at, int m) {
-    JB_SYNC();
-    JB_LANES(l) { for (int q = l; q < n - m; q += 32) s.b[q] = q < at ? s.t[q] : s.t[q + m]; }
-    JB_SYNC();
-  }
+  JB_W void fill_b(uint8_t v, int m) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < m; q += 32) s.b[q] = v; } JB_SYNC(); }
 
-  // src/jasper.py:392-406 then :409-419
+  // src/jasper.py:392-406 then :409-419: up to three substitutions at k-1 in order 'ACTG', then the deletion of k-1
   JB_WN bool fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
     const uint8_t bad = s.t[k - 1];
     const uint8_t before = get(ga - 1);
     const char order[4] = {'A', 'C', 'T', 'G'};
-    for (int o = 0; o < 4; ++o) {
-      uint8_t bb = (uint8_t)order[o];
-      if (bb == bad) continue;
-      copy_t_to_b(n);
-      set_b(k - 1, bb);
-      if (check_sequence(s.b, n, thr)) {
-        if (!apply_edit(s0 + k - 1, s0 + k, &bb, 1)) return true;
-        emit_row(ga - 1, &bb, 1, 's', &before, 1);
-        return true;
-      }
-    }
-    b_from_t_delete(n, k - 1, 1);
-    if (check_sequence(s.b, n - 1, thr)) {
+    int nc = 0;
+    JB_SYNC();
+    for (int o = 0; o < 4; ++o) if ((uint8_t)order[o] != bad) set_cand(nc++, kSub, (uint8_t)order[o], 0, k - 1, 0);
+    set_cand(nc++, kDel, 0, 0, k - 1, 1);
+    const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
+    if (w < 0) return false;
+    const Cand c = s.cand[w];
+    if (c.kind == kSub) {
+      uint8_t bb = c.base;
+      if (!apply_edit(s0 + k - 1, s0 + k, &bb, 1)) return true;
+      emit_row(ga - 1, &bb, 1, 's', &before, 1);
+    } else {
       if (!apply_edit(s0 + k - 1, s0 + k, nullptr, 0)) return true;
       uint8_t dash = '-';
       emit_row(ga - 1, &dash, 1, 'i', &before, 1);
-      return true;
     }
-    return false;
+    return true;
   }
 
-  // src/jasper.py:422-431
+  // src/jasper.py:422-431: one base inserted in front of k-1, order 'ATCG'
   JB_WN bool fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
     const char order[4] = {'A', 'T', 'C', 'G'};
-    for (int o = 0; o < 4; ++o) {
-      uint8_t bb = (uint8_t)order[o];
-      b_from_t_insert(n, k - 1, bb, 1);
-      if (check_sequence(s.b, n + 1, thr)) {
-        if (!apply_edit(s0 + k - 1, s0 + k - 1, &bb, 1)) return true;
-        uint8_t dash = '-';
-        emit_row(ga, &bb, 1, 'd', &dash, 1);
-        return true;
-      }
-    }
-    return false;
+    JB_SYNC();
+    for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 1, 1);
+    const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
+    if (w < 0) return false;
+    uint8_t bb = s.cand[w].base;
+    if (!apply_edit(s0 + k - 1, s0 + k - 1, &bb, 1)) return true;
+    uint8_t dash = '-';
+    emit_row(ga, &bb, 1, 'd', &dash, 1);
+    return true;
   }
 
   // src/jasper.py:340-388
@@ -546,37 +496,36 @@ struct Walker {
     const int bl = (int)(a1 > a0 ? a1 - a0 : 0);
     const int64_t b0 = g0 - bl + 1 > 0 ? g0 - bl + 1 : 0;
     const int nb = (int)(g0 + 1 - b0);
-    // check string c = before + trial + after ; we stage before/after once
+    // check string = before + trial + after: the flanks are staged once in s.c
     const uint8_t seq_ga1 = get(ga - 1), seq_gb1 = get(gb + 1);
     JB_SYNC();
     JB_LANES(l) {
       for (int q = l; q < nb; q += 32) s.c[q] = get(b0 + q);
       for (int q = l; q < bl; q += 32) s.c[nb + n + q] = get(a0 + q);
+      if (l == 0) { s.dip_nb = nb; s.dip_bl = bl; }
     }
     JB_SYNC();
     const char order[4] = {'A', 'C', 'T', 'G'};
+    int nc = 0;
     for (int xo = 0; xo < 4; ++xo)
       for (int yo = 0; yo < 4; ++yo) {
-        uint8_t x = (uint8_t)order[xo], y = (uint8_t)order[yo];
+        const uint8_t x = (uint8_t)order[xo], y = (uint8_t)order[yo];
         if (x == left_bad && y == right_bad) continue;
         if (x != left_bad && y != right_bad) continue;
-        JB_SYNC();
-        JB_LANES(l) {
-          for (int q = l; q < n; q += 32) s.c[nb + q] = (q == n - k) ? x : ((q == k - 1) ? y : s.t[q]);
-        }
-        JB_SYNC();
-        if (check_sequence(s.c, nb + n + bl, thr)) {
-          // one edit covering both positions: t[n-k : k] with x / y substituted
-          JB_SYNC();
-          JB_LANES(l) { for (int q = l; q < 2 * k - n; q += 32) s.b[q] = s.c[nb + (n - k) + q]; }
-          JB_SYNC();
-          if (!apply_edit(s0 + n - k, s0 + k, s.b, 2 * k - n)) return true;
-          if (x == left_bad) emit_row(gb + 1, &y, 1, 's', &seq_gb1, 1);     // "e": the right-hand base changed
-          else emit_row(ga - 1, &x, 1, 's', &seq_ga1, 1);                   // "s": the left-hand base changed
-          return true;
-        }
+        set_cand(nc++, kDip, x, y, 0, 0);
       }
-    return false;
+    const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
+    if (w < 0) return false;
+    const Cand c = s.cand[w];
+    // one edit covering both positions: t[n-k : k] with x / y substituted
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < 2 * k - n; q += 32) s.b[q] = cand_char(s, c, n, k, nb + (n - k) + q); }
+    JB_SYNC();
+    if (!apply_edit(s0 + n - k, s0 + k, s.b, 2 * k - n)) return true;
+    uint8_t x = c.base, y = c.base2;
+    if (x == left_bad) emit_row(gb + 1, &y, 1, 's', &seq_gb1, 1);       // "e": the right-hand base changed
+    else emit_row(ga - 1, &x, 1, 's', &seq_ga1, 1);                     // "s": the left-hand base changed
+    return true;
   }
 
   // src/jasper.py:434-477
@@ -585,31 +534,30 @@ struct Walker {
     const uint8_t sb = s.t[k - 2];
     const int start_bad = n - k + 1;
     int cur = start_bad, added = 0;
+    uint8_t dash = '-';
     while (added < start_bad) {
       ++added;
-      b_from_t_insert(n, k - 1, sb, added);
-      int nbw = count_weak(s.b, n + added, thr);
+      JB_SYNC();
+      set_cand(0, kIns, sb, 0, k - 1, added);
+      const int nbw = count_weak_cand(db, s, 0, n, k, mask, thr, &lookups);
       if (nbw == 0) {
-        if (!apply_edit(s0 + k - 1, s0 + k - 1, s.b + (k - 1), added)) return true;
-        uint8_t dash = '-';
-        emit_row(k - 1 + s0, s.b + (k - 1), added, 'd', &dash, 1);
+        fill_b(sb, added);
+        if (!apply_edit(s0 + k - 1, s0 + k - 1, s.b, added)) return true;
+        emit_row(k - 1 + s0, s.b, added, 'd', &dash, 1);
         return true;
       }
       if (nbw >= cur) break;
       cur = nbw;
     }
     const char order[4] = {'A', 'T', 'C', 'G'};
-    for (int o = 0; o < 4; ++o) {
-      uint8_t bb = (uint8_t)order[o];
-      b_from_t_insert(n, k - 2, bb, 1);
-      if (check_sequence(s.b, n + 1, thr)) {
-        if (!apply_edit(s0 + k - 2, s0 + k - 2, &bb, 1)) return true;
-        uint8_t dash = '-';
-        emit_row(k - 2 + s0, &bb, 1, 'd', &dash, 1);
-        return true;
-      }
-    }
-    return false;
+    JB_SYNC();
+    for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 2, 1);
+    const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
+    if (w < 0) return false;
+    uint8_t bb = s.cand[w].base;
+    if (!apply_edit(s0 + k - 2, s0 + k - 2, &bb, 1)) return true;
+    emit_row(k - 2 + s0, &bb, 1, 'd', &dash, 1);
+    return true;
   }
 
   // src/jasper.py:479-524
@@ -618,34 +566,32 @@ struct Walker {
     const uint8_t sb = s.t[k - 1];
     const int start_bad = n - k + 1;
     int cur = start_bad, removed = 0;
+    uint8_t dash = '-';
     while (removed < start_bad) {
       --cur; ++removed;
       if (n - removed == k) break;
-      b_from_t_delete(n, k - 1, removed);
-      int nbw = count_weak(s.b, n - removed, thr);
+      JB_SYNC();
+      set_cand(0, kDel, 0, 0, k - 1, removed);
+      const int nbw = count_weak_cand(db, s, 0, n, k, mask, thr, &lookups);
       if (nbw == 0) {
         if (!apply_edit(s0 + k - 1, s0 + k - 1 + removed, nullptr, 0)) return true;
-        JB_SYNC();
-        JB_LANES(l) { for (int q = l; q < removed; q += 32) s.c[q] = sb; }
-        JB_SYNC();
-        uint8_t dash = '-';
-        emit_row(k - 1 + s0, &dash, 1, 'i', s.c, removed);
+        fill_b(sb, removed);
+        emit_row(k - 1 + s0, &dash, 1, 'i', s.b, removed);
         return true;
       }
       if (nbw >= cur) break;
       cur = nbw;
     }
-    for (int m = n - k; m < n - 1; ++m) {
-      b_from_t_delete(n, m, 1);
-      if (check_sequence(s.b, n - 1, thr)) {
-        uint8_t gone = s.t[m];
-        if (!apply_edit(s0 + m, s0 + m + 1, nullptr, 0)) return true;
-        uint8_t dash = '-';
-        emit_row(m + s0, &dash, 1, 'i', &gone, 1);
-        return true;
-      }
-    }
-    return false;
+    int nc = 0;
+    JB_SYNC();
+    for (int m = n - k; m < n - 1 && nc < kMaxCands; ++m) set_cand(nc++, kDel, 0, 0, m, 1);
+    const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
+    if (w < 0) return false;
+    const int m = s.cand[w].pos;
+    uint8_t gone = s.t[m];
+    if (!apply_edit(s0 + m, s0 + m + 1, nullptr, 0)) return true;
+    emit_row(m + s0, &dash, 1, 'i', &gone, 1);
+    return true;
   }
 
   // ---------------------------------------------------------------------------- base_extension
