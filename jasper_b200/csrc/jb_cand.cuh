@@ -44,6 +44,14 @@ enum CandKind : uint8_t { kSub = 0, kIns = 1, kDel = 2, kDip = 3 };
 //   kDel  t[:pos] + t[pos+m:]               kDip  before + t{[n-k] = base, [k-1] = base2} + after   (fixdiploid)
 struct Cand { uint8_t kind, base, base2, pad; int16_t pos, m; };
 
+// The sequence a walker is editing (jb_seq.cuh reads it, jb_walker.cuh publishes it after every edit).
+struct SeqView {
+  const uint8_t* in;         // the contig at the start of the pass
+  const uint8_t* out;        // staging: out[r] = new base r of this segment inside the materialised window
+  const uint32_t* cnt;       // bulk-scan counts of the pass-start contig, [0, in_len]; may be null
+  int64_t base, olen, ipos, wstart, L, in_len, clean_from, seam_margin;
+};
+
 struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint8_t t[kStrCap];        // to_be_fixed
   uint8_t b[kStrCap];        // replacement text / good_k_mer_after
@@ -57,6 +65,12 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint16_t cand_first[kMaxCands + 1];   // first work item of every candidate
   uint32_t failmask[2];
   int32_t dip_nb, dip_bl;    // kDip: chars of flank before (s.c[0:nb)) and after (s.c[nb+n : nb+n+bl))
+  uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
+  SeqView view;              // published copy of the walker's sequence state
+  int64_t wc_base;           // window-count cache: wc[0:wc_n) = C(seq[wc_base + l : ...])
+  int32_t wc_n;
+  uint32_t empty_count;      // C('') = count of poly-A
+  unsigned long long probes; // table probes issued by the out-of-line helpers
 };
 
 // C(buf[m : m+k]) with MerDNA's padding (JF!include/jellyfish/mer_dna.hpp:525-542, 642-644)

@@ -20,6 +20,7 @@
 #include "../../include/jasper_b200.h"
 #include "jb_kmer.cuh"
 #include "jb_cand.cuh"
+#include "jb_seq.cuh"
 #include "jb_segments.cuh"
 
 // Inlined everywhere the kernel is 860 KB of SASS and the warps starve on instruction fetch (ncu: 60 %
@@ -158,10 +159,7 @@ struct Walker {
   int status = 0;
   bool brk = false;
   bool seam_bad = false;
-  int64_t wc_base = 0;
-  int wc_n = 0;
-  bool have_empty = false;
-  uint32_t empty_count = 0;
+  uint32_t vflags = 0;                 // kFlagSeam / kFlagFar raised by reads (lane-local until the end of run)
   uint32_t seqno = 0;
   unsigned long long lookups = 0, events = 0;
 
@@ -203,84 +201,53 @@ struct Walker {
     bs = nullptr; bs_slot = -1;
   }
 
-  // ---------------------------------------------------------------------------- sequence access
+  // ---------------------------------------------------------------------------- sequence access (jb_seq.cuh)
   // new sequence (segment-local coordinates) = in[0:base) ++ out[0:olen) ++ in[ipos:)
-  JB_W uint8_t get(int64_t x) {
-    if (x < base) {                                   // bases the previous segment's walker owns
-      if (x < base - seam_margin) seam_bad = true;    // ...and may have edited: the contig is re-walked whole
-      return u.in[x];
+  // the walker's registers hold the state; the out-of-line helpers read this published copy
+  JB_W void publish() {
+    JB_SYNC();
+    JB_LANES(l) {
+      if (l == 0) {
+        SeqView v;
+        v.in = u.in; v.out = u.out; v.cnt = u.cnt;
+        v.base = base; v.olen = olen; v.ipos = ipos; v.wstart = wstart; v.L = L; v.in_len = u.in_len;
+        v.clean_from = clean_from; v.seam_margin = seam_margin;
+        s.view = v;
+        s.wc_n = 0;                                   // cached window counts do not survive an edit
+      }
     }
-    const int64_t y = x - base;
-    if (y >= olen) return u.in[ipos + (y - olen)];
-    if (y >= wstart) return u.out[y];
-    far_back = true;                                  // behind the window: the contig is re-walked fully materialised
-    return (uint8_t)'A';
+    JB_SYNC();
   }
+  JB_W void note(uint32_t flags) { vflags |= flags & (kFlagSeam | kFlagFar); }
+
+  JB_W uint8_t get(int64_t x) { return view_get(s.view, x, vflags); }
 
   // dst[0:n] = seq[a:b] clamped to [0, L); returns n
-  JB_WN int load(uint8_t* dst, int64_t a, int64_t b) {
-    if (a < 0) a = 0;
-    if (b > L) b = L;
-    int n = b > a ? (int)(b - a) : 0;
-    JB_SYNC();
-    JB_LANES(l) { for (int q = l; q < n; q += 32) dst[q] = get(a + q); if (l == 0) dst[n] = 0; }
-    JB_SYNC();
-    return n;
+  JB_W int load(uint8_t* dst, int64_t a, int64_t b) {
+    const uint32_t r = view_load(&s.view, dst, a, b);
+    note(r >> 16);
+    return (int)(r & 0xFFFFu);
   }
 
-  JB_WN uint32_t count_in(const uint8_t* buf, int len, int m) const {
-    return count_str(db, buf, len, m, k, mask);
-  }
+  JB_W uint32_t count_in(const uint8_t* buf, int len, int m) const { return count_str(db, buf, len, m, k, mask); }
 
   // ---------------------------------------------------------------------------- lookups
-  JB_W uint32_t C_empty() {
-    if (!have_empty) { Key z = {0, 0}; empty_count = db.count(z); have_empty = true; ++lookups; }
-    return empty_count;
-  }
-
-  // C(seq[x:x+k]); a miss refills the cache with 32 consecutive windows in direction `dir`.
-  JB_WN uint32_t Cw(int64_t x, int dir) {
-    if (x < 0) return C_empty();                     // the slices with negative starts are empty (L >= k)
-    if (x >= wc_base && x < wc_base + wc_n) return s.wc[x - wc_base];
-    int64_t b0 = dir > 0 ? x : (x - 31 > 0 ? x - 31 : 0);
-    if (u.cnt && b0 >= clean_from) {
-      // untouched territory: the bulk scan of this pass already counted these windows
-      const int64_t p0 = b0 - (base + olen - ipos);            // pass-start coordinate of window b0
-      if (p0 < base - seam_margin) seam_bad = true;             // (the previous segment's walker may have changed them)
-      JB_SYNC();
-      JB_LANES(l) { int64_t p = p0 + l; s.wc[l] = u.cnt[p < u.in_len ? p : u.in_len]; }
-      JB_SYNC();
-      wc_base = b0; wc_n = 32;
-      return s.wc[x - b0];
-    }
-    int len = load(s.c, b0, b0 + 32 + k - 1);
-    JB_LANES(l) { s.wc[l] = count_in(s.c, len, l < len ? l : len); }
-    JB_SYNC();
-    lookups += 32;
-    wc_base = b0; wc_n = 32;
-    return s.wc[x - b0];
+  // C(seq[x:x+k]); a miss refills the 32-window cache in direction `dir` (jb_seq.cuh)
+  JB_W uint32_t Cw(int64_t x, int dir) {
+    const uint64_t r = view_count(db, s, x, dir, k, mask);
+    note((uint32_t)(r >> 32));
+    return (uint32_t)r;
   }
 
   // n <= 32 windows at arbitrary starts s.px[0..n) (non-negative, within a span that fits s.c)
-  JB_WN void Cpts(int n) {
-    int64_t lo = s.px[0], hi = s.px[0];
-    for (int q = 1; q < n; ++q) { lo = s.px[q] < lo ? s.px[q] : lo; hi = s.px[q] > hi ? s.px[q] : hi; }
-    if (u.cnt && lo >= clean_from) {                 // untouched territory: read the bulk scan's counts
-      const int64_t shift = base + olen - ipos;
-      if (lo - shift < base - seam_margin) seam_bad = true;
-      JB_SYNC();
-      JB_LANES(l) { if (l < n) { int64_t p = s.px[l] - shift; s.pr[l] = u.cnt[p < u.in_len ? p : u.in_len]; } }
-      JB_SYNC();
-      return;
-    }
-    if (hi + k - lo > kStrCap - 8) {                 // cannot happen for the call sites below; stay exact anyway
+  JB_W void Cpts(int n) {
+    const uint32_t f = view_points(db, s, n, k, mask);
+    if (f & kFlagTooWide) {                          // cannot happen for the call sites below; stay exact anyway
       for (int q = 0; q < n; ++q) s.pr[q] = Cw(s.px[q], +1);
       return;
     }
-    int len = load(s.c, lo, hi + k);
-    JB_LANES(l) { if (l < n) { int m = (int)(s.px[l] - lo); s.pr[l] = count_in(s.c, len, m < len ? m : len); } }
-    JB_SYNC();
-    lookups += n;
+    note(f);
+    if (f & kFlagProbed) lookups += n;
   }
 
   // src/jasper.py:585-599 on a string in scratch memory
@@ -400,7 +367,7 @@ struct Walker {
     olen += delta; L += delta;
     int64_t shifted = clean_from + delta;
     clean_from = a_abs + rlen > shifted ? a_abs + rlen : shifted;
-    wc_n = 0;
+    publish();
     return true;
   }
 
@@ -445,10 +412,28 @@ struct Walker {
   JB_W void set_cand(int idx, uint8_t kind, uint8_t b1, uint8_t b2, int pos, int m) {
     JB_LANES(l) { if (l == 0) { Cand c; c.kind = kind; c.base = b1; c.base2 = b2; c.pad = 0; c.pos = (int16_t)pos; c.m = (int16_t)m; s.cand[idx] = c; } }
   }
-  JB_W void fill_b(uint8_t v, int m) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < m; q += 32) s.b[q] = v; } JB_SYNC(); }
+  JB_W void fill(uint8_t* dst, uint8_t v, int m) { JB_SYNC(); JB_LANES(l) { for (int q = l; q < m; q += 32) dst[q] = v; } JB_SYNC(); }
+
+  // What a fix_* function decided: seq = seq[:a] + repl + seq[e:], and the csv row that describes it (text in
+  // s.fx).  fixing_sid applies it in ONE place, so the splice / job / row code exists once in the kernel.
+  struct Fix {
+    bool found = false;
+    int64_t a = 0, e = 0;
+    const uint8_t* repl = nullptr;
+    int64_t rlen = 0;
+    int64_t coord = 0;
+    int fb_len = 0, orig_len = 0;
+    uint8_t tag = 0;                                  // 0: no plain row (bridged patches log their own)
+  };
+  JB_W void fix_row(Fix& f, int64_t coord, uint8_t fb, int fb_len, uint8_t tag, uint8_t orig, int orig_len) {
+    fill(s.fx, fb, fb_len);
+    fill(s.fx + 64, orig, orig_len);
+    f.coord = coord; f.fb_len = fb_len; f.tag = tag; f.orig_len = orig_len;
+  }
 
   // src/jasper.py:392-406 then :409-419: up to three substitutions at k-1 in order 'ACTG', then the deletion of k-1
-  JB_WN bool fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
+  JB_W Fix fix_k_case(int n, int64_t thr, int64_t s0, int64_t ga) {
+    Fix f;
     const uint8_t bad = s.t[k - 1];
     const uint8_t before = get(ga - 1);
     const char order[4] = {'A', 'C', 'T', 'G'};
@@ -457,36 +442,32 @@ struct Walker {
     for (int o = 0; o < 4; ++o) if ((uint8_t)order[o] != bad) set_cand(nc++, kSub, (uint8_t)order[o], 0, k - 1, 0);
     set_cand(nc++, kDel, 0, 0, k - 1, 1);
     const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
-    if (w < 0) return false;
+    if (w < 0) return f;
     const Cand c = s.cand[w];
-    if (c.kind == kSub) {
-      uint8_t bb = c.base;
-      if (!apply_edit(s0 + k - 1, s0 + k, &bb, 1)) return true;
-      emit_row(ga - 1, &bb, 1, 's', &before, 1);
-    } else {
-      if (!apply_edit(s0 + k - 1, s0 + k, nullptr, 0)) return true;
-      uint8_t dash = '-';
-      emit_row(ga - 1, &dash, 1, 'i', &before, 1);
-    }
-    return true;
+    f.found = true; f.a = s0 + k - 1; f.e = s0 + k; f.repl = s.b;
+    if (c.kind == kSub) { fill(s.b, c.base, 1); f.rlen = 1; fix_row(f, ga - 1, c.base, 1, 's', before, 1); }
+    else { f.rlen = 0; fix_row(f, ga - 1, '-', 1, 'i', before, 1); }
+    return f;
   }
 
   // src/jasper.py:422-431: one base inserted in front of k-1, order 'ATCG'
-  JB_WN bool fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
+  JB_W Fix fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
+    Fix f;
     const char order[4] = {'A', 'T', 'C', 'G'};
     JB_SYNC();
     for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 1, 1);
     const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
-    if (w < 0) return false;
-    uint8_t bb = s.cand[w].base;
-    if (!apply_edit(s0 + k - 1, s0 + k - 1, &bb, 1)) return true;
-    uint8_t dash = '-';
-    emit_row(ga, &bb, 1, 'd', &dash, 1);
-    return true;
+    if (w < 0) return f;
+    const uint8_t bb = s.cand[w].base;
+    fill(s.b, bb, 1);
+    f.found = true; f.a = s0 + k - 1; f.e = s0 + k - 1; f.repl = s.b; f.rlen = 1;
+    fix_row(f, ga, bb, 1, 'd', '-', 1);
+    return f;
   }
 
   // src/jasper.py:340-388
-  JB_WC bool fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
+  JB_WC Fix fix_diploid(int n, int64_t thr, int64_t s0, int64_t gb, int64_t ga) {
+    Fix f;
     const uint8_t left_bad = s.t[n - k], right_bad = s.t[k - 1];
     const int64_t g0 = gb - k + 1 > 0 ? gb - k + 1 : 0;
     const int na = (2 * k - 1 - n) / 2;
@@ -498,12 +479,10 @@ struct Walker {
     const int nb = (int)(g0 + 1 - b0);
     // check string = before + trial + after: the flanks are staged once in s.c
     const uint8_t seq_ga1 = get(ga - 1), seq_gb1 = get(gb + 1);
+    load(s.c, b0, b0 + nb);
+    load(s.c + nb + n, a0, a0 + bl);
     JB_SYNC();
-    JB_LANES(l) {
-      for (int q = l; q < nb; q += 32) s.c[q] = get(b0 + q);
-      for (int q = l; q < bl; q += 32) s.c[nb + n + q] = get(a0 + q);
-      if (l == 0) { s.dip_nb = nb; s.dip_bl = bl; }
-    }
+    JB_LANES(l) { if (l == 0) { s.dip_nb = nb; s.dip_bl = bl; } }
     JB_SYNC();
     const char order[4] = {'A', 'C', 'T', 'G'};
     int nc = 0;
@@ -515,36 +494,35 @@ struct Walker {
         set_cand(nc++, kDip, x, y, 0, 0);
       }
     const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
-    if (w < 0) return false;
+    if (w < 0) return f;
     const Cand c = s.cand[w];
     // one edit covering both positions: t[n-k : k] with x / y substituted
     JB_SYNC();
     JB_LANES(l) { for (int q = l; q < 2 * k - n; q += 32) s.b[q] = cand_char(s, c, n, k, nb + (n - k) + q); }
     JB_SYNC();
-    if (!apply_edit(s0 + n - k, s0 + k, s.b, 2 * k - n)) return true;
-    uint8_t x = c.base, y = c.base2;
-    if (x == left_bad) emit_row(gb + 1, &y, 1, 's', &seq_gb1, 1);       // "e": the right-hand base changed
-    else emit_row(ga - 1, &x, 1, 's', &seq_ga1, 1);                     // "s": the left-hand base changed
-    return true;
+    f.found = true; f.a = s0 + n - k; f.e = s0 + k; f.repl = s.b; f.rlen = 2 * k - n;
+    if (c.base == left_bad) fix_row(f, gb + 1, c.base2, 1, 's', seq_gb1, 1);       // "e": the right-hand base changed
+    else fix_row(f, ga - 1, c.base, 1, 's', seq_ga1, 1);                           // "s": the left-hand base changed
+    return f;
   }
 
   // src/jasper.py:434-477
-  JB_WC bool fix_same_base_del(int n, int64_t thr, int64_t s0) {
-    if (thr > solid) return false;
+  JB_WC Fix fix_same_base_del(int n, int64_t thr, int64_t s0) {
+    Fix f;
+    if (thr > solid) return f;
     const uint8_t sb = s.t[k - 2];
     const int start_bad = n - k + 1;
     int cur = start_bad, added = 0;
-    uint8_t dash = '-';
     while (added < start_bad) {
       ++added;
       JB_SYNC();
       set_cand(0, kIns, sb, 0, k - 1, added);
       const int nbw = count_weak_cand(db, s, 0, n, k, mask, thr, &lookups);
       if (nbw == 0) {
-        fill_b(sb, added);
-        if (!apply_edit(s0 + k - 1, s0 + k - 1, s.b, added)) return true;
-        emit_row(k - 1 + s0, s.b, added, 'd', &dash, 1);
-        return true;
+        fill(s.b, sb, added);
+        f.found = true; f.a = s0 + k - 1; f.e = s0 + k - 1; f.repl = s.b; f.rlen = added;
+        fix_row(f, k - 1 + s0, sb, added, 'd', '-', 1);
+        return f;
       }
       if (nbw >= cur) break;
       cur = nbw;
@@ -553,20 +531,21 @@ struct Walker {
     JB_SYNC();
     for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 2, 1);
     const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
-    if (w < 0) return false;
-    uint8_t bb = s.cand[w].base;
-    if (!apply_edit(s0 + k - 2, s0 + k - 2, &bb, 1)) return true;
-    emit_row(k - 2 + s0, &bb, 1, 'd', &dash, 1);
-    return true;
+    if (w < 0) return f;
+    const uint8_t bb = s.cand[w].base;
+    fill(s.b, bb, 1);
+    f.found = true; f.a = s0 + k - 2; f.e = s0 + k - 2; f.repl = s.b; f.rlen = 1;
+    fix_row(f, k - 2 + s0, bb, 1, 'd', '-', 1);
+    return f;
   }
 
   // src/jasper.py:479-524
-  JB_WC bool fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
-    if (thr > solid) return false;
+  JB_WC Fix fix_same_base_insertion(int n, int64_t thr, int64_t s0) {
+    Fix f;
+    if (thr > solid) return f;
     const uint8_t sb = s.t[k - 1];
     const int start_bad = n - k + 1;
     int cur = start_bad, removed = 0;
-    uint8_t dash = '-';
     while (removed < start_bad) {
       --cur; ++removed;
       if (n - removed == k) break;
@@ -574,10 +553,9 @@ struct Walker {
       set_cand(0, kDel, 0, 0, k - 1, removed);
       const int nbw = count_weak_cand(db, s, 0, n, k, mask, thr, &lookups);
       if (nbw == 0) {
-        if (!apply_edit(s0 + k - 1, s0 + k - 1 + removed, nullptr, 0)) return true;
-        fill_b(sb, removed);
-        emit_row(k - 1 + s0, &dash, 1, 'i', s.b, removed);
-        return true;
+        f.found = true; f.a = s0 + k - 1; f.e = s0 + k - 1 + removed; f.repl = s.b; f.rlen = 0;
+        fix_row(f, k - 1 + s0, '-', 1, 'i', sb, removed);
+        return f;
       }
       if (nbw >= cur) break;
       cur = nbw;
@@ -586,12 +564,11 @@ struct Walker {
     JB_SYNC();
     for (int m = n - k; m < n - 1 && nc < kMaxCands; ++m) set_cand(nc++, kDel, 0, 0, m, 1);
     const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
-    if (w < 0) return false;
+    if (w < 0) return f;
     const int m = s.cand[w].pos;
-    uint8_t gone = s.t[m];
-    if (!apply_edit(s0 + m, s0 + m + 1, nullptr, 0)) return true;
-    emit_row(m + s0, &dash, 1, 'i', &gone, 1);
-    return true;
+    f.found = true; f.a = s0 + m; f.e = s0 + m + 1; f.repl = s.b; f.rlen = 0;
+    fix_row(f, m + s0, '-', 1, 'i', s.t[m], 1);
+    return f;
   }
 
   // ---------------------------------------------------------------------------- base_extension
@@ -761,56 +738,70 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- fixing_sid
-  JB_WN void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
+  JB_W void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
+    Fix f;
     if (nbad == k) {
       int n = load(s.t, s0, ga + k - 1);
-      fix_k_case(n, thr, s0, ga);
+      f = fix_k_case(n, thr, s0, ga);
     } else if (nbad == k - 1) {
       int n = load(s.t, s0, ga + k - 1);
-      if (!fix_del(n, thr, s0, ga))
-        if (!fix_diploid(n, thr, s0, gb, ga)) fix_same_base_insertion(n, thr, s0);
+      f = fix_del(n, thr, s0, ga);
+      if (!f.found) f = fix_diploid(n, thr, s0, gb, ga);
+      if (!f.found) f = fix_same_base_insertion(n, thr, s0);
     } else if (nbad < k - 1 && nbad > 1 && n64 >= k) {
       int n = load(s.t, s0, ga + k - 1);
-      if (!fix_same_base_del(n, thr, s0))
-        if (!fix_diploid(n, thr, s0, gb, ga)) fix_same_base_insertion(n, thr, s0);
+      f = fix_same_base_del(n, thr, s0);
+      if (!f.found) f = fix_diploid(n, thr, s0, gb, ga);
+      if (!f.found) f = fix_same_base_insertion(n, thr, s0);
     } else if (nbad > k) {
-      if (gb - k + 1 < 0) return;                          // good_kmer_before comes out shorter than k
-      int ng = load(s.t, gb - k + 1, gb + 1);
-      int na = load(s.b, ga, ga + k);
-      if (ng < k || na < k) return;
-      if (n64 > 0x7fffffff) return;
-      if (thr > solid) return;                             // base_extension returns None (src/jasper.py:529)
-      if (!acquire_bridge()) return;
-      int64_t plen = base_extension((int)n64, thr);
-      if (status || plen <= 0) { release_bridge(); return; }
-      // row material: patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
-      const int64_t olen_old = ga - (gb + 1);
-      unsigned long long off = 0, rslot = 0;
-      JB_SYNC();
-#if defined(__CUDA_ARCH__)
-      if ((threadIdx.x & 31) == 0) { off = atomicAdd(sink.aux_used, (unsigned long long)(plen + olen_old + 8)); rslot = atomicAdd(sink.used, 1ull); }
-      off = __shfl_sync(0xffffffffu, off, 0); rslot = __shfl_sync(0xffffffffu, rslot, 0);
-#else
-      off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old + 8); rslot = (*sink.used)++;
-#endif
-      if (off + plen + olen_old + 8 > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; release_bridge(); return; }
-      JB_LANES(l) {
-        for (int64_t q = l; q < plen; q += 32) sink.aux[off + 8 + q] = bs->patch[q];
-        for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + 8 + plen + q] = get(gb + 1 + q);
-        if (l == 0) {
-          DevRow& r = sink.rows[rslot];
-          r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno; r.kind = (uint8_t)kRowBridge; r.fb_len = 0; r.orig_len = 0;
-          r.aux_off = off;
-          const uint32_t pl = (uint32_t)plen, ol = (uint32_t)olen_old;     // byte-wise: the arena is not aligned
-          for (int q = 0; q < 4; ++q) { sink.aux[off + q] = (uint8_t)(pl >> (8 * q)); sink.aux[off + 4 + q] = (uint8_t)(ol >> (8 * q)); }
-        }
-      }
-      JB_SYNC();
-      seqno += 2;                                         // at most two csv rows come out of one patch
-      apply_edit(gb + 1, ga, bs->patch, plen);
-      release_bridge();
+      f = fix_bridge(n64, thr, gb, ga);
     }
+    if (f.found && !status) {
+      if (apply_edit(f.a, f.e, f.repl, f.rlen) && f.tag) emit_row(f.coord, s.fx, f.fb_len, f.tag, s.fx + 64, f.orig_len);
+    }
+    release_bridge();
+  }
+
+  // src/jasper.py:295-329: bridge a long weak stretch with a de-Bruijn walk; the patch stays in the borrowed
+  // bridging slot until fixing_sid has spliced it in
+  JB_WC Fix fix_bridge(int64_t n64, int64_t thr, int64_t gb, int64_t ga) {
+    Fix f;
+    if (gb - k + 1 < 0) return f;                          // good_kmer_before comes out shorter than k
+    int ng = load(s.t, gb - k + 1, gb + 1);
+    int na = load(s.b, ga, ga + k);
+    if (ng < k || na < k) return f;
+    if (n64 > 0x7fffffff) return f;
+    if (thr > solid) return f;                             // base_extension returns None (src/jasper.py:529)
+    if (!acquire_bridge()) return f;
+    int64_t plen = base_extension((int)n64, thr);
+    if (status || plen <= 0) return f;
+    // row material: patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
+    const int64_t olen_old = ga - (gb + 1);
+    unsigned long long off = 0, rslot = 0;
+    JB_SYNC();
+#if defined(__CUDA_ARCH__)
+    if ((threadIdx.x & 31) == 0) { off = atomicAdd(sink.aux_used, (unsigned long long)(plen + olen_old + 8)); rslot = atomicAdd(sink.used, 1ull); }
+    off = __shfl_sync(0xffffffffu, off, 0); rslot = __shfl_sync(0xffffffffu, rslot, 0);
+#else
+    off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old + 8); rslot = (*sink.used)++;
+#endif
+    if (off + plen + olen_old + 8 > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; return f; }
+    JB_LANES(l) {
+      for (int64_t q = l; q < plen; q += 32) sink.aux[off + 8 + q] = bs->patch[q];
+      for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + 8 + plen + q] = get(gb + 1 + q);
+      if (l == 0) {
+        DevRow& r = sink.rows[rslot];
+        r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno; r.kind = (uint8_t)kRowBridge; r.fb_len = 0; r.orig_len = 0;
+        r.aux_off = off;
+        const uint32_t pl = (uint32_t)plen, ol = (uint32_t)olen_old;     // byte-wise: the arena is not aligned
+        for (int q = 0; q < 4; ++q) { sink.aux[off + q] = (uint8_t)(pl >> (8 * q)); sink.aux[off + 4 + q] = (uint8_t)(ol >> (8 * q)); }
+      }
+    }
+    JB_SYNC();
+    seqno += 2;                                           // at most two csv rows come out of one patch
+    f.found = true; f.a = gb + 1; f.e = ga; f.repl = bs->patch; f.rlen = plen; f.tag = 0;
+    return f;
   }
 
   // ---------------------------------------------------------------------------- handle_bad_kmers
@@ -901,13 +892,22 @@ struct Walker {
 
   JB_W void run() {
     base = u.base; seam_margin = seam_read_margin(k); keep_margin = u.keep_margin; wstart = 0; far_back = false;
-    i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; wc_n = 0;
+    i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; vflags = 0;
+    publish();
+    {
+      // C('') = count of poly-A: the bulk scan's entry for the empty tail window, else one probe
+      uint32_t ec;
+      if (u.cnt) ec = u.cnt[u.in_len]; else { ec = count_str(db, s.c, 0, 0, k, mask); ++lookups; }
+      JB_SYNC();
+      JB_LANES(l) { if (l == 0) { s.empty_count = ec; s.probes = 0; } }
+      JB_SYNC();
+    }
     bool reached = false;
     while (i < L - k + 1 && !brk && !status) {
 #if defined(__CUDA_ARCH__)
-      if (__any_sync(0xffffffffu, far_back || seam_bad)) break;   // the result is void already: stop early
+      if (__any_sync(0xffffffffu, vflags != 0)) break;            // the result is void already: stop early
 #else
-      if (far_back || seam_bad) break;
+      if (vflags) break;
 #endif
       if (u.next_anchor >= 0) {
         const int64_t i_old = i - (L - u.in_len);
@@ -962,6 +962,7 @@ struct Walker {
         i += k - 1;
       }
     }
+    seam_bad = seam_bad || (vflags & kFlagSeam); far_back = far_back || (vflags & kFlagFar);
 #if defined(__CUDA_ARCH__)
     seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdicts warp-uniform
     far_back = __any_sync(0xffffffffu, far_back);
@@ -981,7 +982,7 @@ struct Walker {
     u.wrong = wrong;
     u.status = status;
     u.n_rows = seqno;
-    u.lookups = lookups;
+    u.lookups = lookups + s.probes;
     u.events = events;
   }
 };
