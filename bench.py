@@ -248,9 +248,12 @@ def main():
                  "scan_lookups": capi.counter("scan_lookups"), "walk_lookups": capi.counter("walk_lookups"),
                  "launches": capi.counter("kernel_launches"), "probe_steps": capi.counter("probe_steps"), "events": capi.counter("events"),
                  "plan_ms": capi.timing_ms("polish_plan"), "segments": capi.counter("segments"), "reruns": capi.counter("segment_reruns"),
+                 "full_scans": capi.counter("full_scans"), "full_scan_lookups": capi.counter("full_scan_lookups"),
+                 "recount_probes": capi.counter("recount_probes"), "recount_ms": capi.timing_ms("polish_recount"),
                  "seg_block": capi.counter("seg_block"), "kwalk_ms": capi.timing_ms("polish_kwalk"),
                  "max_seg_events": capi.counter("max_seg_events"), "max_seg_lookups": capi.counter("max_seg_lookups"),
-                 "max_seg_span": capi.counter("max_seg_span")}
+                 "max_seg_span": capi.counter("max_seg_span"),
+                 "slowest_segment_per_pass": [{key: capi.counter("%s%d" % (key, q)) for key in ("slow_cycles", "slow_events", "slow_lookups", "slow_span", "sum_cycles")} for q in range(3)]}
         return b, ms, stats
 
     for _ in range(args.warmup):
@@ -338,8 +341,9 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     gather_gbps, gather_gps = qf.gather_bench(n_probes=1 << 28, sector_bytes=32, iters=3)
-    scan_ms_per_launch = last_stats["scan_ms"] / (PASSES + 1)
-    lookups_per_launch = last_stats["scan_lookups"] / (PASSES + 1)
+    # k_scan runs once per step (pass 0); later passes inherit counts through k_recount
+    scan_ms_per_launch = last_stats["scan_ms"] / max(1, last_stats["full_scans"])
+    lookups_per_launch = last_stats["full_scan_lookups"] / max(1, last_stats["full_scans"])
     achieved = lookups_per_launch * 32 / (scan_ms_per_launch * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy), of measured" if peaks else "fallback 6650, of fallback",
@@ -348,7 +352,8 @@ def main():
                 "lookups_per_s": lookups_per_launch / (scan_ms_per_launch * 1e-3),
                 "random_sector_peak_GBps": gather_gbps, "frac_of_random_sector_peak": achieved / gather_gbps if gather_gbps else None,
                 "ms_per_launch": scan_ms_per_launch, "share_of_step": last_stats["scan_ms"] / (dev_ms / args.steps),
-                "sectors_per_lookup": last_stats["probe_steps"] / max(1, last_stats["scan_lookups"])}
+                "sectors_per_lookup": last_stats["probe_steps"] / max(1, last_stats["full_scan_lookups"]),
+                "launches_per_step": last_stats["full_scans"]}
 
     # ---- CPU baseline beside it (bounded sample of the same workload, all host cores)
     cpu = None
@@ -377,9 +382,9 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "lookups_per_s": (last_stats["scan_lookups"] + last_stats["walk_lookups"]) / (ms_per_step * 1e-3) * world,
-        "detail": {"scan_ms": last_stats["scan_ms"], "plan_ms": last_stats["plan_ms"], "walk_ms": last_stats["walk_ms"], "events": last_stats["events"],
+        "detail": {"scan_ms": last_stats["scan_ms"], "recount_ms": last_stats["recount_ms"], "recount_probes": last_stats["recount_probes"], "plan_ms": last_stats["plan_ms"], "walk_ms": last_stats["walk_ms"], "events": last_stats["events"],
                    "kwalk_ms": last_stats["kwalk_ms"], "max_seg_events": last_stats["max_seg_events"], "max_seg_lookups": last_stats["max_seg_lookups"],
-                   "max_seg_span": last_stats["max_seg_span"], "segments": last_stats["segments"], "segment_reruns": last_stats["reruns"], "seg_block": last_stats["seg_block"],
+                   "max_seg_span": last_stats["max_seg_span"], "slowest_segment_per_pass": last_stats["slowest_segment_per_pass"], "segments": last_stats["segments"], "segment_reruns": last_stats["reruns"], "seg_block": last_stats["seg_block"],
                    "walk_lookups": last_stats["walk_lookups"], "db_open_s": open_s, "table_gb": qf.info["table_bytes"] / 1e9,
                    "workload_gen_s": meta["gen_seconds"], "qv_tallies_all_ranks": list(tallies),
                    "fix_rows_pass0": len(res.rows[0]), "fix_rows_pass1": len(res.rows[1]) if len(res.rows) > 1 else 0},

@@ -30,7 +30,10 @@ struct DevDB {
 };
 
 constexpr int kWalkWarps = 4;               // walkers per CTA
-constexpr int kWalkCtasPerSm = 5;
+#ifndef JB_WALK_CTAS
+#define JB_WALK_CTAS 4
+#endif
+constexpr int kWalkCtasPerSm = JB_WALK_CTAS;
 constexpr uint32_t kTrieCap = 1u << 20;     // de-Bruijn trie nodes per bridging slot
 constexpr uint32_t kPatchCap = 1u << 18;    // longest recoverable patch
 constexpr uint32_t kPoolSlots = 512;        // bridging scratch slots shared by all walkers
@@ -150,7 +153,9 @@ struct PinBuf {
 struct Workspace {
   int device = -1;
   DevBuf<uint8_t> buf[2], stage;
-  DevBuf<uint32_t> counts, okbits, events, weak, events_l1, order, tile_first, block_first;
+  DevBuf<uint32_t> counts[2], events, weak, events_l1, order, tile_first, block_first, slot_unit;
+  DevBuf<uint8_t> okb[2];                   // counts / validity of the current and of the next pass's sequence
+  DevBuf<ScanUnit> scan_units_new;
   DevBuf<UnitIO> segs;
   DevBuf<int64_t> dst_off;
   DevBuf<long long> anchors;
@@ -174,7 +179,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); counts.release(); okbits.release(); events.release(); weak.release(); events_l1.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -287,7 +292,8 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
     JB_CUDA(cudaEventCreateWithFlags(&w.ev_rows, cudaEventDisableTiming));
   }
   JB_TRY(w.buf[0].ensure(total + 64)); JB_TRY(w.buf[1].ensure(total + 64)); JB_TRY(w.stage.ensure(total + 64));
-  JB_TRY(w.counts.ensure(total + 64)); JB_TRY(w.okbits.ensure(total / 32 + 64));
+  for (int q = 0; q < 2; ++q) { JB_TRY(w.counts[q].ensure(total + 64)); JB_TRY(w.okb[q].ensure(total + 64)); }
+  JB_TRY(w.scan_units_new.ensure(n + 1));
   JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
   JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
@@ -364,14 +370,14 @@ int64_t pick_seg_block(int64_t total_len, int sms) {
   return (blk + 31) / 32 * 32;
 }
 
-UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, uint32_t slot, int keep_margin) {
+UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, uint32_t slot, int keep_margin, int cidx) {
   UnitIO u;                                        // (result fields are written by the walker)
   const size_t i = p.unit;
   const Workspace& w = *b->ws;
   u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0;
   u.in = in + b->off[i]; u.in_len = b->len[i];
   u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
-  u.cnt = w.counts.p + b->off[i];
+  u.cnt = w.counts[cidx].p + b->off[i];
   u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
@@ -458,6 +464,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   double scan_ms = 0, walk_ms = 0, plan_ms = 0, kwalk_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
   int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0;
+  int64_t slow_cycles[3] = {0, 0, 0}, slow_events[3] = {0, 0, 0}, slow_lookups[3] = {0, 0, 0}, slow_span[3] = {0, 0, 0}, sum_cycles[3] = {0, 0, 0};
   std::vector<ScanUnit> sunits(n);
   std::vector<SegUnit> gunits(n);
   std::vector<int64_t> caps(n);
@@ -471,6 +478,14 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   if (const char* e = getenv("JB_ANCHOR_MARGIN")) margin = std::max<long>(0, atol(e));   // tests: provoke seam re-runs
   int keep_margin = default_keep_margin(k);
   if (const char* e = getenv("JB_KEEP_MARGIN")) keep_margin = (int)std::max<long>(0, atol(e));   // tests: provoke far-back re-runs
+  int cidx = 0;                        // which counts / validity buffer describes the current sequence
+  bool have_counts = false;
+  int64_t full_scans = 0, full_scan_lookups = 0, recount_probes = 0;
+  double recount_ms = 0;
+  const bool full_rescan = getenv("JB_FULL_RESCAN") != nullptr;      // tests: scan every pass from scratch
+  const bool verify_recount = getenv("JB_VERIFY_RECOUNT") != nullptr; // tests: check k_recount against a full scan
+  cudaEvent_t ev_r0, ev_r1;
+  JB_CUDA(cudaEventCreate(&ev_r0)); JB_CUDA(cudaEventCreate(&ev_r1));
   b->passes.clear();
   b->passes.reserve((size_t)passes + 1);
   const bool trace = getenv("JB_TRACE") != nullptr;
@@ -489,12 +504,12 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     uint8_t* in = w.buf[b->cur].p;
     uint8_t* outb = w.buf[b->cur ^ 1].p;
     std::vector<uint32_t> tile_first(n + 1, 0), block_first(n + 1, 0);
-    int64_t pass_total = 0;
+    int64_t pass_total = 0, pass_lookups = 0;
     for (size_t i = 0; i < n; ++i) {
       pass_total += b->len[i] - k + 1;                                  // may be negative (src/jasper.py:51)
       sunits[i] = ScanUnit{b->off[i], (uint64_t)b->len[i], b->off[i]};
       gunits[i] = SegUnit{b->off[i], (uint64_t)b->len[i]};
-      scan_lookups += b->len[i] + 1 + (b->len[i] > 0 ? k : 0);
+      pass_lookups += b->len[i] + 1;
       tile_first[i + 1] = tile_first[i] + tiles_of((uint64_t)b->len[i]);
       block_first[i + 1] = block_first[i] + (uint32_t)(seg_block > 0 && b->len[i] > 0 ? (b->len[i] - 1) / seg_block : 0);
     }
@@ -512,14 +527,17 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaMemsetAsync(w.events_l1.p, 0, (b->flat_bytes / 32768 + 64) * 4, s));
     ScanArgs a{};
     a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
-    a.counts = w.counts.p; a.okbits = w.okbits.p; a.probe_steps = w.used.p + 2;
+    a.counts = w.counts[cidx].p; a.okb = w.okb[cidx].p; a.probe_steps = w.used.p + 2;
     JB_CUDA(cudaEventRecord(ev_a, s));
-    if (int rc = launch_scan(view, a, s)) return rc;
-    ++launches;
+    if (!have_counts) {                                   // later passes inherit counts from k_recount
+      if (int rc = launch_scan(view, a, s)) return rc;
+      ++launches; ++full_scans;
+      full_scan_lookups += pass_lookups;
+    }
     JB_CUDA(cudaEventRecord(ev_b, s));
     EventArgs ea{};
     ea.units = w.scan_units.p; ea.tile_first = w.tile_first.p; ea.n_units = (uint32_t)n; ea.n_tiles = tile_first[n];
-    ea.counts = w.counts.p; ea.okbits = w.okbits.p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p;
+    ea.counts = w.counts[cidx].p; ea.okb = w.okb[cidx].p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p;
     ea.solid_thre = solid_thre; ea.k = k;
     if (int rc = launch_events(ea, s)) return rc;
     ++launches;
@@ -544,7 +562,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_TRY(w.segs.ensure(n_first + n)); JB_TRY(w.h_segs.ensure(n_first + n));     // room for whole-contig re-runs behind the plan
     JB_TRY(w.order.ensure(n_first + n)); JB_TRY(w.dst_off.ensure(n_first + n));
     UnitIO* hs = w.h_segs.p;
-    for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin);
+    for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin, cidx);
     // queue order: the few long segments (stretches without an anchor) first, the rest as planned
     std::vector<uint32_t> order;
     order.reserve(n_first);
@@ -590,7 +608,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     if (n_redo) {
       size_t na = 0;
       UnitIO* again = hs + n_first;
-      for (size_t i = 0; i < n; ++i) if (redo[i]) { again[na] = make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(n_first + na), keep_margin); ++na; }
+      for (size_t i = 0; i < n; ++i) if (redo[i]) { again[na] = make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(n_first + na), keep_margin, cidx); ++na; }
       std::vector<uint32_t> ord2(na);
       for (size_t q = 0; q < na; ++q) ord2[q] = (uint32_t)(n_first + q);
       JB_CUDA(cudaMemcpyAsync(w.segs.p + n_first, again, na * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
@@ -625,6 +643,11 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       max_seg_events = std::max<int64_t>(max_seg_events, (int64_t)u.events);
       max_seg_lookups = std::max<int64_t>(max_seg_lookups, (int64_t)u.lookups);
       max_seg_span = std::max<int64_t>(max_seg_span, u.end_old - u.base);
+      if ((int64_t)u.cycles > slow_cycles[ite < 3 ? ite : 2]) {
+        slow_cycles[ite < 3 ? ite : 2] = (int64_t)u.cycles; slow_events[ite < 3 ? ite : 2] = (int64_t)u.events;
+        slow_lookups[ite < 3 ? ite : 2] = (int64_t)u.lookups; slow_span[ite < 3 ? ite : 2] = u.end_old - u.base;
+      }
+      sum_cycles[ite < 3 ? ite : 2] += (int64_t)u.cycles;
     }
     probe_steps += (int64_t)used[2];
     if (do_fix) {
@@ -652,6 +675,44 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;
+      // ---- counts of the new sequence: copied for untouched stretches, probed again around the edits
+      have_counts = false;
+      if (!full_rescan && ite + 1 <= passes) {
+        std::vector<uint32_t> slot_unit(n_slots, 0);
+        for (size_t q = 0; q < segs.size(); ++q) slot_unit[segs[q].slot] = segs[q].unit;
+        std::vector<ScanUnit> units_new(n);
+        for (size_t i = 0; i < n; ++i) units_new[i] = ScanUnit{b->off[i], (uint64_t)new_lens[i], b->off[i]};
+        JB_TRY(w.slot_unit.ensure(n_slots + 1));
+        JB_CUDA(cudaMemcpyAsync(w.slot_unit.p, slot_unit.data(), n_slots * 4, cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaMemcpyAsync(w.scan_units_new.p, units_new.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
+        RecountArgs ra{};
+        ra.jobs = w.jobs.p; ra.n_jobs = w.used.p + 3; ra.dst_off = w.dst_off.p; ra.slot_unit = w.slot_unit.p; ra.units_new = w.scan_units_new.p;
+        ra.in_buf = in; ra.flat_bytes = b->flat_bytes; ra.new_bases = outb;
+        ra.cnt_old = w.counts[cidx].p; ra.okb_old = w.okb[cidx].p; ra.cnt_new = w.counts[cidx ^ 1].p; ra.okb_new = w.okb[cidx ^ 1].p;
+        ra.probes = w.used.p + 4;
+        RecountTailArgs rt{w.scan_units.p, w.scan_units_new.p, (uint32_t)n, w.counts[cidx].p, w.counts[cidx ^ 1].p, w.okb[cidx ^ 1].p};
+        JB_CUDA(cudaEventRecord(ev_r0, s));
+        if (int rc = launch_recount(view, ra, rt, used[3], s)) return rc;
+        JB_CUDA(cudaEventRecord(ev_r1, s));
+        launches += 2;
+        JB_CUDA(cudaMemcpyAsync(used + 4, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
+        if (verify_recount) {
+          // full scan of the new sequence into the buffer the old counts lived in, then compare
+          ScanArgs va = a;
+          va.bases = outb; va.units = w.scan_units_new.p; va.counts = w.counts[cidx].p; va.okb = w.okb[cidx].p; va.probe_steps = nullptr;
+          std::vector<uint32_t> tf(n + 1, 0);
+          for (size_t i = 0; i < n; ++i) tf[i + 1] = tf[i] + tiles_of((uint64_t)new_lens[i]);
+          JB_CUDA(cudaMemcpyAsync(w.tile_first.p, tf.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+          va.n_tiles = tf[n];
+          if (int rc = launch_scan(view, va, s)) return rc;
+          unsigned long long bad = 0;
+          if (int rc = compare_counts(w.scan_units_new.p, (uint32_t)n, w.counts[cidx].p, w.okb[cidx].p, w.counts[cidx ^ 1].p, w.okb[cidx ^ 1].p,
+                                      w.used.p + 5, &bad, s)) return rc;
+          if (bad) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "k_recount disagrees with a full scan at " + std::to_string(bad) + " positions (pass " + std::to_string(ite) + ")"); }
+        }
+        cidx ^= 1;
+        have_counts = true;
+      }
       JB_CUDA(cudaStreamWaitEvent(s, w.ev_rows, 0));     // the next walk reuses the row arena
       pending.live = true; pending.buf = hb; pending.pass = (size_t)ite; pending.n_rows = used[0]; pending.n_aux = used[1];
       pending.segs.swap(segs);
@@ -665,6 +726,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     cudaEventElapsedTime(&ms, ev_a, ev_b); scan_ms += ms;
     cudaEventElapsedTime(&ms, ev_b, ev_c); plan_ms += ms;
     cudaEventElapsedTime(&ms, ev_c, ev_d); walk_ms += ms;
+    if (do_fix && have_counts) { cudaEventElapsedTime(&ms, ev_r0, ev_r1); recount_ms += ms; recount_probes += (int64_t)used[4]; }
     mark("pass done", ite);
   }
   if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
@@ -676,9 +738,18 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
   note_timing("polish", ms); note_timing("polish_scan", scan_ms); note_timing("polish_walk", walk_ms); note_timing("polish_plan", plan_ms);
   note_timing("polish_kwalk", kwalk_ms);
-  note_counter("scan_lookups", scan_lookups); note_counter("walk_lookups", walk_lookups);
+  note_timing("polish_recount", recount_ms);
+  note_counter("scan_lookups", full_scan_lookups + recount_probes); note_counter("walk_lookups", walk_lookups);
+  note_counter("full_scans", full_scans); note_counter("full_scan_lookups", full_scan_lookups); note_counter("recount_probes", recount_probes);
+  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
   note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
+  for (int q = 0; q < 3; ++q) {
+    const std::string sfx = std::to_string(q);
+    note_counter(("slow_cycles" + sfx).c_str(), slow_cycles[q]); note_counter(("slow_events" + sfx).c_str(), slow_events[q]);
+    note_counter(("slow_lookups" + sfx).c_str(), slow_lookups[q]); note_counter(("slow_span" + sfx).c_str(), slow_span[q]);
+    note_counter(("sum_cycles" + sfx).c_str(), sum_cycles[q]);
+  }
   note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;

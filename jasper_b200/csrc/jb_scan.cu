@@ -2,6 +2,7 @@
 #include <algorithm>
 
 #include "jb_scan.cuh"
+#include "jb_jobs.cuh"
 
 namespace jb {
 
@@ -125,7 +126,17 @@ k_scan(TableView t, ScanArgs a) {
       const int i = row * 32 + lane;
       if (i < n_out) dst[i] = s_cnt[row * 33 + lane];
     }
-    if (a.okbits && r0 < n_out) a.okbits[((u.out_off + tile.start) >> 5) + lane] = okmask;
+    if (a.okb && r0 < n_out) {                          // 32 validity bytes per lane, two 16-byte stores
+      uint32_t w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t nib = (okmask >> (4 * q)) & 0xFu;
+        w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      }
+      uint4* dst4 = reinterpret_cast<uint4*>(a.okb + u.out_off + tile.start + r0);
+      dst4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
   if (a.probe_steps) {
     for (int o = 16; o; o >>= 1) steps_total += __shfl_xor_sync(0xffffffffu, steps_total, o);
@@ -148,7 +159,7 @@ k_events(EventArgs a) {
     const int64_t p = (int64_t)tile.start + w0 + lane;
     bool ev = false, wk = false;
     if (w0 + lane < n_out) {
-      const bool ok = (a.okbits[(f0 + w0) >> 5] >> lane) & 1u;
+      const bool ok = a.okb[f0 + w0 + lane] != 0;
       const uint32_t c = cnt[p];
       wk = ok && c < a.solid_thre;
       ev = !ok || p < (int64_t)a.k || c < a.solid_thre;
@@ -164,6 +175,94 @@ k_events(EventArgs a) {
   }
 }
 
+
+// one grid row per copy job, gridDim.x CTAs share it
+__global__ void __launch_bounds__(256)
+k_recount(TableView t, RecountArgs a) {
+  const unsigned long long n = *a.n_jobs;
+  const int k = t.g.k;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long probes = 0;
+  for (unsigned long long j = blockIdx.y; j < n; j += gridDim.y) {
+    const CopyJob job = a.jobs[j];
+    const int64_t off = a.dst_off[job.slot];
+    if (off < 0) continue;
+    const ScanUnit u = a.units_new[a.slot_unit[job.slot]];
+    const int64_t D = off + job.rel;                              // flat position of the job's first base
+    const int64_t cend = (int64_t)u.seq_off + (int64_t)u.len;     // flat end of the new contig
+    int64_t dirty0 = D;
+    if (job.src >= a.in_buf && job.src < a.in_buf + a.flat_bytes) {
+      // an untouched stretch: windows that lie inside it keep their counts
+      const int64_t O = job.src - a.in_buf;
+      const int64_t ncopy = job.len - k + 1 > 0 ? job.len - k + 1 : 0;
+      for (int64_t q = tid; q < ncopy; q += nth) { a.cnt_new[D + q] = a.cnt_old[O + q]; a.okb_new[D + q] = a.okb_old[O + q]; }
+      dirty0 = D + ncopy;
+    }
+    for (int64_t p = dirty0 + tid; p < D + job.len; p += nth) {
+      const uint8_t* s = a.new_bases + p;
+      const int64_t avail = cend - p;
+      Key key = {0, 0};
+      int got = 0;
+      while (got < k && got < avail) {
+        const uint8_t c = s[got];
+        if (!base_valid(c)) break;
+        key = key_push(key, base_code(c), t.mask);
+        ++got;
+      }
+      key = key_shl_bases(key, k - got, t.mask);
+      a.cnt_new[p] = table_count(t, key_canonical(key, k));
+      a.okb_new[p] = got == k ? 1 : 0;
+      ++probes;
+    }
+  }
+  if (a.probes) {
+    for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
+    if ((threadIdx.x & 31) == 0 && probes) atomicAdd(a.probes, probes);
+  }
+}
+
+// the empty tail window of every contig: C('') does not change
+__global__ void k_recount_tail(RecountTailArgs a) {
+  const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ui >= a.n_units) return;
+  const ScanUnit o = a.units_old[ui], n = a.units_new[ui];
+  a.cnt_new[n.out_off + n.len] = a.cnt_old[o.out_off + o.len];
+  a.okb_new[n.out_off + n.len] = 0;
+}
+
+__global__ void k_compare(const ScanUnit* units, uint32_t n_units, const uint32_t* cnt_a, const uint8_t* okb_a, const uint32_t* cnt_b,
+                          const uint8_t* okb_b, unsigned long long* out) {
+  unsigned long long bad = 0;
+  for (uint32_t ui = blockIdx.y; ui < n_units; ui += gridDim.y) {
+    const ScanUnit u = units[ui];
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= u.len; p += (uint64_t)gridDim.x * blockDim.x)
+      if (cnt_a[u.out_off + p] != cnt_b[u.out_off + p] || (okb_a[u.out_off + p] != 0) != (okb_b[u.out_off + p] != 0)) ++bad;
+  }
+  if (bad) atomicAdd(out, bad);
+}
+
+int compare_counts(const ScanUnit* d_units, uint32_t n_units, const uint32_t* cnt_a, const uint8_t* okb_a, const uint32_t* cnt_b,
+                   const uint8_t* okb_b, unsigned long long* d_scratch, unsigned long long* mismatches, cudaStream_t s) {
+  cudaMemsetAsync(d_scratch, 0, 8, s);
+  if (n_units) k_compare<<<dim3(64, std::min<uint32_t>(n_units, 1024)), 256, 0, s>>>(d_units, n_units, cnt_a, okb_a, cnt_b, okb_b, d_scratch);
+  cudaMemcpyAsync(mismatches, d_scratch, 8, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("compare_counts: ") + cudaGetErrorString(e));
+  return JB_OK;
+}
+
+int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, unsigned long long n_jobs_hint, cudaStream_t s) {
+  dim3 g(2, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(n_jobs_hint, 1), 32768));
+  k_recount<<<g, 256, 0, s>>>(view, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount launch: ") + cudaGetErrorString(e));
+  if (t.n_units) {
+    k_recount_tail<<<(t.n_units + 127) / 128, 128, 0, s>>>(t);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_tail launch: ") + cudaGetErrorString(e));
+  }
+  return JB_OK;
+}
 
 std::vector<uint32_t> make_tile_prefix(const std::vector<ScanUnit>& units) {
   std::vector<uint32_t> first(units.size() + 1, 0);

@@ -70,7 +70,7 @@ struct ScanArgs {
   uint32_t n_units;
   uint32_t n_tiles;
   uint32_t* counts;             // flat, counts[out_off + p]
-  uint32_t* okbits;             // flat bit words, may be null
+  uint8_t* okb;                 // flat, 1 = window is k chars of ACGTacgt; may be null
   unsigned long long* probe_steps;   // optional statistics: total sector loads
 };
 
@@ -82,7 +82,7 @@ struct EventArgs {
   uint32_t n_units;
   uint32_t n_tiles;
   const uint32_t* counts;
-  const uint32_t* okbits;
+  const uint8_t* okb;
   uint32_t* events;
   uint32_t* weak;
   uint32_t* events_l1;      // pre-zeroed
@@ -90,7 +90,33 @@ struct EventArgs {
   int k;
 };
 
+// Incremental recount after a fixing pass (passes 2.. never rescan everything): the copy jobs that stitched
+// the new contigs say which stretches are untouched, so their windows keep their counts; only windows that
+// touch edited bases, straddle a job boundary or run off a contig end are probed again.
+struct CopyJob;
+struct RecountArgs {
+  const CopyJob* jobs;
+  const unsigned long long* n_jobs;
+  const int64_t* dst_off;       // by launch slot: flat offset of the segment's new bases; < 0 = superseded
+  const uint32_t* slot_unit;    // by launch slot: contig
+  const ScanUnit* units_new;    // per contig: seq_off (= flat offset, unchanged between passes) and the NEW length
+  const uint8_t* in_buf;        // the pass-start flat base buffer (jobs whose src lies in it are untouched stretches)
+  uint64_t flat_bytes;
+  const uint8_t* new_bases;     // the stitched flat base buffer
+  const uint32_t* cnt_old; const uint8_t* okb_old;
+  uint32_t* cnt_new; uint8_t* okb_new;
+  unsigned long long* probes;   // statistics
+};
+struct RecountTailArgs {
+  const ScanUnit* units_old; const ScanUnit* units_new; uint32_t n_units;
+  const uint32_t* cnt_old; uint32_t* cnt_new; uint8_t* okb_new;
+};
+
 // launchers (jb_scan.cu)
+// number of positions p in [0, len_u] of any contig where (count, ok) differ between two flat arrays (test aid)
+int compare_counts(const ScanUnit* d_units, uint32_t n_units, const uint32_t* cnt_a, const uint8_t* okb_a, const uint32_t* cnt_b,
+                   const uint8_t* okb_b, unsigned long long* d_scratch, unsigned long long* mismatches, cudaStream_t s);
+int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, unsigned long long n_jobs_hint, cudaStream_t s);
 int scan_grid(uint32_t n_tiles);
 int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s);
 int launch_events(const EventArgs& a, cudaStream_t s);

@@ -20,6 +20,7 @@
 #include "../../include/jasper_b200.h"
 #include "jb_kmer.cuh"
 #include "jb_cand.cuh"
+#include "jb_jobs.cuh"
 #include "jb_seq.cuh"
 #include "jb_segments.cuh"
 
@@ -90,12 +91,6 @@ struct BridgeScratch {       // global memory, one per resident walker
   uint32_t patch_cap;
 };
 
-// The new bases of a segment are described as copy jobs: materialised windows around edits (src = the
-// segment's staging region) and untouched stretches (src = the pass-start contig).  `rel` = offset inside
-// the segment's new bases; k_concat adds the segment's offset in the new contig.
-struct CopyJob { const uint8_t* src; int64_t rel; int64_t len; uint32_t slot; uint32_t pad; };
-struct JobSink { CopyJob* jobs; unsigned long long cap; unsigned long long* used; };
-
 constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
 constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
 JB_HD int default_keep_margin(int k) { return 3 * k + 64; }
@@ -131,6 +126,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   uint32_t n_rows;
   unsigned long long lookups;
   unsigned long long events;
+  unsigned long long cycles;   // device clock ticks this segment took (profiling aid)
 };
 
 template <class DB>
@@ -891,6 +887,9 @@ struct Walker {
   }
 
   JB_W void run() {
+#if defined(__CUDA_ARCH__)
+    const long long t_begin = clock64();
+#endif
     base = u.base; seam_margin = seam_read_margin(k); keep_margin = u.keep_margin; wstart = 0; far_back = false;
     i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; vflags = 0;
     publish();
@@ -984,6 +983,11 @@ struct Walker {
     u.n_rows = seqno;
     u.lookups = lookups + s.probes;
     u.events = events;
+#if defined(__CUDA_ARCH__)
+    u.cycles = (unsigned long long)(clock64() - t_begin);
+#else
+    u.cycles = 0;
+#endif
   }
 };
 

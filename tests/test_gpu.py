@@ -136,8 +136,25 @@ def test_polish_big_fuzz_segmented_matches_hostsim_and_oracle(tmp_path, hostsim_
         qf.close()
 
 
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_incremental_recount_equals_full_scan(golden_cases, dbs, name, monkeypatch):
+    """Passes 2.. inherit window counts through k_recount: (a) the device checks every inherited count against a
+    full scan of the new sequence (JB_VERIFY_RECOUNT), (b) forcing full rescans gives the same bytes."""
+    case = golden_cases[name]
+    seqs = jo.read_fasta(case["fasta"])
+    monkeypatch.setenv("JB_VERIFY_RECOUNT", "1")
+    a = dbs[name].polish(seqs, case["k"], case["threshold"], 3)
+    assert a.status == 0 and a.counters["recount_probes"] > 0
+    monkeypatch.delenv("JB_VERIFY_RECOUNT")
+    monkeypatch.setenv("JB_FULL_RESCAN", "1")
+    b = dbs[name].polish(seqs, case["k"], case["threshold"], 3)
+    assert b.counters["recount_probes"] == 0
+    assert (a.rows, a.seqs, a.tallies) == (b.rows, b.seqs, b.tallies)
+
+
 @pytest.mark.parametrize("seed", range(40))
-def test_polish_fuzz_matches_oracle(tmp_path, seed):
+def test_polish_fuzz_matches_oracle(tmp_path, seed, monkeypatch):
+    monkeypatch.setenv("JB_VERIFY_RECOUNT", "1")
     k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
     recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k)
     odb = helpers.OracleDB(path)
