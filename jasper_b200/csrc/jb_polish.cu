@@ -424,10 +424,14 @@ int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob
   const size_t n_rows = pr->n_rows, n_aux = pr->n_aux;
   raw->copied.store(false);
   (void)n_aux;
-  j->th = std::thread([raw, src_rows, src_aux, n_rows]() {
+  const bool trace = getenv("JB_TRACE") != nullptr;
+  j->th = std::thread([raw, src_rows, src_aux, n_rows, trace]() {
     // straight from the pinned log (the next pass's log is not copied into it before `copied` is set)
+    const auto t0 = std::chrono::steady_clock::now();
     raw->ok = rows_in_order(src_rows, n_rows, src_aux, raw->segs, raw->place, raw->first_seg, &raw->out);
     raw->copied.store(true, std::memory_order_release);
+    if (trace) fprintf(stderr, "[jb trace] row thread: %zu log rows -> %zu csv rows in %.3f ms\n", n_rows, raw->out.rows.size(),
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   });
   jobs->push_back(std::move(j));
   pr->live = false;
@@ -671,7 +675,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux[hb].p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
       JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
       JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
-      dim3 g(4, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(used[3], 1), 16384));
+      const unsigned long long nj = std::max<unsigned long long>(used[3], 1);
+      dim3 g((unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(4, 65536 / nj)), (unsigned)std::min<unsigned long long>(nj, 16384));
       k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;

@@ -252,7 +252,10 @@ int compare_counts(const ScanUnit* d_units, uint32_t n_units, const uint32_t* cn
 }
 
 int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, unsigned long long n_jobs_hint, cudaStream_t s) {
-  dim3 g(2, (unsigned)std::min<unsigned long long>(std::max<unsigned long long>(n_jobs_hint, 1), 32768));
+  // few jobs = long untouched stretches: give each job more CTAs for the count copy
+  const unsigned long long nj = std::max<unsigned long long>(n_jobs_hint, 1);
+  const unsigned gx = (unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(2, 65536 / nj));
+  dim3 g(gx, (unsigned)std::min<unsigned long long>(nj, 32768));
   k_recount<<<g, 256, 0, s>>>(view, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount launch: ") + cudaGetErrorString(e));

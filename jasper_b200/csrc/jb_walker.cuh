@@ -93,7 +93,7 @@ struct BridgeScratch {       // global memory, one per resident walker
 
 constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
 constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
-JB_HD int default_keep_margin(int k) { return 3 * k + 64; }
+JB_HD int default_keep_margin(int k) { return 2 * k + 32; }
 
 struct BridgePool {          // bridging scratch is borrowed only while a multi-error patch is being searched
   BridgeScratch* slots;

@@ -103,7 +103,7 @@ def hostsim_lib():
     srcs = [os.path.join(d, "walker_hostsim.cpp")] + glob.glob(os.path.join(ROOT, "jasper_b200", "csrc", "*.cuh")) + \
         glob.glob(os.path.join(ROOT, "jasper_b200", "csrc", "*.hpp")) + [os.path.join(ROOT, "jasper_b200", "csrc", "jb_align.cpp")]
     if not _newer(so, *srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so,
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", so,
                                os.path.join(d, "walker_hostsim.cpp"), os.path.join(ROOT, "jasper_b200", "csrc", "jb_align.cpp")])
     sim = C.CDLL(so)
     sim.hostsim_polish.restype = C.c_void_p
