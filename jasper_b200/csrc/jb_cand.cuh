@@ -44,6 +44,55 @@ enum CandKind : uint8_t { kSub = 0, kIns = 1, kDel = 2, kDip = 3 };
 //   kDel  t[:pos] + t[pos+m:]               kDip  before + t{[n-k] = base, [k-1] = base2} + after   (fixdiploid)
 struct Cand { uint8_t kind, base, base2, pad; int16_t pos, m; };
 
+// ---- 2-bit packed strings ---------------------------------------------------------------------
+// Building a k-mer from bytes costs ~20 instructions per base and every probe lane used to do it for its
+// own window (45 % of the walker's instructions, ncu r1n).  A string that many lanes cut windows from is
+// packed once by the whole warp: base q sits in word q/32 at bits 62-2(q%32) (first base on top), invalid
+// bytes are recorded in a bitmask, and a window is three shifts.
+constexpr int kPackBases = 256;
+struct Packed {
+  uint64_t w[kPackBases / 32 + 2];   // two zero words behind the data: windows may read past the end
+  uint32_t inv[kPackBases / 32];     // bit l of inv[c]: byte 32c + l is not ACGTacgt (bytes past len count as invalid)
+  int32_t len;
+};
+
+// bases [q0, q0 + n) of p as a 2n-bit integer, n <= 64, q0 + n <= kPackBases
+JB_HD Key packed_window(const Packed& p, int q0, int n) {
+  const int bit = 2 * q0, j = bit >> 6, r = bit & 63;
+  const uint64_t a = p.w[j], b = p.w[j + 1], c = p.w[j + 2];
+  const uint64_t X = r ? (a << r) | (b >> (64 - r)) : a;        // the 128 bits that start at base q0
+  const uint64_t Y = r ? (b << r) | (c >> (64 - r)) : b;
+  Key key;
+  if (n <= 32) { key.hi = 0; key.lo = n ? X >> (64 - 2 * n) : 0; }
+  else { const int s = 128 - 2 * n; key.lo = s ? (Y >> s) | (X << (64 - s)) : Y; key.hi = s ? X >> s : X; }
+  return key;
+}
+
+// no invalid byte in [q0, q0 + n) and the range lies inside the string
+JB_HD bool packed_clean(const Packed& p, int q0, int n) {
+  if (n <= 0) return true;
+  if (q0 < 0 || q0 + n > p.len) return false;
+  const int c0 = q0 >> 5, c1 = (q0 + n - 1) >> 5;
+  for (int c = c0; c <= c1; ++c) {
+    uint32_t m = p.inv[c];
+    if (c == c0) m &= 0xFFFFFFFFu << (q0 & 31);
+    if (c == c1) { const int top = (q0 + n - 1) & 31; if (top < 31) m &= (2u << top) - 1u; }
+    if (m) return false;
+  }
+  return true;
+}
+
+// (a << 2n) | b for keys of bases
+JB_HD Key key_append(Key a, Key b, int n) {
+  if (n <= 0) return a;
+  Key r;
+  const int s = 2 * n;
+  if (s >= 128) return b;
+  if (s >= 64) { r.hi = (a.lo << (s - 64)) | b.hi; r.lo = b.lo; if (s == 64) r.hi = a.lo | b.hi; }
+  else { r.hi = (a.hi << s) | (a.lo >> (64 - s)) | b.hi; r.lo = (a.lo << s) | b.lo; }
+  return r;
+}
+
 // The sequence a walker is editing (jb_seq.cuh reads it, jb_walker.cuh publishes it after every edit).
 struct SeqView {
   const uint8_t* in;         // the contig at the start of the pass
@@ -67,11 +116,55 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   int32_t dip_nb, dip_bl;    // kDip: chars of flank before (s.c[0:nb)) and after (s.c[nb+n : nb+n+bl))
   uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
   SeqView view;              // published copy of the walker's sequence state
+  Packed pt;                 // packed to_be_fixed (or, for kDip, the whole check string before + t + after)
+  Packed pc;                 // packed staging buffer (window refills, point queries, bridging checks)
   int64_t wc_base;           // window-count cache: wc[0:wc_n) = C(seq[wc_base + l : ...])
   int32_t wc_n;
   uint32_t empty_count;      // C('') = count of poly-A
   unsigned long long probes; // table probes issued by the out-of-line helpers
 };
+
+// pack buf[0:len) (len <= kPackBases) with the whole warp
+JB_FREE_NOINLINE void pack_bytes(Packed& p, const uint8_t* buf, int len) {
+  if (len > kPackBases) len = kPackBases;
+  const int chunks = (len + 31) >> 5;
+  JB_SYNC();
+#if defined(__CUDA_ARCH__)
+  const int l = threadIdx.x & 31;
+  for (int c = 0; c < chunks; ++c) {
+    const int q = 32 * c + l;
+    const uint8_t ch = q < len ? buf[q] : (uint8_t)0;
+    const bool v = q < len && base_valid(ch);
+    const uint32_t code = v ? base_code(ch) : 0u;
+    const uint32_t hi = __reduce_or_sync(0xffffffffu, l < 16 ? code << (30 - 2 * l) : 0u);
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, l >= 16 ? code << (62 - 2 * l) : 0u);
+    const uint32_t inv = __ballot_sync(0xffffffffu, !v);
+    if (l == 0) { p.w[c] = ((uint64_t)hi << 32) | lo; p.inv[c] = inv; }
+  }
+  if (l == 0) { p.w[chunks] = 0; p.w[chunks + 1] = 0; p.len = len; }
+#else
+  for (int c = 0; c < chunks; ++c) {
+    uint64_t w = 0; uint32_t inv = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int q = 32 * c + l;
+      const bool v = q < len && base_valid(buf[q]);
+      if (v) w |= (uint64_t)base_code(buf[q]) << (62 - 2 * l); else inv |= 1u << l;
+    }
+    p.w[c] = w; p.inv[c] = inv;
+  }
+  p.w[chunks] = 0; p.w[chunks + 1] = 0; p.len = len;
+#endif
+  JB_SYNC();
+}
+
+// C(window m of a packed string of len bytes), falling back to the byte loop near invalid bytes / the end
+template <class DB>
+JB_FREE_INLINE uint32_t count_packed(const DB& db, const Packed& p, const uint8_t* buf, int len, int m, int k, Key mask) {
+  Key key;
+  if (packed_clean(p, m, k)) key = packed_window(p, m, k);
+  else key = key_from_chars(buf + m, (int64_t)len - m, k, mask);
+  return db.count(key_canonical(key, k));
+}
 
 // C(buf[m : m+k]) with MerDNA's padding (JF!include/jellyfish/mer_dna.hpp:525-542, 642-644)
 template <class DB>
@@ -96,9 +189,66 @@ JB_FREE_INLINE uint8_t cand_char(const WarpScratch& s, const Cand& c, int n, int
   return r == n - k ? c.base : (r == k - 1 ? c.base2 : s.t[r]);
 }
 
+// bases [q0, q0 + cnt) of the packed to_be_fixed with base `code` substituted at position pos (if inside)
+JB_FREE_INLINE Key sub_base(Key key, int q0, int cnt, int pos, uint32_t code) {
+  if (pos < q0 || pos >= q0 + cnt) return key;
+  const int sh = 2 * (q0 + cnt - 1 - pos);
+  if (sh >= 64) key.hi = (key.hi & ~(3ull << (sh - 64))) | ((uint64_t)code << (sh - 64));
+  else key.lo = (key.lo & ~(3ull << sh)) | ((uint64_t)code << sh);
+  return key;
+}
+
+// fast path of cand_count: the window cut from the packed string s.pt; false = use the byte loop
+JB_FREE_INLINE bool cand_key_packed(const WarpScratch& s, const Cand& c, int n, int len, int m, int k, Key* out) {
+  if (m < 0 || m + k > len) return false;
+  const Packed& p = s.pt;
+  if (c.kind == kSub) {
+    if (!packed_clean(p, m, k)) return false;
+    *out = sub_base(packed_window(p, m, k), m, k, c.pos, base_code(c.base));
+    return true;
+  }
+  if (c.kind == kDip) {                                // s.pt holds before + t + after
+    if (!packed_clean(p, m, k)) return false;
+    Key key = packed_window(p, m, k);
+    key = sub_base(key, m, k, s.dip_nb + k - 1, base_code(c.base2));
+    key = sub_base(key, m, k, s.dip_nb + n - k, base_code(c.base));     // the left base wins when both hit one position
+    *out = key;
+    return true;
+  }
+  // kIns / kDel: a stretch of t, then (kIns) copies of the inserted base, then another stretch of t
+  const int P = c.pos, mi = c.m;
+  const int lenA = P > m ? (P - m < k ? P - m : k) : 0;                  // trial positions [m, min(P, m + k))
+  int cB = 0, cstart;                                                   // t index where the last stretch starts
+  if (c.kind == kIns) {
+    const int b0 = m > P ? m : P, b1 = (P + mi < m + k) ? P + mi : m + k;
+    cB = b1 > b0 ? b1 - b0 : 0;
+    const int q = m > P + mi ? m : P + mi;                              // first trial position behind the insertion
+    cstart = q - mi;
+  } else {
+    const int q = m > P ? m : P;
+    cstart = q + mi;
+  }
+  const int lenC = k - lenA - cB;
+  if (lenC < 0) return false;
+  if (!packed_clean(p, m, lenA) || !packed_clean(p, cstart, lenC)) return false;
+  Key key = lenA ? packed_window(p, m, lenA) : Key{0, 0};
+  if (cB) {
+    const uint64_t rep = 0x5555555555555555ull * base_code(c.base);     // the base repeated
+    Key b;
+    if (cB <= 32) { b.hi = 0; b.lo = cB == 32 ? rep : (rep & ((1ull << (2 * cB)) - 1)); }
+    else { b.lo = rep; b.hi = rep & ((1ull << (2 * (cB - 32))) - 1); }
+    key = key_append(key, b, cB);
+  }
+  if (lenC) key = key_append(key, packed_window(p, cstart, lenC), lenC);
+  *out = key;
+  return true;
+}
+
 // count of the window starting at m of the candidate's check string (len chars)
 template <class DB>
 JB_FREE_INLINE uint32_t cand_count(const DB& db, const WarpScratch& s, const Cand& c, int n, int len, int m, int k, Key mask) {
+  Key fast;
+  if (cand_key_packed(s, c, n, len, m, k, &fast)) return db.count(key_canonical(fast, k));
   Key key = {0, 0};
   int j = 0;
   for (; j < k && m + j < len; ++j) {

@@ -64,7 +64,8 @@ JB_FREE_NOINLINE uint32_t view_refill(const DB& db, WarpScratch& s, int64_t b0, 
   }
   const uint32_t r = view_load(&s.view, s.c, b0, b0 + 32 + k - 1);
   const int len = (int)(r & 0xFFFFu);
-  JB_LANES(l) { s.wc[l] = count_str(db, s.c, len, l < len ? l : len, k, mask); }
+  pack_bytes(s.pc, s.c, len);
+  JB_LANES(l) { s.wc[l] = count_packed(db, s.pc, s.c, len, l < len ? l : len, k, mask); }
   JB_SYNC();
   return (r >> 16) | kFlagProbed;
 }
@@ -100,7 +101,8 @@ JB_FREE_NOINLINE uint32_t view_points(const DB& db, WarpScratch& s, int n, int k
   if (hi + k - lo > kStrCap - 8) return kFlagTooWide;
   const uint32_t r = view_load(&s.view, s.c, lo, hi + k);
   const int len = (int)(r & 0xFFFFu);
-  JB_LANES(l) { if (l < n) { const int m = (int)(s.px[l] - lo); s.pr[l] = count_str(db, s.c, len, m < len ? m : len, k, mask); } }
+  pack_bytes(s.pc, s.c, len);
+  JB_LANES(l) { if (l < n) { const int m = (int)(s.px[l] - lo); s.pr[l] = count_packed(db, s.pc, s.c, len, m < len ? m : len, k, mask); } }
   JB_SYNC();
   return (r >> 16) | kFlagProbed;
 }

@@ -253,6 +253,7 @@ struct Walker {
     for (int m = step; m < len - k; m += step) ++n_mid;
     int total = 2 + n_mid;
     bool ok = true;
+    pack_bytes(s.pc, buf, len);
     for (int w0 = 0; w0 < total && ok; w0 += 32) {
       JB_SYNC();
       JB_LANES(l) {
@@ -260,7 +261,7 @@ struct Walker {
         uint32_t f = 0;
         if (q < total) {
           int m = q == 0 ? 0 : (q == 1 ? (len - k > 0 ? len - k : 0) : step * (q - 1));
-          f = (int64_t)count_in(buf, len, m) < thr ? 1u : 0u;
+          f = (int64_t)count_packed(db, s.pc, buf, len, m, k, mask) < thr ? 1u : 0u;
         }
         s.flag[l] = f;
       }
@@ -434,7 +435,7 @@ struct Walker {
     const uint8_t before = get(ga - 1);
     const char order[4] = {'A', 'C', 'T', 'G'};
     int nc = 0;
-    JB_SYNC();
+    pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) if ((uint8_t)order[o] != bad) set_cand(nc++, kSub, (uint8_t)order[o], 0, k - 1, 0);
     set_cand(nc++, kDel, 0, 0, k - 1, 1);
     const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
@@ -450,7 +451,7 @@ struct Walker {
   JB_W Fix fix_del(int n, int64_t thr, int64_t s0, int64_t ga) {
     Fix f;
     const char order[4] = {'A', 'T', 'C', 'G'};
-    JB_SYNC();
+    pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 1, 1);
     const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
     if (w < 0) return f;
@@ -478,8 +479,12 @@ struct Walker {
     load(s.c, b0, b0 + nb);
     load(s.c + nb + n, a0, a0 + bl);
     JB_SYNC();
-    JB_LANES(l) { if (l == 0) { s.dip_nb = nb; s.dip_bl = bl; } }
+    JB_LANES(l) {
+      for (int q = l; q < n; q += 32) s.c[nb + q] = s.t[q];          // the whole check string, for packing
+      if (l == 0) { s.dip_nb = nb; s.dip_bl = bl; }
+    }
     JB_SYNC();
+    pack_bytes(s.pt, s.c, nb + n + bl);
     const char order[4] = {'A', 'C', 'T', 'G'};
     int nc = 0;
     for (int xo = 0; xo < 4; ++xo)
@@ -509,6 +514,7 @@ struct Walker {
     const uint8_t sb = s.t[k - 2];
     const int start_bad = n - k + 1;
     int cur = start_bad, added = 0;
+    pack_bytes(s.pt, s.t, n);
     while (added < start_bad) {
       ++added;
       JB_SYNC();
@@ -542,6 +548,7 @@ struct Walker {
     const uint8_t sb = s.t[k - 1];
     const int start_bad = n - k + 1;
     int cur = start_bad, removed = 0;
+    pack_bytes(s.pt, s.t, n);
     while (removed < start_bad) {
       --cur; ++removed;
       if (n - removed == k) break;

@@ -121,6 +121,8 @@ def hostsim_lib():
     sim.hostsim_segments.argtypes = [C.c_void_p]
     sim.hostsim_reruns.restype = C.c_ulonglong
     sim.hostsim_reruns.argtypes = [C.c_void_p]
+    sim.hostsim_packed_selfcheck.restype = C.c_longlong
+    sim.hostsim_packed_selfcheck.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_longlong)]
     sim.hostsim_mer.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     sim.hostsim_align.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     return sim

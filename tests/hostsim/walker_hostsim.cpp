@@ -239,3 +239,46 @@ extern "C" int hostsim_align(const char* a, const char* b, char* out_a, char* ou
   snprintf(out_a, cap, "%s", x.c_str()); snprintf(out_b, cap, "%s", y.c_str());
   return 1;
 }
+
+// Self-check of the packed-key fast path (jb_cand.cuh) against the byte loop it replaces: random strings with
+// invalid bytes, every candidate kind, every window.  Returns mismatches; *fast = windows the fast path served.
+extern "C" long long hostsim_packed_selfcheck(unsigned seed, int k, long long* fast) {
+  static WarpScratch s;
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 12345;
+  auto rnd = [&]() { x ^= x >> 12; x ^= x << 25; x ^= x >> 27; return (uint32_t)((x * 0x2545F4914F6CDD1Dull) >> 33); };
+  const char alpha[] = "ACGTacgt";
+  long long bad = 0; *fast = 0;
+  const Key mask = key_mask(k);
+  for (int round = 0; round < 200; ++round) {
+    const int n = k + (int)(rnd() % (unsigned)(k + 10));
+    for (int q = 0; q < n; ++q) s.t[q] = (rnd() % 40 == 0) ? (uint8_t)"NnRy-"[rnd() % 5] : (uint8_t)alpha[rnd() % 8];
+    const int nb = (int)(rnd() % (unsigned)(k / 2 + 1)), bl = (int)(rnd() % (unsigned)(k / 2 + 1));
+    for (int q = 0; q < nb; ++q) s.c[q] = (uint8_t)alpha[rnd() % 8];
+    for (int q = 0; q < bl; ++q) s.c[nb + n + q] = (rnd() % 30 == 0) ? (uint8_t)'N' : (uint8_t)alpha[rnd() % 8];
+    s.dip_nb = nb; s.dip_bl = bl;
+    for (int kind = 0; kind < 4; ++kind) {
+      Cand c; c.kind = (uint8_t)kind; c.base = (uint8_t)"ACGT"[rnd() % 4]; c.base2 = (uint8_t)"ACGT"[rnd() % 4]; c.pad = 0;
+      c.pos = (int16_t)(rnd() % (unsigned)n); c.m = (int16_t)(1 + rnd() % (unsigned)(k - 1));
+      if (kind == kDel && c.pos + c.m > n) c.m = (int16_t)(n - c.pos);
+      if (kind == kDel && c.m <= 0) continue;
+      if (kind == kDip) { for (int q = 0; q < n; ++q) s.c[nb + q] = s.t[q]; pack_bytes(s.pt, s.c, nb + n + bl); }
+      else pack_bytes(s.pt, s.t, n);
+      const int len = cand_len(s, c, n);
+      for (int m = 0; m <= len; ++m) {
+        Key slow = {0, 0}; int j = 0;
+        for (; j < k && m + j < len; ++j) { uint8_t ch = cand_char(s, c, n, k, m + j); if (!base_valid(ch)) break; slow = key_push(slow, base_code(ch), mask); }
+        slow = key_shl_bases(slow, k - j, mask);
+        Key f;
+        if (cand_key_packed(s, c, n, len, m, k, &f)) { ++*fast; if (f.lo != slow.lo || f.hi != slow.hi) ++bad; }
+      }
+    }
+    // plain buffers: count_packed's choice against key_from_chars
+    const int len = n;
+    pack_bytes(s.pc, s.t, len);
+    for (int m = 0; m <= len; ++m) {
+      Key slow = key_from_chars(s.t + m, (int64_t)len - m, k, mask);
+      if (packed_clean(s.pc, m, k)) { ++*fast; Key f = packed_window(s.pc, m, k); if (f.lo != slow.lo || f.hi != slow.hi) ++bad; }
+    }
+  }
+  return bad;
+}

@@ -191,3 +191,13 @@ def test_jasper_py_parse_fasta_quirks(tmp_path):
     d = host.parse_fasta(str(p))
     assert list(d.items()) == [("a", "GG"), ("b", ""), ("", "CC")]       # dict semantics: first position, last value
     assert host._prefixed("x.csv", 3) == "_iter3_x.csv" and host._prefixed("d/x.csv", 0) == "d_iter0_x.csv"
+
+
+@pytest.mark.parametrize("k", [8, 12, 20, 25, 31, 32, 33, 37, 48])
+def test_packed_keys_equal_the_byte_loop(hostsim_lib, k):
+    """jb_cand.cuh cuts candidate k-mers out of 2-bit packed strings; every window of every candidate kind must
+    be the k-mer the byte loop (MerDNA semantics) builds, and the fast path must actually serve most windows."""
+    fast = C.c_longlong()
+    bad = hostsim_lib.hostsim_packed_selfcheck(1234 + k, k, C.byref(fast))
+    assert bad == 0
+    assert fast.value > 5000
