@@ -36,6 +36,8 @@ namespace jb {
 
 constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check string fits (<= 3k + 8)
 constexpr int kMaxCands = 64;
+constexpr int kFastBack = 64;                    // fast_delimit: staged windows in front of the event ...
+constexpr int kFastWin = kFastBack + 2 * JB_MAX_K + 24;   // ... and in all
 
 enum CandKind : uint8_t { kSub = 0, kIns = 1, kDel = 2, kDip = 3 };
 
@@ -115,6 +117,9 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint32_t failmask[2];
   int32_t dip_nb, dip_bl;    // kDip: chars of flank before (s.c[0:nb)) and after (s.c[nb+n : nb+n+bl))
   uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
+  uint32_t fc[kFastWin];     // fast_delimit: bulk-scan counts of the windows around an event (jb_walker.cuh)
+  int32_t fbad[2];           // fast_delimit: last unavailable entry before / first one behind the event
+  uint32_t win[2];           // first_passing_lean: counts of the winner's samples 0 (m = 0) and 1 (m = len - k)
   SeqView view;              // published copy of the walker's sequence state
   Packed pt;                 // packed to_be_fixed (or, for kDip, the whole check string before + t + after)
   Packed pc;                 // packed staging buffer (window refills, point queries, bridging checks)
@@ -303,6 +308,58 @@ JB_FREE_NOINLINE int first_passing(const DB& db, WarpScratch& s, int nc, int n, 
     while (decided < nc && (int)s.cand_first[decided + 1] <= w0 + 32) {
       if (!((s.failmask[decided >> 5] >> (decided & 31)) & 1u)) return decided;
       ++decided;
+    }
+  }
+  return -1;
+}
+
+// first_passing for single-base candidates over a to_be_fixed string WITHOUT invalid bytes (the common case: every
+// isolated substitution / indel).  Same answer as first_passing -- the first candidate in enumeration order whose
+// check_sequence samples are all solid -- with a fixed layout: every candidate owns a slot of S lanes, a wave holds
+// 32 / S candidates, a lane cuts its window from the packed string with shifts.  Returns -2 when the layout does not
+// apply (the caller then uses first_passing).  s.win = counts of the winner's samples 0 and 1.
+template <class DB>
+JB_FREE_NOINLINE int first_passing_lean(const DB& db, WarpScratch& s, int nc, int n, int k, int step, int64_t thr, unsigned long long* lookups) {
+  int S = 0;
+  for (int c = 0; c < nc; ++c) { const int ns = check_samples(cand_len(s, s.cand[c], n), k, step); S = ns > S ? ns : S; }
+  if (S > 16 || S < 2) return -2;
+  const int G = 32 / S;
+  for (int c0 = 0; c0 < nc; c0 += G) {
+    const int c1 = c0 + G < nc ? c0 + G : nc;
+    uint32_t bail = 0;
+    JB_SYNC();
+    JB_LANES(l) {
+      const int ci = c0 + l / S, q = l % S;
+      uint32_t fail = 0, cnt = 0;
+      if (ci < c1) {
+        const Cand cd = s.cand[ci];
+        const int len = cand_len(s, cd, n);
+        if (q < check_samples(len, k, step)) {
+          Key key;
+          if (cand_key_packed(s, cd, n, len, check_sample_at(q, len, k, step), k, &key)) {
+            cnt = db.count(key_canonical(key, k));
+            fail = (int64_t)cnt < thr ? 1u : 0u;
+          } else fail = 2u;
+        }
+      }
+      s.flag[l] = fail; s.pr[l] = cnt;
+    }
+    JB_SYNC();
+    int winner = -1;
+    for (int ci = c0; ci < c1; ++ci) {
+      uint32_t f = 0;
+      for (int q = 0; q < S; ++q) f |= s.flag[(ci - c0) * S + q];
+      bail |= f & 2u;
+      if (!f && winner < 0) winner = ci;
+    }
+    if (bail) return -2;
+    for (int ci = c0; ci < c1; ++ci) *lookups += (unsigned long long)check_samples(cand_len(s, s.cand[ci], n), k, step);
+    if (winner >= 0) {
+      const uint32_t w0 = s.pr[(winner - c0) * S], w1 = s.pr[(winner - c0) * S + 1];
+      JB_SYNC();
+      JB_LANES(l) { if (l == 0) { s.win[0] = w0; s.win[1] = w1; } }
+      JB_SYNC();
+      return winner;
     }
   }
   return -1;

@@ -27,8 +27,8 @@ JB_HD bool key_eq(const Key& a, const Key& b) { return a.lo == b.lo && a.hi == b
 
 // A,a=0 C,c=1 G,g=2 T,t=3; everything else (N, IUPAC, NUL, '\n', '-') is invalid.
 JB_HD bool base_valid(uint8_t c) {
-  uint8_t u = c & 0xDF;
-  return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+  const uint32_t x = (uint32_t)(c & 0xDF) - 0x41u;       // 'A' -> 0, 'C' -> 2, 'G' -> 6, 'T' -> 19
+  return x < 20u && ((0x80045u >> x) & 1u) != 0u;
 }
 JB_HD uint32_t base_code(uint8_t c) { return ((c >> 1) ^ (c >> 2)) & 3u; }
 

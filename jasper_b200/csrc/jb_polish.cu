@@ -24,9 +24,15 @@ namespace jb {
 
 
 
+// One copy of hash + probe in the walker's image: the walker is bound by instruction fetch (ncu: stall_no_instruction
+// > 50 % with the hot loop spread over ~160 KB of SASS), so every call site branches here instead of inlining it.
+__device__ __noinline__ uint32_t probe_count(const TableView* t, uint64_t lo, uint64_t hi) {
+  const Key key = {lo, hi};
+  return table_count(*t, key);
+}
 struct DevDB {
   TableView t;
-  __device__ __forceinline__ uint32_t count(const Key& canonical) const { return table_count(t, canonical); }
+  __device__ __forceinline__ uint32_t count(const Key& canonical) const { return probe_count(&t, canonical.lo, canonical.hi); }
 };
 
 constexpr int kWalkWarps = 4;               // walkers per CTA
@@ -374,10 +380,11 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   UnitIO u;                                        // (result fields are written by the walker)
   const size_t i = p.unit;
   const Workspace& w = *b->ws;
-  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0;
+  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0; u.n_fast = 0; u.n_post = 0;
   u.in = in + b->off[i]; u.in_len = b->len[i];
   u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
   u.cnt = w.counts[cidx].p + b->off[i];
+  u.okb = w.okb[cidx].p + b->off[i];
   u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
@@ -467,7 +474,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   JB_CUDA(cudaEventCreate(&ev_a)); JB_CUDA(cudaEventCreate(&ev_b)); JB_CUDA(cudaEventCreate(&ev_c)); JB_CUDA(cudaEventCreate(&ev_d));
   double scan_ms = 0, walk_ms = 0, plan_ms = 0, kwalk_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
-  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0;
+  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0, n_fast = 0, n_post = 0;
   int64_t slow_cycles[3] = {0, 0, 0}, slow_events[3] = {0, 0, 0}, slow_lookups[3] = {0, 0, 0}, slow_span[3] = {0, 0, 0}, sum_cycles[3] = {0, 0, 0};
   std::vector<ScanUnit> sunits(n);
   std::vector<SegUnit> gunits(n);
@@ -643,7 +650,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       segs.assign(hs, hs + n_first);
     }
     for (const UnitIO& u : segs) {
-      b->passes[ite].wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events;
+      b->passes[ite].wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events; n_fast += u.n_fast; n_post += u.n_post;
       max_seg_events = std::max<int64_t>(max_seg_events, (int64_t)u.events);
       max_seg_lookups = std::max<int64_t>(max_seg_lookups, (int64_t)u.lookups);
       max_seg_span = std::max<int64_t>(max_seg_span, u.end_old - u.base);
@@ -755,7 +762,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     note_counter(("slow_lookups" + sfx).c_str(), slow_lookups[q]); note_counter(("slow_span" + sfx).c_str(), slow_span[q]);
     note_counter(("sum_cycles" + sfx).c_str(), sum_cycles[q]);
   }
-  note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
+  note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
   while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});

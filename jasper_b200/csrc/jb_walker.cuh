@@ -91,6 +91,7 @@ struct BridgeScratch {       // global memory, one per resident walker
   uint32_t patch_cap;
 };
 
+enum PostKind : int { kPostNone = 0, kPostSub = 1, kPostDel = 2, kPostIns = 3 };
 constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
 constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
 JB_HD int default_keep_margin(int k) { return 2 * k + 32; }
@@ -107,6 +108,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   uint8_t* out;              // staging: out[r] = new base r of this segment, valid inside materialised windows
   int64_t out_cap;
   const uint32_t* cnt;       // C(window) for every position of the pass-start contig, [0, in_len]; may be null
+  const uint8_t* okb;        // 1 = the pass-start window at that position is k chars of ACGTacgt; may be null
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
   uint64_t ev_bit_base;      // flat bit index of contig position 0
@@ -124,10 +126,28 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   int64_t wrong;
   int32_t status;
   uint32_t n_rows;
+  uint32_t n_fast;             // events delimited from the bulk scan's counts (fast_delimit)
+  uint32_t n_post;             // ... whose following scan step was taken from data in hand
   unsigned long long lookups;
   unsigned long long events;
   unsigned long long cycles;   // device clock ticks this segment took (profiling aid)
 };
+
+// append one copy job (out of line: four call sites in the walker)
+JB_FREE_NOINLINE bool push_job(JobSink jobs, uint32_t seg_slot, const uint8_t* src, int64_t rel, int64_t len) {
+  JB_SYNC();
+  unsigned long long slot = 0;
+#if defined(__CUDA_ARCH__)
+  if ((threadIdx.x & 31) == 0) slot = atomicAdd(jobs.used, 1ull);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+#else
+  slot = (*jobs.used)++;
+#endif
+  if (slot >= jobs.cap) return false;
+  JB_LANES(l) { if (l == 0) { CopyJob j; j.src = src; j.rel = rel; j.len = len; j.slot = seg_slot; j.pad = 0; jobs.jobs[slot] = j; } }
+  JB_SYNC();
+  return true;
+}
 
 template <class DB>
 struct Walker {
@@ -158,6 +178,8 @@ struct Walker {
   uint32_t vflags = 0;                 // kFlagSeam / kFlagFar raised by reads (lane-local until the end of run)
   uint32_t seqno = 0;
   unsigned long long lookups = 0, events = 0;
+  uint32_t n_fast = 0, n_post = 0;
+  int64_t fast_W0 = 0;                 // new coordinate of s.fc[0] (fast_delimit)
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
                BridgePool pool_, RowSink sink_, JobSink jobs_)
@@ -274,19 +296,9 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- edits
-  JB_WN bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
+  JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
     if (len <= 0) return true;
-    JB_SYNC();
-    unsigned long long slot = 0;
-#if defined(__CUDA_ARCH__)
-    if ((threadIdx.x & 31) == 0) slot = atomicAdd(jobs.used, 1ull);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-#else
-    slot = (*jobs.used)++;
-#endif
-    if (slot >= jobs.cap) { status = JB_E_SCRATCH; return false; }
-    JB_LANES(l) { if (l == 0) { CopyJob j; j.src = src; j.rel = rel; j.len = len; j.slot = u.slot; j.pad = 0; jobs.jobs[slot] = j; } }
-    JB_SYNC();
+    if (!push_job(jobs, u.slot, src, rel, len)) { status = JB_E_SCRATCH; return false; }
     return true;
   }
 
@@ -421,6 +433,7 @@ struct Walker {
     int64_t coord = 0;
     int fb_len = 0, orig_len = 0;
     uint8_t tag = 0;                                  // 0: no plain row (bridged patches log their own)
+    int post = 0;                                     // PostKind: a single-base fix scored by first_passing_lean (s.win holds its counts)
   };
   JB_W void fix_row(Fix& f, int64_t coord, uint8_t fb, int fb_len, uint8_t tag, uint8_t orig, int orig_len) {
     fill(s.fx, fb, fb_len);
@@ -438,12 +451,15 @@ struct Walker {
     pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) if ((uint8_t)order[o] != bad) set_cand(nc++, kSub, (uint8_t)order[o], 0, k - 1, 0);
     set_cand(nc++, kDel, 0, 0, k - 1, 1);
-    const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
+    JB_SYNC();
+    int w = packed_clean(s.pt, 0, n) ? first_passing_lean(db, s, nc, n, k, step, thr, &lookups) : -2;
+    const bool lean = w != -2;
+    if (!lean) w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
     if (w < 0) return f;
     const Cand c = s.cand[w];
     f.found = true; f.a = s0 + k - 1; f.e = s0 + k; f.repl = s.b;
-    if (c.kind == kSub) { fill(s.b, c.base, 1); f.rlen = 1; fix_row(f, ga - 1, c.base, 1, 's', before, 1); }
-    else { f.rlen = 0; fix_row(f, ga - 1, '-', 1, 'i', before, 1); }
+    if (c.kind == kSub) { fill(s.b, c.base, 1); f.rlen = 1; fix_row(f, ga - 1, c.base, 1, 's', before, 1); f.post = lean ? kPostSub : kPostNone; }
+    else { f.rlen = 0; fix_row(f, ga - 1, '-', 1, 'i', before, 1); f.post = lean ? kPostDel : kPostNone; }
     return f;
   }
 
@@ -453,12 +469,16 @@ struct Walker {
     const char order[4] = {'A', 'T', 'C', 'G'};
     pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 1, 1);
-    const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
+    JB_SYNC();
+    int w = packed_clean(s.pt, 0, n) ? first_passing_lean(db, s, 4, n, k, step, thr, &lookups) : -2;
+    const bool lean = w != -2;
+    if (!lean) w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
     if (w < 0) return f;
     const uint8_t bb = s.cand[w].base;
     fill(s.b, bb, 1);
     f.found = true; f.a = s0 + k - 1; f.e = s0 + k - 1; f.repl = s.b; f.rlen = 1;
     fix_row(f, ga, bb, 1, 'd', '-', 1);
+    f.post = lean ? kPostIns : kPostNone;
     return f;
   }
 
@@ -741,7 +761,8 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- fixing_sid
-  JB_W void fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
+  // returns the PostKind of an applied single-base fix (kPostNone otherwise)
+  JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
     Fix f;
     if (nbad == k) {
@@ -760,10 +781,15 @@ struct Walker {
     } else if (nbad > k) {
       f = fix_bridge(n64, thr, gb, ga);
     }
+    int post = kPostNone;
     if (f.found && !status) {
-      if (apply_edit(f.a, f.e, f.repl, f.rlen) && f.tag) emit_row(f.coord, s.fx, f.fb_len, f.tag, s.fx + 64, f.orig_len);
+      if (apply_edit(f.a, f.e, f.repl, f.rlen)) {
+        post = f.post;
+        if (f.tag) emit_row(f.coord, s.fx, f.fb_len, f.tag, s.fx + 64, f.orig_len);
+      }
     }
     release_bridge();
+    return status ? kPostNone : post;
   }
 
   // src/jasper.py:295-329: bridge a long weak stretch with a de-Bruijn walk; the patch stays in the borrowed
@@ -808,48 +834,126 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- handle_bad_kmers
+  // ---------------------------------------------------------------------------- fast path (untouched territory)
+  // While the walker stands in bases no edit has touched, every count the reference's run delimiting reads
+  // (src/jasper.py:150-214) is in the bulk scan's arrays.  fast_delimit stages a window of them around i and
+  // evaluates the same loops on it: no window cache, no point queries, no probes.  It either produces exactly
+  // what the generic code below would (same i, gb, ga, s0) or returns false with the walker's state untouched.
+  JB_W bool fast_delimit(int64_t& gb, int64_t& ga, int64_t& s0) {
+    if (!u.cnt || !u.okb) return false;
+    const int64_t shift = base + olen - ipos;           // new = old + shift for everything >= clean_from
+    const int W = kFastBack + 2 * k + 24;
+    const int64_t W0 = i - kFastBack;
+    int64_t lo_x = clean_from > shift ? clean_from : shift;
+    if (base - seam_margin > lo_x) lo_x = base - seam_margin;      // (further back the previous segment's walker may have edited)
+    const int64_t hi_p = u.in_len - 2 * (int64_t)k - 3;            // keeps every end-of-contig clamp of the generic code out of play
+    JB_SYNC();
+    JB_LANES(l) { if (l == 0) { s.fbad[0] = -1; s.fbad[1] = W; } }
+    JB_SYNC();
+    JB_LANES(l) {
+      for (int q = l; q < W; q += 32) {
+        const int64_t x = W0 + q, p = x - shift;
+        bool ok = x >= lo_x && p <= hi_p;
+        if (ok) ok = u.okb[p] != 0;
+        s.fc[q] = ok ? u.cnt[p] : 0u;
+        if (!ok) {
+#if defined(__CUDA_ARCH__)
+          if (q < kFastBack) atomicMax(&s.fbad[0], q); else atomicMin(&s.fbad[1], q);
+#else
+          if (q < kFastBack) { if (q > s.fbad[0]) s.fbad[0] = q; } else if (q < s.fbad[1]) s.fbad[1] = q;
+#endif
+        }
+      }
+    }
+    JB_SYNC();
+    const int blo = s.fbad[0];                          // entries (blo, bhi) are all available
+    int hi_lim = s.fbad[1] - k - 3;
+    if (W - k - 4 < hi_lim) hi_lim = W - k - 4;
+    const int a = kFastBack;
+    if (a >= hi_lim || (int64_t)s.fc[a] >= solid) return false;
+    int jq = a - 1;
+    while (jq > blo && (int64_t)s.fc[jq] < solid) --jq;
+    if (jq <= blo) return false;
+    int gq = a;
+    while (gq < hi_lim && (int64_t)s.fc[gq] < solid) ++gq;
+    if (gq >= hi_lim) return false;
+    uint64_t prev = s.fc[jq];
+    int g = jq;                                         // g = gb - k + 1
+    if (!(2 * (int64_t)s.fc[g + 1] < solid && 2 * (int64_t)s.fc[g + 2] < solid)) {
+      while (2 * (uint64_t)s.fc[g + 1] >= prev && g < gq) {
+        if (2 * (int64_t)prev >= solid && 2 * (int64_t)s.fc[g + 1] < solid && 2 * (int64_t)s.fc[g + 2] < solid) break;
+        prev = s.fc[g + 1];
+        ++g;
+      }
+    }
+    const int s0q = g + 1;
+    int gaq = gq;
+    if ((int64_t)s.fc[s0q + 1] < solid && (int64_t)s.fc[s0q + k - 2] < solid && (int64_t)s.fc[s0q + k - 1] < solid &&
+        (int64_t)s.fc[s0q + k] >= solid) gaq = s0q + k;
+    i = W0 + gq;
+    gb = W0 + g + k - 1; ga = W0 + gaq; s0 = W0 + s0q;
+    fast_W0 = W0;
+    ++n_fast;
+    return true;
+  }
+
+  // ---------------------------------------------------------------------------- handle_bad_kmers
   JB_WN void handle_bad_kmers(int64_t rolling_thre) {
     ++events;
     const int64_t thre = rolling_thre > 0 ? rolling_thre : solid;
-    int64_t j = i - 1;
-    uint32_t occ = Cw(j, -1);
-    while ((int64_t)occ < thre && j >= 0) { --j; occ = Cw(j, -1); }
-    int64_t gb = j + k - 1;
-    uint64_t prev = occ;
-    uint32_t cur = Cw(i, +1);
-    if (j == -1) gb = -1;
-    if (rolling_thre == 0) {
-      while ((int64_t)cur < thre && i < L - k + 1) { ++i; cur = Cw(i, +1); }
-    } else {
-      while ((int64_t)cur < thre && i < L - k + 1) {
-        if (i - j > k) { i = i + 1; return; }
-        ++i; cur = Cw(i, +1);
+    int64_t gb = 0, ga = 0, s0 = 0;
+    const bool fast = rolling_thre == 0 && fast_delimit(gb, ga, s0);
+    if (!fast) {
+      int64_t j = i - 1;
+      uint32_t occ = Cw(j, -1);
+      while ((int64_t)occ < thre && j >= 0) { --j; occ = Cw(j, -1); }
+      gb = j + k - 1;
+      uint64_t prev = occ;
+      uint32_t cur = Cw(i, +1);
+      if (j == -1) gb = -1;
+      if (rolling_thre == 0) {
+        while ((int64_t)cur < thre && i < L - k + 1) { ++i; cur = Cw(i, +1); }
+      } else {
+        while ((int64_t)cur < thre && i < L - k + 1) {
+          if (i - j > k) { i = i + 1; return; }
+          ++i; cur = Cw(i, +1);
+        }
       }
-    }
-    int64_t ga = i;
-    if (2 * (int64_t)Cw(gb - k + 2, +1) < solid && 2 * (int64_t)Cw(gb - k + 3, +1) < solid) {
-      // "too low" -- flag only
-    } else if (rolling_thre == 0) {
-      while (2 * (uint64_t)Cw(gb - k + 2, +1) >= prev && gb - k + 1 < ga) {
-        if (gb == -1) break;
-        if (2 * (int64_t)prev >= thre && 2 * (int64_t)Cw(gb - k + 2, +1) < thre && 2 * (int64_t)Cw(gb - k + 3, +1) < thre) break;
-        prev = Cw(gb - k + 2, +1);
-        ++gb;
+      ga = i;
+      if (2 * (int64_t)Cw(gb - k + 2, +1) < solid && 2 * (int64_t)Cw(gb - k + 3, +1) < solid) {
+        // "too low" -- flag only
+      } else if (rolling_thre == 0) {
+        while (2 * (uint64_t)Cw(gb - k + 2, +1) >= prev && gb - k + 1 < ga) {
+          if (gb == -1) break;
+          if (2 * (int64_t)prev >= thre && 2 * (int64_t)Cw(gb - k + 2, +1) < thre && 2 * (int64_t)Cw(gb - k + 3, +1) < thre) break;
+          prev = Cw(gb - k + 2, +1);
+          ++gb;
+        }
+        if (gb >= L - 1) { brk = true; return; }
       }
-      if (gb >= L - 1) { brk = true; return; }
+      s0 = gb - k + 2 > 0 ? gb - k + 2 : 0;
+      if (s0 + k + k >= L) { i = s0 + k + k; brk = true; return; }
+      s.px[0] = s0 + 1; s.px[1] = s0 + k - 2; s.px[2] = s0 + k - 1; s.px[3] = s0 + k;
+      JB_SYNC();
+      Cpts(4);
+      if ((int64_t)s.pr[0] < thre && (int64_t)s.pr[1] < thre && (int64_t)s.pr[2] < thre && (int64_t)s.pr[3] >= thre) ga = s0 + k;
     }
-    const int64_t s0 = gb - k + 2 > 0 ? gb - k + 2 : 0;
-    if (s0 + k + k >= L) { i = s0 + k + k; brk = true; return; }
-    s.px[0] = s0 + 1; s.px[1] = s0 + k - 2; s.px[2] = s0 + k - 1; s.px[3] = s0 + k;
-    JB_SYNC();
-    Cpts(4);
-    if ((int64_t)s.pr[0] < thre && (int64_t)s.pr[1] < thre && (int64_t)s.pr[2] < thre && (int64_t)s.pr[3] >= thre) ga = s0 + k;
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
     wrong += nbad;
-    if (fix) {
-      if (gb < 0) return;
-      fixing_sid(s0, nbad, thre, gb, ga);
-    }
+    if (!fix || gb < 0) return;
+    const int done = fixing_sid(s0, nbad, thre, gb, ga);
+    if (!fast || !done || status || brk) return;
+    // ---- the scan step that follows a single-base fix (src/jasper.py:56-100 at the new i), from data in hand: the window at
+    // i is untouched (staged count) or a sample of the winning trial; so is the one k bases back.  Anything but the plain
+    // `i += k-1` outcome is left to the loop.
+    int64_t occ, prevk;
+    const int64_t s0q = s0 - fast_W0;
+    if (done == kPostSub && i == s0 + k) { occ = s.fc[s0q + k]; prevk = s.win[0]; }
+    else if (done == kPostDel && i == s0 + k) { occ = s.fc[s0q + k + 1]; prevk = s.win[0]; }
+    else if (done == kPostIns && i == s0 + k - 1) { occ = s.win[1]; prevk = s.fc[s0q - 1]; }
+    else return;
+    if (u.next_anchor >= 0 && i - (L - u.in_len) >= u.next_anchor) return;       // the loop re-checks the seam first
+    if (occ >= solid && !((uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) { i += k - 1; ++n_post; }
   }
 
   // ---------------------------------------------------------------------------- scan loop
@@ -930,29 +1034,40 @@ struct Walker {
       if (!(i < L - k + 1)) break;
       if (u.next_anchor >= 0 && i - (L - u.in_len) >= u.next_anchor) continue;   // re-check the seam first
       // ---- the reference's loop body at position i (src/jasper.py:56-100)
-      int n = load(s.t, i, i + k);                      // n == k here
-      int firstN = -1, firstn = -1, bad = 0;
-      for (int q = 0; q < n; ++q) {
-        uint8_t c = s.t[q];
-        if (c == 'N' && firstN < 0) firstN = q;
-        if (c == 'n' && firstn < 0) firstn = q;
-        if (!base_valid(c)) bad = 1;
+      int64_t occ = 0, prevk = 0;
+      bool direct = false;
+      if (u.okb && u.cnt && i - k >= clean_from && i - k >= base - seam_margin) {
+        // untouched territory: validity and both counts come straight from the bulk scan
+        const int64_t p = i - (base + olen - ipos);
+        if (p >= k && p + k <= u.in_len && u.okb[p]) { occ = u.cnt[p]; prevk = u.cnt[p - k]; direct = true; }
       }
-      if (firstN >= 0) {
-        i += firstN + 1;
-        // a run of N: every following window starts with 'N' and advances by one; jump the run
-        while (i < L - k + 1 && get(i) == 'N') ++i;
-        continue;
+      if (!direct) {
+        int n = load(s.t, i, i + k);                      // n == k here
+        int firstN = -1, firstn = -1, bad = 0;
+        for (int q = 0; q < n; ++q) {
+          uint8_t c = s.t[q];
+          if (c == 'N' && firstN < 0) firstN = q;
+          if (c == 'n' && firstn < 0) firstn = q;
+          if (!base_valid(c)) bad = 1;
+        }
+        if (firstN >= 0) {
+          i += firstN + 1;
+          // a run of N: every following window starts with 'N' and advances by one; jump the run
+          while (i < L - k + 1 && get(i) == 'N') ++i;
+          continue;
+        }
+        if (firstn >= 0) { i += firstn + 1; continue; }
+        if (bad) { i += 1; continue; }
+        s.px[0] = i; s.px[1] = i - k > 0 ? i - k : 0;
+        JB_SYNC();
+        Cpts(i > 0 ? 2 : 1);
+        occ = s.pr[0];
+        prevk = i > 0 ? (int64_t)s.pr[1] : 0;
       }
-      if (firstn >= 0) { i += firstn + 1; continue; }
-      if (bad) { i += 1; continue; }
-      s.px[0] = i; s.px[1] = i - k > 0 ? i - k : 0;
-      JB_SYNC();
-      Cpts(i > 0 ? 2 : 1);
-      const int64_t occ = s.pr[0];
+      int64_t handle = -1;                              // >= 0: handle_bad_kmers(handle) -- one call site keeps the image small
       if (occ < solid) {
-        handle_bad_kmers(0);
-      } else if (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)s.pr[1]) {
+        handle = 0;
+      } else if (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk) {
         int64_t ind = i - k > 0 ? i - k : 0;
         int num = 0;
         while (ind < i) { ind += step; s.px[num] = ind; ++num; }
@@ -962,11 +1077,10 @@ struct Walker {
         for (int q = 0; q < num; ++q) sum += s.pr[q];
         const double mean = (double)sum / (double)num;
         const int64_t rt = (int64_t)rint(mean / (double)JB_DIVISOR);
-        if (occ < rt) handle_bad_kmers((int64_t)rint(mean / 2.0));
-        else i += k - 1;
-      } else {
-        i += k - 1;
+        if (occ < rt) handle = (int64_t)rint(mean / 2.0);
       }
+      if (handle >= 0) handle_bad_kmers(handle);
+      else i += k - 1;
     }
     seam_bad = seam_bad || (vflags & kFlagSeam); far_back = far_back || (vflags & kFlagFar);
 #if defined(__CUDA_ARCH__)
@@ -988,6 +1102,7 @@ struct Walker {
     u.wrong = wrong;
     u.status = status;
     u.n_rows = seqno;
+    u.n_fast = n_fast; u.n_post = n_post;
     u.lookups = lookups + s.probes;
     u.events = events;
 #if defined(__CUDA_ARCH__)

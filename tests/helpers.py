@@ -121,6 +121,9 @@ def hostsim_lib():
     sim.hostsim_segments.argtypes = [C.c_void_p]
     sim.hostsim_reruns.restype = C.c_ulonglong
     sim.hostsim_reruns.argtypes = [C.c_void_p]
+    for fn in (sim.hostsim_events, sim.hostsim_fast, sim.hostsim_post):
+        fn.restype = C.c_ulonglong
+        fn.argtypes = [C.c_void_p]
     sim.hostsim_packed_selfcheck.restype = C.c_longlong
     sim.hostsim_packed_selfcheck.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_longlong)]
     sim.hostsim_mer.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -154,6 +157,9 @@ def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=No
         if stats is not None:
             stats["segments"] = sim.hostsim_segments(r)
             stats["reruns"] = sim.hostsim_reruns(r)
+            stats["events"] = sim.hostsim_events(r)
+            stats["fast"] = sim.hostsim_fast(r)
+            stats["post"] = sim.hostsim_post(r)
         return st, txt, out, tallies
     finally:
         sim.hostsim_free(r)

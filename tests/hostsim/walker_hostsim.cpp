@@ -26,16 +26,17 @@ struct SimResult {
   std::vector<PassOut> passes;
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
-  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0;
+  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0;
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
 static void scan_bits(const HostDB& db, const std::string& seq, int k, uint32_t solid, std::vector<uint32_t>* ev, std::vector<uint32_t>* weak,
-                      std::vector<uint32_t>* cnt_out) {
+                      std::vector<uint32_t>* cnt_out, std::vector<uint8_t>* ok_out) {
   const int64_t L = (int64_t)seq.size();
   std::vector<uint32_t>& cnt = *cnt_out;
   cnt.assign(L + 1, 0);
-  std::vector<uint8_t> ok(L + 1);
+  std::vector<uint8_t>& ok = *ok_out;
+  ok.assign(L + 1, 0);
   Key mask = key_mask(k);
   for (int64_t p = 0; p <= L; ++p) {
     Key m = key_from_chars((const uint8_t*)seq.data() + p, L - p, k, mask);
@@ -88,13 +89,13 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
     JobSink jobs{jobv.data(), jobv.size(), &jobs_used};
     std::vector<int64_t> len(n);
     std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n), cnts(n);
-    std::vector<std::vector<uint8_t>> stage(n);
+    std::vector<std::vector<uint8_t>> stage(n), okbs(n);
     for (size_t i = 0; i < n; ++i) {
       len[i] = (int64_t)cur[i].size();
       po.total += len[i] - k + 1;
       stage[i].resize((size_t)caps[i] + 64);
       if (!use_events) continue;
-      scan_bits(db, cur[i], k, solid, &ev[i], &weak[i], &cnts[i]);
+      scan_bits(db, cur[i], k, solid, &ev[i], &weak[i], &cnts[i], &okbs[i]);
       // level-1 summary over this contig's own bit positions (ev_bit_base = 0)
       l1[i].assign((size_t)(len[i] + 1) / 32768 + 2, 0);
       for (int64_t p = 0; p <= len[i]; ++p)
@@ -116,6 +117,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
       u.out = stage[i].data() + p.stage_off; u.out_cap = p.stage_cap;
       u.cnt = use_events ? cnts[i].data() : nullptr;
+      u.okb = (use_events && !getenv("JB_SIM_NO_OKB")) ? okbs[i].data() : nullptr;
       u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
       u.slot = slot; u.materialize_all = gen ? 1u : 0u;
@@ -154,7 +156,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       }
       segs.swap(merged);
     }
-    for (const UnitIO& u : segs) { po.wrong += u.wrong; res->lookups += u.lookups; res->events += u.events; }
+    for (const UnitIO& u : segs) { po.wrong += u.wrong; res->lookups += u.lookups; res->events += u.events; res->fast += u.n_fast; res->post += u.n_post; }
     if (do_fix) {
       std::vector<int64_t> new_lens(len);
       std::vector<SegPlace> place = place_segments(segs, &new_lens);
@@ -221,6 +223,9 @@ extern "C" int hostsim_iterations(const SimResult* r) { return (int)r->passes.si
 extern "C" void hostsim_tally(const SimResult* r, int ite, long long* wrong, long long* total) { *wrong = r->passes[ite].wrong; *total = r->passes[ite].total; }
 extern "C" const char* hostsim_seq(const SimResult* r, int i, uint64_t* len) { *len = r->seqs[i].size(); return r->seqs[i].data(); }
 extern "C" unsigned long long hostsim_lookups(const SimResult* r) { return r->lookups; }
+extern "C" unsigned long long hostsim_events(const SimResult* r) { return r->events; }
+extern "C" unsigned long long hostsim_fast(const SimResult* r) { return r->fast; }
+extern "C" unsigned long long hostsim_post(const SimResult* r) { return r->post; }
 extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->segments; }
 extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
 extern "C" unsigned long long hostsim_far_backs(const SimResult* r) { return r->far_backs; }

@@ -201,3 +201,27 @@ def test_packed_keys_equal_the_byte_loop(hostsim_lib, k):
     bad = hostsim_lib.hostsim_packed_selfcheck(1234 + k, k, C.byref(fast))
     assert bad == 0
     assert fast.value > 5000
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_fast_path_is_taken_and_changes_nothing(golden_cases, hostsim_lib, name, monkeypatch):
+    """Events in untouched territory are delimited from the bulk scan's counts (fast_delimit), single-base fixes are
+    scored by first_passing_lean and the scan step behind them is taken from data in hand; with the validity bytes
+    withheld the walker runs its generic code for everything.  Both must give the same bytes, and the fast path must
+    really carry most events."""
+    case = golden_cases[name]
+    odb = helpers.OracleDB(case["db"])
+    seqs = jo.read_fasta(case["fasta"])
+    for use_events in (1, 300):
+        st_fast, st_slow = {}, {}
+        monkeypatch.delenv("JB_SIM_NO_OKB", raising=False)
+        fast = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events, stats=st_fast)
+        monkeypatch.setenv("JB_SIM_NO_OKB", "1")
+        slow = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events, stats=st_slow)
+        monkeypatch.delenv("JB_SIM_NO_OKB", raising=False)
+        assert fast == slow
+        assert st_slow["fast"] == 0 and st_slow["events"] == st_fast["events"]
+        print(name, use_events, st_fast)
+        if name != "k31_dirty":
+            assert st_fast["fast"] * 2 > st_fast["events"], st_fast
+            assert st_fast["post"] * 4 > st_fast["events"], st_fast
