@@ -119,7 +119,7 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
   uint32_t fc[kFastWin];     // fast_delimit: bulk-scan counts of the windows around an event (jb_walker.cuh)
   int32_t fbad[2];           // fast_delimit: last unavailable entry before / first one behind the event
-  uint32_t win[2];           // first_passing_lean: counts of the winner's samples 0 (m = 0) and 1 (m = len - k)
+  uint32_t win[2];           // score_single_base: counts of the winner's samples 0 (m = 0) and 1 (m = len - k)
   SeqView view;              // published copy of the walker's sequence state
   Packed pt;                 // packed to_be_fixed (or, for kDip, the whole check string before + t + after)
   Packed pc;                 // packed staging buffer (window refills, point queries, bridging checks)
@@ -136,6 +136,7 @@ JB_FREE_NOINLINE void pack_bytes(Packed& p, const uint8_t* buf, int len) {
   JB_SYNC();
 #if defined(__CUDA_ARCH__)
   const int l = threadIdx.x & 31;
+#pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     const int q = 32 * c + l;
     const uint8_t ch = q < len ? buf[q] : (uint8_t)0;
@@ -313,53 +314,70 @@ JB_FREE_NOINLINE int first_passing(const DB& db, WarpScratch& s, int nc, int n, 
   return -1;
 }
 
-// first_passing for single-base candidates over a to_be_fixed string WITHOUT invalid bytes (the common case: every
-// isolated substitution / indel).  Same answer as first_passing -- the first candidate in enumeration order whose
-// check_sequence samples are all solid -- with a fixed layout: every candidate owns a slot of S lanes, a wave holds
-// 32 / S candidates, a lane cuts its window from the packed string with shifts.  Returns -2 when the layout does not
-// apply (the caller then uses first_passing).  s.win = counts of the winner's samples 0 and 1.
+// Single-base candidates of an isolated error, scored from the packed to_be_fixed string s.pt (n valid bases, the suspect
+// base at k-1), in the reference's enumeration order:
+//   ins == 0 (src/jasper.py:392-419): substitutions at k-1 by 'A','C','T','G' except the base that stands there
+//                                     (skip_code), then the deletion of k-1;
+//   ins == 1 (src/jasper.py:422-431): one base 'A','T','C','G' inserted in front of k-1.
+// Every candidate owns S lanes (one per check_sequence sample, src/jasper.py:585-599), a wave holds 32 / S candidates,
+// a lane builds its window as  t[m : k-1] ++ (the new base) ++ t[cstart : ...]  with shifts.  Returns the first
+// candidate whose samples are all solid (0..3), -1 for none, -2 if the layout does not apply (nothing was probed).
+// s.win = counts of the winner's samples 0 (window at 0) and 1 (window at len - k).  Compact on purpose: this and the
+// probe are the walker's hot loop, which has to stay inside the SM's instruction cache (tools/icache_probe.cu).
 template <class DB>
-JB_FREE_NOINLINE int first_passing_lean(const DB& db, WarpScratch& s, int nc, int n, int k, int step, int64_t thr, unsigned long long* lookups) {
-  int S = 0;
-  for (int c = 0; c < nc; ++c) { const int ns = check_samples(cand_len(s, s.cand[c], n), k, step); S = ns > S ? ns : S; }
-  if (S > 16 || S < 2) return -2;
-  const int G = 32 / S;
-  for (int c0 = 0; c0 < nc; c0 += G) {
-    const int c1 = c0 + G < nc ? c0 + G : nc;
-    uint32_t bail = 0;
+JB_FREE_NOINLINE int score_single_base(const DB& db, WarpScratch& s, int ins, uint32_t skip_code, int n, int k, int step, int64_t thr) {
+  const int P = k - 1;
+  const int len0 = ins ? n + 1 : n;                                  // trial length of candidates 0..2 (and of 3 when ins)
+  const int ns0 = check_samples(len0, k, step);
+  const int ns3 = ins ? ns0 : check_samples(n - 1, k, step);
+  const int S = ns0 > ns3 ? ns0 : ns3;
+  if (S > 16 || n - 1 < k) return -2;
+  int G = 1;
+  while ((G + 1) * S <= 32 && G < 4) ++G;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int c0 = 0; c0 < 4; c0 += G) {
     JB_SYNC();
     JB_LANES(l) {
-      const int ci = c0 + l / S, q = l % S;
+      int ci = c0, q = l;
+      while (q >= S && ci < c0 + G - 1) { q -= S; ++ci; }
+      const bool del = !ins && ci == 3;
+      const int len = del ? n - 1 : len0;
       uint32_t fail = 0, cnt = 0;
-      if (ci < c1) {
-        const Cand cd = s.cand[ci];
-        const int len = cand_len(s, cd, n);
-        if (q < check_samples(len, k, step)) {
-          Key key;
-          if (cand_key_packed(s, cd, n, len, check_sample_at(q, len, k, step), k, &key)) {
-            cnt = db.count(key_canonical(key, k));
-            fail = (int64_t)cnt < thr ? 1u : 0u;
-          } else fail = 2u;
-        }
+      if (ci < 4 && q < (ci == 3 ? ns3 : ns0)) {
+        uint32_t code;                                               // the new base
+        if (ins) code = ci == 0 ? 0u : (ci == 1 ? 3u : (ci == 2 ? 1u : 2u));          // 'A','T','C','G'
+        else { const uint32_t o0 = ci + (ci >= (skip_code == 0u ? 0 : (skip_code == 1u ? 1 : (skip_code == 3u ? 2 : 3))) ? 1u : 0u);
+               code = o0 == 0 ? 0u : (o0 == 1 ? 1u : (o0 == 2 ? 3u : 2u)); }         // 'A','C','T','G' without skip_code
+        const int m = check_sample_at(q, len, k, step);
+        const int lenA = P - m, mid = del ? 0 : 1, cstart = ins ? P : P + 1, lenC = k - lenA - mid;
+        Key key = packed_window(s.pt, m, lenA);
+        if (mid) { const Key b = {code, 0}; key = key_append(key, b, 1); }
+        key = key_append(key, packed_window(s.pt, cstart, lenC), lenC);
+        cnt = db.count(key_canonical(key, k));
+        fail = (int64_t)cnt < thr ? 1u : 0u;
       }
       s.flag[l] = fail; s.pr[l] = cnt;
     }
     JB_SYNC();
-    int winner = -1;
+    const int c1 = c0 + G < 4 ? c0 + G : 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int ci = c0; ci < c1; ++ci) {
       uint32_t f = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
       for (int q = 0; q < S; ++q) f |= s.flag[(ci - c0) * S + q];
-      bail |= f & 2u;
-      if (!f && winner < 0) winner = ci;
-    }
-    if (bail) return -2;
-    for (int ci = c0; ci < c1; ++ci) *lookups += (unsigned long long)check_samples(cand_len(s, s.cand[ci], n), k, step);
-    if (winner >= 0) {
-      const uint32_t w0 = s.pr[(winner - c0) * S], w1 = s.pr[(winner - c0) * S + 1];
-      JB_SYNC();
-      JB_LANES(l) { if (l == 0) { s.win[0] = w0; s.win[1] = w1; } }
-      JB_SYNC();
-      return winner;
+      if (!f) {
+        const uint32_t w0 = s.pr[(ci - c0) * S], w1 = s.pr[(ci - c0) * S + 1];
+        JB_SYNC();
+        JB_LANES(l) { if (l == 0) { s.win[0] = w0; s.win[1] = w1; } }
+        JB_SYNC();
+        return ci;
+      }
     }
   }
   return -1;

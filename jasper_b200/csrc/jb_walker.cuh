@@ -433,7 +433,7 @@ struct Walker {
     int64_t coord = 0;
     int fb_len = 0, orig_len = 0;
     uint8_t tag = 0;                                  // 0: no plain row (bridged patches log their own)
-    int post = 0;                                     // PostKind: a single-base fix scored by first_passing_lean (s.win holds its counts)
+    int post = 0;                                     // PostKind: a single-base fix scored by score_single_base (s.win holds its counts)
   };
   JB_W void fix_row(Fix& f, int64_t coord, uint8_t fb, int fb_len, uint8_t tag, uint8_t orig, int orig_len) {
     fill(s.fx, fb, fb_len);
@@ -451,15 +451,12 @@ struct Walker {
     pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) if ((uint8_t)order[o] != bad) set_cand(nc++, kSub, (uint8_t)order[o], 0, k - 1, 0);
     set_cand(nc++, kDel, 0, 0, k - 1, 1);
-    JB_SYNC();
-    int w = packed_clean(s.pt, 0, n) ? first_passing_lean(db, s, nc, n, k, step, thr, &lookups) : -2;
-    const bool lean = w != -2;
-    if (!lean) w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
+    const int w = first_passing(db, s, nc, n, k, step, mask, thr, &lookups);
     if (w < 0) return f;
     const Cand c = s.cand[w];
     f.found = true; f.a = s0 + k - 1; f.e = s0 + k; f.repl = s.b;
-    if (c.kind == kSub) { fill(s.b, c.base, 1); f.rlen = 1; fix_row(f, ga - 1, c.base, 1, 's', before, 1); f.post = lean ? kPostSub : kPostNone; }
-    else { f.rlen = 0; fix_row(f, ga - 1, '-', 1, 'i', before, 1); f.post = lean ? kPostDel : kPostNone; }
+    if (c.kind == kSub) { fill(s.b, c.base, 1); f.rlen = 1; fix_row(f, ga - 1, c.base, 1, 's', before, 1); }
+    else { f.rlen = 0; fix_row(f, ga - 1, '-', 1, 'i', before, 1); }
     return f;
   }
 
@@ -469,16 +466,12 @@ struct Walker {
     const char order[4] = {'A', 'T', 'C', 'G'};
     pack_bytes(s.pt, s.t, n);
     for (int o = 0; o < 4; ++o) set_cand(o, kIns, (uint8_t)order[o], 0, k - 1, 1);
-    JB_SYNC();
-    int w = packed_clean(s.pt, 0, n) ? first_passing_lean(db, s, 4, n, k, step, thr, &lookups) : -2;
-    const bool lean = w != -2;
-    if (!lean) w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
+    const int w = first_passing(db, s, 4, n, k, step, mask, thr, &lookups);
     if (w < 0) return f;
     const uint8_t bb = s.cand[w].base;
     fill(s.b, bb, 1);
     f.found = true; f.a = s0 + k - 1; f.e = s0 + k - 1; f.repl = s.b; f.rlen = 1;
     fix_row(f, ga, bb, 1, 'd', '-', 1);
-    f.post = lean ? kPostIns : kPostNone;
     return f;
   }
 
@@ -761,8 +754,49 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- fixing_sid
-  // returns the PostKind of an applied single-base fix (kPostNone otherwise)
-  JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
+  // The isolated error in untouched territory (fast_delimit succeeded, nbad is k or k-1): the to_be_fixed string is a
+  // stretch of pass-start bases, its single-base candidates are scored by score_single_base.  handled = false leaves
+  // everything to slow_fix (lower-case suspect base, layout does not apply, or nothing passed where the reference goes
+  // on to the diploid / homopolymer repairs).
+  JB_W Fix fast_fix(int64_t s0, int64_t nbad, int64_t ga, bool& handled) {
+    Fix f;
+    handled = false;
+    const int n = (int)nbad + k - 1;
+    const int ins = nbad == k - 1 ? 1 : 0;
+    const uint8_t* src = u.in + (s0 - (base + olen - ipos));
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < n; q += 32) s.t[q] = src[q]; }
+    JB_SYNC();
+    const uint8_t bad = s.t[k - 1];
+    if (!ins && bad != 'A' && bad != 'C' && bad != 'G' && bad != 'T') return f;
+    pack_bytes(s.pt, s.t, n);
+    const int w = score_single_base(db, s, ins, base_code(bad), n, k, step, solid);
+    if (w == -2 || (w < 0 && ins)) return f;
+    handled = true;
+    lookups += (unsigned long long)(w < 0 ? 36 : 9 * (w + 1));       // (statistics only: about 9 samples per candidate tried)
+    if (w < 0) return f;
+    f.found = true; f.repl = s.b;
+    if (ins) {
+      const uint8_t bb = (uint8_t)("ATCG"[w]);
+      fill(s.b, bb, 1);
+      f.a = s0 + k - 1; f.e = s0 + k - 1; f.rlen = 1; f.post = kPostIns;
+      fix_row(f, ga, bb, 1, 'd', '-', 1);
+    } else if (w == 3) {
+      f.a = s0 + k - 1; f.e = s0 + k; f.rlen = 0; f.post = kPostDel;
+      fix_row(f, ga - 1, '-', 1, 'i', bad, 1);
+    } else {
+      int o = 0, left = w;                                           // the w-th of 'A','C','T','G' that is not the suspect base
+      while (true) { if ((uint8_t)("ACTG"[o]) != bad) { if (left == 0) break; --left; } ++o; }
+      const uint8_t bb = (uint8_t)("ACTG"[o]);
+      fill(s.b, bb, 1);
+      f.a = s0 + k - 1; f.e = s0 + k; f.rlen = 1; f.post = kPostSub;
+      fix_row(f, ga - 1, bb, 1, 's', bad, 1);
+    }
+    return f;
+  }
+
+  // the reference's dispatch (src/jasper.py:226-338), out of line: the hot loop only comes here for the events fast_fix declines
+  JB_WC Fix slow_fix(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
     Fix f;
     if (nbad == k) {
@@ -781,6 +815,16 @@ struct Walker {
     } else if (nbad > k) {
       f = fix_bridge(n64, thr, gb, ga);
     }
+    return f;
+  }
+
+  // ---------------------------------------------------------------------------- fixing_sid
+  // returns the PostKind of an applied single-base fix (kPostNone otherwise)
+  JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga, bool fast) {
+    Fix f;
+    bool handled = false;
+    if (fast && (nbad == k || nbad == k - 1)) f = fast_fix(s0, nbad, ga, handled);
+    if (!handled) f = slow_fix(s0, nbad, thr, gb, ga);
     int post = kPostNone;
     if (f.found && !status) {
       if (apply_edit(f.a, f.e, f.repl, f.rlen)) {
@@ -831,6 +875,45 @@ struct Walker {
     seqno += 2;                                           // at most two csv rows come out of one patch
     f.found = true; f.a = gb + 1; f.e = ga; f.repl = bs->patch; f.rlen = plen; f.tag = 0;
     return f;
+  }
+
+  // src/jasper.py:150-214 through the window cache / point queries (edited territory, rolling threshold, contig ends, N);
+  // false = the reference returns before it reaches the fix
+  JB_WC bool generic_delimit(int64_t rolling_thre, int64_t thre, int64_t& gb, int64_t& ga, int64_t& s0) {
+    int64_t j = i - 1;
+    uint32_t occ = Cw(j, -1);
+    while ((int64_t)occ < thre && j >= 0) { --j; occ = Cw(j, -1); }
+    gb = j + k - 1;
+    uint64_t prev = occ;
+    uint32_t cur = Cw(i, +1);
+    if (j == -1) gb = -1;
+    if (rolling_thre == 0) {
+      while ((int64_t)cur < thre && i < L - k + 1) { ++i; cur = Cw(i, +1); }
+    } else {
+      while ((int64_t)cur < thre && i < L - k + 1) {
+        if (i - j > k) { i = i + 1; return false; }
+        ++i; cur = Cw(i, +1);
+      }
+    }
+    ga = i;
+    if (2 * (int64_t)Cw(gb - k + 2, +1) < solid && 2 * (int64_t)Cw(gb - k + 3, +1) < solid) {
+      // "too low" -- flag only
+    } else if (rolling_thre == 0) {
+      while (2 * (uint64_t)Cw(gb - k + 2, +1) >= prev && gb - k + 1 < ga) {
+        if (gb == -1) break;
+        if (2 * (int64_t)prev >= thre && 2 * (int64_t)Cw(gb - k + 2, +1) < thre && 2 * (int64_t)Cw(gb - k + 3, +1) < thre) break;
+        prev = Cw(gb - k + 2, +1);
+        ++gb;
+      }
+      if (gb >= L - 1) { brk = true; return false; }
+    }
+    s0 = gb - k + 2 > 0 ? gb - k + 2 : 0;
+    if (s0 + k + k >= L) { i = s0 + k + k; brk = true; return false; }
+    s.px[0] = s0 + 1; s.px[1] = s0 + k - 2; s.px[2] = s0 + k - 1; s.px[3] = s0 + k;
+    JB_SYNC();
+    Cpts(4);
+    if ((int64_t)s.pr[0] < thre && (int64_t)s.pr[1] < thre && (int64_t)s.pr[2] < thre && (int64_t)s.pr[3] >= thre) ga = s0 + k;
+    return true;
   }
 
   // ---------------------------------------------------------------------------- handle_bad_kmers
@@ -903,45 +986,11 @@ struct Walker {
     const int64_t thre = rolling_thre > 0 ? rolling_thre : solid;
     int64_t gb = 0, ga = 0, s0 = 0;
     const bool fast = rolling_thre == 0 && fast_delimit(gb, ga, s0);
-    if (!fast) {
-      int64_t j = i - 1;
-      uint32_t occ = Cw(j, -1);
-      while ((int64_t)occ < thre && j >= 0) { --j; occ = Cw(j, -1); }
-      gb = j + k - 1;
-      uint64_t prev = occ;
-      uint32_t cur = Cw(i, +1);
-      if (j == -1) gb = -1;
-      if (rolling_thre == 0) {
-        while ((int64_t)cur < thre && i < L - k + 1) { ++i; cur = Cw(i, +1); }
-      } else {
-        while ((int64_t)cur < thre && i < L - k + 1) {
-          if (i - j > k) { i = i + 1; return; }
-          ++i; cur = Cw(i, +1);
-        }
-      }
-      ga = i;
-      if (2 * (int64_t)Cw(gb - k + 2, +1) < solid && 2 * (int64_t)Cw(gb - k + 3, +1) < solid) {
-        // "too low" -- flag only
-      } else if (rolling_thre == 0) {
-        while (2 * (uint64_t)Cw(gb - k + 2, +1) >= prev && gb - k + 1 < ga) {
-          if (gb == -1) break;
-          if (2 * (int64_t)prev >= thre && 2 * (int64_t)Cw(gb - k + 2, +1) < thre && 2 * (int64_t)Cw(gb - k + 3, +1) < thre) break;
-          prev = Cw(gb - k + 2, +1);
-          ++gb;
-        }
-        if (gb >= L - 1) { brk = true; return; }
-      }
-      s0 = gb - k + 2 > 0 ? gb - k + 2 : 0;
-      if (s0 + k + k >= L) { i = s0 + k + k; brk = true; return; }
-      s.px[0] = s0 + 1; s.px[1] = s0 + k - 2; s.px[2] = s0 + k - 1; s.px[3] = s0 + k;
-      JB_SYNC();
-      Cpts(4);
-      if ((int64_t)s.pr[0] < thre && (int64_t)s.pr[1] < thre && (int64_t)s.pr[2] < thre && (int64_t)s.pr[3] >= thre) ga = s0 + k;
-    }
+    if (!fast && !generic_delimit(rolling_thre, thre, gb, ga, s0)) return;
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
     wrong += nbad;
     if (!fix || gb < 0) return;
-    const int done = fixing_sid(s0, nbad, thre, gb, ga);
+    const int done = fixing_sid(s0, nbad, thre, gb, ga, fast);
     if (!fast || !done || status || brk) return;
     // ---- the scan step that follows a single-base fix (src/jasper.py:56-100 at the new i), from data in hand: the window at
     // i is untouched (staged count) or a sample of the winning trial; so is the one k bases back.  Anything but the plain
@@ -997,6 +1046,47 @@ struct Walker {
     return true;                                        // all clear: keep hopping
   }
 
+  // the loop body's window checks and its two counts through the generic machinery (src/jasper.py:56-71); true = the
+  // window held an invalid byte and i moved on
+  JB_WC bool generic_body(int64_t& occ, int64_t& prevk) {
+    int n = load(s.t, i, i + k);                      // n == k here
+    int firstN = -1, firstn = -1, bad = 0;
+    for (int q = 0; q < n; ++q) {
+      uint8_t c = s.t[q];
+      if (c == 'N' && firstN < 0) firstN = q;
+      if (c == 'n' && firstn < 0) firstn = q;
+      if (!base_valid(c)) bad = 1;
+    }
+    if (firstN >= 0) {
+      i += firstN + 1;
+      // a run of N: every following window starts with 'N' and advances by one; jump the run
+      while (i < L - k + 1 && get(i) == 'N') ++i;
+      return true;
+    }
+    if (firstn >= 0) { i += firstn + 1; return true; }
+    if (bad) { i += 1; return true; }
+    s.px[0] = i; s.px[1] = i - k > 0 ? i - k : 0;
+    JB_SYNC();
+    Cpts(i > 0 ? 2 : 1);
+    occ = s.pr[0];
+    prevk = i > 0 ? (int64_t)s.pr[1] : 0;
+    return false;
+  }
+
+  // src/jasper.py:80-100: the count dropped below 1/50 of the one k bases back; the threshold handle_bad_kmers gets, or -1
+  JB_WC int64_t rolling_threshold(int64_t occ) {
+    int64_t ind = i - k > 0 ? i - k : 0;
+    int num = 0;
+    while (ind < i) { ind += step; s.px[num] = ind; ++num; }
+    JB_SYNC();
+    Cpts(num);
+    uint64_t sum = 0;
+    for (int q = 0; q < num; ++q) sum += s.pr[q];
+    const double mean = (double)sum / (double)num;
+    const int64_t rt = (int64_t)rint(mean / (double)JB_DIVISOR);
+    return occ < rt ? (int64_t)rint(mean / 2.0) : -1;
+  }
+
   JB_W void run() {
 #if defined(__CUDA_ARCH__)
     const long long t_begin = clock64();
@@ -1041,44 +1131,10 @@ struct Walker {
         const int64_t p = i - (base + olen - ipos);
         if (p >= k && p + k <= u.in_len && u.okb[p]) { occ = u.cnt[p]; prevk = u.cnt[p - k]; direct = true; }
       }
-      if (!direct) {
-        int n = load(s.t, i, i + k);                      // n == k here
-        int firstN = -1, firstn = -1, bad = 0;
-        for (int q = 0; q < n; ++q) {
-          uint8_t c = s.t[q];
-          if (c == 'N' && firstN < 0) firstN = q;
-          if (c == 'n' && firstn < 0) firstn = q;
-          if (!base_valid(c)) bad = 1;
-        }
-        if (firstN >= 0) {
-          i += firstN + 1;
-          // a run of N: every following window starts with 'N' and advances by one; jump the run
-          while (i < L - k + 1 && get(i) == 'N') ++i;
-          continue;
-        }
-        if (firstn >= 0) { i += firstn + 1; continue; }
-        if (bad) { i += 1; continue; }
-        s.px[0] = i; s.px[1] = i - k > 0 ? i - k : 0;
-        JB_SYNC();
-        Cpts(i > 0 ? 2 : 1);
-        occ = s.pr[0];
-        prevk = i > 0 ? (int64_t)s.pr[1] : 0;
-      }
+      if (!direct && generic_body(occ, prevk)) continue;
       int64_t handle = -1;                              // >= 0: handle_bad_kmers(handle) -- one call site keeps the image small
-      if (occ < solid) {
-        handle = 0;
-      } else if (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk) {
-        int64_t ind = i - k > 0 ? i - k : 0;
-        int num = 0;
-        while (ind < i) { ind += step; s.px[num] = ind; ++num; }
-        JB_SYNC();
-        Cpts(num);
-        uint64_t sum = 0;
-        for (int q = 0; q < num; ++q) sum += s.pr[q];
-        const double mean = (double)sum / (double)num;
-        const int64_t rt = (int64_t)rint(mean / (double)JB_DIVISOR);
-        if (occ < rt) handle = (int64_t)rint(mean / 2.0);
-      }
+      if (occ < solid) handle = 0;
+      else if (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk) handle = rolling_threshold(occ);
       if (handle >= 0) handle_bad_kmers(handle);
       else i += k - 1;
     }
