@@ -158,6 +158,7 @@ struct Walker {
   const bool fix;
   const Key mask;
   UnitIO& u;
+  UnitIO c;                            // the segment descriptor, read once (u lives in global memory)
   WarpScratch& s;
   BridgePool pool;
   BridgeScratch* bs = nullptr;
@@ -227,8 +228,8 @@ struct Walker {
     JB_LANES(l) {
       if (l == 0) {
         SeqView v;
-        v.in = u.in; v.out = u.out; v.cnt = u.cnt;
-        v.base = base; v.olen = olen; v.ipos = ipos; v.wstart = wstart; v.L = L; v.in_len = u.in_len;
+        v.in = c.in; v.out = c.out; v.cnt = c.cnt;
+        v.base = base; v.olen = olen; v.ipos = ipos; v.wstart = wstart; v.L = L; v.in_len = c.in_len;
         v.clean_from = clean_from; v.seam_margin = seam_margin;
         s.view = v;
         s.wc_n = 0;                                   // cached window counts do not survive an edit
@@ -298,7 +299,7 @@ struct Walker {
   // ---------------------------------------------------------------------------- edits
   JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
     if (len <= 0) return true;
-    if (!push_job(jobs, u.slot, src, rel, len)) { status = JB_E_SCRATCH; return false; }
+    if (!push_job(jobs, c.slot, src, rel, len)) { status = JB_E_SCRATCH; return false; }
     return true;
   }
 
@@ -307,13 +308,13 @@ struct Walker {
   JB_WN bool ensure_out(int64_t a_abs, int64_t upto_abs) {
     const int64_t upto = upto_abs - base;
     if (upto <= olen) return true;
-    if (upto > u.out_cap) { status = JB_E_SCRATCH; return false; }
-    if (!u.materialize_all) {
+    if (upto > c.out_cap) { status = JB_E_SCRATCH; return false; }
+    if (!c.materialize_all) {
       const int64_t keep_from = (a_abs - base) - keep_margin;
       if (keep_from > olen + kMinGap) {
-        if (!emit_job(u.out + wstart, wstart, olen - wstart)) return false;
+        if (!emit_job(c.out + wstart, wstart, olen - wstart)) return false;
         const int64_t gap = keep_from - olen;
-        if (!emit_job(u.in + ipos, olen, gap)) return false;
+        if (!emit_job(c.in + ipos, olen, gap)) return false;
         ipos += gap; olen += gap; wstart = olen;
       }
     }
@@ -323,9 +324,9 @@ struct Walker {
       uint8_t v[8];
       JB_LANES(l) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; v[j] = q < n ? u.in[ipos + q] : (uint8_t)0; }
+        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; v[j] = q < n ? c.in[ipos + q] : (uint8_t)0; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; if (q < n) u.out[olen + q] = v[j]; }
+        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; if (q < n) c.out[olen + q] = v[j]; }
       }
     }
     JB_SYNC();
@@ -341,7 +342,7 @@ struct Walker {
     const int64_t a = a_abs - base, e = e_abs - base;   // offsets into out
     const int64_t delta = rlen - (e - a);
     const int64_t tail = olen - e;
-    if (olen + delta > u.out_cap) { status = JB_E_SCRATCH; return false; }
+    if (olen + delta > c.out_cap) { status = JB_E_SCRATCH; return false; }
     if (delta != 0 && tail > 0) {
       // shift out[e:olen) by delta, 32 bytes per step, in the safe direction
       if (delta > 0) {
@@ -350,10 +351,10 @@ struct Walker {
           uint8_t v = 0;
           JB_SYNC();
 #if defined(__CUDA_ARCH__)
-          { int l = threadIdx.x & 31; if (lo + l < hi) v = u.out[e + lo + l]; __syncwarp(); if (lo + l < hi) u.out[e + lo + l + delta] = v; }
+          { int l = threadIdx.x & 31; if (lo + l < hi) v = c.out[e + lo + l]; __syncwarp(); if (lo + l < hi) c.out[e + lo + l + delta] = v; }
 #else
-          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = u.out[e + lo + l];
-            for (int l = 0; l < 32; ++l) if (lo + l < hi) u.out[e + lo + l + delta] = tmp[l]; (void)v; }
+          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = c.out[e + lo + l];
+            for (int l = 0; l < 32; ++l) if (lo + l < hi) c.out[e + lo + l + delta] = tmp[l]; (void)v; }
 #endif
         }
       } else {
@@ -362,16 +363,16 @@ struct Walker {
           uint8_t v = 0;
           JB_SYNC();
 #if defined(__CUDA_ARCH__)
-          { int l = threadIdx.x & 31; if (lo + l < hi) v = u.out[e + lo + l]; __syncwarp(); if (lo + l < hi) u.out[e + lo + l + delta] = v; }
+          { int l = threadIdx.x & 31; if (lo + l < hi) v = c.out[e + lo + l]; __syncwarp(); if (lo + l < hi) c.out[e + lo + l + delta] = v; }
 #else
-          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = u.out[e + lo + l];
-            for (int l = 0; l < 32; ++l) if (lo + l < hi) u.out[e + lo + l + delta] = tmp[l]; (void)v; }
+          { uint8_t tmp[32]; for (int l = 0; l < 32; ++l) if (lo + l < hi) tmp[l] = c.out[e + lo + l];
+            for (int l = 0; l < 32; ++l) if (lo + l < hi) c.out[e + lo + l + delta] = tmp[l]; (void)v; }
 #endif
         }
       }
     }
     JB_SYNC();
-    JB_LANES(l) { for (int64_t q = l; q < rlen; q += 32) u.out[a + q] = repl[q]; }
+    JB_LANES(l) { for (int64_t q = l; q < rlen; q += 32) c.out[a + q] = repl[q]; }
     JB_SYNC();
     olen += delta; L += delta;
     int64_t shifted = clean_from + delta;
@@ -399,7 +400,7 @@ struct Walker {
     char* text = total > 8 ? (char*)sink.aux + off : r.text;
     JB_LANES(l) {
       if (l == 0) {
-        r.coord = coord; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno;
+        r.coord = coord; r.unit = c.unit; r.seg = c.seg; r.gen = (uint8_t)c.gen; r.seqno = seqno;
         r.kind = (uint8_t)(total > 8 ? kRowSpill : kRowPlain);
         r.fb_len = (uint8_t)fb_len; r.orig_len = (uint8_t)(orig_len + 1);
         if (total > 8) r.aux_off = off;
@@ -763,7 +764,7 @@ struct Walker {
     handled = false;
     const int n = (int)nbad + k - 1;
     const int ins = nbad == k - 1 ? 1 : 0;
-    const uint8_t* src = u.in + (s0 - (base + olen - ipos));
+    const uint8_t* src = c.in + (s0 - (base + olen - ipos));
     JB_SYNC();
     JB_LANES(l) { for (int q = l; q < n; q += 32) s.t[q] = src[q]; }
     JB_SYNC();
@@ -865,7 +866,7 @@ struct Walker {
       for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + 8 + plen + q] = get(gb + 1 + q);
       if (l == 0) {
         DevRow& r = sink.rows[rslot];
-        r.coord = gb + 1; r.unit = u.unit; r.seg = u.seg; r.gen = (uint8_t)u.gen; r.seqno = seqno; r.kind = (uint8_t)kRowBridge; r.fb_len = 0; r.orig_len = 0;
+        r.coord = gb + 1; r.unit = c.unit; r.seg = c.seg; r.gen = (uint8_t)c.gen; r.seqno = seqno; r.kind = (uint8_t)kRowBridge; r.fb_len = 0; r.orig_len = 0;
         r.aux_off = off;
         const uint32_t pl = (uint32_t)plen, ol = (uint32_t)olen_old;     // byte-wise: the arena is not aligned
         for (int q = 0; q < 4; ++q) { sink.aux[off + q] = (uint8_t)(pl >> (8 * q)); sink.aux[off + 4 + q] = (uint8_t)(ol >> (8 * q)); }
@@ -923,13 +924,13 @@ struct Walker {
   // evaluates the same loops on it: no window cache, no point queries, no probes.  It either produces exactly
   // what the generic code below would (same i, gb, ga, s0) or returns false with the walker's state untouched.
   JB_W bool fast_delimit(int64_t& gb, int64_t& ga, int64_t& s0) {
-    if (!u.cnt || !u.okb) return false;
+    if (!c.cnt || !c.okb) return false;
     const int64_t shift = base + olen - ipos;           // new = old + shift for everything >= clean_from
     const int W = kFastBack + 2 * k + 24;
     const int64_t W0 = i - kFastBack;
     int64_t lo_x = clean_from > shift ? clean_from : shift;
     if (base - seam_margin > lo_x) lo_x = base - seam_margin;      // (further back the previous segment's walker may have edited)
-    const int64_t hi_p = u.in_len - 2 * (int64_t)k - 3;            // keeps every end-of-contig clamp of the generic code out of play
+    const int64_t hi_p = c.in_len - 2 * (int64_t)k - 3;            // keeps every end-of-contig clamp of the generic code out of play
     JB_SYNC();
     JB_LANES(l) { if (l == 0) { s.fbad[0] = -1; s.fbad[1] = W; } }
     JB_SYNC();
@@ -937,8 +938,8 @@ struct Walker {
       for (int q = l; q < W; q += 32) {
         const int64_t x = W0 + q, p = x - shift;
         bool ok = x >= lo_x && p <= hi_p;
-        if (ok) ok = u.okb[p] != 0;
-        s.fc[q] = ok ? u.cnt[p] : 0u;
+        if (ok) ok = c.okb[p] != 0;
+        s.fc[q] = ok ? c.cnt[p] : 0u;
         if (!ok) {
 #if defined(__CUDA_ARCH__)
           if (q < kFastBack) atomicMax(&s.fbad[0], q); else atomicMin(&s.fbad[1], q);
@@ -1001,7 +1002,7 @@ struct Walker {
     else if (done == kPostDel && i == s0 + k) { occ = s.fc[s0q + k + 1]; prevk = s.win[0]; }
     else if (done == kPostIns && i == s0 + k - 1) { occ = s.win[1]; prevk = s.fc[s0q - 1]; }
     else return;
-    if (u.next_anchor >= 0 && i - (L - u.in_len) >= u.next_anchor) return;       // the loop re-checks the seam first
+    if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;       // the loop re-checks the seam first
     if (occ >= solid && !((uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) { i += k - 1; ++n_post; }
   }
 
@@ -1009,37 +1010,54 @@ struct Walker {
   // Fast hop: while the walker is in untouched territory, 32 strided event bits decide in one step
   // how far the plain `i += k-1` branch carries it.
   JB_WN bool fast_hop() {
-    if (!u.ev || i - k < clean_from) return false;
+    if (!c.ev || i - k < clean_from) return false;
     const int64_t shift = base + olen - ipos;          // new = old + shift for everything >= clean_from
     const int64_t p = i - shift;
     const int64_t stride = k - 1;
-    JB_SYNC();
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31);
+    int l;
+    {
+      const int64_t q = p + (int64_t)lane * stride;
+      const bool f = q > c.in_len || ((c.ev[q >> 5] >> (q & 31)) & 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      l = m ? __ffs(m) - 1 : 32;
+    }
+#else
     JB_LANES(l) {
       int64_t q = p + (int64_t)l * stride;
       uint32_t f = 1;
-      if (q <= u.in_len) f = (u.ev[q >> 5] >> (q & 31)) & 1u;
+      if (q <= c.in_len) f = (c.ev[q >> 5] >> (q & 31)) & 1u;
       s.flag[l] = f;
     }
-    JB_SYNC();
     int l = 0;
     while (l < 32 && !s.flag[l]) ++l;
+#endif
     i += (int64_t)l * stride;
     if (l < 32) return false;                           // an event (or the end) at the new i
-    if (u.ev_l1) {
+    if (c.ev_l1) {
       // 32 clear strides: consult the level-1 summary to leap over event-free 1024-position blocks
       const int64_t p2 = i - shift;
-      const uint64_t blk = (u.ev_bit_base + (uint64_t)p2) >> 10;
-      const uint64_t last_blk = (u.ev_bit_base + (uint64_t)u.in_len) >> 10;
-      JB_SYNC();
+      const uint64_t blk = (c.ev_bit_base + (uint64_t)p2) >> 10;
+      const uint64_t last_blk = (c.ev_bit_base + (uint64_t)c.in_len) >> 10;
+#if defined(__CUDA_ARCH__)
+      int m;
+      {
+        const uint64_t bq = blk + (uint64_t)lane;
+        const bool f = bq > last_blk || ((c.ev_l1[bq >> 5] >> (bq & 31)) & 1u);
+        const unsigned mm = __ballot_sync(0xffffffffu, f);
+        m = mm ? __ffs(mm) - 1 : 32;
+      }
+#else
       JB_LANES(l2) {
         uint64_t bq = blk + (uint64_t)l2;
-        s.flag[l2] = bq > last_blk ? 1u : ((u.ev_l1[bq >> 5] >> (bq & 31)) & 1u);
+        s.flag[l2] = bq > last_blk ? 1u : ((c.ev_l1[bq >> 5] >> (bq & 31)) & 1u);
       }
-      JB_SYNC();
       int m = 0;
       while (m < 32 && !s.flag[m]) ++m;
+#endif
       if (m >= 2) {
-        const int64_t T = (int64_t)(((blk + (uint64_t)m) << 10) - u.ev_bit_base);   // first position of a non-empty block
+        const int64_t T = (int64_t)(((blk + (uint64_t)m) << 10) - c.ev_bit_base);   // first position of a non-empty block
         if (T - 1 > p2) i += ((T - 1 - p2) / stride) * stride;
       }
     }
@@ -1091,13 +1109,14 @@ struct Walker {
 #if defined(__CUDA_ARCH__)
     const long long t_begin = clock64();
 #endif
-    base = u.base; seam_margin = seam_read_margin(k); keep_margin = u.keep_margin; wstart = 0; far_back = false;
-    i = base; olen = 0; ipos = base; L = u.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; vflags = 0;
+    c = u;
+    base = c.base; seam_margin = seam_read_margin(k); keep_margin = c.keep_margin; wstart = 0; far_back = false;
+    i = base; olen = 0; ipos = base; L = c.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; vflags = 0;
     publish();
     {
       // C('') = count of poly-A: the bulk scan's entry for the empty tail window, else one probe
       uint32_t ec;
-      if (u.cnt) ec = u.cnt[u.in_len]; else { ec = count_str(db, s.c, 0, 0, k, mask); ++lookups; }
+      if (c.cnt) ec = c.cnt[c.in_len]; else { ec = count_str(db, s.c, 0, 0, k, mask); ++lookups; }
       JB_SYNC();
       JB_LANES(l) { if (l == 0) { s.empty_count = ec; s.probes = 0; } }
       JB_SYNC();
@@ -1109,27 +1128,27 @@ struct Walker {
 #else
       if (vflags) break;
 #endif
-      if (u.next_anchor >= 0) {
-        const int64_t i_old = i - (L - u.in_len);
-        if (i_old >= u.next_anchor) {
+      if (c.next_anchor >= 0) {
+        const int64_t i_old = i - (L - c.in_len);
+        if (i_old >= c.next_anchor) {
           // the next segment starts here: we must arrive clean and land inside its anchor run
           // (everything from seam_margin before the anchor on is untouched, so the next walker reads pass-start bases)
-          const int64_t a_new = u.next_anchor + (L - u.in_len);
-          if (clean_from > a_new - seam_margin || i_old > u.next_anchor + k - 2) status = kSeamViolation;
+          const int64_t a_new = c.next_anchor + (L - c.in_len);
+          if (clean_from > a_new - seam_margin || i_old > c.next_anchor + k - 2) status = kSeamViolation;
           reached = true;
           break;
         }
       }
       if (fast_hop()) continue;
       if (!(i < L - k + 1)) break;
-      if (u.next_anchor >= 0 && i - (L - u.in_len) >= u.next_anchor) continue;   // re-check the seam first
+      if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) continue;   // re-check the seam first
       // ---- the reference's loop body at position i (src/jasper.py:56-100)
       int64_t occ = 0, prevk = 0;
       bool direct = false;
-      if (u.okb && u.cnt && i - k >= clean_from && i - k >= base - seam_margin) {
+      if (c.okb && c.cnt && i - k >= clean_from && i - k >= base - seam_margin) {
         // untouched territory: validity and both counts come straight from the bulk scan
         const int64_t p = i - (base + olen - ipos);
-        if (p >= k && p + k <= u.in_len && u.okb[p]) { occ = u.cnt[p]; prevk = u.cnt[p - k]; direct = true; }
+        if (p >= k && p + k <= c.in_len && c.okb[p]) { occ = c.cnt[p]; prevk = c.cnt[p - k]; direct = true; }
       }
       if (!direct && generic_body(occ, prevk)) continue;
       int64_t handle = -1;                              // >= 0: handle_bad_kmers(handle) -- one call site keeps the image small
@@ -1145,13 +1164,13 @@ struct Walker {
 #endif
     if (!status && seam_bad) status = kSeamViolation;
     if (!status && far_back) status = kFarBack;
-    if (!status && u.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
-    const int64_t end_old = u.next_anchor >= 0 ? u.next_anchor : u.in_len;
+    if (!status && c.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
+    const int64_t end_old = c.next_anchor >= 0 ? c.next_anchor : c.in_len;
     if (!status && ipos > end_old) status = kSeamViolation;
     // new bases of old [base, end_old) = closed jobs ++ out[wstart:olen) ++ in[ipos:end_old)
     if (fix && !status) {
-      emit_job(u.out + wstart, wstart, olen - wstart);
-      emit_job(u.in + ipos, olen, end_old - ipos);
+      emit_job(c.out + wstart, wstart, olen - wstart);
+      emit_job(c.in + ipos, olen, end_old - ipos);
     }
     u.end_old = end_old;
     u.new_len = status ? 0 : olen + (end_old - ipos);
