@@ -69,6 +69,61 @@ k_walk(TableView t, UnitIO* segs, const uint32_t* order, uint32_t n_segs, WalkCf
   }
 }
 
+// One warp per 1024-position tile of the weak bitmask: every weak run that ENDS inside the tile gets its verdict
+// (jb_verdict.cuh), published under the run's end in vmap.  All warps run the same few KB of code (delimit, pack,
+// score, probe), which is the point: this work used to sit inside the walkers' divergent, fetch-starved kernel.
+struct VerdictArgs {
+  const uint8_t* bases; const ScanUnit* units; const uint32_t* tile_first; uint32_t n_units, n_tiles;
+  const uint32_t* counts; const uint8_t* okb; const uint32_t* weak;
+  Verdict* verdicts; unsigned long long cap; unsigned long long* used; uint32_t* vmap;
+  int k, step; uint32_t solid;
+};
+constexpr int kVerdictWarps = 4;
+__global__ void __launch_bounds__(kVerdictWarps * 32)
+k_verdicts(TableView t, VerdictArgs a) {
+  __shared__ WarpScratch scratch[kVerdictWarps];
+  __shared__ DevDB db;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) db.t = t;
+  __syncthreads();
+  WarpScratch& s = scratch[warp];
+  for (uint32_t ti = blockIdx.x * kVerdictWarps + warp; ti < a.n_tiles; ti += gridDim.x * kVerdictWarps) {
+    const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
+    const ScanUnit u = a.units[tile.unit];
+    const int64_t len = (int64_t)u.len;
+    const uint32_t* wk = a.weak + (u.out_off >> 5);
+    const int64_t wp = (int64_t)tile.start + 32 * lane;                  // first position of this lane's word
+    uint32_t ends = 0;                                                   // positions whose bit is clear and whose predecessor's is set
+    if (wp <= len) {
+      const uint32_t cur = wk[wp >> 5];
+      const uint32_t prev_bit = wp > 0 ? (wk[(wp >> 5) - 1] >> 31) : 0u;
+      ends = ~cur & ((cur << 1) | prev_bit);
+    }
+    while (true) {
+      const unsigned ball = __ballot_sync(0xffffffffu, ends != 0u);
+      if (!ball) break;
+      const int L = __ffs((int)ball) - 1;
+      const uint32_t e = __shfl_sync(0xffffffffu, ends, L);
+      const int64_t re = (int64_t)tile.start + 32 * L + (__ffs((int)e) - 1);
+      if (lane == L) ends &= ends - 1;
+      if (re > len || re < 1) continue;
+      Verdict* slot = reinterpret_cast<Verdict*>(s.fx);                  // (16 bytes of scratch: the row text area is idle here)
+      int64_t re2 = -1;
+      const bool ok = make_verdict(db, s, a.bases + u.seq_off, a.counts + u.out_off, a.okb + u.out_off, len, a.k, a.step,
+                                   (int64_t)a.solid, re - 1, slot, &re2);
+      if (ok && re2 == re && lane == 0) {
+        const unsigned long long id = atomicAdd(a.used, 1ull);
+        if (id < a.cap) {
+          a.verdicts[id] = *slot;
+          uint32_t* cell = a.vmap + ((u.out_off + (uint64_t)re) >> 5);
+          if (atomicCAS(cell, 0u, (uint32_t)id + 1u) != 0u) atomicExch(cell, kVmapAmbiguous);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // dst[0:n) = src[0:n), the CTAs of one grid row share the job; 16-byte stores, byte-funnelled loads when
 // the two streams are misaligned against each other (indels shift them)
 __device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int64_t n) {
@@ -159,7 +214,8 @@ struct PinBuf {
 struct Workspace {
   int device = -1;
   DevBuf<uint8_t> buf[2], stage;
-  DevBuf<uint32_t> counts[2], events, weak, events_l1, order, tile_first, block_first, slot_unit;
+  DevBuf<uint32_t> counts[2], events, weak, events_l1, order, tile_first, block_first, slot_unit, vmap;
+  DevBuf<Verdict> verdicts;
   DevBuf<uint8_t> okb[2];                   // counts / validity of the current and of the next pass's sequence
   DevBuf<ScanUnit> scan_units_new;
   DevBuf<UnitIO> segs;
@@ -185,7 +241,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -249,6 +305,7 @@ void jb_release_cached_workspaces(int device) {           // jb_db_close: nothin
 }
 
 struct jb_batch {
+  bool use_verdicts = true;
   const jb_db* db = nullptr;
   Workspace* ws = nullptr;
   size_t n = 0;
@@ -301,6 +358,7 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   for (int q = 0; q < 2; ++q) { JB_TRY(w.counts[q].ensure(total + 64)); JB_TRY(w.okb[q].ensure(total + 64)); }
   JB_TRY(w.scan_units_new.ensure(n + 1));
   JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
+  JB_TRY(w.vmap.ensure(total / 32 + 64)); JB_TRY(w.verdicts.ensure(total / 64 + 4096));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
   JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
   JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20)));
@@ -385,6 +443,7 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
   u.cnt = w.counts[cidx].p + b->off[i];
   u.okb = w.okb[cidx].p + b->off[i];
+  u.weak = w.weak.p + b->off[i] / 32; u.vmap = b->use_verdicts ? w.vmap.p : nullptr; u.verdicts = w.verdicts.p;
   u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
@@ -495,8 +554,11 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   double recount_ms = 0;
   const bool full_rescan = getenv("JB_FULL_RESCAN") != nullptr;      // tests: scan every pass from scratch
   const bool verify_recount = getenv("JB_VERIFY_RECOUNT") != nullptr; // tests: check k_recount against a full scan
-  cudaEvent_t ev_r0, ev_r1;
-  JB_CUDA(cudaEventCreate(&ev_r0)); JB_CUDA(cudaEventCreate(&ev_r1));
+  cudaEvent_t ev_r0, ev_r1, ev_v0, ev_v1;
+  JB_CUDA(cudaEventCreate(&ev_r0)); JB_CUDA(cudaEventCreate(&ev_r1)); JB_CUDA(cudaEventCreate(&ev_v0)); JB_CUDA(cudaEventCreate(&ev_v1));
+  const bool do_fix_verdicts = getenv("JB_NO_VERDICTS") == nullptr;      // tests: walkers decide everything themselves
+  double verdict_ms = 0;
+  int64_t n_verdicts = 0;
   b->passes.clear();
   b->passes.reserve((size_t)passes + 1);
   const bool trace = getenv("JB_TRACE") != nullptr;
@@ -552,6 +614,23 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     ea.solid_thre = solid_thre; ea.k = k;
     if (int rc = launch_events(ea, s)) return rc;
     ++launches;
+    // ---- verdicts: every isolated error decided in bulk (jb_verdict.cuh)
+    b->use_verdicts = do_fix_verdicts;
+    if (b->use_verdicts) {
+      JB_CUDA(cudaMemsetAsync(w.vmap.p, 0, (b->flat_bytes / 32 + 64) * 4, s));
+      JB_CUDA(cudaMemsetAsync(w.used.p + 6, 0, 8, s));
+      VerdictArgs va{};
+      va.bases = in; va.units = w.scan_units.p; va.tile_first = w.tile_first.p; va.n_units = (uint32_t)n; va.n_tiles = tile_first[n];
+      va.counts = w.counts[cidx].p; va.okb = w.okb[cidx].p; va.weak = w.weak.p;
+      va.verdicts = w.verdicts.p; va.cap = w.verdicts.cap; va.used = w.used.p + 6; va.vmap = w.vmap.p;
+      va.k = k; va.step = cfg.step; va.solid = solid_thre;
+      const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
+      JB_CUDA(cudaEventRecord(ev_v0, s));
+      k_verdicts<<<std::max(1u, vgrid), kVerdictWarps * 32, 0, s>>>(view, va);
+      JB_CUDA(cudaGetLastError());
+      JB_CUDA(cudaEventRecord(ev_v1, s));
+      ++launches;
+    }
     // ---- anchors -> segments
     long long* anchors = w.h_anchors.p;
     if (!blocks.empty()) {
@@ -598,6 +677,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaEventRecord(ev_e, s));
     JB_CUDA(cudaMemcpyAsync(hs, w.segs.p, n_first * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
     JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
+    JB_CUDA(cudaMemcpyAsync(used + 6, w.used.p + 6, 8, cudaMemcpyDeviceToHost, s));
     mark("walk launched", ite);
     JB_CUDA(cudaStreamSynchronize(s));
     mark("walk done", ite);
@@ -739,6 +819,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     cudaEventElapsedTime(&ms, ev_b, ev_c); plan_ms += ms;
     cudaEventElapsedTime(&ms, ev_c, ev_d); walk_ms += ms;
     if (do_fix && have_counts) { cudaEventElapsedTime(&ms, ev_r0, ev_r1); recount_ms += ms; recount_probes += (int64_t)used[4]; }
+    if (b->use_verdicts) { cudaEventElapsedTime(&ms, ev_v0, ev_v1); verdict_ms += ms; n_verdicts += (int64_t)used[6]; }
     mark("pass done", ite);
   }
   if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
@@ -753,7 +834,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   note_timing("polish_recount", recount_ms);
   note_counter("scan_lookups", full_scan_lookups + recount_probes); note_counter("walk_lookups", walk_lookups);
   note_counter("full_scans", full_scans); note_counter("full_scan_lookups", full_scan_lookups); note_counter("recount_probes", recount_probes);
-  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1);
+  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1); cudaEventDestroy(ev_v0); cudaEventDestroy(ev_v1);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
   note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
   for (int q = 0; q < 3; ++q) {
@@ -762,7 +843,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     note_counter(("slow_lookups" + sfx).c_str(), slow_lookups[q]); note_counter(("slow_span" + sfx).c_str(), slow_span[q]);
     note_counter(("sum_cycles" + sfx).c_str(), sum_cycles[q]);
   }
-  note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
+  note_counter("verdicts", n_verdicts); note_timing("polish_verdicts", verdict_ms); note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
   while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});

@@ -23,6 +23,7 @@
 #include "jb_jobs.cuh"
 #include "jb_seq.cuh"
 #include "jb_segments.cuh"
+#include "jb_verdict.cuh"
 
 // Inlined everywhere the kernel is 860 KB of SASS and the warps starve on instruction fetch (ncu: 60 %
 // stall_no_inst); everything out of line costs registers and call overhead.  JB_WC marks the cold, bulky
@@ -109,6 +110,9 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   int64_t out_cap;
   const uint32_t* cnt;       // C(window) for every position of the pass-start contig, [0, in_len]; may be null
   const uint8_t* okb;        // 1 = the pass-start window at that position is k chars of ACGTacgt; may be null
+  const uint32_t* weak;      // weak-window bit words of this contig (valid window with count < solid); null = no verdicts
+  const uint32_t* vmap;      // flat: word (ev_bit_base + re) >> 5 holds verdict id + 1 of the run that ends at re, 0, or kVmapAmbiguous
+  const Verdict* verdicts;   // k_verdicts output
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
   uint64_t ev_bit_base;      // flat bit index of contig position 0
@@ -126,7 +130,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   int64_t wrong;
   int32_t status;
   uint32_t n_rows;
-  uint32_t n_fast;             // events delimited from the bulk scan's counts (fast_delimit)
+  uint32_t n_fast;             // events taken from a verdict (jb_verdict.cuh)
   uint32_t n_post;             // ... whose following scan step was taken from data in hand
   unsigned long long lookups;
   unsigned long long events;
@@ -180,7 +184,7 @@ struct Walker {
   uint32_t seqno = 0;
   unsigned long long lookups = 0, events = 0;
   uint32_t n_fast = 0, n_post = 0;
-  int64_t fast_W0 = 0;                 // new coordinate of s.fc[0] (fast_delimit)
+  long long t_begin = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
                BridgePool pool_, RowSink sink_, JobSink jobs_)
@@ -320,13 +324,16 @@ struct Walker {
     }
     const int64_t n = upto - olen;
     JB_SYNC();
-    for (int64_t q0 = 0; q0 < n; q0 += 256) {           // 8 independent loads per lane before the stores
-      uint8_t v[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t q0 = 0; q0 < n; q0 += 128) {           // 4 independent loads per lane before the stores (a window is ~2k+32 bases)
+      uint8_t v[4];
       JB_LANES(l) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; v[j] = q < n ? c.in[ipos + q] : (uint8_t)0; }
+        for (int j = 0; j < 4; ++j) { int64_t q = q0 + l + 32 * j; v[j] = q < n ? c.in[ipos + q] : (uint8_t)0; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { int64_t q = q0 + l + 32 * j; if (q < n) c.out[olen + q] = v[j]; }
+        for (int j = 0; j < 4; ++j) { int64_t q = q0 + l + 32 * j; if (q < n) c.out[olen + q] = v[j]; }
       }
     }
     JB_SYNC();
@@ -755,48 +762,27 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- fixing_sid
-  // The isolated error in untouched territory (fast_delimit succeeded, nbad is k or k-1): the to_be_fixed string is a
-  // stretch of pass-start bases, its single-base candidates are scored by score_single_base.  handled = false leaves
-  // everything to slow_fix (lower-case suspect base, layout does not apply, or nothing passed where the reference goes
-  // on to the diploid / homopolymer repairs).
-  JB_W Fix fast_fix(int64_t s0, int64_t nbad, int64_t ga, bool& handled) {
+  // the fix a verdict describes (jb_verdict.cuh)
+  JB_W Fix verdict_fix(const Verdict& v, int64_t s0, int64_t ga) {
     Fix f;
-    handled = false;
-    const int n = (int)nbad + k - 1;
-    const int ins = nbad == k - 1 ? 1 : 0;
-    const uint8_t* src = c.in + (s0 - (base + olen - ipos));
-    JB_SYNC();
-    JB_LANES(l) { for (int q = l; q < n; q += 32) s.t[q] = src[q]; }
-    JB_SYNC();
-    const uint8_t bad = s.t[k - 1];
-    if (!ins && bad != 'A' && bad != 'C' && bad != 'G' && bad != 'T') return f;
-    pack_bytes(s.pt, s.t, n);
-    const int w = score_single_base(db, s, ins, base_code(bad), n, k, step, solid);
-    if (w == -2 || (w < 0 && ins)) return f;
-    handled = true;
-    lookups += (unsigned long long)(w < 0 ? 36 : 9 * (w + 1));       // (statistics only: about 9 samples per candidate tried)
-    if (w < 0) return f;
+    if (v.kind == kVNone) return f;
     f.found = true; f.repl = s.b;
-    if (ins) {
-      const uint8_t bb = (uint8_t)("ATCG"[w]);
-      fill(s.b, bb, 1);
+    if (v.kind == kVIns) {
+      fill(s.b, v.base, 1);
       f.a = s0 + k - 1; f.e = s0 + k - 1; f.rlen = 1; f.post = kPostIns;
-      fix_row(f, ga, bb, 1, 'd', '-', 1);
-    } else if (w == 3) {
+      fix_row(f, ga, v.base, 1, 'd', '-', 1);
+    } else if (v.kind == kVDel) {
       f.a = s0 + k - 1; f.e = s0 + k; f.rlen = 0; f.post = kPostDel;
-      fix_row(f, ga - 1, '-', 1, 'i', bad, 1);
+      fix_row(f, ga - 1, '-', 1, 'i', v.bad, 1);
     } else {
-      int o = 0, left = w;                                           // the w-th of 'A','C','T','G' that is not the suspect base
-      while (true) { if ((uint8_t)("ACTG"[o]) != bad) { if (left == 0) break; --left; } ++o; }
-      const uint8_t bb = (uint8_t)("ACTG"[o]);
-      fill(s.b, bb, 1);
+      fill(s.b, v.base, 1);
       f.a = s0 + k - 1; f.e = s0 + k; f.rlen = 1; f.post = kPostSub;
-      fix_row(f, ga - 1, bb, 1, 's', bad, 1);
+      fix_row(f, ga - 1, v.base, 1, 's', v.bad, 1);
     }
     return f;
   }
 
-  // the reference's dispatch (src/jasper.py:226-338), out of line: the hot loop only comes here for the events fast_fix declines
+  // the reference's dispatch (src/jasper.py:226-338), out of line: the hot loop only comes here for events without a verdict
   JB_WC Fix slow_fix(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
     Fix f;
@@ -821,11 +807,10 @@ struct Walker {
 
   // ---------------------------------------------------------------------------- fixing_sid
   // returns the PostKind of an applied single-base fix (kPostNone otherwise)
-  JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga, bool fast) {
+  JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga, const Verdict* v) {
     Fix f;
-    bool handled = false;
-    if (fast && (nbad == k || nbad == k - 1)) f = fast_fix(s0, nbad, ga, handled);
-    if (!handled) f = slow_fix(s0, nbad, thr, gb, ga);
+    if (v && v->kind != kVDelimit) f = verdict_fix(*v, s0, ga);
+    else f = slow_fix(s0, nbad, thr, gb, ga);
     int post = kPostNone;
     if (f.found && !status) {
       if (apply_edit(f.a, f.e, f.repl, f.rlen)) {
@@ -917,66 +902,45 @@ struct Walker {
     return true;
   }
 
-  // ---------------------------------------------------------------------------- handle_bad_kmers
-  // ---------------------------------------------------------------------------- fast path (untouched territory)
-  // While the walker stands in bases no edit has touched, every count the reference's run delimiting reads
-  // (src/jasper.py:150-214) is in the bulk scan's arrays.  fast_delimit stages a window of them around i and
-  // evaluates the same loops on it: no window cache, no point queries, no probes.  It either produces exactly
-  // what the generic code below would (same i, gb, ga, s0) or returns false with the walker's state untouched.
-  JB_W bool fast_delimit(int64_t& gb, int64_t& ga, int64_t& s0) {
-    if (!c.cnt || !c.okb) return false;
+  // ---------------------------------------------------------------------------- verdicts (untouched territory)
+  // The isolated error was decided before the walk (jb_verdict.cuh).  While the walker stands in bases no edit has
+  // touched it looks the weak run up by its end and takes bounds, fix and the following scan step from the verdict;
+  // false leaves the walker's state untouched and the generic code runs.
+  JB_W bool consume_verdict(int64_t& gb, int64_t& ga, int64_t& s0, Verdict& v) {
+    if (!c.vmap) return false;
     const int64_t shift = base + olen - ipos;           // new = old + shift for everything >= clean_from
-    const int W = kFastBack + 2 * k + 24;
-    const int64_t W0 = i - kFastBack;
     int64_t lo_x = clean_from > shift ? clean_from : shift;
     if (base - seam_margin > lo_x) lo_x = base - seam_margin;      // (further back the previous segment's walker may have edited)
-    const int64_t hi_p = c.in_len - 2 * (int64_t)k - 3;            // keeps every end-of-contig clamp of the generic code out of play
-    JB_SYNC();
-    JB_LANES(l) { if (l == 0) { s.fbad[0] = -1; s.fbad[1] = W; } }
-    JB_SYNC();
-    JB_LANES(l) {
-      for (int q = l; q < W; q += 32) {
-        const int64_t x = W0 + q, p = x - shift;
-        bool ok = x >= lo_x && p <= hi_p;
-        if (ok) ok = c.okb[p] != 0;
-        s.fc[q] = ok ? c.cnt[p] : 0u;
-        if (!ok) {
+    if (i < lo_x) return false;
+    const int64_t p = i - shift;
+    if (p > c.in_len) return false;
+    int64_t re = -1;                                    // first position >= p whose weak bit is clear
+    {
+      int64_t w = p >> 5;
+      uint32_t m = ~c.weak[w] & (0xFFFFFFFFu << (p & 31));
+      for (int t = 0; t < 3; ++t) {
+        if (m) {
 #if defined(__CUDA_ARCH__)
-          if (q < kFastBack) atomicMax(&s.fbad[0], q); else atomicMin(&s.fbad[1], q);
+          re = (w << 5) + __ffs((int)m) - 1;
 #else
-          if (q < kFastBack) { if (q > s.fbad[0]) s.fbad[0] = q; } else if (q < s.fbad[1]) s.fbad[1] = q;
+          re = (w << 5) + __builtin_ffs((int)m) - 1;
 #endif
+          break;
         }
+        ++w;
+        if ((w << 5) > c.in_len) break;
+        m = ~c.weak[w];
       }
     }
-    JB_SYNC();
-    const int blo = s.fbad[0];                          // entries (blo, bhi) are all available
-    int hi_lim = s.fbad[1] - k - 3;
-    if (W - k - 4 < hi_lim) hi_lim = W - k - 4;
-    const int a = kFastBack;
-    if (a >= hi_lim || (int64_t)s.fc[a] >= solid) return false;
-    int jq = a - 1;
-    while (jq > blo && (int64_t)s.fc[jq] < solid) --jq;
-    if (jq <= blo) return false;
-    int gq = a;
-    while (gq < hi_lim && (int64_t)s.fc[gq] < solid) ++gq;
-    if (gq >= hi_lim) return false;
-    uint64_t prev = s.fc[jq];
-    int g = jq;                                         // g = gb - k + 1
-    if (!(2 * (int64_t)s.fc[g + 1] < solid && 2 * (int64_t)s.fc[g + 2] < solid)) {
-      while (2 * (uint64_t)s.fc[g + 1] >= prev && g < gq) {
-        if (2 * (int64_t)prev >= solid && 2 * (int64_t)s.fc[g + 1] < solid && 2 * (int64_t)s.fc[g + 2] < solid) break;
-        prev = s.fc[g + 1];
-        ++g;
-      }
-    }
-    const int s0q = g + 1;
-    int gaq = gq;
-    if ((int64_t)s.fc[s0q + 1] < solid && (int64_t)s.fc[s0q + k - 2] < solid && (int64_t)s.fc[s0q + k - 1] < solid &&
-        (int64_t)s.fc[s0q + k] >= solid) gaq = s0q + k;
-    i = W0 + gq;
-    gb = W0 + g + k - 1; ga = W0 + gaq; s0 = W0 + s0q;
-    fast_W0 = W0;
+    if (re < 0) return false;
+    const uint32_t id = c.vmap[(c.ev_bit_base + (uint64_t)re) >> 5];
+    if (id == 0u || id == kVmapAmbiguous) return false;
+    v = c.verdicts[id - 1];
+    if (v.re != (uint32_t)re) return false;
+    const int64_t jq = re - (int64_t)v.d_jq;
+    if (jq + shift < lo_x) return false;                // the verdict read counts this walker's edits have invalidated
+    i = re + shift;
+    s0 = jq + (int64_t)v.d_s0 + shift; ga = jq + (int64_t)v.d_ga + shift; gb = s0 + k - 2;
     ++n_fast;
     return true;
   }
@@ -986,24 +950,18 @@ struct Walker {
     ++events;
     const int64_t thre = rolling_thre > 0 ? rolling_thre : solid;
     int64_t gb = 0, ga = 0, s0 = 0;
-    const bool fast = rolling_thre == 0 && fast_delimit(gb, ga, s0);
+    Verdict v;
+    const bool fast = rolling_thre == 0 && consume_verdict(gb, ga, s0, v);
     if (!fast && !generic_delimit(rolling_thre, thre, gb, ga, s0)) return;
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
     wrong += nbad;
     if (!fix || gb < 0) return;
-    const int done = fixing_sid(s0, nbad, thre, gb, ga, fast);
-    if (!fast || !done || status || brk) return;
-    // ---- the scan step that follows a single-base fix (src/jasper.py:56-100 at the new i), from data in hand: the window at
-    // i is untouched (staged count) or a sample of the winning trial; so is the one k bases back.  Anything but the plain
-    // `i += k-1` outcome is left to the loop.
-    int64_t occ, prevk;
-    const int64_t s0q = s0 - fast_W0;
-    if (done == kPostSub && i == s0 + k) { occ = s.fc[s0q + k]; prevk = s.win[0]; }
-    else if (done == kPostDel && i == s0 + k) { occ = s.fc[s0q + k + 1]; prevk = s.win[0]; }
-    else if (done == kPostIns && i == s0 + k - 1) { occ = s.win[1]; prevk = s.fc[s0q - 1]; }
-    else return;
+    const int done = fixing_sid(s0, nbad, thre, gb, ga, fast ? &v : nullptr);
+    if (!fast || !done || status || brk || !v.post_ok) return;
+    // ---- the scan step behind a single-base fix (src/jasper.py:56-100 at the new i) was evaluated with the verdict
     if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;       // the loop re-checks the seam first
-    if (occ >= solid && !((uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) { i += k - 1; ++n_post; }
+    i += k - 1;
+    ++n_post;
   }
 
   // ---------------------------------------------------------------------------- scan loop
@@ -1105,9 +1063,10 @@ struct Walker {
     return occ < rt ? (int64_t)rint(mean / 2.0) : -1;
   }
 
-  JB_W void run() {
+  // segment set-up and result write-back run once per segment: out of line, so the event loop between them stays small
+  JB_WC void begin() {
 #if defined(__CUDA_ARCH__)
-    const long long t_begin = clock64();
+    t_begin = clock64();
 #endif
     c = u;
     base = c.base; seam_margin = seam_read_margin(k); keep_margin = c.keep_margin; wstart = 0; far_back = false;
@@ -1121,6 +1080,41 @@ struct Walker {
       JB_LANES(l) { if (l == 0) { s.empty_count = ec; s.probes = 0; } }
       JB_SYNC();
     }
+  }
+
+  JB_WC void finish(bool reached) {
+    seam_bad = seam_bad || (vflags & kFlagSeam); far_back = far_back || (vflags & kFlagFar);
+#if defined(__CUDA_ARCH__)
+    seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdicts warp-uniform
+    far_back = __any_sync(0xffffffffu, far_back);
+#endif
+    if (!status && seam_bad) status = kSeamViolation;
+    if (!status && far_back) status = kFarBack;
+    if (!status && c.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
+    const int64_t end_old = c.next_anchor >= 0 ? c.next_anchor : c.in_len;
+    if (!status && ipos > end_old) status = kSeamViolation;
+    // new bases of old [base, end_old) = closed jobs ++ out[wstart:olen) ++ in[ipos:end_old)
+    if (fix && !status) {
+      emit_job(c.out + wstart, wstart, olen - wstart);
+      emit_job(c.in + ipos, olen, end_old - ipos);
+    }
+    u.end_old = end_old;
+    u.new_len = status ? 0 : olen + (end_old - ipos);
+    u.wrong = wrong;
+    u.status = status;
+    u.n_rows = seqno;
+    u.n_fast = n_fast; u.n_post = n_post;
+    u.lookups = lookups + s.probes;
+    u.events = events;
+#if defined(__CUDA_ARCH__)
+    u.cycles = (unsigned long long)(clock64() - t_begin);
+#else
+    u.cycles = 0;
+#endif
+  }
+
+  JB_W void run() {
+    begin();
     bool reached = false;
     while (i < L - k + 1 && !brk && !status) {
 #if defined(__CUDA_ARCH__)
@@ -1157,34 +1151,7 @@ struct Walker {
       if (handle >= 0) handle_bad_kmers(handle);
       else i += k - 1;
     }
-    seam_bad = seam_bad || (vflags & kFlagSeam); far_back = far_back || (vflags & kFlagFar);
-#if defined(__CUDA_ARCH__)
-    seam_bad = __any_sync(0xffffffffu, seam_bad);      // lanes read different bases: make the verdicts warp-uniform
-    far_back = __any_sync(0xffffffffu, far_back);
-#endif
-    if (!status && seam_bad) status = kSeamViolation;
-    if (!status && far_back) status = kFarBack;
-    if (!status && c.next_anchor >= 0 && !reached) status = kSeamViolation;   // scan ended (or broke) before the seam
-    const int64_t end_old = c.next_anchor >= 0 ? c.next_anchor : c.in_len;
-    if (!status && ipos > end_old) status = kSeamViolation;
-    // new bases of old [base, end_old) = closed jobs ++ out[wstart:olen) ++ in[ipos:end_old)
-    if (fix && !status) {
-      emit_job(c.out + wstart, wstart, olen - wstart);
-      emit_job(c.in + ipos, olen, end_old - ipos);
-    }
-    u.end_old = end_old;
-    u.new_len = status ? 0 : olen + (end_old - ipos);
-    u.wrong = wrong;
-    u.status = status;
-    u.n_rows = seqno;
-    u.n_fast = n_fast; u.n_post = n_post;
-    u.lookups = lookups + s.probes;
-    u.events = events;
-#if defined(__CUDA_ARCH__)
-    u.cycles = (unsigned long long)(clock64() - t_begin);
-#else
-    u.cycles = 0;
-#endif
+    finish(reached);
   }
 };
 

@@ -101,6 +101,22 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       for (int64_t p = 0; p <= len[i]; ++p)
         if (bit_at(ev[i].data(), p)) l1[i][p >> 15] |= 1u << ((p >> 10) & 31);
     }
+    // verdicts, the way k_verdicts builds them: one per weak run, published under the run's end
+    std::vector<std::vector<uint32_t>> vmaps(n);
+    std::vector<std::vector<Verdict>> verdicts(n);
+    const bool use_verdicts = use_events && !getenv("JB_SIM_NO_OKB");
+    for (size_t i = 0; i < n && use_verdicts; ++i) {
+      vmaps[i].assign((size_t)(len[i] + 1) / 32 + 4, 0);
+      for (int64_t re = 1; re <= len[i]; ++re) {
+        if (bit_at(weak[i].data(), re) || !bit_at(weak[i].data(), re - 1)) continue;
+        Verdict v; int64_t re2 = -1;
+        if (!make_verdict(db, ws, (const uint8_t*)cur[i].data(), cnts[i].data(), okbs[i].data(), len[i], k, sampling_step(k), (int64_t)solid, re - 1, &v, &re2)) continue;
+        if (re2 != re) continue;
+        verdicts[i].push_back(v);
+        uint32_t& cell = vmaps[i][(size_t)re >> 5];
+        cell = cell == 0 ? (uint32_t)verdicts[i].size() : kVmapAmbiguous;
+      }
+    }
     std::vector<BlockRef> blocks;
     if (seg_block) blocks = make_blocks(len, seg_block);
     std::vector<long long> anchors(blocks.size(), -1);
@@ -118,6 +134,8 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       u.out = stage[i].data() + p.stage_off; u.out_cap = p.stage_cap;
       u.cnt = use_events ? cnts[i].data() : nullptr;
       u.okb = (use_events && !getenv("JB_SIM_NO_OKB")) ? okbs[i].data() : nullptr;
+      u.weak = use_events ? weak[i].data() : nullptr;
+      u.vmap = use_verdicts ? vmaps[i].data() : nullptr; u.verdicts = verdicts[i].data();
       u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
       u.slot = slot; u.materialize_all = gen ? 1u : 0u;
