@@ -283,10 +283,11 @@ class QueryMerFile(object):
             _check(lib.jb_result_seq(res, i, C.byref(p), C.byref(ln)))
             seqs.append((names[i], C.string_at(p, ln.value).decode("latin-1") if ln.value else ""))
         out = PolishResult(status=lib.jb_result_status(res), tallies=tallies, rows=rows, seqs=seqs)
-        for key in ("polish", "polish_scan", "polish_plan", "polish_walk", "polish_kwalk", "polish_recount", "h2d", "d2h"):
+        for key in ("polish", "polish_scan", "polish_plan", "polish_walk", "polish_kwalk", "polish_recount", "polish_verdicts", "h2d", "d2h"):
             out.timings[key] = timing_ms(key)
         for key in ("scan_lookups", "walk_lookups", "kernel_launches", "events", "probe_steps", "h2d_bytes", "d2h_bytes",
-                    "segments", "segment_reruns", "seg_block", "full_scans", "full_scan_lookups", "recount_probes", "max_seg_events", "max_seg_lookups", "max_seg_span"):
+                    "segments", "segment_reruns", "seg_block", "full_scans", "full_scan_lookups", "recount_probes", "max_seg_events", "max_seg_lookups", "max_seg_span",
+                    "verdicts", "fast_events", "fast_steps"):
             out.counters[key] = counter(key)
         return out
 

@@ -813,6 +813,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     }
     JB_CUDA(cudaEventRecord(ev_d, s));
     mark("concat launched", ite);
+    // this pass's fix log lands while k_concat / k_recount run: hand it to its row thread now, not at the next pass
+    if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
     JB_CUDA(cudaStreamSynchronize(s));                   // dst_off (a host vector) must stay alive until k_concat has read it
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_a, ev_b); scan_ms += ms;

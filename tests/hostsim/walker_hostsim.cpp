@@ -125,6 +125,16 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       const int64_t lo = (int64_t)blocks[q].start, hi = std::min<int64_t>(lo + seg_block, len[u]);
       anchors[q] = first_anchor(ev[u].data(), weak[u].data(), lo, hi, k, len[u], margin);
     }
+    if (getenv("JB_SIM_TRACE") && ite > 0 && use_events) {
+      for (size_t u = 0; u < n; ++u)
+        for (int64_t a = 1; a <= len[u]; ++a) {
+          if (!bit_at(weak[u].data(), a) || bit_at(weak[u].data(), a - 1)) continue;
+          int64_t run = 0; while (a + run <= len[u] && bit_at(weak[u].data(), a + run)) ++run;
+          int64_t evb = -1; for (int64_t p2 = a - 1; p2 >= 0 && p2 >= a - margin; --p2) if (bit_at(ev[u].data(), p2)) { evb = a - p2; break; }
+          fprintf(stderr, "[sim]   pass %d weak run at %lld len %lld, nearest event before: %lld back, anchor=%d\n", ite, (long long)a, (long long)run, (long long)evb,
+                  (int)is_anchor(ev[u].data(), weak[u].data(), a, k, len[u], margin));
+        }
+    }
     std::vector<SegPlan> plan = plan_segments(len, caps, blocks, anchors.data());
     auto make_seg = [&](const SegPlan& p, uint32_t gen, uint32_t slot) {
       UnitIO u;
@@ -158,6 +168,12 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       }
     }
     res->segments += plan.size();
+    if (getenv("JB_SIM_TRACE")) {
+      unsigned long long ev = 0, fast = 0; size_t na = 0;
+      for (const UnitIO& u : segs) { ev += u.events; fast += u.n_fast; }
+      for (long long a : anchors) na += a >= 0;
+      fprintf(stderr, "[sim] pass %d: %zu segments, %zu blocks, %zu anchors, %llu events, %llu from verdicts\n", ite, plan.size(), blocks.size(), na, ev, fast);
+    }
     size_t n_slots = plan.size();
     if (any_redo) {
       std::vector<UnitIO> merged;

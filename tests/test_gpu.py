@@ -152,6 +152,21 @@ def test_incremental_recount_equals_full_scan(golden_cases, dbs, name, monkeypat
     assert (a.rows, a.seqs, a.tallies) == (b.rows, b.seqs, b.tallies)
 
 
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_verdicts_change_nothing(golden_cases, dbs, name, monkeypatch):
+    """k_verdicts decides the isolated errors in bulk and the walkers consume its verdicts; with JB_NO_VERDICTS the
+    walkers decide everything themselves.  Same bytes either way, and the verdicts really carry most events."""
+    case = golden_cases[name]
+    seqs = jo.read_fasta(case["fasta"])
+    a = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
+    assert a.status == 0 and a.counters["verdicts"] > 0
+    assert a.counters["fast_events"] * 2 > a.counters["events"], a.counters
+    monkeypatch.setenv("JB_NO_VERDICTS", "1")
+    b = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
+    assert b.counters["verdicts"] == 0 and b.counters["fast_events"] == 0
+    assert (a.rows, a.seqs, a.tallies) == (b.rows, b.seqs, b.tallies)
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_polish_fuzz_matches_oracle(tmp_path, seed, monkeypatch):
     monkeypatch.setenv("JB_VERIFY_RECOUNT", "1")
