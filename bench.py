@@ -181,13 +181,14 @@ def workload_text(genome_mb, meta, n_chunks):
 
 def ncu_traffic_gb():
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch on this workload, from the committed
-    ncu --set full summary (profiles/); None when the summary is missing."""
+    ncu --set full summary (profiles/, written by tools/ncu_keymetrics.py); None when the summary is missing."""
+    import csv
+    scale = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
     try:
         vals = {}
-        for line in open(os.path.join(ROOT, "profiles", "r1_k_scan_ncu_full_keymetrics.csv")):
-            f = line.strip().split(",")
-            if len(f) == 3 and f[0].startswith("dram__bytes_"):
-                vals[f[0]] = float(f[2]) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[f[1]]
+        for row in csv.reader(l for l in open(os.path.join(ROOT, "profiles", "r1s_scan_kernels_ncu_full.csv")) if not l.startswith("#")):
+            if len(row) == 7 and row[1] == "k_scan" and row[4].startswith("dram__bytes_"):
+                vals[row[4]] = float(row[6]) * scale[row[5]]
         return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
     except Exception:
         return None
