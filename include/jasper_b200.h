@@ -95,6 +95,12 @@ const char* jb_version(void);
 int jb_db_open(const char* jf_path, int device, jb_db** out);
 int jb_db_info(const jb_db* db, jb_db_info_t* out);
 int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** outs);
+/* The fallback for a table beyond one GPU's HBM (the reference's answer is mmap + page cache,
+ * JF!include/jellyfish/mapped_file.hpp:30-50): the slots of ONE database partitioned over n devices of this process
+ * (peer access required).  outs[i] lives on devices[i], owns part i and probes every part -- its own in HBM, the
+ * others by 32-byte peer loads over NVLink / NVSwitch.  Every entry point that takes a jb_db works on such a handle
+ * except jb_db_dump and jb_db_replicate.  Close every handle with jb_db_close. */
+int jb_db_open_partitioned(const char* jf_path, int n, const int* devices, jb_db** outs);
 void jb_db_close(jb_db* db);
 /* Dump the resident table back as (key_lo, key_hi, count) triples in slot order (tests: must
  * equal the file's record list).  `cap` = capacity of the three arrays in records. */

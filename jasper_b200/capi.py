@@ -59,7 +59,7 @@ except Exception:                                  # numpy is optional: the slow
 # every symbol include/jasper_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "jb_init", "jb_device_count", "jb_last_error", "jb_version",
-    "jb_db_open", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
+    "jb_db_open", "jb_db_open_partitioned", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
     "jb_lookup", "jb_lookup_flat", "jb_count_positions",
     "jb_polish", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
     "jb_result_status", "jb_result_iterations", "jb_result_tally", "jb_result_num_rows", "jb_result_rows",
@@ -91,6 +91,7 @@ def load_library():
         "jb_last_error": (C.c_char_p, []),
         "jb_version": (C.c_char_p, []),
         "jb_db_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "jb_db_open_partitioned": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
         "jb_db_info": (C.c_int, [vp, C.POINTER(_DbInfo)]),
         "jb_db_replicate": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
         "jb_db_close": (None, [vp]),
@@ -181,6 +182,28 @@ class QueryMerFile(object):
         self.info = {f: getattr(info, f) for f, _ in _DbInfo._fields_}
         self.k = info.k
         self.device = device
+
+    @classmethod
+    def open_partitioned(cls, path: str, devices):
+        """ONE database whose slots are spread over `devices` (the fallback for a table beyond one GPU's HBM, SURVEY.md
+        section 8e): returns one QueryMerFile per device; each owns its part and probes the others by peer loads."""
+        lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(lib.jb_init(len(devices), devs))
+        hs = (C.c_void_p * len(devices))()
+        _check(lib.jb_db_open_partitioned(os.fsencode(path), len(devices), devs, hs))
+        out = []
+        for d, h in zip(devices, hs):
+            qf = cls.__new__(cls)
+            qf._lib = lib
+            qf._h = C.c_void_p(h)
+            info = _DbInfo()
+            _check(lib.jb_db_info(qf._h, C.byref(info)))
+            qf.info = {f: getattr(info, f) for f, _ in _DbInfo._fields_}
+            qf.k = info.k
+            qf.device = d
+            out.append(qf)
+        return out
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -36,17 +36,35 @@ struct __align__(16) Slot {
   uint32_t count;
 };
 
+// A table is either whole (n_parts <= 1: every slot in `slots`) or PARTITIONED over the GPUs of one box (SURVEY.md §8e
+// fallback for tables beyond one GPU's HBM): part p, resident on its own device, holds slots [part_first[p],
+// part_first[p+1] + kPartOverlap), i.e. its own range plus a copy of the start of the next part, so that a probe that
+// starts in part p never leaves part p's memory.  A probe of a foreign part is a peer load over NVLink / NVSwitch.
+constexpr int kMaxParts = 8;
+constexpr uint64_t kPartOverlap = 65536;     // slots; the loader verifies that every probe run entering it ends inside it
 struct TableView {
   const Slot* slots;
   const uint64_t* lut;   // key_bytes * 256 entries
   TableGeom g;
   Key mask;
+  int n_parts;
+  const Slot* part[kMaxParts];
+  uint64_t part_first[kMaxParts + 1];
 };
+
+// the 32-byte sector of slot index `home` (even), wherever it lives
+__device__ __forceinline__ const ulonglong4* home_sector(const TableView& t, uint64_t home) {
+  if (t.n_parts <= 1) return reinterpret_cast<const ulonglong4*>(t.slots) + (home >> 1);
+  int p = 0;
+#pragma unroll 1
+  for (int q = 1; q < t.n_parts; ++q) p += home >= t.part_first[q] ? 1 : 0;      // (rare path: keep it small, no unrolling)
+  return reinterpret_cast<const ulonglong4*>(t.part[p]) + ((home - t.part_first[p]) >> 1);
+}
 
 // Probe: starting at the sector of the home slot, scan slots until the key or an empty slot.
 // 256-bit loads (LDG.E.256) fetch exactly one 32-byte sector per step.
 __device__ __forceinline__ uint32_t table_find(const TableView& t, const Key& key, uint64_t home, int* steps = nullptr) {
-  const ulonglong4* sec = reinterpret_cast<const ulonglong4*>(t.slots) + (home >> 1);
+  const ulonglong4* sec = home_sector(t, home);
   int n = 0;
   while (true) {
     unsigned long long w0, w1, w2, w3;
@@ -85,9 +103,16 @@ struct jb_db {
   uint64_t max_disp = 0;
   double load_seconds = 0, build_ms = 0;
   cudaStream_t stream = nullptr;
+  // partitioned tables (jb_db_open_partitioned): this handle owns part `my_part`; the others are peer memory
+  int n_parts = 1, my_part = 0;
+  jb::Slot* parts[jb::kMaxParts] = {};
+  uint64_t part_first[jb::kMaxParts + 1] = {};
   jb::TableView view() const {
     jb::TableView v;
     v.slots = slots; v.lut = lut; v.g = geom; v.mask = jb::key_mask(hdr.k());
+    v.n_parts = n_parts;
+    for (int q = 0; q < jb::kMaxParts; ++q) v.part[q] = parts[q];
+    for (int q = 0; q <= jb::kMaxParts; ++q) v.part_first[q] = part_first[q];
     return v;
   }
 };

@@ -127,7 +127,7 @@ extern "C" int jb_gather_bench(const jb_db* db, uint64_t n_probes, int sector_by
   if (sector_bytes != 32 && sector_bytes != 64 && sector_bytes != 128) return fail(JB_E_ARG, "sector_bytes must be 32, 64 or 128");
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
-  const uint64_t table_bytes = db->n_slots * sizeof(Slot);
+  const uint64_t table_bytes = (db->n_parts > 1 ? db->part_first[db->my_part + 1] - db->part_first[db->my_part] : db->n_slots) * sizeof(Slot);
   const uint64_t n_sectors = table_bytes / sector_bytes;
   const int threads = 256, blocks = 148 * 8;
   uint64_t per_thread = std::max<uint64_t>(4, (n_probes / ((uint64_t)threads * blocks) + 3) / 4 * 4);

@@ -927,6 +927,7 @@ extern "C" void jb_result_free(jb_result* r) { delete r; }
 
 extern "C" int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** outs) {
   if (!src || (n && (!devices || !outs))) return fail(JB_E_ARG, "jb_db_replicate: null argument");
+  if (src->n_parts > 1) return fail(JB_E_UNSUPPORTED, "jb_db_replicate: the source is a partitioned table");
   for (int i = 0; i < n; ++i) {
     auto d = new jb_db(*src);
     d->device = devices[i]; d->slots = nullptr; d->lut = nullptr; d->stream = nullptr;

@@ -91,7 +91,7 @@ k_scan(TableView t, ScanArgs a) {
             else m = key_canonical(key_from_chars(s_seq + r0 + q, k, k, t.mask), k);   // rare: N / IUPAC / contig tail
             keys[b] = m;
             const uint64_t pos = hash_lut(s_lut, t.g.key_bytes, m);
-            sec[b] = reinterpret_cast<const ulonglong4*>(t.slots) + (home_slot(t.g, pos, m) >> 1);
+            sec[b] = home_sector(t, home_slot(t.g, pos, m));
             asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
                          : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
           }

@@ -103,10 +103,28 @@ __global__ void k_block_carry(long long* block_max, int nblocks, BuildState* st)
   if (lane == 0) st->carry = run;
 }
 
+// Where k_place writes: one array, or the parts of a partitioned table (peer stores for the foreign ones; a slot inside
+// the first `overlap` slots of part p is also written behind the end of part p-1).
+struct PlaceTarget {
+  Slot* slots;
+  int n_parts;
+  uint64_t overlap;
+  Slot* part[kMaxParts];
+  uint64_t part_first[kMaxParts + 1];
+};
+__device__ __forceinline__ void put_slot(const PlaceTarget& T, uint64_t slot, const Slot& v) {
+  if (T.n_parts <= 1) { T.slots[slot] = v; return; }
+  int p = 0;
+#pragma unroll 1
+  for (int q = 1; q < T.n_parts; ++q) p += slot >= T.part_first[q] ? 1 : 0;
+  T.part[p][slot - T.part_first[p]] = v;
+  if (p > 0 && slot < T.part_first[p] + T.overlap) T.part[p - 1][slot - T.part_first[p - 1]] = v;
+}
+
 // K0c: inclusive prefix-max inside the block, then scatter the 16-byte slots.
 __global__ void __launch_bounds__(kThreads)
 k_place(uint64_t n, uint64_t base_index, const uint64_t* __restrict__ key_lo, const uint64_t* __restrict__ key_hicnt,
-        const uint64_t* __restrict__ home, const long long* __restrict__ block_carry, Slot* __restrict__ slots,
+        const uint64_t* __restrict__ home, const long long* __restrict__ block_carry, PlaceTarget target,
         uint64_t n_slots, BuildState* st) {
   __shared__ long long s_warp[kThreads / 32];
   const uint64_t first = (uint64_t)blockIdx.x * kRecPerBlock;
@@ -146,7 +164,7 @@ k_place(uint64_t n, uint64_t base_index, const uint64_t* __restrict__ key_lo, co
     uint64_t hc = key_hicnt[gi];
     Slot s; s.lo = key_lo[gi]; s.hi = (uint32_t)hc; s.count = (uint32_t)(hc >> 32);
     if (s.count == 0) st->err_zero = 1;
-    slots[slot] = s;
+    put_slot(target, slot, s);
     disp = max(disp, (unsigned long long)(slot - h[q]));
     last = slot;
   }
@@ -199,14 +217,35 @@ int ceil_log2(uint64_t x) { int b = 0; while ((1ull << b) < x && b < 63) ++b; re
 
 using namespace jb;
 
-extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
-  if (!path || !out) return fail(JB_E_ARG, "jb_db_open: null argument");
-  *out = nullptr;
+namespace {
+
+// One database, n >= 1 handles.  n == 1: the whole table on devices[0].  n > 1: the slots partitioned over the devices
+// (SURVEY.md §8e fallback): the records are unpacked and placed by kernels on devices[0], whose stores go straight into
+// the owning part (peer stores), so the table never has to fit one GPU; every handle then probes all parts.
+int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
   auto t0 = std::chrono::steady_clock::now();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(JB_E_CUDA, "no CUDA device: libjasper_b200 has no CPU path");
-  if (device < 0 || device >= ndev) return fail(JB_E_ARG, "jb_db_open: bad device index");
+  if (n_dev < 1 || n_dev > kMaxParts) return fail(JB_E_ARG, "jb_db_open: between 1 and " + std::to_string(kMaxParts) + " devices");
+  for (int i = 0; i < n_dev; ++i) {
+    if (devices[i] < 0 || devices[i] >= ndev) return fail(JB_E_ARG, "jb_db_open: bad device index");
+    for (int j = 0; j < i; ++j) if (devices[j] == devices[i]) return fail(JB_E_ARG, "jb_db_open_partitioned: a device is listed twice");
+  }
+  const int device = devices[0];
+  if (n_dev > 1) {
+    for (int i = 0; i < n_dev; ++i)
+      for (int j = 0; j < n_dev; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        JB_CUDA(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+        if (!can) return fail(JB_E_UNSUPPORTED, "jb_db_open_partitioned: devices " + std::to_string(devices[i]) + " and " + std::to_string(devices[j]) + " have no peer access");
+        JB_CUDA(cudaSetDevice(devices[i]));
+        cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(JB_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+        cudaGetLastError();
+      }
+  }
   JB_CUDA(cudaSetDevice(device));
 
   int fd = ::open(path, O_RDONLY);
@@ -220,48 +259,80 @@ extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
   for (int i = 0; i < 9; ++i) hlen = hlen * 10 + (uint64_t)((head[i] >= '0' && head[i] <= '9') ? head[i] - '0' : 0);
   head.resize(9 + std::min<uint64_t>(hlen, fsize - 9));
   if ((uint64_t)pread(fd, head.data(), head.size(), 0) != head.size()) { ::close(fd); return fail(JB_E_IO, "short read of header"); }
-  auto db = new jb_db();
+  std::vector<jb_db*> dbs((size_t)n_dev, nullptr);
+  for (int i = 0; i < n_dev; ++i) dbs[i] = new jb_db();
+  auto drop = [&]() { for (jb_db* d : dbs) jb_db_close(d); };
+  jb_db* db = dbs[0];
   std::string err = parse_jf_header(head.data(), head.size(), &db->hdr);
-  if (!err.empty()) { ::close(fd); delete db; return fail(JB_E_FORMAT, err); }
+  if (!err.empty()) { ::close(fd); drop(); return fail(JB_E_FORMAT, err); }
   const JfHeader& h = db->hdr;
-  if (h.k() > JB_MAX_K || h.k() < 1) { ::close(fd); delete db; return fail(JB_E_UNSUPPORTED, "k = " + std::to_string(h.k()) + " outside [1, " + std::to_string(JB_MAX_K) + "]"); }
+  if (h.k() > JB_MAX_K || h.k() < 1) { ::close(fd); drop(); return fail(JB_E_UNSUPPORTED, "k = " + std::to_string(h.k()) + " outside [1, " + std::to_string(JB_MAX_K) + "]"); }
   const uint64_t body = fsize - h.data_offset;
   const int rec = h.record_bytes();
-  if (body % rec) { ::close(fd); delete db; return fail(JB_E_FORMAT, "Size of database (" + std::to_string(body) + ") must be a multiple of the length of a record (" + std::to_string(rec) + ")"); }
+  if (body % rec) { ::close(fd); drop(); return fail(JB_E_FORMAT, "Size of database (" + std::to_string(body) + ") must be a multiple of the length of a record (" + std::to_string(rec) + ")"); }
   const uint64_t n = body / rec;
-  db->n_records = n;
-  db->device = device;
 
   // ---- geometry -------------------------------------------------------------------------------
   double load = 0.5;
   if (const char* e = getenv("JB_TABLE_LOAD")) { double v = atof(e); if (v > 0.05 && v <= 0.95) load = v; }
-  size_t free_b = 0, total_b = 0;
-  JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t free_b = ~(size_t)0, total_b = 0;
+  for (int i = 0; i < n_dev; ++i) {                       // the tightest device decides
+    size_t f = 0;
+    JB_CUDA(cudaSetDevice(devices[i]));
+    JB_CUDA(cudaMemGetInfo(&f, &total_b));
+    free_b = std::min(free_b, f);
+  }
+  JB_CUDA(cudaSetDevice(device));
   uint64_t cap = 0, tail = 0, n_slots = 0;
   for (int attempt = 0; attempt < 8; ++attempt) {
     uint64_t half = std::max<uint64_t>(256, (uint64_t)((double)n / load / 2.0) + 1);
     cap = 2 * half;
     tail = std::max<uint64_t>(65536, cap / 64);
     n_slots = cap + tail + 8;
-    if (n_slots * sizeof(Slot) + (512ull << 20) < free_b) break;
-    if (load >= 0.9) { ::close(fd); delete db; return fail(JB_E_NOMEM, "k-mer table (" + std::to_string(n) + " records) does not fit in device memory"); }
+    if ((n_slots / (uint64_t)n_dev + kPartOverlap + tail) * sizeof(Slot) + (512ull << 20) < free_b) break;
+    if (load >= 0.9) { ::close(fd); drop(); return fail(JB_E_NOMEM, "k-mer table (" + std::to_string(n) + " records) does not fit in device memory"); }
     load = std::min(0.9, load + 0.1);
   }
   int r = ceil_log2(h.size);
   int want = ceil_log2(cap / 2) + 6 - r;
   int ext = std::max(0, std::min({want, h.key_bits, 64 - r}));
-  TableGeom& g = db->geom;
+  TableGeom g{};
   g.half_cap = cap / 2; g.pos_mask = h.size - 1; g.k = h.k(); g.key_bytes = h.key_bytes();
   g.ext_bits = ext; g.left_shift = 64 - (r + ext); g.key_top_shift = h.key_bits - ext;
-  db->cap = cap; db->n_slots = n_slots;
 
-  JB_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
-  cudaStream_t s = db->stream;
-  JB_CUDA(cudaMalloc(&db->slots, n_slots * sizeof(Slot)));
-  JB_CUDA(cudaMemsetAsync(db->slots, 0, n_slots * sizeof(Slot), s));
+  // parts: equal shares of [0, cap), the last one also takes the overflow tail
+  uint64_t part_first[kMaxParts + 1] = {};
+  uint64_t overlap = n_dev > 1 ? kPartOverlap : 0;
+  for (int p2 = 0; p2 <= n_dev; ++p2) part_first[p2] = p2 == n_dev ? n_slots : (cap / (uint64_t)n_dev * (uint64_t)p2) & ~1ull;
+  for (int p2 = 0; p2 + 1 < n_dev; ++p2) overlap = std::min<uint64_t>(overlap, (part_first[p2 + 2] - part_first[p2 + 1]) & ~(uint64_t)1);
   std::vector<uint64_t> lut = build_hash_lut(h);
-  JB_CUDA(cudaMalloc(&db->lut, lut.size() * 8));
-  JB_CUDA(cudaMemcpyAsync(db->lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, s));
+  Slot* parts[kMaxParts] = {};
+  for (int i = 0; i < n_dev; ++i) {
+    jb_db* d = dbs[i];
+    if (i) d->hdr = db->hdr;
+    d->n_records = n; d->device = devices[i]; d->geom = g; d->cap = cap; d->n_slots = n_slots;
+    JB_CUDA(cudaSetDevice(devices[i]));
+    JB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    const uint64_t mine = part_first[i + 1] - part_first[i] + (i + 1 < n_dev ? overlap : 0);
+    if (cudaMalloc(&d->slots, mine * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); ::close(fd); drop(); return fail(JB_E_NOMEM, "cannot allocate the k-mer table part on device " + std::to_string(devices[i])); }
+    JB_CUDA(cudaMemsetAsync(d->slots, 0, mine * sizeof(Slot), d->stream));
+    JB_CUDA(cudaMalloc(&d->lut, lut.size() * 8));
+    JB_CUDA(cudaMemcpyAsync(d->lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, d->stream));
+    JB_CUDA(cudaStreamSynchronize(d->stream));
+    parts[i] = d->slots;
+  }
+  for (int i = 0; i < n_dev; ++i) {
+    jb_db* d = dbs[i];
+    d->n_parts = n_dev; d->my_part = i;
+    for (int q = 0; q < n_dev; ++q) d->parts[q] = parts[q];
+    for (int q = 0; q <= n_dev; ++q) d->part_first[q] = part_first[q];
+  }
+  JB_CUDA(cudaSetDevice(device));
+  cudaStream_t s = db->stream;
+  PlaceTarget target{};
+  target.slots = db->slots; target.n_parts = n_dev; target.overlap = overlap;
+  for (int q = 0; q < n_dev; ++q) target.part[q] = parts[q];
+  for (int q = 0; q <= n_dev; ++q) target.part_first[q] = part_first[q];
 
   // ---- stream the records ---------------------------------------------------------------------
   const uint64_t chunk_rec = std::min<uint64_t>(std::max<uint64_t>(n, 1), 4ull << 20);
@@ -306,7 +377,7 @@ extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
     k_unpack<<<nb, kThreads, (size_t)kRecPerBlock * rec + 16, s>>>(d_raw[buf], m, done, rec, h.key_bytes(), h.counter_len, view,
                                                                     d_lo, d_hc, d_home, d_bmax);
     k_block_carry<<<1, 32, 0, s>>>(d_bmax, nb, d_st);
-    k_place<<<nb, kThreads, 0, s>>>(m, done, d_lo, d_hc, d_home, d_bmax, db->slots, n_slots, d_st);
+    k_place<<<nb, kThreads, 0, s>>>(m, done, d_lo, d_hc, d_home, d_bmax, target, n_slots, d_st);
     done += m;
     buf ^= 1;
   }
@@ -320,16 +391,37 @@ extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
   for (int b = 0; b < 2; ++b) { cudaFreeHost(pinned[b]); cudaFree(d_raw[b]); cudaEventDestroy(copied[b]); }
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   cudaFree(d_lo); cudaFree(d_hc); cudaFree(d_home); cudaFree(d_bmax); cudaFree(d_st);
-  if (ce != cudaSuccess) { jb_db_close(db); return fail(JB_E_CUDA, std::string("table build: ") + cudaGetErrorString(ce)); }
-  if (io_error) { jb_db_close(db); return fail(JB_E_IO, "short read while streaming records"); }
-  if (fin.err_unsorted) { jb_db_close(db); return fail(JB_E_FORMAT, "records are not sorted by (hash position, key): not a jellyfish binary/sorted file"); }
-  if (fin.err_zero) { jb_db_close(db); return fail(JB_E_UNSUPPORTED, "database holds a record whose count is 0 modulo 2^32"); }
-  if (fin.err_overflow) { jb_db_close(db); return fail(JB_E_NOMEM, "table overflow tail exhausted (hash positions are badly skewed); lower JB_TABLE_LOAD"); }
-  db->max_disp = fin.max_disp;
-  db->build_ms = ms;
-  db->load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  *out = db;
+  if (ce != cudaSuccess) { drop(); return fail(JB_E_CUDA, std::string("table build: ") + cudaGetErrorString(ce)); }
+  if (io_error) { drop(); return fail(JB_E_IO, "short read while streaming records"); }
+  if (fin.err_unsorted) { drop(); return fail(JB_E_FORMAT, "records are not sorted by (hash position, key): not a jellyfish binary/sorted file"); }
+  if (fin.err_zero) { drop(); return fail(JB_E_UNSUPPORTED, "database holds a record whose count is 0 modulo 2^32"); }
+  if (fin.err_overflow) { drop(); return fail(JB_E_NOMEM, "table overflow tail exhausted (hash positions are badly skewed); lower JB_TABLE_LOAD"); }
+  // a probe that starts in part p ends at the first empty slot: there must be one inside p's copy of the next part's start
+  for (int p2 = 0; p2 + 1 < n_dev; ++p2) {
+    std::vector<Slot> ov((size_t)overlap);
+    JB_CUDA(cudaSetDevice(devices[p2]));
+    JB_CUDA(cudaMemcpy(ov.data(), parts[p2] + (part_first[p2 + 1] - part_first[p2]), (size_t)overlap * sizeof(Slot), cudaMemcpyDeviceToHost));
+    bool empty = false;
+    for (uint64_t q = 0; q + 2 < overlap && !empty; ++q) empty = ov[q].count == 0;
+    if (!empty) { drop(); return fail(JB_E_NOMEM, "a run of occupied slots crosses a whole partition overlap (" + std::to_string(overlap) + " slots); lower JB_TABLE_LOAD"); }
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int i = 0; i < n_dev; ++i) { dbs[i]->max_disp = fin.max_disp; dbs[i]->build_ms = ms; dbs[i]->load_seconds = secs; outs[i] = dbs[i]; }
   return JB_OK;
+}
+
+}  // namespace
+
+extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
+  if (!path || !out) return fail(JB_E_ARG, "jb_db_open: null argument");
+  *out = nullptr;
+  return open_impl(path, 1, &device, out);
+}
+
+extern "C" int jb_db_open_partitioned(const char* path, int n, const int* devices, jb_db** outs) {
+  if (!path || !devices || !outs || n < 1) return fail(JB_E_ARG, "jb_db_open_partitioned: bad argument");
+  for (int i = 0; i < n; ++i) outs[i] = nullptr;
+  return open_impl(path, n, devices, outs);
 }
 
 void jb_release_cached_workspaces(int device);      // jb_polish.cu
@@ -357,6 +449,7 @@ extern "C" int jb_db_info(const jb_db* db, jb_db_info_t* o) {
 
 extern "C" int jb_db_dump(const jb_db* db, uint64_t* key_lo, uint64_t* key_hi, uint32_t* count, uint64_t cap, uint64_t* n_out) {
   if (!db || !n_out) return fail(JB_E_ARG, "jb_db_dump: null argument");
+  if (db->n_parts > 1) return fail(JB_E_UNSUPPORTED, "jb_db_dump: not available on a partitioned table");
   JB_CUDA(cudaSetDevice(db->device));
   *n_out = db->n_records;
   if (cap < db->n_records) return fail(JB_E_ARG, "jb_db_dump: arrays too small");
@@ -391,7 +484,11 @@ extern "C" int jb_db_histogram(const jb_db* db, uint64_t high, uint64_t* hist) {
   unsigned long long* d_h = nullptr;
   JB_CUDA(cudaMalloc(&d_h, (high + 2) * 8));
   JB_CUDA(cudaMemsetAsync(d_h, 0, (high + 2) * 8, db->stream));
-  k_histogram<<<148 * 8, 256, 0, db->stream>>>(db->slots, db->n_slots, high, d_h);
+  if (db->n_parts > 1) {
+    for (int p = 0; p < db->n_parts; ++p)                 // every part's own range (peer reads for the foreign ones)
+      k_histogram<<<148 * 8, 256, 0, db->stream>>>(db->parts[p], db->part_first[p + 1] - db->part_first[p], high, d_h);
+  } else
+    k_histogram<<<148 * 8, 256, 0, db->stream>>>(db->slots, db->n_slots, high, d_h);
   JB_CUDA(cudaMemcpyAsync(hist, d_h, (high + 2) * 8, cudaMemcpyDeviceToHost, db->stream));
   JB_CUDA(cudaStreamSynchronize(db->stream));
   cudaFree(d_h);

@@ -293,3 +293,37 @@ def test_jasper_py_cli_is_drop_in(golden_cases, name, tmp_path):
     # a wrong k is refused with exit 1 (the reference would silently mis-read k-mers)
     bad = subprocess.run([c if c != str(case["k"]) else str(case["k"] - 2) for c in cmd], cwd=tmp_path, capture_output=True, text=True)
     assert bad.returncode == 1
+
+
+def _n_gpus():
+    try:
+        return capi.load_library().jb_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name", ["k37_mix", "k25_mix"])
+def test_partitioned_table_equals_the_whole_one(golden_cases, dbs, name, monkeypatch):
+    """SURVEY.md section 8e fallback: the slots of one database spread over two GPUs, foreign parts probed by peer
+    loads.  Every handle must answer exactly like the single-GPU table: edge-case lookups, per-position counts,
+    histogram, and the whole polishing loop (run from both devices)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs with peer access")
+    case = golden_cases[name]
+    whole = dbs[name]
+    parts = capi.QueryMerFile.open_partitioned(case["db"], [0, 1])
+    try:
+        strings = [s for s, _, _ in case["lookups"]]
+        seqs = jo.read_fasta(case["fasta"])
+        want = whole.polish(seqs, case["k"], case["threshold"], case["passes"])
+        for qf in parts:
+            assert qf.lookup(strings) == [c for _, _, c in case["lookups"]]
+            assert (qf.count_positions(seqs[0][1]) == whole.count_positions(seqs[0][1])).all()
+            assert list(qf.histogram(1000)) == list(whole.histogram(1000))
+            got = qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+            assert (got.rows, got.seqs, got.tallies) == (want.rows, want.seqs, want.tallies)
+        with pytest.raises(capi.JasperError):
+            parts[0].dump()
+    finally:
+        for qf in parts:
+            qf.close()
