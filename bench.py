@@ -252,7 +252,7 @@ def main():
                  "full_scans": capi.counter("full_scans"), "full_scan_lookups": capi.counter("full_scan_lookups"),
                  "recount_probes": capi.counter("recount_probes"), "recount_ms": capi.timing_ms("polish_recount"),
                  "seg_block": capi.counter("seg_block"), "fast_events": capi.counter("fast_events"), "fast_steps": capi.counter("fast_steps"),
-                 "verdicts": capi.counter("verdicts"), "verdict_ms": capi.timing_ms("polish_verdicts"), "kwalk_ms": capi.timing_ms("polish_kwalk"),
+                 "verdicts": capi.counter("verdicts"), "verdict2_events": capi.counter("verdict2_events"), "verdict_ms": capi.timing_ms("polish_verdicts"), "kwalk_ms": capi.timing_ms("polish_kwalk"),
                  "max_seg_events": capi.counter("max_seg_events"), "max_seg_lookups": capi.counter("max_seg_lookups"),
                  "max_seg_span": capi.counter("max_seg_span"),
                  "slowest_segment_per_pass": [{key: capi.counter("%s%d" % (key, q)) for key in ("slow_cycles", "slow_events", "slow_lookups", "slow_span", "sum_cycles")} for q in range(3)]}
@@ -385,7 +385,7 @@ def main():
         "cpu_baseline": cpu,
         "lookups_per_s": (last_stats["scan_lookups"] + last_stats["walk_lookups"]) / (ms_per_step * 1e-3) * world,
         "detail": {"scan_ms": last_stats["scan_ms"], "recount_ms": last_stats["recount_ms"], "recount_probes": last_stats["recount_probes"], "plan_ms": last_stats["plan_ms"], "walk_ms": last_stats["walk_ms"], "events": last_stats["events"], "verdicts": last_stats["verdicts"], "verdict_ms": last_stats["verdict_ms"],
-                   "events_from_verdicts": last_stats["fast_events"], "scan_steps_from_verdicts": last_stats["fast_steps"],
+                   "events_from_verdicts": last_stats["fast_events"], "scan_steps_from_verdicts": last_stats["fast_steps"], "fixes_from_second_stage_verdicts": last_stats["verdict2_events"],
                    "kwalk_ms": last_stats["kwalk_ms"], "max_seg_events": last_stats["max_seg_events"], "max_seg_lookups": last_stats["max_seg_lookups"],
                    "max_seg_span": last_stats["max_seg_span"], "slowest_segment_per_pass": last_stats["slowest_segment_per_pass"], "segments": last_stats["segments"], "segment_reruns": last_stats["reruns"], "seg_block": last_stats["seg_block"],
                    "walk_lookups": last_stats["walk_lookups"], "db_open_s": open_s, "table_gb": qf.info["table_bytes"] / 1e9,

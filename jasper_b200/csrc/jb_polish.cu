@@ -76,6 +76,8 @@ struct VerdictArgs {
   const uint8_t* bases; const ScanUnit* units; const uint32_t* tile_first; uint32_t n_units, n_tiles;
   const uint32_t* counts; const uint8_t* okb; const uint32_t* weak;
   Verdict* verdicts; unsigned long long cap; unsigned long long* used; uint32_t* vmap;
+  uint32_t* verdict_unit;       // contig of every verdict (k_verdicts2 needs it)
+  Verdict2* verdicts2;
   int k, step; uint32_t solid;
 };
 constexpr int kVerdictWarps = 4;
@@ -115,12 +117,49 @@ k_verdicts(TableView t, VerdictArgs a) {
         const unsigned long long id = atomicAdd(a.used, 1ull);
         if (id < a.cap) {
           a.verdicts[id] = *slot;
+          a.verdict_unit[id] = tile.unit;
           uint32_t* cell = a.vmap + ((u.out_off + (uint64_t)re) >> 5);
           if (atomicCAS(cell, 0u, (uint32_t)id + 1u) != 0u) atomicExch(cell, kVmapAmbiguous);
         }
       }
       __syncwarp();
     }
+  }
+}
+
+// Second stage: one warp per verdict that only carries bounds (kVDelimit) and is no longer than k windows runs the
+// walker's own dispatch on the pristine contig (Walker::dry_fix) and stores what it decided.  Same code as in k_walk,
+// but one independent event per warp: the homopolymer / diploid repairs leave the walkers' sequential chains.
+__global__ void __launch_bounds__(kWalkWarps * 32, JB_WALK_MINBLOCKS)
+k_verdicts2(TableView t, VerdictArgs a) {
+  __shared__ WarpScratch scratch[kWalkWarps];
+  __shared__ DevDB db;
+  __shared__ UnitIO units[kWalkWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) db.t = t;
+  __syncthreads();
+  const unsigned long long n = min(*a.used, a.cap);
+  const BridgePool no_pool{nullptr, 0, nullptr};
+  const RowSink no_rows{nullptr, 0, nullptr, nullptr, 0, nullptr};
+  const JobSink no_jobs{nullptr, 0, nullptr};
+  for (unsigned long long id = (unsigned long long)blockIdx.x * kWalkWarps + warp; id < n; id += (unsigned long long)gridDim.x * kWalkWarps) {
+    const Verdict v = a.verdicts[id];
+    Verdict2* out = a.verdicts2 + id;
+    const ScanUnit su = a.units[a.verdict_unit[id]];
+    const int nbad = (int)v.d_ga - (int)v.d_s0;
+    if (v.kind != kVDelimit || nbad > a.k || su.len >= 0xFFFFFFFFull) { if (lane == 0) out->valid = 0; continue; }
+    UnitIO& u = units[warp];
+    __syncwarp();
+    if (lane == 0) {
+      u = UnitIO{};
+      u.in = a.bases + su.seq_off; u.in_len = (int64_t)su.len;
+      u.cnt = a.counts + su.out_off; u.okb = a.okb + su.out_off;
+      u.next_anchor = -1; u.keep_margin = default_keep_margin(a.k);
+    }
+    __syncwarp();
+    Walker<DevDB> w(db, a.k, a.step, a.solid, true, u, scratch[warp], no_pool, no_rows, no_jobs);
+    w.dry_fix(v, (int64_t)v.re, out);
+    __syncwarp();
   }
 }
 
@@ -216,6 +255,8 @@ struct Workspace {
   DevBuf<uint8_t> buf[2], stage;
   DevBuf<uint32_t> counts[2], events, weak, events_l1, order, tile_first, block_first, slot_unit, vmap;
   DevBuf<Verdict> verdicts;
+  DevBuf<Verdict2> verdicts2;
+  DevBuf<uint32_t> verdict_unit;
   DevBuf<uint8_t> okb[2];                   // counts / validity of the current and of the next pass's sequence
   DevBuf<ScanUnit> scan_units_new;
   DevBuf<UnitIO> segs;
@@ -241,7 +282,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -305,7 +346,7 @@ void jb_release_cached_workspaces(int device) {           // jb_db_close: nothin
 }
 
 struct jb_batch {
-  bool use_verdicts = true;
+  bool use_verdicts = true, use_verdicts2 = true;
   const jb_db* db = nullptr;
   Workspace* ws = nullptr;
   size_t n = 0;
@@ -359,6 +400,7 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   JB_TRY(w.scan_units_new.ensure(n + 1));
   JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
   JB_TRY(w.vmap.ensure(total / 32 + 64)); JB_TRY(w.verdicts.ensure(total / 64 + 4096));
+  JB_TRY(w.verdicts2.ensure(total / 64 + 4096)); JB_TRY(w.verdict_unit.ensure(total / 64 + 4096));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
   JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
   JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20)));
@@ -438,12 +480,13 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   UnitIO u;                                        // (result fields are written by the walker)
   const size_t i = p.unit;
   const Workspace& w = *b->ws;
-  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0; u.n_fast = 0; u.n_post = 0;
+  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0; u.n_fast = 0; u.n_post = 0; u.n_v2 = 0;
   u.in = in + b->off[i]; u.in_len = b->len[i];
   u.out = w.stage.p + b->off[i] + p.stage_off; u.out_cap = p.stage_cap;
   u.cnt = w.counts[cidx].p + b->off[i];
   u.okb = w.okb[cidx].p + b->off[i];
   u.weak = w.weak.p + b->off[i] / 32; u.vmap = b->use_verdicts ? w.vmap.p : nullptr; u.verdicts = w.verdicts.p;
+  u.verdicts2 = b->use_verdicts2 ? w.verdicts2.p : nullptr;
   u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
@@ -533,7 +576,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   JB_CUDA(cudaEventCreate(&ev_a)); JB_CUDA(cudaEventCreate(&ev_b)); JB_CUDA(cudaEventCreate(&ev_c)); JB_CUDA(cudaEventCreate(&ev_d));
   double scan_ms = 0, walk_ms = 0, plan_ms = 0, kwalk_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
-  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0, n_fast = 0, n_post = 0;
+  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0, n_fast = 0, n_post = 0, n_v2 = 0;
   int64_t slow_cycles[3] = {0, 0, 0}, slow_events[3] = {0, 0, 0}, slow_lookups[3] = {0, 0, 0}, slow_span[3] = {0, 0, 0}, sum_cycles[3] = {0, 0, 0};
   std::vector<ScanUnit> sunits(n);
   std::vector<SegUnit> gunits(n);
@@ -554,7 +597,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   double recount_ms = 0;
   const bool full_rescan = getenv("JB_FULL_RESCAN") != nullptr;      // tests: scan every pass from scratch
   const bool verify_recount = getenv("JB_VERIFY_RECOUNT") != nullptr; // tests: check k_recount against a full scan
-  cudaEvent_t ev_r0, ev_r1, ev_v0, ev_v1;
+  cudaEvent_t ev_r0, ev_r1, ev_v0, ev_v1, ev_anchors;
+  JB_CUDA(cudaEventCreateWithFlags(&ev_anchors, cudaEventDisableTiming));
   JB_CUDA(cudaEventCreate(&ev_r0)); JB_CUDA(cudaEventCreate(&ev_r1)); JB_CUDA(cudaEventCreate(&ev_v0)); JB_CUDA(cudaEventCreate(&ev_v1));
   const bool do_fix_verdicts = getenv("JB_NO_VERDICTS") == nullptr;      // tests: walkers decide everything themselves
   double verdict_ms = 0;
@@ -614,23 +658,6 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     ea.solid_thre = solid_thre; ea.k = k;
     if (int rc = launch_events(ea, s)) return rc;
     ++launches;
-    // ---- verdicts: every isolated error decided in bulk (jb_verdict.cuh)
-    b->use_verdicts = do_fix_verdicts;
-    if (b->use_verdicts) {
-      JB_CUDA(cudaMemsetAsync(w.vmap.p, 0, (b->flat_bytes / 32 + 64) * 4, s));
-      JB_CUDA(cudaMemsetAsync(w.used.p + 6, 0, 8, s));
-      VerdictArgs va{};
-      va.bases = in; va.units = w.scan_units.p; va.tile_first = w.tile_first.p; va.n_units = (uint32_t)n; va.n_tiles = tile_first[n];
-      va.counts = w.counts[cidx].p; va.okb = w.okb[cidx].p; va.weak = w.weak.p;
-      va.verdicts = w.verdicts.p; va.cap = w.verdicts.cap; va.used = w.used.p + 6; va.vmap = w.vmap.p;
-      va.k = k; va.step = cfg.step; va.solid = solid_thre;
-      const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
-      JB_CUDA(cudaEventRecord(ev_v0, s));
-      k_verdicts<<<std::max(1u, vgrid), kVerdictWarps * 32, 0, s>>>(view, va);
-      JB_CUDA(cudaGetLastError());
-      JB_CUDA(cudaEventRecord(ev_v1, s));
-      ++launches;
-    }
     // ---- anchors -> segments
     long long* anchors = w.h_anchors.p;
     if (!blocks.empty()) {
@@ -641,11 +668,37 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       ++launches;
       JB_CUDA(cudaMemcpyAsync(anchors, w.anchors.p, nb * sizeof(long long), cudaMemcpyDeviceToHost, s));
     }
+    JB_CUDA(cudaEventRecord(ev_anchors, s));             // the host plans segments from here on, while the verdict kernels run
+    // ---- verdicts: every isolated error decided in bulk (jb_verdict.cuh)
+    b->use_verdicts = do_fix_verdicts;
+    b->use_verdicts2 = false;
+    if (b->use_verdicts) {
+      JB_CUDA(cudaMemsetAsync(w.vmap.p, 0, (b->flat_bytes / 32 + 64) * 4, s));
+      JB_CUDA(cudaMemsetAsync(w.used.p + 6, 0, 8, s));
+      VerdictArgs va{};
+      va.bases = in; va.units = w.scan_units.p; va.tile_first = w.tile_first.p; va.n_units = (uint32_t)n; va.n_tiles = tile_first[n];
+      va.counts = w.counts[cidx].p; va.okb = w.okb[cidx].p; va.weak = w.weak.p;
+      va.verdicts = w.verdicts.p; va.cap = std::min(w.verdicts.cap, std::min(w.verdicts2.cap, w.verdict_unit.cap)); va.used = w.used.p + 6; va.vmap = w.vmap.p;
+      va.verdict_unit = w.verdict_unit.p; va.verdicts2 = w.verdicts2.p;
+      va.k = k; va.step = cfg.step; va.solid = solid_thre;
+      const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
+      JB_CUDA(cudaEventRecord(ev_v0, s));
+      k_verdicts<<<std::max(1u, vgrid), kVerdictWarps * 32, 0, s>>>(view, va);
+      JB_CUDA(cudaGetLastError());
+      ++launches;
+      b->use_verdicts2 = do_fix && getenv("JB_NO_VERDICTS2") == nullptr;   // (a count-only pass applies nothing)
+      if (b->use_verdicts2) {
+        k_verdicts2<<<(unsigned)b->sms * kWalkCtasPerSm, kWalkWarps * 32, 0, s>>>(view, va);
+        JB_CUDA(cudaGetLastError());
+        ++launches;
+      }
+      JB_CUDA(cudaEventRecord(ev_v1, s));
+    }
     // while the scan runs: turn the previous pass's fix log into csv rows
     mark("scan launched", ite);
     if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
     mark("rows handed off", ite);
-    JB_CUDA(cudaStreamSynchronize(s));
+    JB_CUDA(cudaEventSynchronize(ev_anchors));
     mark("scan+anchors done", ite);
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
     const size_t n_first = plan.size();
@@ -730,7 +783,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       segs.assign(hs, hs + n_first);
     }
     for (const UnitIO& u : segs) {
-      b->passes[ite].wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events; n_fast += u.n_fast; n_post += u.n_post;
+      b->passes[ite].wrong += u.wrong; walk_lookups += (int64_t)u.lookups; n_events += (int64_t)u.events; n_fast += u.n_fast; n_post += u.n_post; n_v2 += u.n_v2;
       max_seg_events = std::max<int64_t>(max_seg_events, (int64_t)u.events);
       max_seg_lookups = std::max<int64_t>(max_seg_lookups, (int64_t)u.lookups);
       max_seg_span = std::max<int64_t>(max_seg_span, u.end_old - u.base);
@@ -836,7 +889,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   note_timing("polish_recount", recount_ms);
   note_counter("scan_lookups", full_scan_lookups + recount_probes); note_counter("walk_lookups", walk_lookups);
   note_counter("full_scans", full_scans); note_counter("full_scan_lookups", full_scan_lookups); note_counter("recount_probes", recount_probes);
-  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1); cudaEventDestroy(ev_v0); cudaEventDestroy(ev_v1);
+  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1); cudaEventDestroy(ev_v0); cudaEventDestroy(ev_v1); cudaEventDestroy(ev_anchors);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
   note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
   for (int q = 0; q < 3; ++q) {
@@ -845,7 +898,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     note_counter(("slow_lookups" + sfx).c_str(), slow_lookups[q]); note_counter(("slow_span" + sfx).c_str(), slow_span[q]);
     note_counter(("sum_cycles" + sfx).c_str(), sum_cycles[q]);
   }
-  note_counter("verdicts", n_verdicts); note_timing("polish_verdicts", verdict_ms); note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
+  note_counter("verdicts", n_verdicts); note_timing("polish_verdicts", verdict_ms); note_counter("verdict2_events", n_v2); note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
   b->polished = true;
   while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});

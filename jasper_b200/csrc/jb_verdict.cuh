@@ -34,7 +34,25 @@ struct Verdict {
   uint16_t pad;
 };
 static_assert(sizeof(Verdict) == 16, "Verdict is meant to be 16 bytes");
-constexpr uint32_t kVmapAmbiguous = 0xFFFFFFFFu;      // two runs end inside the same 32 positions: no verdict for either
+constexpr uint32_t kVmapAmbiguous = 0xFFFFFFFFu;
+
+// Second-stage verdict of a run whose first verdict is kVDelimit and that is no longer than k windows: what the
+// reference's dispatch (src/jasper.py:226-338: homopolymer repairs, diploid, lower-case substitutions) decides on
+// the pass-start sequence.  k_verdicts2 runs the walker's own slow_fix for it, one warp per run, so that this work
+// is spread over the whole chip instead of sitting in the walkers' sequential chains.  Multi-error patches
+// (nbad > k, de-Bruijn bridging) stay with the walkers.
+constexpr int kV2Repl = 108;
+struct Verdict2 {
+  uint8_t valid;        // 0: the walker runs slow_fix itself
+  uint8_t found;
+  int16_t a_rel, e_rel; // seq = seq[:s0 + a_rel] + repl + seq[s0 + e_rel:]
+  int16_t rlen;
+  int16_t coord_rel;    // fix row: coordinate - s0
+  uint8_t fb, fb_len, tag, orig, orig_len;    // mutation = fb * fb_len, original = tag + orig * orig_len
+  uint8_t pad[5];
+  uint8_t repl[kV2Repl];
+};
+static_assert(sizeof(Verdict2) == 128, "Verdict2 is meant to be 128 bytes");      // two runs end inside the same 32 positions: no verdict for either
 
 // Verdict of the weak run that contains position a_pos (pass-start coordinates; the window at a_pos is valid and weak).
 // False: no verdict (the run touches invalid windows, a contig end, or is longer than the staged window).

@@ -113,6 +113,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   const uint32_t* weak;      // weak-window bit words of this contig (valid window with count < solid); null = no verdicts
   const uint32_t* vmap;      // flat: word (ev_bit_base + re) >> 5 holds verdict id + 1 of the run that ends at re, 0, or kVmapAmbiguous
   const Verdict* verdicts;   // k_verdicts output
+  const Verdict2* verdicts2; // k_verdicts2 output, same index; may be null
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
   uint64_t ev_bit_base;      // flat bit index of contig position 0
@@ -132,6 +133,8 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   uint32_t n_rows;
   uint32_t n_fast;             // events taken from a verdict (jb_verdict.cuh)
   uint32_t n_post;             // ... whose following scan step was taken from data in hand
+  uint32_t n_v2;               // events whose fix (or "no fix") came from a second-stage verdict
+  uint32_t pad2;
   unsigned long long lookups;
   unsigned long long events;
   unsigned long long cycles;   // device clock ticks this segment took (profiling aid)
@@ -183,7 +186,8 @@ struct Walker {
   uint32_t vflags = 0;                 // kFlagSeam / kFlagFar raised by reads (lane-local until the end of run)
   uint32_t seqno = 0;
   unsigned long long lookups = 0, events = 0;
-  uint32_t n_fast = 0, n_post = 0;
+  uint32_t n_fast = 0, n_post = 0, n_v2 = 0;
+  uint32_t vid = 0;                    // index of the verdict consume_verdict returned
   long long t_begin = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
@@ -782,6 +786,51 @@ struct Walker {
     return f;
   }
 
+  // the fix a second-stage verdict describes; false = there is none the walker may use
+  JB_W bool verdict2_fix(Fix& f, int64_t s0) {
+    if (!c.verdicts2) return false;
+    const Verdict2* v2 = c.verdicts2 + vid;
+    if (!v2->valid) return false;
+    // slow_fix read bases as far back as the diploid flank (< k + 2 in front of s0): they must be untouched for this walker too
+    const int64_t shift = base + olen - ipos;
+    int64_t lo_x = clean_from > shift ? clean_from : shift;
+    if (base - seam_margin > lo_x) lo_x = base - seam_margin;
+    if (s0 - k - 2 < lo_x) return false;
+    ++n_v2;
+    if (!v2->found) return true;                         // decided: nothing to apply
+    const int rl = v2->rlen;
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < rl; q += 32) s.b[q] = v2->repl[q]; }
+    JB_SYNC();
+    f.found = true; f.a = s0 + v2->a_rel; f.e = s0 + v2->e_rel; f.repl = s.b; f.rlen = rl;
+    fix_row(f, s0 + v2->coord_rel, v2->fb, v2->fb_len, v2->tag, v2->orig, v2->orig_len);
+    return true;
+  }
+
+  // k_verdicts2: the reference's dispatch on the pass-start sequence, nothing applied (the walker is set up on the whole
+  // pristine contig, so every read goes to pass-start bases)
+  JB_W void dry_fix(const Verdict& v, int64_t re, Verdict2* out) {
+    begin();
+    const int64_t jq = re - (int64_t)v.d_jq;
+    const int64_t s0 = jq + (int64_t)v.d_s0, ga = jq + (int64_t)v.d_ga, gb = s0 + k - 2;
+    const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
+    const Fix f = slow_fix(s0, nbad, solid, gb, ga);
+    const bool ok = !status && !(f.found && (f.rlen > kV2Repl || f.tag == 0));
+    JB_SYNC();
+    JB_LANES(l) {
+      if (l == 0) {
+        out->found = f.found ? 1 : 0;
+        out->a_rel = (int16_t)(f.a - s0); out->e_rel = (int16_t)(f.e - s0); out->rlen = (int16_t)f.rlen;
+        out->coord_rel = (int16_t)(f.coord - s0);
+        out->fb = s.fx[0]; out->fb_len = (uint8_t)f.fb_len; out->tag = f.tag; out->orig = s.fx[64]; out->orig_len = (uint8_t)f.orig_len;
+      }
+      if (ok && f.found) for (int q = l; q < (int)f.rlen; q += 32) out->repl[q] = f.repl[q];
+    }
+    JB_SYNC();
+    JB_LANES(l) { if (l == 0) out->valid = ok ? 1 : 0; }
+    JB_SYNC();
+  }
+
   // the reference's dispatch (src/jasper.py:226-338), out of line: the hot loop only comes here for events without a verdict
   JB_WC Fix slow_fix(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga) {
     const int64_t n64 = ga + k - 1 - s0;
@@ -810,6 +859,7 @@ struct Walker {
   JB_W int fixing_sid(int64_t s0, int64_t nbad, int64_t thr, int64_t gb, int64_t ga, const Verdict* v) {
     Fix f;
     if (v && v->kind != kVDelimit) f = verdict_fix(*v, s0, ga);
+    else if (v && verdict2_fix(f, s0)) { }
     else f = slow_fix(s0, nbad, thr, gb, ga);
     int post = kPostNone;
     if (f.found && !status) {
@@ -936,6 +986,7 @@ struct Walker {
     const uint32_t id = c.vmap[(c.ev_bit_base + (uint64_t)re) >> 5];
     if (id == 0u || id == kVmapAmbiguous) return false;
     v = c.verdicts[id - 1];
+    vid = id - 1;
     if (v.re != (uint32_t)re) return false;
     const int64_t jq = re - (int64_t)v.d_jq;
     if (jq + shift < lo_x) return false;                // the verdict read counts this walker's edits have invalidated
@@ -1103,7 +1154,7 @@ struct Walker {
     u.wrong = wrong;
     u.status = status;
     u.n_rows = seqno;
-    u.n_fast = n_fast; u.n_post = n_post;
+    u.n_fast = n_fast; u.n_post = n_post; u.n_v2 = n_v2;
     u.lookups = lookups + s.probes;
     u.events = events;
 #if defined(__CUDA_ARCH__)

@@ -121,7 +121,7 @@ def hostsim_lib():
     sim.hostsim_segments.argtypes = [C.c_void_p]
     sim.hostsim_reruns.restype = C.c_ulonglong
     sim.hostsim_reruns.argtypes = [C.c_void_p]
-    for fn in (sim.hostsim_events, sim.hostsim_fast, sim.hostsim_post):
+    for fn in (sim.hostsim_events, sim.hostsim_fast, sim.hostsim_post, sim.hostsim_v2):
         fn.restype = C.c_ulonglong
         fn.argtypes = [C.c_void_p]
     sim.hostsim_packed_selfcheck.restype = C.c_longlong
@@ -160,6 +160,7 @@ def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=No
             stats["events"] = sim.hostsim_events(r)
             stats["fast"] = sim.hostsim_fast(r)
             stats["post"] = sim.hostsim_post(r)
+            stats["v2"] = sim.hostsim_v2(r)
         return st, txt, out, tallies
     finally:
         sim.hostsim_free(r)

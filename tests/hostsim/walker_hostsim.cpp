@@ -26,7 +26,7 @@ struct SimResult {
   std::vector<PassOut> passes;
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
-  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0;
+  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0, v2 = 0;
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
@@ -104,6 +104,8 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
     // verdicts, the way k_verdicts builds them: one per weak run, published under the run's end
     std::vector<std::vector<uint32_t>> vmaps(n);
     std::vector<std::vector<Verdict>> verdicts(n);
+    std::vector<std::vector<Verdict2>> verdicts2(n);
+    const bool use_verdicts2 = do_fix && !getenv("JB_SIM_NO_VERDICTS2");
     const bool use_verdicts = use_events && !getenv("JB_SIM_NO_OKB");
     for (size_t i = 0; i < n && use_verdicts; ++i) {
       vmaps[i].assign((size_t)(len[i] + 1) / 32 + 4, 0);
@@ -115,6 +117,21 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
         verdicts[i].push_back(v);
         uint32_t& cell = vmaps[i][(size_t)re >> 5];
         cell = cell == 0 ? (uint32_t)verdicts[i].size() : kVmapAmbiguous;
+      }
+      // second stage, the way k_verdicts2 does it: the walker's own dispatch on the pristine contig
+      verdicts2[i].resize(verdicts[i].size());
+      for (size_t q = 0; q < verdicts[i].size() && use_verdicts2; ++q) {
+        const Verdict& v = verdicts[i][q];
+        Verdict2& v2 = verdicts2[i][q];
+        memset(&v2, 0, sizeof v2);
+        if (v.kind != kVDelimit || (int)v.d_ga - (int)v.d_s0 > k) continue;
+        UnitIO u;
+        memset(&u, 0, sizeof u);
+        u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
+        u.cnt = cnts[i].data(); u.okb = okbs[i].data();
+        u.next_anchor = -1; u.keep_margin = keep_margin;
+        Walker<HostDB> w(db, k, sampling_step(k), solid, true, u, ws, pool, sink, jobs);
+        w.dry_fix(v, (int64_t)v.re, &v2);
       }
     }
     std::vector<BlockRef> blocks;
@@ -146,6 +163,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       u.okb = (use_events && !getenv("JB_SIM_NO_OKB")) ? okbs[i].data() : nullptr;
       u.weak = use_events ? weak[i].data() : nullptr;
       u.vmap = use_verdicts ? vmaps[i].data() : nullptr; u.verdicts = verdicts[i].data();
+      u.verdicts2 = (use_verdicts && use_verdicts2) ? verdicts2[i].data() : nullptr;
       u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
       u.slot = slot; u.materialize_all = gen ? 1u : 0u;
@@ -190,7 +208,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       }
       segs.swap(merged);
     }
-    for (const UnitIO& u : segs) { po.wrong += u.wrong; res->lookups += u.lookups; res->events += u.events; res->fast += u.n_fast; res->post += u.n_post; }
+    for (const UnitIO& u : segs) { po.wrong += u.wrong; res->lookups += u.lookups; res->events += u.events; res->fast += u.n_fast; res->post += u.n_post; res->v2 += u.n_v2; }
     if (do_fix) {
       std::vector<int64_t> new_lens(len);
       std::vector<SegPlace> place = place_segments(segs, &new_lens);
@@ -260,6 +278,7 @@ extern "C" unsigned long long hostsim_lookups(const SimResult* r) { return r->lo
 extern "C" unsigned long long hostsim_events(const SimResult* r) { return r->events; }
 extern "C" unsigned long long hostsim_fast(const SimResult* r) { return r->fast; }
 extern "C" unsigned long long hostsim_post(const SimResult* r) { return r->post; }
+extern "C" unsigned long long hostsim_v2(const SimResult* r) { return r->v2; }
 extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->segments; }
 extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
 extern "C" unsigned long long hostsim_far_backs(const SimResult* r) { return r->far_backs; }

@@ -161,6 +161,11 @@ def test_verdicts_change_nothing(golden_cases, dbs, name, monkeypatch):
     a = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
     assert a.status == 0 and a.counters["verdicts"] > 0
     assert a.counters["fast_events"] * 2 > a.counters["events"], a.counters
+    assert a.counters["verdict2_events"] > 0, a.counters
+    monkeypatch.setenv("JB_NO_VERDICTS2", "1")               # first stage only: the walkers run the dispatch for the rest
+    c = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
+    assert c.counters["verdict2_events"] == 0 and c.counters["fast_events"] == a.counters["fast_events"]
+    assert (a.rows, a.seqs, a.tallies) == (c.rows, c.seqs, c.tallies)
     monkeypatch.setenv("JB_NO_VERDICTS", "1")
     b = dbs[name].polish(seqs, case["k"], case["threshold"], case["passes"])
     assert b.counters["verdicts"] == 0 and b.counters["fast_events"] == 0

@@ -221,6 +221,11 @@ def test_fast_path_is_taken_and_changes_nothing(golden_cases, hostsim_lib, name,
         monkeypatch.delenv("JB_SIM_NO_OKB", raising=False)
         assert fast == slow
         assert st_slow["fast"] == 0 and st_slow["events"] == st_fast["events"]
+        st_one = {}
+        monkeypatch.setenv("JB_SIM_NO_VERDICTS2", "1")           # first-stage verdicts only
+        one = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events, stats=st_one)
+        monkeypatch.delenv("JB_SIM_NO_VERDICTS2", raising=False)
+        assert one == fast and st_one["v2"] == 0 and st_fast["v2"] > 0
         print(name, use_events, st_fast)
         if name != "k31_dirty":
             assert st_fast["fast"] * 2 > st_fast["events"], st_fast
