@@ -278,7 +278,8 @@ struct Workspace {
   PinBuf<uint8_t> h_aux[2];
   PinBuf<unsigned long long> h_used;
   cudaStream_t s2 = nullptr;                // side stream: fix rows travel while the next pass scans
-  cudaEvent_t ev_walk = nullptr, ev_rows = nullptr;
+  cudaEvent_t ev_walk = nullptr, ev_rows = nullptr, ev_concat = nullptr, ev_group = nullptr;
+  DevBuf<uint32_t> tile_first_groups;
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
@@ -290,6 +291,9 @@ struct Workspace {
     if (s2) cudaStreamDestroy(s2);
     if (ev_walk) cudaEventDestroy(ev_walk);
     if (ev_rows) cudaEventDestroy(ev_rows);
+    if (ev_concat) cudaEventDestroy(ev_concat);
+    if (ev_group) cudaEventDestroy(ev_group);
+    tile_first_groups.release();
   }
 };
 
@@ -358,7 +362,20 @@ struct jb_batch {
   std::vector<PassOut> passes;
   int status = JB_OK;
   bool polished = false;
-  ~jb_batch() { park_workspace(ws); }
+  // the final bases are known once the last FIXING pass has stitched them: their copy to the host starts there, on the
+  // side stream, beside the count-only pass (jb_batch_fetch picks it up)
+  bool prescanned = false;             // jb_polish: the first pass's k_scan already ran behind the upload
+  int64_t prescan_lookups = 0;
+  cudaEvent_t ev_tmp[2] = {nullptr, nullptr};
+  uint8_t* early = nullptr; size_t early_cap = 0;
+  cudaEvent_t ev_early = nullptr;
+  double early_ms_hint = 0;
+  ~jb_batch() {
+    if (ev_early) { cudaEventSynchronize(ev_early); cudaEventDestroy(ev_early); }
+    for (cudaEvent_t e : ev_tmp) if (e) { cudaEventSynchronize(e); cudaEventDestroy(e); }
+    if (early) park_out_buffer(early, early_cap);
+    park_workspace(ws);
+  }
 };
 
 struct jb_result {
@@ -371,7 +388,16 @@ struct jb_result {
 
 #define JB_TRY(expr) do { int rc_ = (expr); if (rc_ != JB_OK) return fail(rc_, "out of memory for polishing work buffers"); } while (0)
 
+namespace {
+int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out, bool prescan);
+}
 extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out) {
+  return upload_impl(db, seqs, n, out, false);
+}
+namespace {
+// prescan (jb_polish): the copies go to the side stream in groups of contigs and the first pass's k_scan of a group starts
+// as soon as the group has landed, so the PCIe transfer of the next group runs beside it
+int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out, bool prescan) {
   if (!db || (!seqs && n) || !out) return fail(JB_E_ARG, "jb_batch_upload: null argument");
   *out = nullptr;
   JB_CUDA(cudaSetDevice(db->device));
@@ -394,6 +420,7 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
     JB_CUDA(cudaStreamCreateWithFlags(&w.s2, cudaStreamNonBlocking));
     JB_CUDA(cudaEventCreateWithFlags(&w.ev_walk, cudaEventDisableTiming));
     JB_CUDA(cudaEventCreateWithFlags(&w.ev_rows, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&w.ev_concat, cudaEventDisableTiming));
   }
   JB_TRY(w.buf[0].ensure(total + 64)); JB_TRY(w.buf[1].ensure(total + 64)); JB_TRY(w.stage.ensure(total + 64));
   for (int q = 0; q < 2; ++q) { JB_TRY(w.counts[q].ensure(total + 64)); JB_TRY(w.okb[q].ensure(total + 64)); }
@@ -420,14 +447,14 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
   JB_CUDA(cudaEventRecord(e0, s));
   // stage through pinned memory in slices: a few host threads copy slices while the DMA engine drains the
   // ones already staged (one thread saturates at ~9 GB/s, the link takes 3x that)
-  struct Slice { const char* src; uint64_t dev_off, pin_off, len; };
+  struct Slice { const char* src; uint64_t dev_off, pin_off, len; size_t unit; bool last; };
   std::vector<Slice> slices;
   constexpr uint64_t kSlice = 4ull << 20;
   uint64_t p = 0;
   for (size_t i = 0; i < n; ++i)
     for (uint64_t at = 0; at < seqs[i].len; at += kSlice) {
       const uint64_t m = std::min<uint64_t>(kSlice, seqs[i].len - at);
-      slices.push_back(Slice{seqs[i].seq + at, b->off[i] + at, p, m});
+      slices.push_back(Slice{seqs[i].seq + at, b->off[i] + at, p, m, i, at + m == seqs[i].len});
       p += m;
     }
   const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, slices.size() / 2));
@@ -442,25 +469,83 @@ extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, 
         ready[j].store(1, std::memory_order_release);
       }
     });
+  struct Joiner { std::vector<std::thread>* t; ~Joiner() { for (auto& x : *t) if (x.joinable()) x.join(); } } joiner{&copiers};
+  // groups of whole contigs for the pipelined first scan
+  prescan = prescan && total_len > 0 && getenv("JB_NO_PRESCAN") == nullptr;
+  std::vector<size_t> group_end;                        // contig index one past each group
+  std::vector<ScanUnit> sunits(n);
+  std::vector<uint32_t> tf;                             // per group: its own tile prefix, back to back
+  std::vector<size_t> tf_at;
+  if (prescan) {
+    constexpr uint64_t kGroupBytes = 12ull << 20;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; ++i) {
+      sunits[i] = ScanUnit{b->off[i], (uint64_t)b->len[i], b->off[i]};
+      acc += seqs[i].len;
+      if (acc >= kGroupBytes || i + 1 == n) { group_end.push_back(i + 1); acc = 0; }
+    }
+    size_t first = 0;
+    for (size_t g = 0; g < group_end.size(); ++g) {
+      tf_at.push_back(tf.size());
+      tf.push_back(0);
+      for (size_t i = first; i < group_end[g]; ++i) tf.push_back(tf.back() + tiles_of((uint64_t)b->len[i]));
+      first = group_end[g];
+    }
+    JB_TRY(w.tile_first_groups.ensure(tf.size() + 1));
+    JB_CUDA(cudaMemcpyAsync(w.scan_units.p, sunits.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.tile_first_groups.p, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice, s));
+    if (!w.ev_group) JB_CUDA(cudaEventCreateWithFlags(&w.ev_group, cudaEventDisableTiming));
+    JB_CUDA(cudaEventRecord(w.ev_group, s));            // (the copies must not overtake earlier work on s that still reads buf[0])
+    JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_group, 0));
+  }
+  cudaStream_t cs = prescan ? w.s2 : s;
+  if (prescan) JB_CUDA(cudaEventRecord(e0, cs));
+  const TableView view = db->view();
   cudaError_t copy_err = cudaSuccess;
+  size_t g = 0, g_first = 0;
   for (size_t j = 0; j < slices.size(); ++j) {
     if (j % (size_t)n_thr == 0) std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
     else while (!ready[j].load(std::memory_order_acquire)) std::this_thread::yield();
     if (copy_err == cudaSuccess)
-      copy_err = cudaMemcpyAsync(w.buf[0].p + slices[j].dev_off, pin + slices[j].pin_off, slices[j].len, cudaMemcpyHostToDevice, s);
+      copy_err = cudaMemcpyAsync(w.buf[0].p + slices[j].dev_off, pin + slices[j].pin_off, slices[j].len, cudaMemcpyHostToDevice, cs);
+    if (!prescan) continue;
+    if (!slices[j].last) continue;
+    size_t done_units = slices[j].unit + 1;               // contigs fully enqueued (empty ones have no slices)
+    while (done_units < n && seqs[done_units].len == 0) ++done_units;
+    while (g < group_end.size() && group_end[g] <= done_units && copy_err == cudaSuccess) {
+      JB_CUDA(cudaEventRecord(w.ev_group, cs));
+      JB_CUDA(cudaStreamWaitEvent(s, w.ev_group, 0));
+      ScanArgs a{};
+      a.bases = w.buf[0].p; a.units = w.scan_units.p + g_first; a.tile_first = w.tile_first_groups.p + tf_at[g];
+      a.n_units = (uint32_t)(group_end[g] - g_first); a.n_tiles = tf[tf_at[g] + (group_end[g] - g_first)];
+      a.counts = w.counts[0].p; a.okb = w.okb[0].p; a.probe_steps = nullptr;
+      if (int rc = launch_scan(view, a, s)) return rc;
+      g_first = group_end[g];
+      ++g;
+    }
   }
   for (auto& t : copiers) t.join();
   JB_CUDA(copy_err);
-  JB_CUDA(cudaEventRecord(e1, s));
-  JB_CUDA(cudaStreamSynchronize(s));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  note_timing("h2d", ms);
+  JB_CUDA(cudaEventRecord(e1, cs));
+  if (prescan) {
+    b->prescanned = true;
+    b->prescan_lookups = 0;
+    for (size_t i = 0; i < n; ++i) b->prescan_lookups += b->len[i] + 1;
+    // no wait here: jb_batch_polish queues behind the scans on s; the pinned staging area belongs to the workspace
+    note_timing("h2d", -1.0);
+  } else {
+    JB_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    note_timing("h2d", ms);
+  }
   note_counter("h2d_bytes", (int64_t)total_len);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (!prescan) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  else { b->ev_tmp[0] = e0; b->ev_tmp[1] = e1; }
   *out = b.release();
   return JB_OK;
 }
+}  // namespace
 
 extern "C" void jb_batch_free(jb_batch* b) { delete b; }
 
@@ -646,6 +731,10 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
     a.counts = w.counts[cidx].p; a.okb = w.okb[cidx].p; a.probe_steps = w.used.p + 2;
     JB_CUDA(cudaEventRecord(ev_a, s));
+    if (ite == 0 && b->prescanned && !have_counts) {      // jb_polish: scanned group by group behind the upload
+      have_counts = true;
+      ++full_scans; full_scan_lookups += b->prescan_lookups;
+    }
     if (!have_counts) {                                   // later passes inherit counts from k_recount
       if (int rc = launch_scan(view, a, s)) return rc;
       ++launches; ++full_scans;
@@ -820,6 +909,22 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;
+      if (ite == passes - 1 && !b->early && getenv("JB_NO_EARLY_FETCH") == nullptr) {
+        uint64_t total_new = 0;
+        for (size_t i = 0; i < n; ++i) total_new += (uint64_t)new_lens[i];
+        b->early = take_out_buffer(std::max<uint64_t>(total_new, 1), &b->early_cap);
+        if (b->early) {
+          if (!b->ev_early) JB_CUDA(cudaEventCreateWithFlags(&b->ev_early, cudaEventDisableTiming));
+          JB_CUDA(cudaEventRecord(w.ev_concat, s));
+          JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_concat, 0));
+          uint64_t at = 0;
+          for (size_t i = 0; i < n; ++i) {
+            if (new_lens[i]) JB_CUDA(cudaMemcpyAsync(b->early + at, outb + b->off[i], (size_t)new_lens[i], cudaMemcpyDeviceToHost, w.s2));
+            at += (uint64_t)new_lens[i];
+          }
+          JB_CUDA(cudaEventRecord(b->ev_early, w.s2));
+        }
+      }
       // ---- counts of the new sequence: copied for untouched stretches, probed again around the edits
       have_counts = false;
       if (!full_rescan && ite + 1 <= passes) {
@@ -915,6 +1020,14 @@ extern "C" int jb_batch_fetch(jb_batch* b, jb_result** out) {
   r->seq_off.resize(b->n); r->seq_len.resize(b->n);
   uint64_t total = 0;
   for (size_t i = 0; i < b->n; ++i) { r->seq_off[i] = total; r->seq_len[i] = (uint64_t)b->len[i]; total += (uint64_t)b->len[i]; }
+  if (b->early && b->ev_early) {                        // the copy started behind the last fixing pass
+    JB_CUDA(cudaEventSynchronize(b->ev_early));
+    r->data = b->early; r->data_cap = b->early_cap;
+    b->early = nullptr; b->early_cap = 0;
+    note_timing("d2h", 0.0); note_counter("d2h_bytes", (int64_t)total);
+    *out = r.release();
+    return JB_OK;
+  }
   r->data = take_out_buffer(std::max<uint64_t>(total, 1), &r->data_cap);
   if (!r->data) return fail(JB_E_NOMEM, "cannot allocate the pinned result buffer");
   cudaEvent_t e0, e1;
@@ -938,7 +1051,7 @@ extern "C" int jb_polish(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, i
   *out = nullptr;
   jb_batch* b = nullptr;
   auto t0 = std::chrono::steady_clock::now();
-  int rc = jb_batch_upload(db, seqs, n_seqs, &b);
+  int rc = upload_impl(db, seqs, n_seqs, &b, true);
   if (rc) return rc;
   auto t1 = std::chrono::steady_clock::now();
   rc = jb_batch_polish(b, k, solid_thre, passes, fix);
