@@ -127,11 +127,11 @@ k_verdicts(TableView t, VerdictArgs a) {
   }
 }
 
-// Second stage: one warp per verdict that only carries bounds (kVDelimit) and is no longer than k windows runs the
+// Second stage: one warp per verdict that only carries bounds (kVDelimit) runs the
 // walker's own dispatch on the pristine contig (Walker::dry_fix) and stores what it decided.  Same code as in k_walk,
 // but one independent event per warp: the homopolymer / diploid repairs leave the walkers' sequential chains.
 __global__ void __launch_bounds__(kWalkWarps * 32, JB_WALK_MINBLOCKS)
-k_verdicts2(TableView t, VerdictArgs a) {
+k_verdicts2(TableView t, VerdictArgs a, BridgePool pool) {
   __shared__ WarpScratch scratch[kWalkWarps];
   __shared__ DevDB db;
   __shared__ UnitIO units[kWalkWarps];
@@ -139,7 +139,6 @@ k_verdicts2(TableView t, VerdictArgs a) {
   if (threadIdx.x == 0) db.t = t;
   __syncthreads();
   const unsigned long long n = min(*a.used, a.cap);
-  const BridgePool no_pool{nullptr, 0, nullptr};
   const RowSink no_rows{nullptr, 0, nullptr, nullptr, 0, nullptr};
   const JobSink no_jobs{nullptr, 0, nullptr};
   for (unsigned long long id = (unsigned long long)blockIdx.x * kWalkWarps + warp; id < n; id += (unsigned long long)gridDim.x * kWalkWarps) {
@@ -147,7 +146,8 @@ k_verdicts2(TableView t, VerdictArgs a) {
     Verdict2* out = a.verdicts2 + id;
     const ScanUnit su = a.units[a.verdict_unit[id]];
     const int nbad = (int)v.d_ga - (int)v.d_s0;
-    if (v.kind != kVDelimit || nbad > a.k || su.len >= 0xFFFFFFFFull) { if (lane == 0) out->valid = 0; continue; }
+    (void)nbad;
+    if (v.kind != kVDelimit || su.len >= 0xFFFFFFFFull) { if (lane == 0) out->valid = 0; continue; }
     UnitIO& u = units[warp];
     __syncwarp();
     if (lane == 0) {
@@ -157,7 +157,7 @@ k_verdicts2(TableView t, VerdictArgs a) {
       u.next_anchor = -1; u.keep_margin = default_keep_margin(a.k);
     }
     __syncwarp();
-    Walker<DevDB> w(db, a.k, a.step, a.solid, true, u, scratch[warp], no_pool, no_rows, no_jobs);
+    Walker<DevDB> w(db, a.k, a.step, a.solid, true, u, scratch[warp], pool, no_rows, no_jobs);
     w.dry_fix(v, (int64_t)v.re, out);
     __syncwarp();
   }
@@ -777,7 +777,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       ++launches;
       b->use_verdicts2 = do_fix && getenv("JB_NO_VERDICTS2") == nullptr;   // (a count-only pass applies nothing)
       if (b->use_verdicts2) {
-        k_verdicts2<<<(unsigned)b->sms * kWalkCtasPerSm, kWalkWarps * 32, 0, s>>>(view, va);
+        k_verdicts2<<<(unsigned)b->sms * kWalkCtasPerSm, kWalkWarps * 32, 0, s>>>(view, va, pool);
         JB_CUDA(cudaGetLastError());
         ++launches;
       }

@@ -36,11 +36,11 @@ struct Verdict {
 static_assert(sizeof(Verdict) == 16, "Verdict is meant to be 16 bytes");
 constexpr uint32_t kVmapAmbiguous = 0xFFFFFFFFu;
 
-// Second-stage verdict of a run whose first verdict is kVDelimit and that is no longer than k windows: what the
-// reference's dispatch (src/jasper.py:226-338: homopolymer repairs, diploid, lower-case substitutions) decides on
-// the pass-start sequence.  k_verdicts2 runs the walker's own slow_fix for it, one warp per run, so that this work
-// is spread over the whole chip instead of sitting in the walkers' sequential chains.  Multi-error patches
-// (nbad > k, de-Bruijn bridging) stay with the walkers.
+// Second-stage verdict of a run whose first verdict is kVDelimit: what the reference's dispatch (src/jasper.py:226-338:
+// homopolymer repairs, diploid, lower-case substitutions, and the de-Bruijn bridging of multi-error stretches) decides
+// on the pass-start sequence.  k_verdicts2 runs the walker's own code for it (Walker::dry_fix), one warp per run, so
+// that this work is spread over the whole chip instead of sitting in the walkers' sequential chains.  Patches longer
+// than kV2Repl bases stay with the walkers.
 constexpr int kV2Repl = 108;
 struct Verdict2 {
   uint8_t valid;        // 0: the walker runs slow_fix itself

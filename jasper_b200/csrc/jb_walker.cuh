@@ -92,6 +92,7 @@ struct BridgeScratch {       // global memory, one per resident walker
   uint32_t patch_cap;
 };
 
+constexpr uint8_t kTagBridge = 0xFF;      // Verdict2.tag of a bridged multi-error patch
 enum PostKind : int { kPostNone = 0, kPostSub = 1, kPostDel = 2, kPostIns = 3 };
 constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
 constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
@@ -803,7 +804,10 @@ struct Walker {
     JB_LANES(l) { for (int q = l; q < rl; q += 32) s.b[q] = v2->repl[q]; }
     JB_SYNC();
     f.found = true; f.a = s0 + v2->a_rel; f.e = s0 + v2->e_rel; f.repl = s.b; f.rlen = rl;
-    fix_row(f, s0 + v2->coord_rel, v2->fb, v2->fb_len, v2->tag, v2->orig, v2->orig_len);
+    if (v2->tag == kTagBridge) {                         // a bridged patch logs its own row (the replaced bases are still in place)
+      if (!bridge_row(f.a - 1, f.e, s.b, rl)) f.found = false;
+      f.tag = 0;
+    } else fix_row(f, s0 + v2->coord_rel, v2->fb, v2->fb_len, v2->tag, v2->orig, v2->orig_len);
     return true;
   }
 
@@ -814,7 +818,11 @@ struct Walker {
     const int64_t jq = re - (int64_t)v.d_jq;
     const int64_t s0 = jq + (int64_t)v.d_s0, ga = jq + (int64_t)v.d_ga, gb = s0 + k - 2;
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
-    const Fix f = slow_fix(s0, nbad, solid, gb, ga);
+    Fix f;
+    if (nbad > k) {                                      // the multi-error patch: search only, the walker logs the row
+      const int64_t plen = bridge_search(ga + k - 1 - s0, solid, gb, ga);
+      if (plen > 0) { f.found = true; f.a = gb + 1; f.e = ga; f.repl = bs->patch; f.rlen = plen; f.tag = kTagBridge; }
+    } else f = slow_fix(s0, nbad, solid, gb, ga);
     const bool ok = !status && !(f.found && (f.rlen > kV2Repl || f.tag == 0));
     JB_SYNC();
     JB_LANES(l) {
@@ -827,6 +835,7 @@ struct Walker {
       if (ok && f.found) for (int q = l; q < (int)f.rlen; q += 32) out->repl[q] = f.repl[q];
     }
     JB_SYNC();
+    release_bridge();
     JB_LANES(l) { if (l == 0) out->valid = ok ? 1 : 0; }
     JB_SYNC();
   }
@@ -874,18 +883,21 @@ struct Walker {
 
   // src/jasper.py:295-329: bridge a long weak stretch with a de-Bruijn walk; the patch stays in the borrowed
   // bridging slot until fixing_sid has spliced it in
-  JB_WC Fix fix_bridge(int64_t n64, int64_t thr, int64_t gb, int64_t ga) {
-    Fix f;
-    if (gb - k + 1 < 0) return f;                          // good_kmer_before comes out shorter than k
+  // the search of fix_bridge: patch length (>= 1; the patch is in bs->patch and the bridging slot stays held) or 0
+  JB_WC int64_t bridge_search(int64_t n64, int64_t thr, int64_t gb, int64_t ga) {
+    if (gb - k + 1 < 0) return 0;                          // good_kmer_before comes out shorter than k
     int ng = load(s.t, gb - k + 1, gb + 1);
     int na = load(s.b, ga, ga + k);
-    if (ng < k || na < k) return f;
-    if (n64 > 0x7fffffff) return f;
-    if (thr > solid) return f;                             // base_extension returns None (src/jasper.py:529)
-    if (!acquire_bridge()) return f;
-    int64_t plen = base_extension((int)n64, thr);
-    if (status || plen <= 0) return f;
-    // row material: patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
+    if (ng < k || na < k) return 0;
+    if (n64 > 0x7fffffff) return 0;
+    if (thr > solid) return 0;                             // base_extension returns None (src/jasper.py:529)
+    if (!acquire_bridge()) return 0;
+    const int64_t plen = base_extension((int)n64, thr);
+    return (status || plen <= 0) ? 0 : plen;
+  }
+
+  // row material of a bridged patch: the patch and the original seq[gb+1:ga] go to the aux arena (aligned on the host)
+  JB_WC bool bridge_row(int64_t gb, int64_t ga, const uint8_t* patch, int64_t plen) {
     const int64_t olen_old = ga - (gb + 1);
     unsigned long long off = 0, rslot = 0;
     JB_SYNC();
@@ -895,9 +907,9 @@ struct Walker {
 #else
     off = *sink.aux_used; *sink.aux_used += (unsigned long long)(plen + olen_old + 8); rslot = (*sink.used)++;
 #endif
-    if (off + plen + olen_old + 8 > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; return f; }
+    if (off + plen + olen_old + 8 > sink.aux_cap || rslot >= sink.cap) { status = JB_E_SCRATCH; return false; }
     JB_LANES(l) {
-      for (int64_t q = l; q < plen; q += 32) sink.aux[off + 8 + q] = bs->patch[q];
+      for (int64_t q = l; q < plen; q += 32) sink.aux[off + 8 + q] = patch[q];
       for (int64_t q = l; q < olen_old; q += 32) sink.aux[off + 8 + plen + q] = get(gb + 1 + q);
       if (l == 0) {
         DevRow& r = sink.rows[rslot];
@@ -909,6 +921,14 @@ struct Walker {
     }
     JB_SYNC();
     seqno += 2;                                           // at most two csv rows come out of one patch
+    return true;
+  }
+
+  JB_WC Fix fix_bridge(int64_t n64, int64_t thr, int64_t gb, int64_t ga) {
+    Fix f;
+    const int64_t plen = bridge_search(n64, thr, gb, ga);
+    if (plen <= 0) return f;
+    if (!bridge_row(gb, ga, bs->patch, plen)) return f;
     f.found = true; f.a = gb + 1; f.e = ga; f.repl = bs->patch; f.rlen = plen; f.tag = 0;
     return f;
   }

@@ -124,7 +124,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
         const Verdict& v = verdicts[i][q];
         Verdict2& v2 = verdicts2[i][q];
         memset(&v2, 0, sizeof v2);
-        if (v.kind != kVDelimit || (int)v.d_ga - (int)v.d_s0 > k) continue;
+        if (v.kind != kVDelimit) continue;
         UnitIO u;
         memset(&u, 0, sizeof u);
         u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
