@@ -1,5 +1,5 @@
 """Host-side restatement of the chunking / joining that src/jasper.sh does around the polisher
-(the rows SURVEY.md §8f-3 marks "next"; bench.py and jasper_b200/jasper.sh use it so that the units
+(the rows SURVEY.md §8f-3 marks "next"; bench.py and jasper_b200/pipeline.py use it so that the units
 polished on the GPU are exactly the reference's units).
 
   split   src/jasper.sh:132-139 (BATCH_SIZE), :155 (pieces named "<first header token>:<offset>")

@@ -192,18 +192,29 @@ class QueryMerFile(object):
         _check(lib.jb_init(len(devices), devs))
         hs = (C.c_void_p * len(devices))()
         _check(lib.jb_db_open_partitioned(os.fsencode(path), len(devices), devs, hs))
-        out = []
-        for d, h in zip(devices, hs):
-            qf = cls.__new__(cls)
-            qf._lib = lib
-            qf._h = C.c_void_p(h)
-            info = _DbInfo()
-            _check(lib.jb_db_info(qf._h, C.byref(info)))
-            qf.info = {f: getattr(info, f) for f, _ in _DbInfo._fields_}
-            qf.k = info.k
-            qf.device = d
-            out.append(qf)
-        return out
+        return [cls._wrap(lib, h, d) for d, h in zip(devices, hs)]
+
+    @classmethod
+    def _wrap(cls, lib, handle, device):
+        qf = cls.__new__(cls)
+        qf._lib = lib
+        qf._h = C.c_void_p(handle)
+        info = _DbInfo()
+        _check(lib.jb_db_info(qf._h, C.byref(info)))
+        qf.info = {f: getattr(info, f) for f, _ in _DbInfo._fields_}
+        qf.k = info.k
+        qf.device = device
+        return qf
+
+    def replicate(self, devices):
+        """Copies of this (whole) table on other GPUs of the box: one disk read, device-to-device copies over NVLink."""
+        n = len(devices)
+        if n == 0:
+            return []
+        devs = (C.c_int * n)(*devices)
+        hs = (C.c_void_p * n)()
+        _check(self._lib.jb_db_replicate(self._h, n, devs, hs))
+        return [self._wrap(self._lib, h, d) for d, h in zip(devices, hs)]
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -1,0 +1,104 @@
+"""jasper_b200/pipeline.py against the UNMODIFIED src/jasper.sh (tests/golden/*/expected_sh, made by
+tests/golden/make_golden_sh.py): threshold, histogram file, polished FASTA and the sorted, awk-mangled fixes.csv.
+On CPUs the oracle stands in for the GPU tables (this file is test infrastructure); the GPU test runs the product."""
+import json
+import os
+
+import pytest
+
+import helpers
+import jasper_oracle as jo
+from jasper_b200 import capi, pipeline
+
+SH_CASES = ["k31_dirty", "k21_even"]
+
+
+class _OracleTable(object):
+    def __init__(self, db_path, histo_rows):
+        self.odb = helpers.OracleDB(db_path)
+        self.rows = histo_rows
+
+    def histogram(self, high):
+        return self.rows
+
+    def solid_threshold(self, rows):
+        return capi.solid_threshold(rows)          # host arithmetic of the library (src/jellyfish.py), no GPU involved
+
+    def polish(self, seqs, k, thre, passes):
+        res, _ = helpers.oracle_polish(self.odb, seqs, k, thre, passes)
+
+        class R(object):
+            pass
+        r = R()
+        r.status = 0
+        r.tallies = [(p.wrong, p.total) for p in res.passes]
+        r.rows = [[list(x) for x in p.rows] for p in res.passes]
+        r.seqs = res.seqs
+        return r
+
+    def close(self):
+        pass
+
+
+def _records(path):
+    out, name = {}, None
+    for line in open(path):
+        if line.startswith(">"):
+            name = line[1:].rstrip("\n")
+            assert name not in out
+            out[name] = ""
+        else:
+            out[name] += line.rstrip("\n")
+    return out
+
+
+def _check_outputs(case, work, k):
+    exp = os.path.join(case["dir"], "expected_sh")
+    assert open(os.path.join(work, "threshold.txt")).read() == open(os.path.join(exp, "threshold.txt")).read()
+    assert open(os.path.join(work, "jfhisto%d.csv" % k)).read() == open(os.path.join(exp, "jfhisto%d.csv" % k)).read()
+    assert open(os.path.join(work, "asm.fa.fixes.csv"), "rb").read() == open(os.path.join(exp, "asm.fa.fixes.csv"), "rb").read()
+    # the reference prints contigs in perl's hash order (random per run): compare the records, not the order
+    assert _records(os.path.join(work, "asm.fa.polished.fasta")) == _records(os.path.join(exp, "asm.fa.polished.fasta"))
+
+
+@pytest.mark.parametrize("name", SH_CASES)
+def test_pipeline_reproduces_jasper_sh_with_the_oracle(golden_cases, name, tmp_path):
+    case = golden_cases[name]
+    meta = json.load(open(os.path.join(case["dir"], "expected_sh", "meta.json")))
+    histo = [tuple(int(x) for x in l.split()) for l in open(os.path.join(case["dir"], "histo.csv"))]
+    out = pipeline.run(case["fasta"], case["db"], k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=str(tmp_path),
+                       open_tables=lambda path, devices: [_OracleTable(path, histo)])
+    assert out["batch_size"] == meta["batch_size"]
+    assert out["threshold"] == case["threshold"]
+    _check_outputs(case, str(tmp_path), meta["k"])
+
+
+def test_fix_row_merge_is_the_awk_sort_chain():
+    """Header mangling, ':' splitting (only the first two ':' fields survive), numeric keys, CRLF kept in the last field."""
+    rows0 = [["c:0", 10, "A", "sT"], ["c:0", 9, "-", "iG"], ["b:100", 5, "AA", "d-"], ["odd:name:0", 3, "C", "sG"]]
+    rows1 = [["c:0", 10, "C", "sA"]]
+    got = pipeline.merge_fix_rows([rows0, rows1]).decode()
+    assert got.split("\n") == [
+        "Contig:Base_coord Original Mutation\r ",       # the header goes through the same awk chain
+        "b:100 5 AA d-\r",
+        "c:0 9 - iG\r",
+        "c:0 10 A sT\r",                                # equal keys: the whole line decides
+        "c:0 10 C sA\r",
+        "odd:name   ",                                  # awk -F ':' keeps two fields: a name with ':' loses the rest of its row
+        "",
+    ]
+
+
+def test_q_value_matches_the_oracle_emulation():
+    for wrong, total, k in ((2270316, 63999135, 37), (1627, 63999312, 37), (0, 1000, 25), (3284, 29980, 37)):
+        assert pipeline.q_value(wrong, total, k) == jo.qv_like_bc(wrong, total, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SH_CASES)
+def test_pipeline_reproduces_jasper_sh_on_the_gpu(golden_cases, name, tmp_path):
+    case = golden_cases[name]
+    meta = json.load(open(os.path.join(case["dir"], "expected_sh", "meta.json")))
+    out = pipeline.run(case["fasta"], case["db"], k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=str(tmp_path))
+    assert out["batch_size"] == meta["batch_size"] and out["threshold"] == case["threshold"]
+    _check_outputs(case, str(tmp_path), meta["k"])
