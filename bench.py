@@ -363,7 +363,16 @@ def main():
         cores = len(os.sched_getaffinity(0))
         sample = (args.cpu_sample_kb * 1000) or min(total_bp, 3_000_000 * cores)
         cb = cpu_baseline(db_path, chunks, sample, cores)
+        # the same slices through the GPU path: the baseline run doubles as a parity check on the bench workload itself
+        slices = [job[1][0] for job in cb["jobs"]]
+        got = qf.polish(slices, K, SOLID_THRE, PASSES)
+        same_bases = [s for _, s in got.seqs] == [o[5][0] for o in cb["outs"]]
+        want_t = [[sum(o[3][ite][q] for o in cb["outs"]) for q in (0, 1)] for ite in range(PASSES + 1)]
+        same_tallies = [list(t) for t in got.tallies] == want_t
+        if not (same_bases and same_tallies):
+            raise SystemExit("bench: the GPU path and the CPU baseline disagree on the bench workload (bases %s, tallies %s)" % (same_bases, same_tallies))
         cpu = {"value": cb["bp"] * PASSES / cb["wall"], "unit": "bp polished/s", "cores": cb["procs"],
+               "parity": "polished bases and QV tallies of all %d slices (%d bp) identical to the GPU path" % (len(slices), cb["bp"]),
                "kind": "reference" if cb["kind"] == "reference-binding" else "port",
                "sample": "%d slices of %d bp of the same chunks, k=%d p=%d, python oracle over %s, %.1f s wall" % (
                    cb["procs"], cb["bp"] // max(1, cb["procs"]), K, PASSES,

@@ -945,7 +945,10 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
         if (int rc = launch_recount(view, ra, rt, used[3], s)) return rc;
         JB_CUDA(cudaEventRecord(ev_r1, s));
         launches += 2;
-        JB_CUDA(cudaMemcpyAsync(used + 4, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
+        // (not while the polished bases travel on the side stream: a device-to-host copy on this stream would queue behind
+        //  them in the copy engine and hold the stream for the whole transfer; the statistic of that pass is dropped)
+        used[4] = 0;
+        if (!(b->early && ite == passes - 1)) JB_CUDA(cudaMemcpyAsync(used + 4, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
         if (verify_recount) {
           // full scan of the new sequence into the buffer the old counts lived in, then compare
           ScanArgs va = a;
