@@ -78,9 +78,11 @@ struct VerdictArgs {
   Verdict* verdicts; unsigned long long cap; unsigned long long* used; uint32_t* vmap;
   uint32_t* verdict_unit;       // contig of every verdict (k_verdicts2 needs it)
   Verdict2* verdicts2;
+  uint8_t* dry_out;             // k_verdicts2: kDryOut bytes of edit scratch per resident warp
   int k, step; uint32_t solid;
 };
 constexpr int kVerdictWarps = 4;
+constexpr int kDryOut = 1024;
 __global__ void __launch_bounds__(kVerdictWarps * 32)
 k_verdicts(TableView t, VerdictArgs a) {
   __shared__ WarpScratch scratch[kVerdictWarps];
@@ -155,6 +157,10 @@ k_verdicts2(TableView t, VerdictArgs a, BridgePool pool) {
       u.in = a.bases + su.seq_off; u.in_len = (int64_t)su.len;
       u.cnt = a.counts + su.out_off; u.okb = a.okb + su.out_off;
       u.next_anchor = -1; u.keep_margin = default_keep_margin(a.k);
+      // a segment that starts shortly in front of the run: the edit and the scan step behind it fit kDryOut bytes of scratch
+      const int64_t s0 = (int64_t)v.re - (int64_t)v.d_jq + (int64_t)v.d_s0;
+      u.base = s0 > 64 ? s0 - 64 : 0;
+      u.out = a.dry_out + ((size_t)blockIdx.x * kWalkWarps + warp) * kDryOut; u.out_cap = kDryOut;
     }
     __syncwarp();
     Walker<DevDB> w(db, a.k, a.step, a.solid, true, u, scratch[warp], pool, no_rows, no_jobs);
@@ -257,6 +263,7 @@ struct Workspace {
   DevBuf<Verdict> verdicts;
   DevBuf<Verdict2> verdicts2;
   DevBuf<uint32_t> verdict_unit;
+  DevBuf<uint8_t> dry_out;
   DevBuf<uint8_t> okb[2];                   // counts / validity of the current and of the next pass's sequence
   DevBuf<ScanUnit> scan_units_new;
   DevBuf<UnitIO> segs;
@@ -283,7 +290,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); dry_out.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -769,6 +776,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       va.counts = w.counts[cidx].p; va.okb = w.okb[cidx].p; va.weak = w.weak.p;
       va.verdicts = w.verdicts.p; va.cap = std::min(w.verdicts.cap, std::min(w.verdicts2.cap, w.verdict_unit.cap)); va.used = w.used.p + 6; va.vmap = w.vmap.p;
       va.verdict_unit = w.verdict_unit.p; va.verdicts2 = w.verdicts2.p;
+      JB_TRY(w.dry_out.ensure((size_t)b->sms * kWalkCtasPerSm * kWalkWarps * kDryOut));
+      va.dry_out = w.dry_out.p;
       va.k = k; va.step = cfg.step; va.solid = solid_thre;
       const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
       JB_CUDA(cudaEventRecord(ev_v0, s));

@@ -49,7 +49,8 @@ struct Verdict2 {
   int16_t rlen;
   int16_t coord_rel;    // fix row: coordinate - s0
   uint8_t fb, fb_len, tag, orig, orig_len;    // mutation = fb * fb_len, original = tag + orig * orig_len
-  uint8_t pad[5];
+  uint8_t post_ok;      // the scan step behind the applied fix is the plain `i += k-1` (evaluated on the edited sequence)
+  uint8_t pad[4];
   uint8_t repl[kV2Repl];
 };
 static_assert(sizeof(Verdict2) == 128, "Verdict2 is meant to be 128 bytes");      // two runs end inside the same 32 positions: no verdict for either

@@ -189,6 +189,8 @@ struct Walker {
   unsigned long long lookups = 0, events = 0;
   uint32_t n_fast = 0, n_post = 0, n_v2 = 0;
   uint32_t vid = 0;                    // index of the verdict consume_verdict returned
+  bool dry = false;                    // k_verdicts2: edits go to scratch, nothing is logged
+  bool v2_post = false;                // the second-stage verdict just applied also knows the following scan step
   long long t_begin = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
@@ -307,7 +309,7 @@ struct Walker {
 
   // ---------------------------------------------------------------------------- edits
   JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
-    if (len <= 0) return true;
+    if (len <= 0 || dry) return true;                 // (a dry run, k_verdicts2, describes no output)
     if (!push_job(jobs, c.slot, src, rel, len)) { status = JB_E_SCRATCH; return false; }
     return true;
   }
@@ -798,6 +800,7 @@ struct Walker {
     if (base - seam_margin > lo_x) lo_x = base - seam_margin;
     if (s0 - k - 2 < lo_x) return false;
     ++n_v2;
+    v2_post = v2->found && v2->post_ok;
     if (!v2->found) return true;                         // decided: nothing to apply
     const int rl = v2->rlen;
     JB_SYNC();
@@ -805,7 +808,7 @@ struct Walker {
     JB_SYNC();
     f.found = true; f.a = s0 + v2->a_rel; f.e = s0 + v2->e_rel; f.repl = s.b; f.rlen = rl;
     if (v2->tag == kTagBridge) {                         // a bridged patch logs its own row (the replaced bases are still in place)
-      if (!bridge_row(f.a - 1, f.e, s.b, rl)) f.found = false;
+      if (!bridge_row(f.a - 1, f.e, s.b, rl)) { f.found = false; v2_post = false; }
       f.tag = 0;
     } else fix_row(f, s0 + v2->coord_rel, v2->fb, v2->fb_len, v2->tag, v2->orig, v2->orig_len);
     return true;
@@ -814,6 +817,7 @@ struct Walker {
   // k_verdicts2: the reference's dispatch on the pass-start sequence, nothing applied (the walker is set up on the whole
   // pristine contig, so every read goes to pass-start bases)
   JB_W void dry_fix(const Verdict& v, int64_t re, Verdict2* out) {
+    dry = true;
     begin();
     const int64_t jq = re - (int64_t)v.d_jq;
     const int64_t s0 = jq + (int64_t)v.d_s0, ga = jq + (int64_t)v.d_ga, gb = s0 + k - 2;
@@ -831,9 +835,20 @@ struct Walker {
         out->a_rel = (int16_t)(f.a - s0); out->e_rel = (int16_t)(f.e - s0); out->rlen = (int16_t)f.rlen;
         out->coord_rel = (int16_t)(f.coord - s0);
         out->fb = s.fx[0]; out->fb_len = (uint8_t)f.fb_len; out->tag = f.tag; out->orig = s.fx[64]; out->orig_len = (uint8_t)f.orig_len;
+        out->post_ok = 0;
       }
       if (ok && f.found) for (int q = l; q < (int)f.rlen; q += 32) out->repl[q] = f.repl[q];
     }
+    JB_SYNC();
+    // the scan step behind the fix (src/jasper.py:56-100 at i = re), on the edited sequence in scratch
+    if (ok && f.found && c.out && apply_edit(f.a, f.e, f.repl, f.rlen)) {
+      i = re;
+      int64_t occ = 0, prevk = 0;
+      if (i < L - k + 1 && !generic_body(occ, prevk) && !status && occ >= solid && !(i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) {
+        JB_LANES(l) { if (l == 0) out->post_ok = 1; }
+      }
+    }
+    status = 0;
     JB_SYNC();
     release_bridge();
     JB_LANES(l) { if (l == 0) out->valid = ok ? 1 : 0; }
@@ -1027,8 +1042,10 @@ struct Walker {
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
     wrong += nbad;
     if (!fix || gb < 0) return;
+    v2_post = false;
     const int done = fixing_sid(s0, nbad, thre, gb, ga, fast ? &v : nullptr);
-    if (!fast || !done || status || brk || !v.post_ok) return;
+    if (!fast || status || brk) return;
+    if (!((done && v.post_ok) || (done == kPostNone && v2_post))) return;
     // ---- the scan step behind a single-base fix (src/jasper.py:56-100 at the new i) was evaluated with the verdict
     if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;       // the loop re-checks the seam first
     i += k - 1;

@@ -130,6 +130,9 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
         u.in = (const uint8_t*)cur[i].data(); u.in_len = len[i];
         u.cnt = cnts[i].data(); u.okb = okbs[i].data();
         u.next_anchor = -1; u.keep_margin = keep_margin;
+        const int64_t s0v = (int64_t)v.re - (int64_t)v.d_jq + (int64_t)v.d_s0;
+        static uint8_t dry_out[1024];
+        u.base = s0v > 64 ? s0v - 64 : 0; u.out = dry_out; u.out_cap = sizeof dry_out;
         Walker<HostDB> w(db, k, sampling_step(k), solid, true, u, ws, pool, sink, jobs);
         w.dry_fix(v, (int64_t)v.re, &v2);
       }
