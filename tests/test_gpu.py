@@ -332,3 +332,24 @@ def test_partitioned_table_equals_the_whole_one(golden_cases, dbs, name, monkeyp
     finally:
         for qf in parts:
             qf.close()
+
+
+def test_bench_contract_on_a_small_genome(tmp_path):
+    """bench.py end to end on a 4 Mb genome: one JSON line with the contract's keys, and its built-in parity check
+    (the CPU-baseline slices also go through the GPU path and must agree) passes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JB_BENCH_DIR=str(tmp_path / "bench"))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--genome-mb", "4", "--steps", "1", "--warmup", "1", "--cpu-sample-kb", "400"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and "identical to the GPU path" in line["cpu_baseline"]["parity"]
