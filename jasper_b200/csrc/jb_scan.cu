@@ -181,9 +181,20 @@ __global__ void __launch_bounds__(256)
 k_recount(TableView t, RecountArgs a) {
   const unsigned long long n = *a.n_jobs;
   const int k = t.g.k;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // many short jobs (a fixing pass over a dirty assembly: ~3 jobs per edit, a few hundred positions each): a team of
+  // a.team threads per job, teams spread over a 1-D grid.  Few long jobs: the CTAs of one grid row share a job.
+  int64_t tid, nth;
+  unsigned long long j0, jstep;
+  if (a.team) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    tid = (int64_t)(g % (unsigned)a.team); nth = a.team;
+    j0 = g / (unsigned)a.team; jstep = (unsigned long long)gridDim.x * blockDim.x / (unsigned)a.team;
+  } else {
+    tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nth = (int64_t)gridDim.x * blockDim.x;
+    j0 = blockIdx.y; jstep = gridDim.y;
+  }
   unsigned long long probes = 0;
-  for (unsigned long long j = blockIdx.y; j < n; j += gridDim.y) {
+  for (unsigned long long j = j0; j < n; j += jstep) {
     const CopyJob job = a.jobs[j];
     const int64_t off = a.dst_off[job.slot];
     if (off < 0) continue;
@@ -256,7 +267,13 @@ int launch_recount(const TableView& view, const RecountArgs& a, const RecountTai
   const unsigned long long nj = std::max<unsigned long long>(n_jobs_hint, 1);
   const unsigned gx = (unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(2, 65536 / nj));
   dim3 g(gx, (unsigned)std::min<unsigned long long>(nj, 32768));
-  k_recount<<<g, 256, 0, s>>>(view, a);
+  RecountArgs a2 = a;
+  a2.team = 0;
+  if (nj >= 16384 && getenv("JB_RECOUNT_ROWS") == nullptr) {     // short jobs: 64 threads each
+    a2.team = 64;
+    g = dim3((unsigned)std::min<unsigned long long>((nj * 64 + 255) / 256, 148ull * 64), 1);
+  }
+  k_recount<<<g, 256, 0, s>>>(view, a2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount launch: ") + cudaGetErrorString(e));
   if (t.n_units) {

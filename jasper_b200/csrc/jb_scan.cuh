@@ -106,6 +106,7 @@ struct RecountArgs {
   const uint32_t* cnt_old; const uint8_t* okb_old;
   uint32_t* cnt_new; uint8_t* okb_new;
   unsigned long long* probes;   // statistics
+  int team;                     // threads per job (multiple of 32) on a 1-D grid; 0 = one grid row of CTAs per job
 };
 struct RecountTailArgs {
   const ScanUnit* units_old; const ScanUnit* units_new; uint32_t n_units;
