@@ -101,6 +101,14 @@ int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** outs);
  * others by 32-byte peer loads over NVLink / NVSwitch.  Every entry point that takes a jb_db works on such a handle
  * except jb_db_dump and jb_db_replicate.  Close every handle with jb_db_close. */
 int jb_db_open_partitioned(const char* jf_path, int n, const int* devices, jb_db** outs);
+/* The same with one PROCESS per GPU (torchrun): every rank streams the file and keeps the slots of part `rank` on its
+ * device; the ranks then publish a handle each (CUDA IPC), the host side gathers the world * JB_PART_HANDLE_BYTES bytes
+ * in rank order (e.g. torch.distributed.all_gather_object) and every rank attaches the other parts.  Until then the
+ * handle refuses lookups and polishing. */
+#define JB_PART_HANDLE_BYTES 128
+int jb_db_open_part(const char* jf_path, int device, int rank, int world, jb_db** out);
+int jb_db_part_handle(const jb_db* db, char* handle /* JB_PART_HANDLE_BYTES */);
+int jb_db_attach_parts(jb_db* db, const char* handles /* world * JB_PART_HANDLE_BYTES, rank order */);
 void jb_db_close(jb_db* db);
 /* Dump the resident table back as (key_lo, key_hi, count) triples in slot order (tests: must
  * equal the file's record list).  `cap` = capacity of the three arrays in records. */

@@ -59,7 +59,7 @@ except Exception:                                  # numpy is optional: the slow
 # every symbol include/jasper_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "jb_init", "jb_device_count", "jb_last_error", "jb_version",
-    "jb_db_open", "jb_db_open_partitioned", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
+    "jb_db_open", "jb_db_open_partitioned", "jb_db_open_part", "jb_db_part_handle", "jb_db_attach_parts", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
     "jb_lookup", "jb_lookup_flat", "jb_count_positions",
     "jb_polish", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
     "jb_result_status", "jb_result_iterations", "jb_result_tally", "jb_result_num_rows", "jb_result_rows",
@@ -92,6 +92,9 @@ def load_library():
         "jb_version": (C.c_char_p, []),
         "jb_db_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "jb_db_open_partitioned": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
+        "jb_db_open_part": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "jb_db_part_handle": (C.c_int, [vp, C.c_char_p]),
+        "jb_db_attach_parts": (C.c_int, [vp, C.c_char_p]),
         "jb_db_info": (C.c_int, [vp, C.POINTER(_DbInfo)]),
         "jb_db_replicate": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
         "jb_db_close": (None, [vp]),
@@ -193,6 +196,27 @@ class QueryMerFile(object):
         hs = (C.c_void_p * len(devices))()
         _check(lib.jb_db_open_partitioned(os.fsencode(path), len(devices), devs, hs))
         return [cls._wrap(lib, h, d) for d, h in zip(devices, hs)]
+
+    PART_HANDLE_BYTES = 128
+
+    @classmethod
+    def open_part(cls, path: str, device: int, rank: int, world: int):
+        """One process per GPU: build and keep part `rank` of the table on `device`.  Exchange part_handle() between the
+        ranks (any host-side all-gather), then attach_parts(handles in rank order) before the first lookup."""
+        lib = load_library()
+        _check(lib.jb_init(1, (C.c_int * 1)(device)))
+        h = C.c_void_p()
+        _check(lib.jb_db_open_part(os.fsencode(path), device, rank, world, C.byref(h)))
+        return cls._wrap(lib, h.value, device)
+
+    def part_handle(self) -> bytes:
+        buf = C.create_string_buffer(self.PART_HANDLE_BYTES)
+        _check(self._lib.jb_db_part_handle(self._h, buf))
+        return buf.raw
+
+    def attach_parts(self, handles) -> None:
+        blob = b"".join(handles)
+        _check(self._lib.jb_db_attach_parts(self._h, blob))
 
     @classmethod
     def _wrap(cls, lib, handle, device):

@@ -91,6 +91,9 @@ __device__ __forceinline__ uint32_t table_count(const TableView& t, const Key& c
 
 }  // namespace jb
 
+struct jb_db;
+int jb_check_ready(const jb_db* db);   // JB_OK, or an error while a part-wise opened table still lacks its other parts
+
 struct jb_db {
   jb::JfHeader hdr;
   int device = 0;
@@ -105,6 +108,9 @@ struct jb_db {
   cudaStream_t stream = nullptr;
   // partitioned tables (jb_db_open_partitioned): this handle owns part `my_part`; the others are peer memory
   int n_parts = 1, my_part = 0;
+  bool parts_ready = true;             // false between jb_db_open_part and jb_db_attach_parts
+  bool ipc_mapped[jb::kMaxParts] = {};
+  uint64_t part_overlap = 0;
   jb::Slot* parts[jb::kMaxParts] = {};
   uint64_t part_first[jb::kMaxParts + 1] = {};
   jb::TableView view() const {

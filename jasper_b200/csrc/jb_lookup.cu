@@ -53,6 +53,7 @@ __global__ void k_gather(const uint8_t* __restrict__ base, uint64_t n_sectors, u
 using namespace jb;
 
 extern "C" int jb_lookup_flat(const jb_db* db, const char* buf, const uint64_t* offsets, size_t n, uint32_t* counts) {
+  if (int rc_ready = jb_check_ready(db)) return rc_ready;
   if (!db || (!buf && n && offsets[n]) || !offsets || !counts) return fail(JB_E_ARG, "jb_lookup_flat: null argument");
   if (n == 0) return JB_OK;
   JB_CUDA(cudaSetDevice(db->device));
@@ -87,6 +88,7 @@ extern "C" int jb_lookup(const jb_db* db, const char* const* strs, size_t n, uin
 }
 
 extern "C" int jb_count_positions(const jb_db* db, const char* seq, size_t len, uint32_t* counts) {
+  if (int rc_ready = jb_check_ready(db)) return rc_ready;
   if (!db || (!seq && len) || !counts) return fail(JB_E_ARG, "jb_count_positions: null argument");
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;

@@ -79,6 +79,7 @@ struct VerdictArgs {
   uint32_t* verdict_unit;       // contig of every verdict (k_verdicts2 needs it)
   Verdict2* verdicts2;
   uint8_t* dry_out;             // k_verdicts2: kDryOut bytes of edit scratch per resident warp
+  int dry_post;                 // k_verdicts2 also evaluates the scan step behind the fix
   int k, step; uint32_t solid;
 };
 constexpr int kVerdictWarps = 4;
@@ -160,7 +161,7 @@ k_verdicts2(TableView t, VerdictArgs a, BridgePool pool) {
       // a segment that starts shortly in front of the run: the edit and the scan step behind it fit kDryOut bytes of scratch
       const int64_t s0 = (int64_t)v.re - (int64_t)v.d_jq + (int64_t)v.d_s0;
       u.base = s0 > 64 ? s0 - 64 : 0;
-      u.out = a.dry_out + ((size_t)blockIdx.x * kWalkWarps + warp) * kDryOut; u.out_cap = kDryOut;
+      u.out = a.dry_out + ((size_t)blockIdx.x * kWalkWarps + warp) * kDryOut; u.out_cap = a.dry_post ? kDryOut : 0;
     }
     __syncwarp();
     Walker<DevDB> w(db, a.k, a.step, a.solid, true, u, scratch[warp], pool, no_rows, no_jobs);
@@ -407,6 +408,7 @@ namespace {
 int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out, bool prescan) {
   if (!db || (!seqs && n) || !out) return fail(JB_E_ARG, "jb_batch_upload: null argument");
   *out = nullptr;
+  if (int rc_ready = jb_check_ready(db)) return rc_ready;
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
   std::unique_ptr<jb_batch> b(new jb_batch());
@@ -777,7 +779,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       va.verdicts = w.verdicts.p; va.cap = std::min(w.verdicts.cap, std::min(w.verdicts2.cap, w.verdict_unit.cap)); va.used = w.used.p + 6; va.vmap = w.vmap.p;
       va.verdict_unit = w.verdict_unit.p; va.verdicts2 = w.verdicts2.p;
       JB_TRY(w.dry_out.ensure((size_t)b->sms * kWalkCtasPerSm * kWalkWarps * kDryOut));
-      va.dry_out = w.dry_out.p;
+      va.dry_out = w.dry_out.p; va.dry_post = getenv("JB_NO_V2_POST") ? 0 : 1;
       va.k = k; va.step = cfg.step; va.solid = solid_thre;
       const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
       JB_CUDA(cudaEventRecord(ev_v0, s));

@@ -117,8 +117,8 @@ __device__ __forceinline__ void put_slot(const PlaceTarget& T, uint64_t slot, co
   int p = 0;
 #pragma unroll 1
   for (int q = 1; q < T.n_parts; ++q) p += slot >= T.part_first[q] ? 1 : 0;
-  T.part[p][slot - T.part_first[p]] = v;
-  if (p > 0 && slot < T.part_first[p] + T.overlap) T.part[p - 1][slot - T.part_first[p - 1]] = v;
+  if (T.part[p]) T.part[p][slot - T.part_first[p]] = v;                     // (a rank of jb_db_open_part keeps its own part only)
+  if (p > 0 && slot < T.part_first[p] + T.overlap && T.part[p - 1]) T.part[p - 1][slot - T.part_first[p - 1]] = v;
 }
 
 // K0c: inclusive prefix-max inside the block, then scatter the 16-byte slots.
@@ -222,18 +222,21 @@ namespace {
 // One database, n >= 1 handles.  n == 1: the whole table on devices[0].  n > 1: the slots partitioned over the devices
 // (SURVEY.md §8e fallback): the records are unpacked and placed by kernels on devices[0], whose stores go straight into
 // the owning part (peer stores), so the table never has to fit one GPU; every handle then probes all parts.
-int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
+// only_part >= 0 (jb_db_open_part, one process per GPU): n_dev parts in all, this process builds and keeps part only_part
+// on devices[0]; the other parts are attached later through CUDA IPC handles.
+int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs, int only_part = -1) {
   auto t0 = std::chrono::steady_clock::now();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(JB_E_CUDA, "no CUDA device: libjasper_b200 has no CPU path");
   if (n_dev < 1 || n_dev > kMaxParts) return fail(JB_E_ARG, "jb_db_open: between 1 and " + std::to_string(kMaxParts) + " devices");
-  for (int i = 0; i < n_dev; ++i) {
+  const int n_local = only_part >= 0 ? 1 : n_dev;       // handles (and devices) of this process
+  for (int i = 0; i < n_local; ++i) {
     if (devices[i] < 0 || devices[i] >= ndev) return fail(JB_E_ARG, "jb_db_open: bad device index");
     for (int j = 0; j < i; ++j) if (devices[j] == devices[i]) return fail(JB_E_ARG, "jb_db_open_partitioned: a device is listed twice");
   }
   const int device = devices[0];
-  if (n_dev > 1) {
+  if (n_dev > 1 && only_part < 0) {
     for (int i = 0; i < n_dev; ++i)
       for (int j = 0; j < n_dev; ++j) {
         if (i == j) continue;
@@ -259,8 +262,8 @@ int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
   for (int i = 0; i < 9; ++i) hlen = hlen * 10 + (uint64_t)((head[i] >= '0' && head[i] <= '9') ? head[i] - '0' : 0);
   head.resize(9 + std::min<uint64_t>(hlen, fsize - 9));
   if ((uint64_t)pread(fd, head.data(), head.size(), 0) != head.size()) { ::close(fd); return fail(JB_E_IO, "short read of header"); }
-  std::vector<jb_db*> dbs((size_t)n_dev, nullptr);
-  for (int i = 0; i < n_dev; ++i) dbs[i] = new jb_db();
+  std::vector<jb_db*> dbs((size_t)n_local, nullptr);
+  for (int i = 0; i < n_local; ++i) dbs[i] = new jb_db();
   auto drop = [&]() { for (jb_db* d : dbs) jb_db_close(d); };
   jb_db* db = dbs[0];
   std::string err = parse_jf_header(head.data(), head.size(), &db->hdr);
@@ -276,7 +279,7 @@ int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
   double load = 0.5;
   if (const char* e = getenv("JB_TABLE_LOAD")) { double v = atof(e); if (v > 0.05 && v <= 0.95) load = v; }
   size_t free_b = ~(size_t)0, total_b = 0;
-  for (int i = 0; i < n_dev; ++i) {                       // the tightest device decides
+  for (int i = 0; i < n_local; ++i) {                     // the tightest device decides
     size_t f = 0;
     JB_CUDA(cudaSetDevice(devices[i]));
     JB_CUDA(cudaMemGetInfo(&f, &total_b));
@@ -307,23 +310,26 @@ int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
   for (int p2 = 0; p2 + 1 < n_dev; ++p2) overlap = std::min<uint64_t>(overlap, (part_first[p2 + 2] - part_first[p2 + 1]) & ~(uint64_t)1);
   std::vector<uint64_t> lut = build_hash_lut(h);
   Slot* parts[kMaxParts] = {};
-  for (int i = 0; i < n_dev; ++i) {
-    jb_db* d = dbs[i];
-    if (i) d->hdr = db->hdr;
-    d->n_records = n; d->device = devices[i]; d->geom = g; d->cap = cap; d->n_slots = n_slots;
-    JB_CUDA(cudaSetDevice(devices[i]));
+  for (int li = 0; li < n_local; ++li) {
+    const int i = only_part >= 0 ? only_part : li;        // which part this handle owns
+    jb_db* d = dbs[li];
+    if (li) d->hdr = db->hdr;
+    d->n_records = n; d->device = devices[li]; d->geom = g; d->cap = cap; d->n_slots = n_slots;
+    JB_CUDA(cudaSetDevice(devices[li]));
     JB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     const uint64_t mine = part_first[i + 1] - part_first[i] + (i + 1 < n_dev ? overlap : 0);
-    if (cudaMalloc(&d->slots, mine * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); ::close(fd); drop(); return fail(JB_E_NOMEM, "cannot allocate the k-mer table part on device " + std::to_string(devices[i])); }
+    if (cudaMalloc(&d->slots, mine * sizeof(Slot)) != cudaSuccess) { cudaGetLastError(); ::close(fd); drop(); return fail(JB_E_NOMEM, "cannot allocate the k-mer table part on device " + std::to_string(devices[li])); }
     JB_CUDA(cudaMemsetAsync(d->slots, 0, mine * sizeof(Slot), d->stream));
     JB_CUDA(cudaMalloc(&d->lut, lut.size() * 8));
     JB_CUDA(cudaMemcpyAsync(d->lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, d->stream));
     JB_CUDA(cudaStreamSynchronize(d->stream));
     parts[i] = d->slots;
   }
-  for (int i = 0; i < n_dev; ++i) {
-    jb_db* d = dbs[i];
-    d->n_parts = n_dev; d->my_part = i;
+  for (int li = 0; li < n_local; ++li) {
+    jb_db* d = dbs[li];
+    d->n_parts = n_dev; d->my_part = only_part >= 0 ? only_part : li;
+    d->parts_ready = only_part < 0 || n_dev == 1;
+    d->part_overlap = overlap;
     for (int q = 0; q < n_dev; ++q) d->parts[q] = parts[q];
     for (int q = 0; q <= n_dev; ++q) d->part_first[q] = part_first[q];
   }
@@ -398,15 +404,16 @@ int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs) {
   if (fin.err_overflow) { drop(); return fail(JB_E_NOMEM, "table overflow tail exhausted (hash positions are badly skewed); lower JB_TABLE_LOAD"); }
   // a probe that starts in part p ends at the first empty slot: there must be one inside p's copy of the next part's start
   for (int p2 = 0; p2 + 1 < n_dev; ++p2) {
+    if (only_part >= 0 && p2 != only_part) continue;
     std::vector<Slot> ov((size_t)overlap);
-    JB_CUDA(cudaSetDevice(devices[p2]));
+    JB_CUDA(cudaSetDevice(devices[only_part >= 0 ? 0 : p2]));
     JB_CUDA(cudaMemcpy(ov.data(), parts[p2] + (part_first[p2 + 1] - part_first[p2]), (size_t)overlap * sizeof(Slot), cudaMemcpyDeviceToHost));
     bool empty = false;
     for (uint64_t q = 0; q + 2 < overlap && !empty; ++q) empty = ov[q].count == 0;
     if (!empty) { drop(); return fail(JB_E_NOMEM, "a run of occupied slots crosses a whole partition overlap (" + std::to_string(overlap) + " slots); lower JB_TABLE_LOAD"); }
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  for (int i = 0; i < n_dev; ++i) { dbs[i]->max_disp = fin.max_disp; dbs[i]->build_ms = ms; dbs[i]->load_seconds = secs; outs[i] = dbs[i]; }
+  for (int i = 0; i < n_local; ++i) { dbs[i]->max_disp = fin.max_disp; dbs[i]->build_ms = ms; dbs[i]->load_seconds = secs; outs[i] = dbs[i]; }
   return JB_OK;
 }
 
@@ -418,10 +425,58 @@ extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
   return open_impl(path, 1, &device, out);
 }
 
+// ---- one process per GPU: build the own part, swap CUDA IPC handles through the host, attach the others
+struct PartHandle {             // the 64 + 24 bytes a rank publishes
+  cudaIpcMemHandle_t mem;
+  uint64_t cap, n_slots, overlap;
+};
+static_assert(sizeof(PartHandle) <= JB_PART_HANDLE_BYTES, "JB_PART_HANDLE_BYTES is too small");
+
+extern "C" int jb_db_open_part(const char* path, int device, int rank, int world, jb_db** out) {
+  if (!path || !out || world < 1 || world > kMaxParts || rank < 0 || rank >= world) return fail(JB_E_ARG, "jb_db_open_part: bad argument");
+  *out = nullptr;
+  return open_impl(path, world, &device, out, rank);
+}
+
+extern "C" int jb_db_part_handle(const jb_db* db, char* handle) {
+  if (!db || !handle) return fail(JB_E_ARG, "jb_db_part_handle: null argument");
+  JB_CUDA(cudaSetDevice(db->device));
+  PartHandle h{};
+  JB_CUDA(cudaIpcGetMemHandle(&h.mem, db->slots));
+  h.cap = db->cap; h.n_slots = db->n_slots; h.overlap = db->part_overlap;
+  std::memset(handle, 0, JB_PART_HANDLE_BYTES);
+  std::memcpy(handle, &h, sizeof h);
+  return JB_OK;
+}
+
+extern "C" int jb_db_attach_parts(jb_db* db, const char* handles) {
+  if (!db || !handles) return fail(JB_E_ARG, "jb_db_attach_parts: null argument");
+  if (db->parts_ready) return JB_OK;
+  JB_CUDA(cudaSetDevice(db->device));
+  for (int p = 0; p < db->n_parts; ++p) {
+    PartHandle h;
+    std::memcpy(&h, handles + (size_t)p * JB_PART_HANDLE_BYTES, sizeof h);
+    if (h.cap != db->cap || h.n_slots != db->n_slots || h.overlap != db->part_overlap)
+      return fail(JB_E_ARG, "jb_db_attach_parts: rank " + std::to_string(p) + " built a table of another geometry (set JB_TABLE_LOAD to the same value on every rank)");
+    if (p == db->my_part) continue;
+    void* ptr = nullptr;
+    JB_CUDA(cudaIpcOpenMemHandle(&ptr, h.mem, cudaIpcMemLazyEnablePeerAccess));
+    db->parts[p] = static_cast<Slot*>(ptr);
+    db->ipc_mapped[p] = true;
+  }
+  db->parts_ready = true;
+  return JB_OK;
+}
+
 extern "C" int jb_db_open_partitioned(const char* path, int n, const int* devices, jb_db** outs) {
   if (!path || !devices || !outs || n < 1) return fail(JB_E_ARG, "jb_db_open_partitioned: bad argument");
   for (int i = 0; i < n; ++i) outs[i] = nullptr;
   return open_impl(path, n, devices, outs);
+}
+
+int jb_check_ready(const jb_db* db) {
+  if (db && !db->parts_ready) return jb::fail(JB_E_ARG, "partitioned table: attach the other parts first (jb_db_attach_parts)");
+  return JB_OK;
 }
 
 void jb_release_cached_workspaces(int device);      // jb_polish.cu
@@ -430,6 +485,7 @@ extern "C" void jb_db_close(jb_db* db) {
   if (!db) return;
   cudaSetDevice(db->device);
   jb_release_cached_workspaces(db->device);
+  for (int p = 0; p < kMaxParts; ++p) if (db->ipc_mapped[p] && db->parts[p]) cudaIpcCloseMemHandle(db->parts[p]);
   if (db->slots) cudaFree(db->slots);
   if (db->lut) cudaFree(db->lut);
   if (db->stream) cudaStreamDestroy(db->stream);
@@ -480,6 +536,7 @@ extern "C" int jb_db_dump(const jb_db* db, uint64_t* key_lo, uint64_t* key_hi, u
 
 extern "C" int jb_db_histogram(const jb_db* db, uint64_t high, uint64_t* hist) {
   if (!db || !hist) return fail(JB_E_ARG, "jb_db_histogram: null argument");
+  if (!db->parts_ready) return fail(JB_E_ARG, "partitioned table: attach the other parts first (jb_db_attach_parts)");
   JB_CUDA(cudaSetDevice(db->device));
   unsigned long long* d_h = nullptr;
   JB_CUDA(cudaMalloc(&d_h, (high + 2) * 8));

@@ -841,7 +841,7 @@ struct Walker {
     }
     JB_SYNC();
     // the scan step behind the fix (src/jasper.py:56-100 at i = re), on the edited sequence in scratch
-    if (ok && f.found && c.out && apply_edit(f.a, f.e, f.repl, f.rlen)) {
+    if (ok && f.found && c.out && c.out_cap && apply_edit(f.a, f.e, f.repl, f.rlen)) {
       i = re;
       int64_t occ = 0, prevk = 0;
       if (i < L - k + 1 && !generic_body(occ, prevk) && !status && occ >= solid && !(i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) {

@@ -1,5 +1,6 @@
 """Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -353,3 +354,66 @@ def test_bench_contract_on_a_small_genome(tmp_path):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and "identical to the GPU path" in line["cpu_baseline"]["parity"]
+
+
+def _part_rank(rank, world, case, tmp, q):
+    """One rank of the per-process partitioned table: build the own part, swap handles through files, attach, answer."""
+    import time
+    try:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+        qf = capi.QueryMerFile.open_part(case["db"], rank, rank, world)
+        try:
+            qf.lookup(["ACGT"])
+            q.put((rank, "lookup before attach did not fail"))
+            return
+        except capi.JasperError:
+            pass
+        with open(os.path.join(tmp, "h%d.tmp" % rank), "wb") as f:
+            f.write(qf.part_handle())
+        os.rename(os.path.join(tmp, "h%d.tmp" % rank), os.path.join(tmp, "h%d.bin" % rank))
+        handles = []
+        for r in range(world):
+            path = os.path.join(tmp, "h%d.bin" % r)
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > 120:
+                    raise RuntimeError("rank %d never published its handle" % r)
+                time.sleep(0.01)
+            handles.append(open(path, "rb").read())
+        qf.attach_parts(handles)
+        strings = [s for s, _, _ in case["lookups"]]
+        got = qf.lookup(strings)
+        seqs = jo.read_fasta(case["fasta"])
+        res = qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+        fasta = jo.format_fasta(res.seqs)
+        # keep the mapping alive until every rank is done with its peers' memory
+        open(os.path.join(tmp, "done%d" % rank), "w").close()
+        t0 = time.time()
+        while not all(os.path.exists(os.path.join(tmp, "done%d" % r)) for r in range(world)) and time.time() - t0 < 120:
+            time.sleep(0.01)
+        qf.close()
+        q.put((rank, got, res.tallies, fasta))
+    except BaseException as e:      # noqa: BLE001
+        q.put((rank, "error: %r" % (e,)))
+
+
+def test_partitioned_table_one_process_per_gpu(golden_cases, tmp_path):
+    """jb_db_open_part / jb_db_part_handle / jb_db_attach_parts: two processes, one GPU each, every rank holds half of the
+    slots and reads the other half through CUDA IPC; both must reproduce the golden lookups and polished FASTA."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs with peer access")
+    import multiprocessing as mp
+    case = golden_cases["k37_mix"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_part_rank, args=(r, 2, case, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    want_fasta = helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+    for out in outs:
+        assert len(out) == 4, out
+        assert out[1] == [c for _, _, c in case["lookups"]]
+        assert out[3] == want_fasta
