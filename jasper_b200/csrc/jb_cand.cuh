@@ -36,7 +36,7 @@ namespace jb {
 
 constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check string fits (<= 3k + 8)
 constexpr int kMaxCands = 64;
-constexpr int kFastBack = 64;                    // fast_delimit: staged windows in front of the event ...
+constexpr int kFastBack = 64;                    // make_verdict: staged windows in front of the event ...
 constexpr int kFastWin = kFastBack + 2 * JB_MAX_K + 24;   // ... and in all
 
 enum CandKind : uint8_t { kSub = 0, kIns = 1, kDel = 2, kDip = 3 };
@@ -117,8 +117,8 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint32_t failmask[2];
   int32_t dip_nb, dip_bl;    // kDip: chars of flank before (s.c[0:nb)) and after (s.c[nb+n : nb+n+bl))
   uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
-  uint32_t fc[kFastWin];     // fast_delimit: bulk-scan counts of the windows around an event (jb_walker.cuh)
-  int32_t fbad[2];           // fast_delimit: last unavailable entry before / first one behind the event
+  uint32_t fc[kFastWin];     // make_verdict: bulk-scan counts of the windows around an event (jb_verdict.cuh)
+  int32_t fbad[2];           // make_verdict: last unavailable entry before / first one behind the event
   uint32_t win[2];           // score_single_base: counts of the winner's samples 0 (m = 0) and 1 (m = len - k)
   SeqView view;              // published copy of the walker's sequence state
   Packed pt;                 // packed to_be_fixed (or, for kDip, the whole check string before + t + after)

@@ -205,8 +205,8 @@ def test_packed_keys_equal_the_byte_loop(hostsim_lib, k):
 
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 def test_fast_path_is_taken_and_changes_nothing(golden_cases, hostsim_lib, name, monkeypatch):
-    """Events in untouched territory are delimited from the bulk scan's counts (fast_delimit), single-base fixes are
-    scored by first_passing_lean and the scan step behind them is taken from data in hand; with the validity bytes
+    """Events in untouched territory take bounds, fix and the following scan step from verdicts (jb_verdict.cuh: first
+    stage for single-base fixes, second stage = the walker's own dispatch run dry); with the validity bytes
     withheld the walker runs its generic code for everything.  Both must give the same bytes, and the fast path must
     really carry most events."""
     case = golden_cases[name]
