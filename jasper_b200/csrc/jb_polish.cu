@@ -115,7 +115,7 @@ k_verdicts(TableView t, VerdictArgs a) {
       Verdict* slot = reinterpret_cast<Verdict*>(s.fx);                  // (16 bytes of scratch: the row text area is idle here)
       int64_t re2 = -1;
       const bool ok = make_verdict(db, s, a.bases + u.seq_off, a.counts + u.out_off, a.okb + u.out_off, len, a.k, a.step,
-                                   (int64_t)a.solid, re - 1, slot, &re2);
+                                   (int64_t)a.solid, re - 1, slot, &re2, a.dry_post != 2);
       if (ok && re2 == re && lane == 0) {
         const unsigned long long id = atomicAdd(a.used, 1ull);
         if (id < a.cap) {
@@ -779,7 +779,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       va.verdicts = w.verdicts.p; va.cap = std::min(w.verdicts.cap, std::min(w.verdicts2.cap, w.verdict_unit.cap)); va.used = w.used.p + 6; va.vmap = w.vmap.p;
       va.verdict_unit = w.verdict_unit.p; va.verdicts2 = w.verdicts2.p;
       JB_TRY(w.dry_out.ensure((size_t)b->sms * kWalkCtasPerSm * kWalkWarps * kDryOut));
-      va.dry_out = w.dry_out.p; va.dry_post = getenv("JB_NO_V2_POST") ? 0 : 1;
+      va.dry_out = w.dry_out.p; va.dry_post = getenv("JB_NO_V2_POST") ? 0 : (getenv("JB_NO_POST2") ? 2 : 1);
       va.k = k; va.step = cfg.step; va.solid = solid_thre;
       const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
       JB_CUDA(cudaEventRecord(ev_v0, s));

@@ -30,7 +30,7 @@ struct Verdict {
   uint8_t kind;         // VerdictKind: kVDelimit = bounds only (the walker runs the reference's dispatch itself)
   uint8_t base;         // kVSub / kVIns: the new base
   uint8_t bad;          // the base at s0 + k - 1
-  uint8_t post_ok;      // the scan step behind the fix is the plain `i += k-1`
+  uint8_t post_ok;      // bit 0: the scan step behind the fix is the plain `i += k-1`; bit 1: so is the one after it
   uint16_t pad;
 };
 static_assert(sizeof(Verdict) == 16, "Verdict is meant to be 16 bytes");
@@ -59,7 +59,7 @@ static_assert(sizeof(Verdict2) == 128, "Verdict2 is meant to be 128 bytes");    
 // False: no verdict (the run touches invalid windows, a contig end, or is longer than the staged window).
 template <class DB>
 JB_FREE_NOINLINE bool make_verdict(const DB& db, WarpScratch& s, const uint8_t* in, const uint32_t* cnt, const uint8_t* okb,
-                                   int64_t in_len, int k, int step, int64_t solid, int64_t a_pos, Verdict* out, int64_t* re_out) {
+                                   int64_t in_len, int k, int step, int64_t solid, int64_t a_pos, Verdict* out, int64_t* re_out, bool second_step = true) {
   const int W = kFastBack + 2 * k + 24;
   const int64_t W0 = a_pos - kFastBack;
   const int64_t hi_p = in_len - 2 * (int64_t)k - 3;            // keeps every end-of-contig clamp of the reference out of play
@@ -137,6 +137,25 @@ JB_FREE_NOINLINE bool make_verdict(const DB& db, WarpScratch& s, const uint8_t* 
         }
         // src/jasper.py:56-100 at the new i: neither weak nor below 1/50 of the window k bases back
         v.post_ok = (at && (int64_t)occ >= solid && !(occ * JB_DIVISOR < prevk)) ? 1 : 0;
+        if (v.post_ok && second_step) {
+          // ... and once more at i + k - 1: that window is untouched, the one k bases back still holds the new base
+          // (substitution: the trial's last sample; insertion: one extra probe; deletion: untouched as well)
+          const int64_t i2 = W0 + gq + (k - 1) - (ins ? 1 : 0) + (v.kind == kVDel ? 1 : 0);     // pass-start coordinate of the window
+          if (i2 <= hi_p && okb[i2] != 0) {
+            const uint64_t occ2 = cnt[i2];
+            uint64_t prevk2;
+            if (v.kind == kVSub) prevk2 = s.win[1];
+            else if (v.kind == kVDel) prevk2 = s.fc[s0q + k];
+            else {
+              Key key = packed_window(s.pt, k - 2, 1);
+              const Key b = {base_code(v.base), 0};
+              key = key_append(key, b, 1);
+              key = key_append(key, packed_window(s.pt, k - 1, k - 2), k - 2);
+              prevk2 = db.count(key_canonical(key, k));
+            }
+            if ((int64_t)occ2 >= solid && !(occ2 * JB_DIVISOR < prevk2)) v.post_ok |= 2;
+          }
+        }
       } else if (w == -1 && !ins) {
         v.kind = kVNone;                                          // nothing passes and the reference stops there
       }

@@ -1045,10 +1045,14 @@ struct Walker {
     v2_post = false;
     const int done = fixing_sid(s0, nbad, thre, gb, ga, fast ? &v : nullptr);
     if (!fast || status || brk) return;
-    if (!((done && v.post_ok) || (done == kPostNone && v2_post))) return;
+    if (!((done && (v.post_ok & 1)) || (done == kPostNone && v2_post))) return;
     // ---- the scan step behind a single-base fix (src/jasper.py:56-100 at the new i) was evaluated with the verdict
     if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;       // the loop re-checks the seam first
     i += k - 1;
+    ++n_post;
+    if (!(done && (v.post_ok & 2))) return;
+    if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;
+    i += k - 1;                                                                     // the step after that was evaluated too
     ++n_post;
   }
 
