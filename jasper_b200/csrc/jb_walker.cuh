@@ -190,7 +190,7 @@ struct Walker {
   uint32_t n_fast = 0, n_post = 0, n_v2 = 0;
   uint32_t vid = 0;                    // index of the verdict consume_verdict returned
   bool dry = false;                    // k_verdicts2: edits go to scratch, nothing is logged
-  bool v2_post = false;                // the second-stage verdict just applied also knows the following scan step
+  int v2_post = 0;                     // scan-step bits of the second-stage verdict just applied (bit 0: next step plain, bit 1: the one after)
   long long t_begin = 0;
 
   JB_W Walker(const DB& db_, int k_, int step_, uint32_t solid_, bool fix_, UnitIO& u_, WarpScratch& s_,
@@ -800,7 +800,7 @@ struct Walker {
     if (base - seam_margin > lo_x) lo_x = base - seam_margin;
     if (s0 - k - 2 < lo_x) return false;
     ++n_v2;
-    v2_post = v2->found && v2->post_ok;
+    v2_post = v2->found ? v2->post_ok : 0;
     if (!v2->found) return true;                         // decided: nothing to apply
     const int rl = v2->rlen;
     JB_SYNC();
@@ -808,7 +808,7 @@ struct Walker {
     JB_SYNC();
     f.found = true; f.a = s0 + v2->a_rel; f.e = s0 + v2->e_rel; f.repl = s.b; f.rlen = rl;
     if (v2->tag == kTagBridge) {                         // a bridged patch logs its own row (the replaced bases are still in place)
-      if (!bridge_row(f.a - 1, f.e, s.b, rl)) { f.found = false; v2_post = false; }
+      if (!bridge_row(f.a - 1, f.e, s.b, rl)) { f.found = false; v2_post = 0; }
       f.tag = 0;
     } else fix_row(f, s0 + v2->coord_rel, v2->fb, v2->fb_len, v2->tag, v2->orig, v2->orig_len);
     return true;
@@ -843,10 +843,14 @@ struct Walker {
     // the scan step behind the fix (src/jasper.py:56-100 at i = re), on the edited sequence in scratch
     if (ok && f.found && c.out && c.out_cap && apply_edit(f.a, f.e, f.repl, f.rlen)) {
       i = re;
-      int64_t occ = 0, prevk = 0;
-      if (i < L - k + 1 && !generic_body(occ, prevk) && !status && occ >= solid && !(i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) {
-        JB_LANES(l) { if (l == 0) out->post_ok = 1; }
+      int steps = 0;
+      for (int st = 0; st < 2; ++st) {                   // the next two scan steps, while they are the plain `i += k-1`
+        int64_t occ = 0, prevk = 0;
+        if (!(i < L - k + 1) || generic_body(occ, prevk) || status || occ < solid || (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) break;
+        ++steps;
+        i += k - 1;
       }
+      JB_LANES(l) { if (l == 0) out->post_ok = (uint8_t)(steps == 2 ? 3 : steps); }
     }
     status = 0;
     JB_SYNC();
@@ -1042,15 +1046,16 @@ struct Walker {
     const int64_t nbad = ga - s0 > 0 ? ga - s0 : 0;
     wrong += nbad;
     if (!fix || gb < 0) return;
-    v2_post = false;
+    v2_post = 0;
     const int done = fixing_sid(s0, nbad, thre, gb, ga, fast ? &v : nullptr);
     if (!fast || status || brk) return;
-    if (!((done && (v.post_ok & 1)) || (done == kPostNone && v2_post))) return;
+    const int bits = done ? v.post_ok : v2_post;
+    if (!(bits & 1)) return;
     // ---- the scan step behind a single-base fix (src/jasper.py:56-100 at the new i) was evaluated with the verdict
     if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;       // the loop re-checks the seam first
     i += k - 1;
     ++n_post;
-    if (!(done && (v.post_ok & 2))) return;
+    if (!(bits & 2)) return;
     if (c.next_anchor >= 0 && i - (L - c.in_len) >= c.next_anchor) return;
     i += k - 1;                                                                     // the step after that was evaluated too
     ++n_post;
