@@ -175,6 +175,16 @@ k_verdicts2(TableView t, VerdictArgs a, BridgePool pool) {
   }
 }
 
+// Small results go to pinned host memory either through the copy engine or -- while the polished bases occupy it
+// (early fetch, side stream) -- by a kernel that stores straight into the mapped host buffer: a device-to-host copy on
+// the main stream would queue behind the whole 64 MB transfer.
+__global__ void k_store_host(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const size_t nv = n / 16;
+  for (size_t v = i; v < nv; v += nth) reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(src)[v];
+  for (size_t q = nv * 16 + i; q < n; q += nth) dst[q] = src[q];
+}
+
 // dst[0:n) = src[0:n), the CTAs of one grid row share the job; 16-byte stores, byte-funnelled loads when
 // the two streams are misaligned against each other (indels shift them)
 __device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int64_t n) {
@@ -378,6 +388,7 @@ struct jb_batch {
   // the final bases are known once the last FIXING pass has stitched them: their copy to the host starts there, on the
   // side stream, beside the count-only pass (jb_batch_fetch picks it up)
   bool prescanned = false;             // jb_polish: the first pass's k_scan already ran behind the upload
+  bool fetch_follows = false;          // jb_polish: the caller wants the bases on the host right after polishing
   int64_t prescan_lookups = 0;
   cudaEvent_t ev_tmp[2] = {nullptr, nullptr};
   uint8_t* early = nullptr; size_t early_cap = 0;
@@ -564,6 +575,16 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
 extern "C" void jb_batch_free(jb_batch* b) { delete b; }
 
 namespace {
+
+// dst: pinned host memory (mapped), src: device memory, both 16-byte aligned
+int small_d2h(void* dst, const void* src, size_t n, bool by_kernel, cudaStream_t s) {
+  if (n == 0) return JB_OK;
+  if (!by_kernel) { JB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s)); return JB_OK; }
+  const unsigned blocks = (unsigned)std::min<size_t>(64, (n / 16 + 255) / 256 + 1);
+  k_store_host<<<blocks, 256, 0, s>>>(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n);
+  JB_CUDA(cudaGetLastError());
+  return JB_OK;
+}
 
 int64_t pick_seg_block(int64_t total_len, int sms) {
   // (multiples of 32: k_find_anchors walks whole bitmask words)
@@ -766,10 +787,9 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     if (!blocks.empty()) {
       const uint32_t nb = (uint32_t)blocks.size();
       k_find_anchors<<<(nb + 7) / 8, 256, 0, s>>>(w.events.p, w.weak.p, w.seg_units.p, w.block_first.p, (uint32_t)n, nb, k, (int)seg_block,
-                                                   (int)margin, w.anchors.p);
+                                                   (int)margin, anchors);        // (straight into mapped pinned memory: no copy to queue)
       JB_CUDA(cudaGetLastError());
       ++launches;
-      JB_CUDA(cudaMemcpyAsync(anchors, w.anchors.p, nb * sizeof(long long), cudaMemcpyDeviceToHost, s));
     }
     JB_CUDA(cudaEventRecord(ev_anchors, s));             // the host plans segments from here on, while the verdict kernels run
     // ---- verdicts: every isolated error decided in bulk (jb_verdict.cuh)
@@ -834,9 +854,9 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaGetLastError());
     ++launches;
     JB_CUDA(cudaEventRecord(ev_e, s));
-    JB_CUDA(cudaMemcpyAsync(hs, w.segs.p, n_first * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
-    JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
-    JB_CUDA(cudaMemcpyAsync(used + 6, w.used.p + 6, 8, cudaMemcpyDeviceToHost, s));
+    const bool engine_busy = b->early != nullptr;        // the polished bases are travelling on the side stream
+    if (int rc = small_d2h(hs, w.segs.p, n_first * sizeof(UnitIO), engine_busy, s)) return rc;
+    if (int rc = small_d2h(used, w.used.p, 64, engine_busy, s)) return rc;
     mark("walk launched", ite);
     JB_CUDA(cudaStreamSynchronize(s));
     mark("walk done", ite);
@@ -926,7 +946,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
       JB_CUDA(cudaGetLastError());
       ++launches;
-      if (ite == passes - 1 && !b->early && getenv("JB_NO_EARLY_FETCH") == nullptr) {
+      if (ite == passes - 1 && !b->early && b->fetch_follows && getenv("JB_NO_EARLY_FETCH") == nullptr) {
         uint64_t total_new = 0;
         for (size_t i = 0; i < n; ++i) total_new += (uint64_t)new_lens[i];
         b->early = take_out_buffer(std::max<uint64_t>(total_new, 1), &b->early_cap);
@@ -1074,6 +1094,7 @@ extern "C" int jb_polish(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, i
   int rc = upload_impl(db, seqs, n_seqs, &b, true);
   if (rc) return rc;
   auto t1 = std::chrono::steady_clock::now();
+  b->fetch_follows = true;
   rc = jb_batch_polish(b, k, solid_thre, passes, fix);
   auto t2 = std::chrono::steady_clock::now();
   if (!rc) rc = jb_batch_fetch(b, out);
