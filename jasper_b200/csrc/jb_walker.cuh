@@ -845,8 +845,17 @@ struct Walker {
       i = re;
       int steps = 0;
       for (int st = 0; st < 2; ++st) {                   // the next two scan steps, while they are the plain `i += k-1`
-        int64_t occ = 0, prevk = 0;
-        if (!(i < L - k + 1) || generic_body(occ, prevk) || status || occ < solid || (i > 0 && (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk)) break;
+        // both windows of the step in one staged stretch seq[i-k : i+k): 2k bases, packed, two probes (a compact
+        // restatement of generic_body for clean bases; anything else ends the evaluation)
+        if (!(i < L - k + 1) || i < k) break;
+        const int n2 = load(s.t, i - k, i + k);
+        if (n2 != 2 * k) break;
+        pack_bytes(s.pc, s.t, n2);
+        if (!packed_clean(s.pc, 0, n2)) break;
+        const int64_t prevk = db.count(key_canonical(packed_window(s.pc, 0, k), k));
+        const int64_t occ = db.count(key_canonical(packed_window(s.pc, k, k), k));
+        lookups += 2;
+        if (occ < solid || (uint64_t)occ * JB_DIVISOR < (uint64_t)prevk) break;
         ++steps;
         i += k - 1;
       }
