@@ -119,6 +119,7 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint8_t fx[128];           // text of the fix row being prepared: mutation at [0:64), original at [64:128)
   uint32_t fc[kFastWin];     // make_verdict: bulk-scan counts of the windows around an event (jb_verdict.cuh)
   int32_t fbad[2];           // make_verdict: last unavailable entry before / first one behind the event
+  uint32_t hc[64];           // make_verdict: counts of every window of a homopolymer trial string
   uint32_t win[2];           // score_single_base: counts of the winner's samples 0 (m = 0) and 1 (m = len - k)
   SeqView view;              // published copy of the walker's sequence state
   Packed pt;                 // packed to_be_fixed (or, for kDip, the whole check string before + t + after)

@@ -20,7 +20,7 @@
 
 namespace jb {
 
-enum VerdictKind : uint8_t { kVDelimit = 0, kVSub = 1, kVDel = 2, kVIns = 3, kVNone = 4 };
+enum VerdictKind : uint8_t { kVDelimit = 0, kVSub = 1, kVDel = 2, kVIns = 3, kVNone = 4, kVHomoIns = 5 };
 
 struct Verdict {
   uint32_t re;          // low 32 bits of the contig position of the first window behind the run (= the walker's i after delimiting)
@@ -158,6 +158,55 @@ JB_FREE_NOINLINE bool make_verdict(const DB& db, WarpScratch& s, const uint8_t* 
         }
       } else if (w == -1 && !ins) {
         v.kind = kVNone;                                          // nothing passes and the reference stops there
+      }
+    }
+  }
+  else if (nbad > 1 && nbad < k - 1) {
+    // src/jasper.py:434-459, first round: a base missing from a homopolymer run.  One more copy of the base in front of
+    // k-1 and EVERY window of the trial string must be solid (nbad + 1 windows, each  t[m : k-1] ++ base ++ t[k-1 : ...]).
+    // Anything but that immediate success is left to the second stage.
+    const int n = nbad + k - 1;
+    const uint8_t* src = in + (W0 + s0q);
+    JB_SYNC();
+    JB_LANES(l) { for (int q = l; q < n; q += 32) s.t[q] = src[q]; }
+    JB_SYNC();
+    const uint8_t sb = s.t[k - 2];
+    pack_bytes(s.pt, s.t, n);
+    const int total = nbad + 1;
+    uint32_t weak_any = 0;
+    for (int w0 = 0; w0 < total; w0 += 32) {
+      JB_SYNC();
+      JB_LANES(l) {
+        const int m = w0 + l;
+        uint32_t fail = 0;
+        if (m < total) {
+          const int lenA = (k - 1) - m;
+          Key key = packed_window(s.pt, m, lenA);
+          const Key b = {base_code(sb), 0};
+          key = key_append(key, b, 1);
+          key = key_append(key, packed_window(s.pt, k - 1, k - lenA - 1), k - lenA - 1);
+          const uint32_t c2 = db.count(key_canonical(key, k));
+          s.hc[m] = c2;
+          fail = (int64_t)c2 < solid ? 1u : 0u;
+        }
+        s.flag[l] = fail;
+      }
+      JB_SYNC();
+      for (int q = 0; q < 32; ++q) weak_any |= s.flag[q];
+    }
+    if (!weak_any) {
+      v.kind = kVHomoIns; v.base = sb; v.bad = sb;
+      // the two scan steps behind the fix: the windows that hold the new base are windows of the trial string
+      const int64_t p1 = W0 + gq - k, p2 = W0 + gq + k - 2;
+      if (gaq == gq && second_step && p1 >= 0 && okb[p1] != 0) {
+        const uint64_t occ = s.hc[nbad], prevk = cnt[p1];
+        if ((int64_t)occ >= solid && !(occ * JB_DIVISOR < prevk)) {
+          v.post_ok = 1;
+          if (p2 <= hi_p && okb[p2] != 0) {
+            const uint64_t occ2 = cnt[p2], prevk2 = s.hc[nbad - 1];
+            if ((int64_t)occ2 >= solid && !(occ2 * JB_DIVISOR < prevk2)) v.post_ok |= 2;
+          }
+        }
       }
     }
   }

@@ -778,6 +778,10 @@ struct Walker {
       fill(s.b, v.base, 1);
       f.a = s0 + k - 1; f.e = s0 + k - 1; f.rlen = 1; f.post = kPostIns;
       fix_row(f, ga, v.base, 1, 'd', '-', 1);
+    } else if (v.kind == kVHomoIns) {                    // src/jasper.py:434-459: one more copy of the homopolymer's base
+      fill(s.b, v.base, 1);
+      f.a = s0 + k - 1; f.e = s0 + k - 1; f.rlen = 1; f.post = kPostIns;
+      fix_row(f, k - 1 + s0, v.base, 1, 'd', '-', 1);
     } else if (v.kind == kVDel) {
       f.a = s0 + k - 1; f.e = s0 + k; f.rlen = 0; f.post = kPostDel;
       fix_row(f, ga - 1, '-', 1, 'i', v.bad, 1);

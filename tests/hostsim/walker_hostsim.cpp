@@ -135,6 +135,11 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
         u.base = s0v > 64 ? s0v - 64 : 0; u.out = dry_out; u.out_cap = sizeof dry_out;
         Walker<HostDB> w(db, k, sampling_step(k), solid, true, u, ws, pool, sink, jobs);
         w.dry_fix(v, (int64_t)v.re, &v2);
+        if (getenv("JB_SIM_TRACE")) {
+          const int nb = (int)v.d_ga - (int)v.d_s0;
+          fprintf(stderr, "[sim] v2 pass %d nbad %d (k %d) valid %d found %d a_rel %d e_rel %d rlen %d tag %c post %d\n", ite, nb, k, v2.valid, v2.found, v2.a_rel, v2.e_rel, v2.rlen,
+                  v2.tag == 0xFF ? 'B' : (v2.tag ? v2.tag : '-'), v2.post_ok);
+        }
       }
     }
     std::vector<BlockRef> blocks;
