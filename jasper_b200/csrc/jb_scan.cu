@@ -155,16 +155,24 @@ k_events(EventArgs a) {
   const int64_t n_out = (int64_t)min((uint64_t)kTile, u.len + 1 - tile.start);
   const uint32_t* cnt = a.counts + u.out_off;
   const uint64_t f0 = u.out_off + tile.start;                       // flat bit index of the tile, multiple of 1024
-  for (int w0 = 0; w0 < n_out; w0 += 32) {
-    const int64_t p = (int64_t)tile.start + w0 + lane;
-    bool ev = false, wk = false;
-    if (w0 + lane < n_out) {
-      const bool ok = a.okb[f0 + w0 + lane] != 0;
-      const uint32_t c = cnt[p];
-      wk = ok && c < a.solid_thre;
-      ev = !ok || p < (int64_t)a.k || c < a.solid_thre;
-      if (!ev) ev = (unsigned long long)c * JB_DIVISOR < (unsigned long long)cnt[p - a.k];
-    }
+  // branch-free per position (the 1/50 test reads its second count unconditionally: an L1/L2 hit k positions back),
+  // four words per trip so that the loads of one trip are in flight together
+  const uint32_t* cnt_t = cnt + tile.start;
+  const uint8_t* okb_t = a.okb + f0;
+  const int n = (int)n_out;
+  const int k = a.k;
+  const bool head = tile.start == 0;                                  // only the first tile of a contig holds positions < k
+#pragma unroll 4
+  for (int w0 = 0; w0 < n; w0 += 32) {
+    const int q = w0 + lane;
+    const bool in = q < n;
+    const uint32_t c = in ? cnt_t[q] : 0u;
+    const bool ok = in && okb_t[q] != 0;
+    const bool early = head && q < k;
+    const uint32_t prev = (in && !early) ? cnt_t[q - k] : 0u;          // (q - k < 0 reaches into the previous tile of the same contig)
+    const bool low = c < a.solid_thre;
+    const bool wk = ok && low;
+    const bool ev = in && (!ok || early || low || (unsigned long long)c * JB_DIVISOR < (unsigned long long)prev);
     const unsigned int word = __ballot_sync(0xffffffffu, ev);
     const unsigned int wword = __ballot_sync(0xffffffffu, wk);
     if (lane == 0) {
