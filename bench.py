@@ -186,7 +186,7 @@ def ncu_traffic_gb():
     scale = {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}
     try:
         vals = {}
-        for row in csv.reader(l for l in open(os.path.join(ROOT, "profiles", "r1w_scan_kernels_ncu_full.csv")) if not l.startswith("#")):
+        for row in csv.reader(l for l in open(os.path.join(ROOT, "profiles", "r1x_scan_kernels_ncu_full.csv")) if not l.startswith("#")):
             if len(row) == 7 and row[1] == "k_scan" and row[4].startswith("dram__bytes_"):
                 vals[row[4]] = float(row[6]) * scale[row[5]]
         return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]

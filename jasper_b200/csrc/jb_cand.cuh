@@ -131,7 +131,7 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
 };
 
 // pack buf[0:len) (len <= kPackBases) with the whole warp
-JB_FREE_NOINLINE void pack_bytes(Packed& p, const uint8_t* buf, int len) {
+static JB_FREE_NOINLINE void pack_bytes(Packed& p, const uint8_t* buf, int len) {
   if (len > kPackBases) len = kPackBases;
   const int chunks = (len + 31) >> 5;
   JB_SYNC();
