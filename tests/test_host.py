@@ -230,3 +230,17 @@ def test_fast_path_is_taken_and_changes_nothing(golden_cases, hostsim_lib, name,
         if name != "k31_dirty":
             assert st_fast["fast"] * 2 > st_fast["events"], st_fast
             assert st_fast["post"] * 4 > st_fast["events"], st_fast
+
+
+@pytest.mark.parametrize("name", ["k31_dirty", "k25_mix"])
+def test_fix_rows_assembled_on_several_threads(golden_cases, hostsim_lib, name, monkeypatch):
+    """The fix log becomes csv rows on up to four host threads (index, convert, splice); small inputs use one.  Forcing
+    three and five threads must give the same rows (hostsim also checks them against the sorting path)."""
+    case = golden_cases[name]
+    odb = helpers.OracleDB(case["db"])
+    seqs = jo.read_fasta(case["fasta"])
+    base = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], 300)
+    for n in ("3", "5"):
+        monkeypatch.setenv("JB_ROW_THREADS", n)
+        assert helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], 300) == base
+    monkeypatch.delenv("JB_ROW_THREADS", raising=False)
