@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 namespace jb {
 namespace {
@@ -24,32 +25,55 @@ struct Frame {
 bool first_global_alignment(const std::string& A, const std::string& B, std::string* out_a, std::string* out_b) {
   const int la = (int)A.size(), lb = (int)B.size();
   if (la == 0 || lb == 0) return false;
+  // Equal lengths and at most two mismatches -- nearly every bridged multi-error patch is two substitutions -- need no
+  // matrix: a column with a gap costs as much as a mismatch and gaps come in pairs, so the gapless alignment (score -h)
+  // is the only optimal one unless h == 2 and one deletion plus one insertion line everything else up
+  // (A[m1+1 : m2+1] == B[m1 : m2] or A[m1 : m2] == B[m1+1 : m2+1]); only that tie needs the traceback order below.
+  if (la == lb && !getenv("JB_ALIGN_NO_FAST")) {
+    int h = 0, m1 = -1, m2 = -1;
+    for (int i = 0; i < la && h <= 2; ++i)
+      if (A[i] != B[i]) { if (h == 0) m1 = i; else m2 = i; ++h; }
+    bool unique = h <= 1;
+    if (h == 2) unique = A.compare(m1 + 1, m2 - m1, B, m1, m2 - m1) != 0 && A.compare(m1, m2 - m1, B, m1 + 1, m2 - m1) != 0;
+    if (unique) { *out_a = A; *out_b = B; return true; }
+  }
   const int W = lb + 1;
-  std::vector<long> score((size_t)(la + 1) * W);
-  std::vector<uint8_t> trace((size_t)(la + 1) * W, 0);
+  // (thousands of short alignments per pass on the row threads: keep the matrices between calls)
+  static thread_local std::vector<long> score_tl;
+  static thread_local std::vector<uint8_t> trace_tl;
+  static thread_local std::vector<long> col_score_tl;
+  score_tl.assign((size_t)(la + 1) * W, 0);
+  trace_tl.assign((size_t)(la + 1) * W, 0);
+  col_score_tl.assign(lb + 1, 0);
+  long* const score = score_tl.data();                  // (one TLS lookup each, not one per matrix access)
+  uint8_t* const trace = trace_tl.data();
+  long* const col_score = col_score_tl.data();
   const long first_gap = gap_cost(1, kOpen);
   for (int i = 0; i <= la; ++i) score[(size_t)i * W] = gap_cost(i, kOpen);
   for (int j = 0; j <= lb; ++j) score[j] = gap_cost(j, kOpen);
-  std::vector<long> col_score(lb + 1, 0);
   for (int j = 1; j <= lb; ++j) col_score[j] = gap_cost(j, 2 * kOpen);
   for (int row = 1; row <= la; ++row) {
     long row_score = gap_cost(row, 2 * kOpen);
+    const long* up = score + (size_t)(row - 1) * W;     // (row pointers: the index arithmetic was a third of the loop)
+    long* cur = score + (size_t)row * W;
+    uint8_t* tcur = trace + (size_t)row * W;
+    const char ar = A[row - 1];
     for (int col = 1; col <= lb; ++col) {
-      long nogap = score[(size_t)(row - 1) * W + col - 1] + (A[row - 1] == B[col - 1] ? kMatch : kMismatch);
-      long row_open = score[(size_t)row * W + col - 1] + first_gap;
-      long row_extend = row_score + kExtend;
-      row_score = std::max(row_open, row_extend);
-      long col_open = score[(size_t)(row - 1) * W + col] + first_gap;
-      long col_extend = col_score[col] + kExtend;
-      col_score[col] = std::max(col_open, col_extend);
-      long best = std::max(nogap, std::max(col_score[col], row_score));
-      score[(size_t)row * W + col] = best;
-      int rt = (row_open == row_score ? 1 : 0) + (row_extend == row_score ? 8 : 0);
-      int ct = (col_open == col_score[col] ? 4 : 0) + (col_extend == col_score[col] ? 16 : 0);
+      const long nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
+      const long row_open = cur[col - 1] + first_gap;
+      const long row_extend = row_score + kExtend;
+      row_score = row_open > row_extend ? row_open : row_extend;
+      const long col_open = up[col] + first_gap;
+      const long col_extend = col_score[col] + kExtend;
+      const long cs = col_open > col_extend ? col_open : col_extend;
+      col_score[col] = cs;
+      long best = nogap > cs ? nogap : cs;
+      if (row_score > best) best = row_score;
+      cur[col] = best;
       int t = nogap == best ? 2 : 0;
-      if (row_score == best) t += rt;
-      if (col_score[col] == best) t += ct;
-      trace[(size_t)row * W + col] = (uint8_t)t;
+      if (row_score == best) t += (row_open == row_score ? 1 : 0) + (row_extend == row_score ? 8 : 0);
+      if (cs == best) t += (col_open == cs ? 4 : 0) + (col_extend == cs ? 16 : 0);
+      tcur[col] = (uint8_t)t;
     }
   }
   auto tr = [&](int r, int c) { return (int)trace[(size_t)r * W + c]; };
@@ -66,7 +90,11 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
     int row = f.row, col = f.col, t = f.trace;
     bool col_gap = f.col_gap;
     while ((row > 0 || col > 0) && !dead) {
-      Frame cache{a, b, row, col, col_gap, 0};
+      // the state to come back to when this cell offers more than one way on: a and b only grow during the step, so
+      // their lengths are enough to rebuild it (copying both strings at every step was most of the run time)
+      const size_t a0 = a.size(), b0 = b.size();
+      const int row0 = row, col0 = col;
+      const bool col_gap0 = col_gap;
       if (!t) {
         if (col && col_gap) dead = true;
         else {                                        // _finish_backtrace
@@ -110,7 +138,7 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
           }
         }
       }
-      if (t) { cache.trace = t; stack.push_back(std::move(cache)); }
+      if (t) stack.push_back(Frame{a.substr(0, a0), b.substr(0, b0), row0, col0, col_gap0, t});
       t = tr(row, col);
     }
     if (!dead) {

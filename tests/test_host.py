@@ -97,6 +97,34 @@ def test_alignment_matches_shim(hostsim_lib):
         assert (oa.value.decode(), ob.value.decode()) == (want[0], want[1]), (a, b)
 
 
+def test_alignment_shortcut_equals_the_matrix(hostsim_lib, monkeypatch):
+    """Equal-length pairs with up to two mismatches skip the matrix when the gapless alignment is the only optimum; the
+    result must equal the full traceback on every such pair, ties (shifted repeats, homopolymers) included."""
+    rng = np.random.default_rng(5)
+    pairs = []
+    for _ in range(6000):
+        n = int(rng.integers(1, 30))
+        alpha = "ACGT"[:int(rng.integers(1, 5))]                 # small alphabets make repeats and ties frequent
+        a = "".join(alpha[int(x)] for x in rng.integers(0, len(alpha), n))
+        b = list(a)
+        for _ in range(int(rng.integers(0, 4))):
+            b[int(rng.integers(0, n))] = "ACGT"[int(rng.integers(0, 4))]
+        pairs.append((a.encode(), "".join(b).encode()))
+
+    def run():
+        out = []
+        oa, ob = C.create_string_buffer(256), C.create_string_buffer(256)
+        for a, b in pairs:
+            ok = hostsim_lib.hostsim_align(a, b, oa, ob, 256)
+            out.append((ok, oa.value, ob.value) if ok else (0, b"", b""))
+        return out
+    fast = run()
+    monkeypatch.setenv("JB_ALIGN_NO_FAST", "1")
+    slow = run()
+    monkeypatch.delenv("JB_ALIGN_NO_FAST")
+    assert fast == slow
+
+
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 @pytest.mark.parametrize("use_events", [0, 1, 64, 300, 2048])
 def test_walker_source_matches_golden(golden_cases, hostsim_lib, name, use_events):
