@@ -7,6 +7,7 @@
 //   ->  place_segments (prefix sums of the segments' new lengths)  ->  concat + fix rows.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <functional>
 #include <cstdint>
 #include <cstdlib>
@@ -118,60 +119,75 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
   for (size_t q = 0; q < segs.size(); ++q) slot0[q + 1] = slot0[q] + segs[q].n_rows;
   std::vector<uint32_t> at((size_t)slot0[segs.size()], 0xFFFFFFFFu);
   const size_t n_slots = at.size();
-  // Three phases on a few threads (the 63 k rows of a 64 Mb pass cost ~8 ms on one, and this runs beside the GPU work of
-  // the following passes): index the log by (segment, emission order), convert slot ranges, splice the parts in order.
+  // Three phases on a few threads spawned once (the 63 k rows of a 64 Mb pass cost ~8 ms on one, and this runs beside the
+  // GPU work of the following passes): index the log by (segment, emission order), convert slot ranges, splice in order.
   int n_thr = n_slots > 8192 ? 4 : 1;
   if (const char* e = getenv("JB_ROW_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 16) n_thr = v; }   // tests
-  auto run = [&](const std::function<void(int)>& work) {
+  // the few per-segment facts the index phase needs, packed (the descriptors are 250 bytes apiece)
+  std::vector<uint32_t> seg_gen(segs.size()), seg_rows(segs.size());
+  for (size_t q = 0; q < segs.size(); ++q) { seg_gen[q] = segs[q].gen; seg_rows[q] = segs[q].n_rows; }
+  std::vector<PassOut> part((size_t)n_thr);
+  std::vector<char> part_ok((size_t)n_thr, 1);
+  std::vector<size_t> row_at((size_t)n_thr + 1, out->rows.size());
+  std::vector<uint32_t> spill_at((size_t)n_thr + 1, (uint32_t)out->spill.size());
+  std::atomic<int> arrived{0};
+  auto barrier = [&](int phase) {                      // all workers reach phase `phase`; the threads are spawned once
+    arrived.fetch_add(1, std::memory_order_acq_rel);
+    while (arrived.load(std::memory_order_acquire) < phase * n_thr) std::this_thread::yield();
+  };
+  auto work = [&](int t) {
+    {                                                   // 1. index: every live row has its own slot, the scatter needs no locks
+      const size_t lo = n_rows * (size_t)t / (size_t)n_thr, hi = n_rows * (size_t)(t + 1) / (size_t)n_thr;
+      for (size_t i = lo; i < hi; ++i) {
+        const DevRow& r = rows[i];
+        const size_t s0 = first_seg[r.unit];
+        if (seg_gen[s0] != r.gen) continue;            // superseded attempt
+        const size_t q = s0 + r.seg;
+        if (r.seqno >= seg_rows[q]) continue;
+        at[(size_t)slot0[q] + r.seqno] = (uint32_t)i;
+      }
+    }
+    barrier(1);
+    {                                                   // 2. convert a range of slots
+      const size_t lo = n_slots * (size_t)t / (size_t)n_thr, hi = n_slots * (size_t)(t + 1) / (size_t)n_thr;
+      size_t q = (size_t)(std::upper_bound(slot0.begin(), slot0.end(), (uint64_t)lo) - slot0.begin());
+      q = q ? q - 1 : 0;
+      part[(size_t)t].rows.reserve((hi - lo) + 16);
+      for (size_t sl = lo; sl < hi; ++sl) {
+        while (sl >= slot0[q + 1]) ++q;
+        if (at[sl] == 0xFFFFFFFFu) continue;
+        const DevRow& r = rows[at[sl]];
+        if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)t])) part_ok[(size_t)t] = 0;
+      }
+    }
+    barrier(2);
+    if (t == 0) {                                       // (sizes are known now: worker 0 lays the output out)
+      for (int u = 0; u < n_thr; ++u) {
+        row_at[(size_t)u + 1] = row_at[(size_t)u] + part[(size_t)u].rows.size();
+        spill_at[(size_t)u + 1] = spill_at[(size_t)u] + (uint32_t)part[(size_t)u].spill.size();
+      }
+      out->rows.resize(row_at[(size_t)n_thr]);
+      for (int u = 0; u < n_thr; ++u) out->spill += part[(size_t)u].spill;
+    }
+    barrier(3);
+    {                                                   // 3. splice in order
+      HostRow* dst = out->rows.data() + row_at[(size_t)t];
+      const std::vector<HostRow>& src = part[(size_t)t].rows;
+      for (size_t i = 0; i < src.size(); ++i) {
+        HostRow h = src[i];
+        if (h.mut_len + h.orig_len > (int)sizeof h.text) h.spill += spill_at[(size_t)t];
+        dst[i] = h;
+      }
+    }
+  };
+  {
     std::vector<std::thread> pool;
     for (int t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
     work(0);
     for (auto& th : pool) th.join();
-  };
-  run([&](int t) {                                     // every live row has its own slot: the scatter needs no locks
-    const size_t lo = n_rows * (size_t)t / (size_t)n_thr, hi = n_rows * (size_t)(t + 1) / (size_t)n_thr;
-    for (size_t i = lo; i < hi; ++i) {
-      const DevRow& r = rows[i];
-      const size_t s0 = first_seg[r.unit];
-      if (segs[s0].gen != r.gen) continue;             // superseded attempt
-      const size_t q = s0 + r.seg;
-      if (r.seqno >= segs[q].n_rows) continue;
-      at[(size_t)slot0[q] + r.seqno] = (uint32_t)i;
-    }
-  });
-  std::vector<PassOut> part((size_t)n_thr);
-  std::vector<char> part_ok((size_t)n_thr, 1);
-  run([&](int t) {
-    const size_t lo = n_slots * (size_t)t / (size_t)n_thr, hi = n_slots * (size_t)(t + 1) / (size_t)n_thr;
-    size_t q = (size_t)(std::upper_bound(slot0.begin(), slot0.end(), (uint64_t)lo) - slot0.begin());
-    q = q ? q - 1 : 0;
-    part[(size_t)t].rows.reserve((hi - lo) + 16);
-    for (size_t sl = lo; sl < hi; ++sl) {
-      while (sl >= slot0[q + 1]) ++q;
-      if (at[sl] == 0xFFFFFFFFu) continue;
-      const DevRow& r = rows[at[sl]];
-      if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)t])) part_ok[(size_t)t] = 0;
-    }
-  });
-  bool ok = true;
-  std::vector<size_t> row_at((size_t)n_thr + 1, out->rows.size());
-  std::vector<uint32_t> spill_at((size_t)n_thr + 1, (uint32_t)out->spill.size());
-  for (int t = 0; t < n_thr; ++t) {
-    row_at[(size_t)t + 1] = row_at[(size_t)t] + part[(size_t)t].rows.size();
-    spill_at[(size_t)t + 1] = spill_at[(size_t)t] + (uint32_t)part[(size_t)t].spill.size();
-    ok = ok && part_ok[(size_t)t];
   }
-  out->rows.resize(row_at[(size_t)n_thr]);
-  for (int t = 0; t < n_thr; ++t) out->spill += part[(size_t)t].spill;
-  run([&](int t) {
-    HostRow* dst = out->rows.data() + row_at[(size_t)t];
-    const std::vector<HostRow>& src = part[(size_t)t].rows;
-    for (size_t i = 0; i < src.size(); ++i) {
-      HostRow h = src[i];
-      if (h.mut_len + h.orig_len > (int)sizeof h.text) h.spill += spill_at[(size_t)t];
-      dst[i] = h;
-    }
-  });
+  bool ok = true;
+  for (int t = 0; t < n_thr; ++t) ok = ok && part_ok[(size_t)t];
   return ok;
 }
 
