@@ -102,3 +102,24 @@ def test_pipeline_reproduces_jasper_sh_on_the_gpu(golden_cases, name, tmp_path):
     out = pipeline.run(case["fasta"], case["db"], k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=str(tmp_path))
     assert out["batch_size"] == meta["batch_size"] and out["threshold"] == case["threshold"]
     _check_outputs(case, str(tmp_path), meta["k"])
+
+
+def test_pipeline_shards_pieces_over_several_tables(golden_cases, tmp_path):
+    """Two table stand-ins = two GPUs: the pieces are sharded by length, polished on two threads, and the outputs are the
+    same bytes as with one."""
+    case = golden_cases["k31_dirty"]
+    meta = json.load(open(os.path.join(case["dir"], "expected_sh", "meta.json")))
+    histo = [tuple(int(x) for x in l.split()) for l in open(os.path.join(case["dir"], "histo.csv"))]
+    tables = []
+
+    def two(path, devices):
+        tables.extend([_OracleTable(path, histo), _OracleTable(path, histo)])
+        calls = []
+        for t in tables:
+            orig = t.polish
+            t.polish = (lambda o: (lambda seqs, k, thre, passes: (calls.append(len(seqs)), o(seqs, k, thre, passes))[1]))(orig)
+        two.calls = calls
+        return tables
+    pipeline.run(case["fasta"], case["db"], k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=str(tmp_path), open_tables=two)
+    assert len(two.calls) == 2 and all(n > 0 for n in two.calls)          # both tables got work
+    _check_outputs(case, str(tmp_path), meta["k"])
