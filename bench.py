@@ -124,33 +124,115 @@ def build_workload(work_dir: str, genome_mb: float, rank: int, make_db: bool):
     return meta, chunks
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle = checker, timed as the reference's CPU path)
+# ----------------------------------------------------------------------------- the reference's CPU path
+# oracle/_ref/ (git-ignored, built by `make -C oracle ref`, shipped to the GPU box by gpurun) holds the UNMODIFIED reference:
+# jasper/jasper.py, jasper/jasper.sh, jasper/jellyfish.py, bin/jellyfish and the compiled Jellyfish Python binding.
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_JASPER = os.path.join(REF_DIR, "jasper", "jasper.py")
+
+
+def reference_available():
+    import glob
+    return os.path.exists(REF_JASPER) and bool(glob.glob(os.path.join(REF_DIR, "_dna_jellyfish*.so")))
+
+
+def touch_reference_binding(db_path):
+    """Import the reference's compiled binding in THIS process and open the database with it once (the workers below
+    are separate processes: this makes the .so visible to whoever records what the bench process loaded) -> C('A'*k)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dna_jellyfish as jf
+    qf = jf.QueryMerFile(db_path)
+    return int(qf[jf.MerDNA("A" * K).get_canonical()])
+
+
+class ReferenceRun(object):
+    """The polishing stage of the unmodified src/jasper.sh (:206-212) over the workload's chunks: one batch file per chunk
+    (what the split at :155-156 writes: '>name' line, sequence on one line), run_jasper.sh written as jasper.sh writes it,
+    `ls *.batch.*.fa | xargs -P <cores> -I{} ./run_jasper.sh {}`, every worker the unmodified src/jasper.py importing the
+    reference's compiled Jellyfish binding."""
+
+    def __init__(self, work_dir, db_path, chunks, procs):
+        self.dir = os.path.join(work_dir, "ref_run")
+        shutil.rmtree(self.dir, ignore_errors=True)
+        os.makedirs(self.dir)
+        self.db, self.procs, self.chunks = db_path, procs, chunks
+        self.files = []
+        for i, (name, seq) in enumerate(chunks):
+            fn = "asm.fa.batch.%d.fa" % i
+            with open(os.path.join(self.dir, fn), "w") as f:
+                f.write(">%s\n%s\n" % (name, seq))
+            self.files.append(fn)
+        last = PASSES - 1
+        with open(os.path.join(self.dir, "run_jasper.sh"), "w") as f:          # src/jasper.sh:207-208, verbatim but for the paths
+            f.write("#!/bin/bash\n")
+            f.write("%s --db %s --query $1 --ksize %d -p %d --fix --fout $1.fix.csv -ff $1.fixed.fa.tmp --test -thre %d 1>jasper.out 2>jasper.err "
+                    "&& mv _iter%d_$1.fixed.fa.tmp _iter%d_$1.fixed.fa\n" % (REF_JASPER, db_path, K, PASSES, SOLID_THRE, last, last))
+        os.chmod(os.path.join(self.dir, "run_jasper.sh"), 0o755)
+        self.env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "oracle"))
+
+    def step(self):
+        """-> wall seconds of the xargs line"""
+        for fn in os.listdir(self.dir):
+            if fn.startswith("_iter") or fn.endswith("qValCalcHelper.csv"):
+                os.remove(os.path.join(self.dir, fn))
+        t0 = time.perf_counter()
+        subprocess.check_call("ls asm.fa.batch.*.fa | xargs -P %d -I{} ./run_jasper.sh {}" % self.procs, shell=True, cwd=self.dir, env=self.env)
+        return time.perf_counter() - t0
+
+    def outputs(self):
+        """-> (polished sequence per chunk, {iteration: [wrong, total]} summed like src/jasper.sh:235-238, fix.csv text per pass)"""
+        last = PASSES - 1
+        seqs = []
+        for fn in self.files:
+            lines = open(os.path.join(self.dir, "_iter%d_%s.fixed.fa" % (last, fn))).read().split("\n")
+            seqs.append("".join(l for l in lines if not l.startswith(">")))
+        tallies = {}
+        for ite in (0, PASSES):
+            w = t = 0
+            for l in open(os.path.join(self.dir, "%dqValCalcHelper.csv" % ite)):
+                a, b = l.split()
+                w += int(a); t += int(b)
+            tallies[ite] = [w, t]
+        rows = ["".join(open(os.path.join(self.dir, "_iter%d_%s.fix.csv" % (ite, fn))).read() for fn in self.files) for ite in range(PASSES)]
+        return seqs, tallies, rows
+
+
+def product_fix_csv_text(res, chunks):
+    """What src/jasper.py would have written for every chunk file, from the GPU result (jasper_b200/jasper.py's writer)."""
+    import csv
+    import io
+    out = []
+    for ite in range(PASSES):
+        by_name = {}
+        for row in res.rows[ite]:
+            by_name.setdefault(row[0], []).append(row)
+        buf = io.StringIO()
+        for name, _ in chunks:
+            w = csv.writer(buf, delimiter=" ")
+            w.writerow(["Contig", "Base_coord", "Original", "Mutation"])
+            w.writerows(by_name.get(name, []))
+        out.append(buf.getvalue())                    # (csv's "\r\n" line ends, like the reference's files)
+    return out
+
+
+# ----------------------------------------------------------------------------- CPU port (fallback where oracle/_ref is absent)
 def _cpu_polish_worker(args):
     db_path, seqs, k, thr, passes = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import jasper_oracle as jo
-    try:
-        import dna_jellyfish as jf             # the reference's own compiled Jellyfish binding (oracle/_ref)
-        qf = jf.QueryMerFile(db_path)
-        count = lambda s: qf[jf.MerDNA(s).get_canonical()]
-        kind = "reference-binding"
-    except Exception:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import helpers
-        odb = helpers.OracleDB(db_path)
-        count = odb.count
-        kind = "port"
-    o = jo.PolishOracle(count, k, thr)
+    import helpers
+    odb = helpers.OracleDB(db_path)
+    o = jo.PolishOracle(odb.count, k, thr)
     t0 = time.perf_counter()
     res = o.polish(seqs, passes)
     dt = time.perf_counter() - t0
-    return dt, res.lookups, sum(len(s) for _, s in seqs), [(p.wrong, p.total) for p in res.passes], kind, [s for _, s in res.seqs]
+    return dt, res.lookups, sum(len(s) for _, s in seqs), [(p.wrong, p.total) for p in res.passes], "port", [s for _, s in res.seqs]
 
 
-def cpu_baseline(db_path, chunks, sample_bp: int, procs: int):
-    """The oracle (Python restatement of src/jasper.py over the reference's compiled lookup when
-    oracle/_ref is present) on a bounded sample: `procs` worker processes, one slice each --
-    the reference's own parallel model (xargs -P, src/jasper.sh:212)."""
+def cpu_port_baseline(db_path, chunks, sample_bp: int, procs: int):
+    """The oracle (Python restatement of src/jasper.py over oracle/libjf_oracle.so) on a bounded sample: `procs` worker
+    processes, one slice each.  Only used where the reference itself (oracle/_ref) is not installed."""
     import multiprocessing as mp
     whole = "".join(s for _, s in chunks)
     per = int(max(2000, min(sample_bp // procs, len(whole) // procs)))
@@ -170,7 +252,7 @@ def cpu_baseline(db_path, chunks, sample_bp: int, procs: int):
     wall = time.perf_counter() - t0
     bp = sum(o[2] for o in outs)
     lookups = sum(o[1] for o in outs)
-    return {"wall": wall, "bp": bp, "lookups": lookups, "kind": outs[0][4], "procs": len(jobs), "jobs": jobs, "outs": outs}
+    return {"wall": wall, "bp": bp, "lookups": lookups, "kind": "port", "procs": len(jobs), "jobs": jobs, "outs": outs}
 
 
 def workload_text(genome_mb, meta, n_chunks):
@@ -343,6 +425,7 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     gather_gbps, gather_gps = qf.gather_bench(n_probes=1 << 28, sector_bytes=32, iters=3)
+    _, line_gps = qf.gather_bench(n_probes=1 << 28, sector_bytes=128, iters=3)      # whole 128-byte lines, four lanes per line
     # k_scan runs once per step (pass 0); later passes inherit counts through k_recount
     scan_ms_per_launch = last_stats["scan_ms"] / max(1, last_stats["full_scans"])
     lookups_per_launch = last_stats["full_scan_lookups"] / max(1, last_stats["full_scans"])
@@ -354,7 +437,10 @@ def main():
                 "lookups_per_s": lookups_per_launch / (scan_ms_per_launch * 1e-3),
                 "random_sector_peak_GBps": gather_gbps, "frac_of_random_sector_peak": achieved / gather_gbps if gather_gbps else None,
                 "ms_per_launch": scan_ms_per_launch, "share_of_step": last_stats["scan_ms"] / (dev_ms / args.steps),
-                "sectors_per_lookup": last_stats["probe_steps"] / max(1, last_stats["full_scan_lookups"]),
+                "probe_units_per_lookup": last_stats["probe_steps"] / max(1, last_stats["full_scan_lookups"]),
+                "probe_unit": "32-byte sector (four 8-byte slots)" if qf.info["layout"] == 1 else "32-byte sector (two 16-byte slots)",
+                "random_sector_peak_Gsectors_per_s": gather_gps, "random_line_peak_Glines_per_s": line_gps,
+                "table": {k2: qf.info[k2] for k2 in ("layout", "slot_bytes", "remainder_bits", "tag_bits", "count_bits", "load_factor", "bytes_per_record", "n_stash", "table_bytes", "n_records", "max_displacement", "load_seconds", "read_seconds", "file_bytes")},
                 "launches_per_step": last_stats["full_scans"]}
 
     # ---- CPU baseline beside it (bounded sample of the same workload, all host cores)

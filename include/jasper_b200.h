@@ -47,7 +47,10 @@ extern "C" {
 #define JB_SLACK 10
 #define JB_MAX_PATHS 5000
 #define JB_FASTA_WIDTH 60
-#define JB_MAX_K 48              /* 16-byte slots: 96 key bits + 32 count bits */
+#define JB_MAX_K 48              /* wide 16-byte slots: 96 key bits + 32 count bits; the compact 8-byte layout covers
+                                    every k whose remainder key_len - log2(size) fits (k = 37 always does)          */
+#define JB_LAYOUT_WIDE 0         /* 16-byte slots {key, count}, two per 32-byte sector, linear probing             */
+#define JB_LAYOUT_COMPACT 1      /* 8-byte slots {key >> r, tag, count}, four per 32-byte sector (default)          */
 
 typedef struct jb_db jb_db;
 typedef struct jb_batch jb_batch;
@@ -67,6 +70,16 @@ typedef struct {
   uint64_t max_displacement; /* longest probe distance of any record, in slots      */
   double load_seconds;       /* wall time of jb_db_open                             */
   double build_kernel_ms;    /* device time spent in the table-build kernels        */
+  int32_t layout;            /* JB_LAYOUT_*                                         */
+  int32_t slot_bytes;        /* 8 or 16                                             */
+  int32_t remainder_bits, tag_bits, count_bits;   /* compact slot fields            */
+  int32_t n_parts;           /* 1, or the devices a partitioned table spans         */
+  uint64_t home_units;       /* 32-byte sectors the hash maps to                    */
+  uint64_t n_stash;          /* records kept in the stash of a compact table        */
+  double load_factor;        /* n_records / (home_units * slots per unit)           */
+  double bytes_per_record;   /* table_bytes / n_records                             */
+  double read_seconds;       /* busiest reader thread's time inside read()          */
+  uint64_t file_bytes;
 } jb_db_info_t;
 
 typedef struct {
@@ -92,6 +105,8 @@ const char* jb_last_error(void);
 const char* jb_version(void);
 
 /* ---- database ------------------------------------------------------------------------------ */
+/* Environment knobs of the loader (all optional): JB_TABLE_LAYOUT=wide|compact, JB_TABLE_LOAD=<0.05..0.95> (default 0.70
+ * compact / 0.5 wide, raised until the table fits), JB_READERS=<threads> (default 4), JB_ODIRECT=1 (bypass the page cache). */
 int jb_db_open(const char* jf_path, int device, jb_db** out);
 int jb_db_info(const jb_db* db, jb_db_info_t* out);
 int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** outs);

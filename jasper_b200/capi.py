@@ -32,7 +32,13 @@ class _DbInfo(C.Structure):
                 ("matrix_r", C.c_int32), ("matrix_c", C.c_int32), ("matrix_identity", C.c_int32), ("device", C.c_int32),
                 ("hash_size", C.c_uint64), ("n_records", C.c_uint64), ("table_slots", C.c_uint64),
                 ("table_bytes", C.c_uint64), ("max_displacement", C.c_uint64), ("load_seconds", C.c_double),
-                ("build_kernel_ms", C.c_double)]
+                ("build_kernel_ms", C.c_double), ("layout", C.c_int32), ("slot_bytes", C.c_int32), ("remainder_bits", C.c_int32),
+                ("tag_bits", C.c_int32), ("count_bits", C.c_int32), ("n_parts", C.c_int32), ("home_units", C.c_uint64),
+                ("n_stash", C.c_uint64), ("load_factor", C.c_double), ("bytes_per_record", C.c_double), ("read_seconds", C.c_double),
+                ("file_bytes", C.c_uint64)]
+
+
+LAYOUT_WIDE, LAYOUT_COMPACT = 0, 1
 
 
 class _Seq(C.Structure):

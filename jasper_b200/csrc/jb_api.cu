@@ -41,8 +41,8 @@ extern "C" int jb_init(int n_devices, const int* device_ids) {
     if (d < 0 || d >= have) return fail(JB_E_ARG, "jb_init: bad device index " + std::to_string(d));
     JB_CUDA(cudaSetDevice(d));
     JB_CUDA(cudaFree(0));
-    // probes fetch single 32-byte sectors: do not let L2 promote misses to 64/128-byte fetches
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    // (no per-device limits: cudaLimitMaxL2FetchGranularity changes nothing here -- a random sector miss fetches its whole
+    // 128-byte line at any setting, profiles/r1_gather_probe.log)
   }
   return JB_OK;
 }

@@ -121,17 +121,40 @@ JB_HD uint64_t hash_lut(const uint64_t* lut, int nbytes, const Key& key) {
 }
 
 // ---- table geometry -------------------------------------------------------------------------
-// Slots are 16 bytes {key.lo : 64, key.hi : 32, count : 32}; count == 0 marks an empty slot.
-// home(key) = 2 * floor(posx * (cap/2) / 2^xbits) with posx = (pos << E) | (top E bits of key),
-// which is monotone in the file order (pos, key) so the loader can place records by a scan.
+// Two layouts share the probe unit -- one 32-byte sector, what a thread loads with one LDG.256 -- and the home function
+//     unit(key) = floor(posx * units / 2^xbits),  posx = (pos << E) | (top E bits of key),
+// which is monotone in the file order (pos, key), so the loader places records by a prefix-max scan (jb_table.cu).
+//
+//  compact (default): four 8-byte slots per sector.  Jellyfish draws its matrix so that the r x r block over the LOW r
+//    key bits is invertible (JF!lib/rectangular_binary_matrix.cc:160-204, pseudo_inverse), so (pos, key >> r) identifies
+//    the key and a slot only stores
+//        [ remainder = key >> r | tag = low tag_bits of posx | count field of cnt_bits ]
+//    The tag disambiguates posx among the sectors a record may have been displaced from (at most kMaxHops).  Count
+//    field: bit cnt_bits-1 = "the run of occupied slots continues into the next sector" (kept in the LAST slot of a
+//    sector), low cnt_bits-1 bits = cval: 0 empty, kCvalTomb / kCvalEsc reserved (record lives in the stash), else the
+//    count.  Runs start at sector starts, so the occupied slots of a sector are a prefix: "last slot empty" = "has room".
+//    A 128-byte DRAM line (the granule a random access costs here, tools/gather_probe.cu) holds 16 slots instead of 8.
+//    (r2a tried whole-line buckets probed by four lanes per line: 1.02 lines per lookup, but 128 landing bytes per
+//    probe in flight instead of 32 starve the memory-level parallelism: k_scan 6.0 ms against 2.2; profiles/README.md.)
+//  wide (fallback: remainder too long for 64 bits, singular low block, or JB_TABLE_LAYOUT=wide): two 16-byte slots
+//    {key.lo : 64, key.hi : 32, count : 32} per sector, count == 0 marks an empty slot, linear probing.
+enum : int { kLayoutWide = 0, kLayoutCompact = 1 };
+constexpr int kCompactSlots = 4;       // 8-byte slots per 32-byte sector
+constexpr int kMaxHops = 15;           // a compact probe reads the home sector and at most this many more
+constexpr int kMaxCvalBits = 28;
+
 struct TableGeom {
-  uint64_t half_cap;     // cap / 2 (sectors of two slots)
+  uint64_t units;        // sectors the home function maps to
   uint64_t pos_mask;     // size - 1
   int k;
   int key_bytes;
   int ext_bits;          // E
   int left_shift;        // 64 - (r + E)
   int key_top_shift;     // 2k - E
+  int layout;
+  int r_bits;            // compact: remainder = key >> r_bits
+  int tag_bits;
+  int cnt_bits;
 };
 
 JB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
@@ -148,10 +171,23 @@ JB_HD uint64_t key_top_bits(const Key& key, int shift) {   // key >> shift (shif
   return (key.lo >> shift) | (key.hi << (64 - shift));
 }
 
-JB_HD uint64_t home_slot(const TableGeom& g, uint64_t pos, const Key& key) {
+JB_HD uint64_t key_posx(const TableGeom& g, uint64_t pos, const Key& key) {
   uint64_t ext = g.ext_bits ? (key_top_bits(key, g.key_top_shift) & ((1ull << g.ext_bits) - 1)) : 0;
-  uint64_t posx = ((pos & g.pos_mask) << g.ext_bits) | ext;
-  return 2 * mulhi64(posx << g.left_shift, g.half_cap);
+  return ((pos & g.pos_mask) << g.ext_bits) | ext;
+}
+JB_HD uint64_t home_unit_of_posx(const TableGeom& g, uint64_t posx) { return mulhi64(posx << g.left_shift, g.units); }
+JB_HD uint64_t home_unit(const TableGeom& g, uint64_t pos, const Key& key) { return home_unit_of_posx(g, key_posx(g, pos, key)); }
+
+// compact slot arithmetic
+JB_HD uint32_t cval_mask(const TableGeom& g) { return (1u << (g.cnt_bits - 1)) - 1u; }
+JB_HD uint32_t cval_esc(const TableGeom& g) { return cval_mask(g); }            // count too large for the field: see the stash
+JB_HD uint32_t cval_tomb(const TableGeom& g) { return cval_mask(g) - 1u; }      // displaced beyond kMaxLineHops: see the stash
+JB_HD uint64_t spill_bit(const TableGeom& g) { return 1ull << (g.cnt_bits - 1); }
+// the slot a key would occupy, with an all-zero count field
+JB_HD uint64_t compact_pattern(const TableGeom& g, uint64_t posx, const Key& key) {
+  const uint64_t rem = key_top_bits(key, g.r_bits);
+  const uint64_t tag = posx & ((1ull << g.tag_bits) - 1);
+  return ((rem << g.tag_bits) | tag) << g.cnt_bits;
 }
 
 }  // namespace jb

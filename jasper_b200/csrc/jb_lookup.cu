@@ -48,6 +48,37 @@ __global__ void k_gather(const uint8_t* __restrict__ base, uint64_t n_sectors, u
   if (acc == 0x1234567ull) *sink = acc;
 }
 
+// Random LINE gather the way k_scan probes a compact table: four adjacent lanes share a probe and load 32 bytes each of
+// one 128-byte line in a single warp instruction (one request per line); every lane owns a stream of probes.
+__global__ void k_gather_line(const uint8_t* __restrict__ base, uint64_t n_lines, uint64_t per_thread, uint64_t seed,
+                              unsigned long long* sink) {
+  const int lane = threadIdx.x & 31, sub = lane & 3;
+  uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t x = seed + tid * 0x9E3779B97F4A7C15ull;
+  unsigned long long acc = 0;
+  for (uint64_t it = 0; it < per_thread; it += 4) {
+    uint64_t mine[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+      mine[b] = mulhi64(x, n_lines) * 128;
+      x += 0x9E3779B97F4A7C15ull;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      unsigned long long w[4][4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint64_t off = __shfl_sync(0xffffffffu, mine[b], (lane & 28) | r);
+        ldg256(base + off + sub * 32, w[b][0], w[b][1], w[b][2], w[b][3]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc += w[b][0] ^ w[b][1] ^ w[b][2] ^ w[b][3];
+    }
+  }
+  if (acc == 0x1234567ull) *sink = acc;
+}
+
 }  // namespace jb
 
 using namespace jb;
@@ -129,7 +160,7 @@ extern "C" int jb_gather_bench(const jb_db* db, uint64_t n_probes, int sector_by
   if (sector_bytes != 32 && sector_bytes != 64 && sector_bytes != 128) return fail(JB_E_ARG, "sector_bytes must be 32, 64 or 128");
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;
-  const uint64_t table_bytes = (db->n_parts > 1 ? db->part_first[db->my_part + 1] - db->part_first[db->my_part] : db->n_slots) * sizeof(Slot);
+  const uint64_t table_bytes = db->my_units() * (uint64_t)db->unit_bytes();
   const uint64_t n_sectors = table_bytes / sector_bytes;
   const int threads = 256, blocks = 148 * 8;
   uint64_t per_thread = std::max<uint64_t>(4, (n_probes / ((uint64_t)threads * blocks) + 3) / 4 * 4);
@@ -140,10 +171,10 @@ extern "C" int jb_gather_bench(const jb_db* db, uint64_t n_probes, int sector_by
   float best = 1e30f;
   for (int it = 0; it < iters + 1; ++it) {
     JB_CUDA(cudaEventRecord(e0, s));
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(db->slots);
+    const uint8_t* base = db->mem;
     if (sector_bytes == 32) k_gather<32><<<blocks, threads, 0, s>>>(base, n_sectors, per_thread, 1234 + it, d_sink);
     else if (sector_bytes == 64) k_gather<64><<<blocks, threads, 0, s>>>(base, n_sectors, per_thread, 1234 + it, d_sink);
-    else k_gather<128><<<blocks, threads, 0, s>>>(base, n_sectors, per_thread, 1234 + it, d_sink);
+    else k_gather_line<<<blocks, threads, 0, s>>>(base, n_sectors, per_thread, 1234 + it, d_sink);      // whole lines, four lanes each
     JB_CUDA(cudaEventRecord(e1, s));
     JB_CUDA(cudaStreamSynchronize(s));
     float ms = 0;

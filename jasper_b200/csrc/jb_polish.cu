@@ -1135,18 +1135,29 @@ extern "C" void jb_result_free(jb_result* r) { delete r; }
 extern "C" int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** outs) {
   if (!src || (n && (!devices || !outs))) return fail(JB_E_ARG, "jb_db_replicate: null argument");
   if (src->n_parts > 1) return fail(JB_E_UNSUPPORTED, "jb_db_replicate: the source is a partitioned table");
+  for (int i = 0; i < n; ++i) outs[i] = nullptr;
+  auto undo = [&]() { for (int i = 0; i < n; ++i) { jb_db_close(outs[i]); outs[i] = nullptr; } };
+  const size_t lut_bytes = (size_t)src->hdr.key_bytes() * 256 * 8;
+  const size_t stash_bytes = src->stash_units ? (size_t)((src->stash_units + std::max<uint64_t>(4096, src->stash_units / 16) + 4) * 2 * sizeof(Slot)) : 0;
   for (int i = 0; i < n; ++i) {
     auto d = new jb_db(*src);
-    d->device = devices[i]; d->slots = nullptr; d->lut = nullptr; d->stream = nullptr;
-    JB_CUDA(cudaSetDevice(devices[i]));
-    JB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-    JB_CUDA(cudaMalloc(&d->slots, src->n_slots * sizeof(Slot)));
-    JB_CUDA(cudaMalloc(&d->lut, (size_t)src->hdr.key_bytes() * 256 * 8));
-    // device-to-device over NVLink; one disk read serves every GPU of the box
-    JB_CUDA(cudaMemcpyPeerAsync(d->slots, devices[i], src->slots, src->device, src->n_slots * sizeof(Slot), d->stream));
-    JB_CUDA(cudaMemcpyPeerAsync(d->lut, devices[i], src->lut, src->device, (size_t)src->hdr.key_bytes() * 256 * 8, d->stream));
-    JB_CUDA(cudaStreamSynchronize(d->stream));
+    d->device = devices[i]; d->mem = nullptr; d->lut = nullptr; d->stream = nullptr; d->stash = nullptr; d->stash_list = nullptr;
+    for (int q = 0; q < kMaxParts; ++q) { d->parts[q] = nullptr; d->ipc_mapped[q] = false; }
     outs[i] = d;
+    cudaError_t e = cudaSetDevice(devices[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d->mem, src->n_units * (uint64_t)src->unit_bytes());
+    if (e == cudaSuccess) e = cudaMalloc(&d->lut, lut_bytes);
+    if (e == cudaSuccess && stash_bytes) e = cudaMalloc(&d->stash, stash_bytes);
+    if (e == cudaSuccess && src->n_stash) e = cudaMalloc(&d->stash_list, src->n_stash * sizeof(Slot));
+    // device-to-device over NVLink; one disk read serves every GPU of the box
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d->mem, devices[i], src->mem, src->device, src->n_units * (uint64_t)src->unit_bytes(), d->stream);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d->lut, devices[i], src->lut, src->device, lut_bytes, d->stream);
+    if (e == cudaSuccess && stash_bytes) e = cudaMemcpyPeerAsync(d->stash, devices[i], src->stash, src->device, stash_bytes, d->stream);
+    if (e == cudaSuccess && src->n_stash) e = cudaMemcpyPeerAsync(d->stash_list, devices[i], src->stash_list, src->device, src->n_stash * sizeof(Slot), d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { undo(); cudaGetLastError(); return fail(JB_E_CUDA, std::string("jb_db_replicate: ") + cudaGetErrorString(e)); }
+    d->parts[0] = d->mem;
   }
   return JB_OK;
 }

@@ -16,8 +16,25 @@ __device__ __forceinline__ Key rc_push(Key rc, uint32_t code, int top_shift) {
   return r;
 }
 
+// rare: the count does not fit the slot's field, or the record was displaced beyond reach -- the owner asks the stash
+__device__ __noinline__ uint32_t scan_stash_lookup(const TableView& t, const uint8_t* window, int k) {
+  const Key m = key_canonical(key_from_chars(window, k, k, t.mask), k);
+  return stash_find(t, m, key_posx(t.g, hash_lut(t.lut, t.g.key_bytes, m), m));
+}
+
+// rare: a window that is not k chars of ACGTacgt (N / IUPAC / the contig tail) goes through MerDNA's own char loop
+#ifdef JB_SCAN_RARE_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+Key scan_rare_window_key(const uint8_t* window, int k, Key mask) {
+  return key_canonical(key_from_chars(window, k, k, mask), k);
+}
+
+template <int kLayout>
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
-k_scan(TableView t, ScanArgs a) {
+k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int k = t.g.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -30,6 +47,8 @@ k_scan(TableView t, ScanArgs a) {
   unsigned long long steps_total = 0;
   const int top_shift = 2 * k - 2;
   const uint32_t warps_total = gridDim.x * kScanWarps;
+  const unsigned long long lim = 1ull << t.g.cnt_bits;
+  const uint32_t cmask = cval_mask(t.g);
 
   for (uint32_t ti = blockIdx.x * kScanWarps + warp; ti < a.n_tiles; ti += warps_total) {
     const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
@@ -61,9 +80,9 @@ k_scan(TableView t, ScanArgs a) {
     const int r0 = lane * kLanePos;
     const int nr = (int)min((int64_t)kLanePos, n_out - r0);      // may be <= 0
     uint32_t okmask = 0;
+    Key fwd = {0, 0}, rc = {0, 0};
+    int nv = 0;
     if (nr > 0) {
-      Key fwd = {0, 0}, rc = {0, 0};
-      int nv = 0;
       for (int j = 0; j < k - 1; ++j) {                           // the first k-1 bases of the first window
         const uint8_t c = s_seq[r0 + j];
         const bool v = base_valid(c);
@@ -72,6 +91,8 @@ k_scan(TableView t, ScanArgs a) {
         fwd = key_push(fwd, code, t.mask);
         rc = rc_push(rc, code, top_shift);
       }
+    }
+    if (kLayout == kLayoutWide) {
       for (int q0 = 0; q0 < nr; q0 += kGroup) {
         Key keys[kGroup];
         const ulonglong4* sec[kGroup];
@@ -88,10 +109,10 @@ k_scan(TableView t, ScanArgs a) {
             rc = rc_push(rc, code, top_shift);
             Key m;
             if (nv >= k) { okmask |= 1u << q; m = key_less(rc, fwd) ? rc : fwd; }
-            else m = key_canonical(key_from_chars(s_seq + r0 + q, k, k, t.mask), k);   // rare: N / IUPAC / contig tail
+            else m = scan_rare_window_key(s_seq + r0 + q, k, t.mask);   // rare: N / IUPAC / contig tail
             keys[b] = m;
             const uint64_t pos = hash_lut(s_lut, t.g.key_bytes, m);
-            sec[b] = home_sector(t, home_slot(t.g, pos, m));
+            sec[b] = reinterpret_cast<const ulonglong4*>(unit_ptr(t, home_unit(t.g, pos, m)));
             asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
                          : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
           }
@@ -115,6 +136,54 @@ k_scan(TableView t, ScanArgs a) {
                            : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
             }
             s_cnt[lane * 33 + q] = r;
+          }
+        }
+      }
+    } else {
+      // Compact table: the same loop over four 8-byte slots per sector.  (r2a probed whole 128-byte lines with four lanes
+      // each: one line per lookup, but four times the landing registers per probe in flight -- 6.0 ms against 2.2.)
+      for (int q0 = 0; q0 < nr; q0 += kGroup) {
+        unsigned long long pat[kGroup];
+        const ulonglong4* sec[kGroup];
+        unsigned long long w[kGroup][4];
+#pragma unroll
+        for (int b = 0; b < kGroup; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            const uint8_t c = s_seq[r0 + q + k - 1];
+            const bool v = base_valid(c);
+            const uint32_t code = v ? base_code(c) : 0u;
+            nv = v ? nv + 1 : 0;
+            fwd = key_push(fwd, code, t.mask);
+            rc = rc_push(rc, code, top_shift);
+            Key m;
+            if (nv >= k) { okmask |= 1u << q; m = key_less(rc, fwd) ? rc : fwd; }
+            else m = scan_rare_window_key(s_seq + r0 + q, k, t.mask);   // rare: N / IUPAC / contig tail
+            const uint64_t px = key_posx(t.g, hash_lut(s_lut, t.g.key_bytes, m), m);
+            pat[b] = compact_pattern(t.g, px, m);
+            sec[b] = reinterpret_cast<const ulonglong4*>(unit_ptr(t, home_unit_of_posx(t.g, px)));
+            asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < kGroup; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            uint32_t cv = 0;
+            int hop = 0;
+            ++steps_total;
+            CompactProbe pr;
+            pr.pat = pat[b]; pr.lim = lim; pr.cmask = cmask;
+            while (!compact_step(pr, w[b][0], w[b][1], w[b][2], w[b][3], &cv)) {
+              if (++hop > kMaxHops) { cv = cmask; break; }          // beyond reach: ask the stash
+              ++sec[b];
+              ++steps_total;
+              asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                           : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
+            }
+            if (cv == cmask) cv = scan_stash_lookup(t, s_seq + r0 + q, k);
+            s_cnt[lane * 33 + q] = cv;
           }
         }
       }
@@ -312,12 +381,14 @@ int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
-    cudaError_t e = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
+    cudaError_t e = cudaFuncSetAttribute(k_scan<kLayoutWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kLayoutCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
     if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("cudaFuncSetAttribute(k_scan): ") + cudaGetErrorString(e));
     configured_device = dev;
   }
   if (a.n_tiles == 0) return JB_OK;
-  k_scan<<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  if (view.g.layout == kLayoutCompact) k_scan<kLayoutCompact><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  else k_scan<kLayoutWide><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_scan launch: ") + cudaGetErrorString(e));
   return JB_OK;

@@ -165,13 +165,33 @@ def unique_keys(lo: np.ndarray, hi: np.ndarray, weights: np.ndarray | None = Non
 
 
 # ----------------------------------------------------------------------------- .jf writer
-def random_matrix(r: int, c: int, rng: np.random.Generator) -> np.ndarray:
-    """c columns of r random bits each (any matrix is readable; `jellyfish count` itself
-    draws a random full-rank one, JF!lib/rectangular_binary_matrix.cc)."""
-    hi = rng.integers(0, 1 << 32, c, dtype=np.uint64)
-    lo = rng.integers(0, 1 << 32, c, dtype=np.uint64)
-    cols = (hi << U64(32)) | lo
-    return cols & U64((1 << r) - 1)
+def low_block_rank(cols: np.ndarray, r: int) -> int:
+    """GF(2) rank of the r x r block over the LOW r key bits (the last r columns)."""
+    m = [int(x) & ((1 << r) - 1) for x in cols[len(cols) - r:]]
+    rank = 0
+    for bit in range(r - 1, -1, -1):
+        p = next((i for i in range(rank, len(m)) if (m[i] >> bit) & 1), None)
+        if p is None:
+            continue
+        m[rank], m[p] = m[p], m[rank]
+        for i in range(len(m)):
+            if i != rank and (m[i] >> bit) & 1:
+                m[i] ^= m[rank]
+        rank += 1
+    return rank
+
+
+def random_matrix(r: int, c: int, rng: np.random.Generator, jellyfish_like: bool = True) -> np.ndarray:
+    """c columns of r random bits each.  `jellyfish count` redraws until the block over the low r key bits is
+    invertible (randomize_pseudo_inverse, JF!lib/rectangular_binary_matrix.cc:160-204,240-247), which is what lets the
+    compact table layout keep key >> r only; jellyfish_like=False returns the first draw whose low block is SINGULAR
+    (any matrix is readable: such a file makes the loader fall back to the wide layout)."""
+    while True:
+        hi = rng.integers(0, 1 << 32, c, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, c, dtype=np.uint64)
+        cols = ((hi << U64(32)) | lo) & U64((1 << r) - 1)
+        if r > c or (low_block_rank(cols, r) == r) == jellyfish_like:
+            return cols
 
 
 def matrix_times(columns: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
@@ -196,14 +216,15 @@ def matrix_times(columns: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndar
 
 
 def write_jf(path: str, lo: np.ndarray, hi: np.ndarray, counts: np.ndarray, k: int, r: int | None = None,
-             seed: int = 7, counter_len: int = 4, canonical: bool = True, identity: bool = False) -> dict:
+             seed: int = 7, counter_len: int = 4, canonical: bool = True, identity: bool = False,
+             jellyfish_like: bool = True) -> dict:
     """Write distinct keys + counts as a Jellyfish binary/sorted file.  Returns the header dict."""
     n = len(lo)
     if r is None:
         r = max(4, int(np.ceil(np.log2(max(16, n) / 0.7))))
     r = min(r, 2 * k)
     rng = np.random.default_rng(seed)
-    cols = random_matrix(r, 2 * k, rng)
+    cols = random_matrix(r, 2 * k, rng, jellyfish_like)
     mask = U64((1 << r) - 1)
     pos = (lo & mask) if identity else (matrix_times(cols, lo, hi) & mask)
     order = np.lexsort((lo, hi, pos))

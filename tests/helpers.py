@@ -131,6 +131,48 @@ def hostsim_lib():
     return sim
 
 
+def table_sim_lib():
+    """tests/hostsim/libtable_hostsim.so: the compact table's arithmetic (jb_kmer.cuh, jb_geom.hpp) on the CPU (test-only)."""
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libtable_hostsim.so")
+    csrc = os.path.join(ROOT, "jasper_b200", "csrc")
+    srcs = [os.path.join(d, "table_hostsim.cpp"), os.path.join(csrc, "jb_header.cpp"), os.path.join(csrc, "jb_geom.hpp"),
+            os.path.join(csrc, "jb_kmer.cuh"), os.path.join(csrc, "jb_header.hpp")]
+    if not _newer(so, *srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, srcs[0], srcs[1]])
+    sim = C.CDLL(so)
+    sim.hostsim_table_check.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_char_p, C.c_int]
+    return sim
+
+
+TABLE_STATS = ("layout", "lines", "tag_bits", "cnt_bits", "n_stash", "max_disp_lines", "lines_per_hit_x1000", "lines_per_miss_x1000", "records")
+
+
+def table_sim_check(sim, path, load=0.0, layout=-1, max_cval_bits=0):
+    """-> (stats dict, message); raises AssertionError when the table arithmetic breaks an invariant."""
+    st = (C.c_longlong * 9)()
+    msg = C.create_string_buffer(512)
+    rc = sim.hostsim_table_check(os.fsencode(path), load, layout, max_cval_bits, st, msg, 512)
+    assert rc == 0, msg.value.decode()
+    return dict(zip(TABLE_STATS, st)), msg.value.decode()
+
+
+def colliding_db(path, k=25, n_random=20000, n_collide=100, r=16, seed=3, big_counts=0):
+    """A .jf whose identity 'matrix' sends n_collide keys to ONE hash position: their run crosses more lines than a compact
+    probe follows, so some end up as tombstones (records kept in the stash).  big_counts: that many records get counts
+    beyond any compact count field."""
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(0, 1 << (2 * k), n_random, dtype=np.uint64)
+    low = np.uint64(int(rng.integers(0, 1 << r)))
+    hi_part = rng.choice(1 << (2 * k - r), n_collide, replace=False).astype(np.uint64)
+    lo = np.unique(np.concatenate([lo, (hi_part << np.uint64(r)) | low]))
+    cnt = rng.integers(1, 200, len(lo)).astype(np.uint64)
+    if big_counts:
+        cnt[rng.choice(len(lo), big_counts, replace=False)] = rng.integers(1 << 29, 1 << 32, big_counts).astype(np.uint64)
+    synth.write_jf(path, lo, np.zeros(len(lo), dtype=np.uint64), cnt, k, r=r, identity=True)
+    return lo, cnt
+
+
 def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=None):
     """Run the CPU build of the device walker; returns (status, rows_text, seqs, tallies).
     use_events: 0 = no event bitmask, 1 = bitmask, >= 64 = also split contigs into segments (one anchor per that many bases)."""

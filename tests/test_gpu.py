@@ -12,11 +12,23 @@ from jasper_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def dbs(golden_cases):
+@pytest.fixture(scope="module", params=["compact", "wide"])
+def dbs(golden_cases, request):
+    """Every golden database resident twice over the module's tests: in the compact layout (8-byte quotient slots, sixteen
+    per 128-byte line; k37_mix's 2^17 hash cannot be quotiented into 64 bits and stays wide) and in the wide fallback."""
+    old = os.environ.get("JB_TABLE_LAYOUT")
+    os.environ["JB_TABLE_LAYOUT"] = request.param
     out = {}
-    for name, case in golden_cases.items():
-        out[name] = capi.QueryMerFile(case["db"])
+    try:
+        for name, case in golden_cases.items():
+            out[name] = capi.QueryMerFile(case["db"])
+            want = capi.LAYOUT_COMPACT if (request.param == "compact" and name != "k37_mix") else capi.LAYOUT_WIDE
+            assert out[name].info["layout"] == want
+    finally:
+        if old is None:
+            del os.environ["JB_TABLE_LAYOUT"]
+        else:
+            os.environ["JB_TABLE_LAYOUT"] = old
     yield out
     for q in out.values():
         q.close()
@@ -257,6 +269,112 @@ def test_count_positions_large_properties(tmp_path):
     assert np.array_equal(c[:n], c2[:n][::-1])
     assert qf.info["max_displacement"] < 4096
     qf.close()
+
+
+@pytest.mark.parametrize("cval_bits", [None, "3"])
+def test_compact_table_stash_tombstones_and_escapes(tmp_path, monkeypatch, cval_bits):
+    """Records a compact probe cannot reach (displaced beyond kMaxHops sectors by a pile-up on one hash position) and counts
+    beyond the slot's count field live in the stash: lookups, dump and histogram still equal the file."""
+    if cval_bits:
+        monkeypatch.setenv("JB_COMPACT_CVAL_BITS", cval_bits)
+        monkeypatch.setenv("JB_STASH_FRAC", "1")             # (almost every record escapes: the default stash, records / 64, would send the loader to the wide layout)
+    path = str(tmp_path / "collide.jf")
+    helpers.colliding_db(path, big_counts=50)
+    odb = helpers.OracleDB(path)
+    lo, hi, cnt = odb.records()
+    qf = capi.QueryMerFile(path)
+    try:
+        assert qf.info["layout"] == capi.LAYOUT_COMPACT and qf.info["n_stash"] >= 50
+        assert qf.info["max_displacement"] > 4 * 16            # some record sits more than kMaxHops sectors from home
+        glo, ghi, gcnt = qf.dump()
+        assert np.array_equal(glo, lo) and np.array_equal(ghi, hi) and np.array_equal(gcnt.astype(np.uint64), cnt & 0xFFFFFFFF)
+        k = qf.k
+        strings = ["".join("ACGT"[(int(x) >> (2 * (k - 1 - i))) & 3] for i in range(k)) for x in lo[::7]]
+        assert qf.lookup(strings) == [odb.count(s) for s in strings]
+        rng = np.random.default_rng(9)
+        absent = ["".join("ACGT"[int(b)] for b in rng.integers(0, 4, k)) for _ in range(3000)]
+        assert qf.lookup(absent) == [odb.count(s) for s in absent]
+        seq = "".join(strings[:400])
+        assert np.array_equal(qf.count_positions(seq), odb.count_positions(seq))
+        hist = dict(qf.histogram(high=250))
+        want = {}
+        for c in (cnt & 0xFFFFFFFF):
+            c = min(int(c), 251)
+            want[c] = want.get(c, 0) + 1
+        assert hist == want
+    finally:
+        qf.close()
+
+
+def test_compact_all_zero_pattern_is_not_shadowed_by_empty_slots(tmp_path):
+    """k = 8 in a 2^16 hash: the remainder is empty, so a key whose tag is 0 has the all-zero pattern that every EMPTY slot
+    also shows (r2b: empty slots behind the record used to win).  Every one of the 4^8 k-mers against the CPU oracle."""
+    k = 8
+    rng = np.random.default_rng(21)
+    lo = np.unique(rng.integers(0, 1 << (2 * k), 26000, dtype=np.uint64))
+    cnt = rng.integers(1, 300, len(lo)).astype(np.uint64)
+    path = str(tmp_path / "k8.jf")
+    synth.write_jf(path, lo, np.zeros(len(lo), dtype=np.uint64), cnt, k, seed=5)
+    odb = helpers.OracleDB(path)
+    qf = capi.QueryMerFile(path)
+    try:
+        assert qf.info["layout"] == capi.LAYOUT_COMPACT and qf.info["remainder_bits"] == 0
+        strings = ["".join("ACGT"[(x >> (2 * (k - 1 - i))) & 3] for i in range(k)) for x in range(1 << (2 * k))]
+        got = qf.lookup(strings)
+        want = [odb.count(s) for s in strings]
+        assert got == want
+        seq = "".join(strings[:3000])
+        assert np.array_equal(qf.count_positions(seq), odb.count_positions(seq))
+    finally:
+        qf.close()
+
+
+def test_singular_matrix_falls_back_to_the_wide_layout(tmp_path):
+    rng = np.random.default_rng(4)
+    lo = np.unique(rng.integers(0, 1 << 50, 5000, dtype=np.uint64))
+    path = str(tmp_path / "singular.jf")
+    synth.write_jf(path, lo, np.zeros(len(lo), dtype=np.uint64), np.arange(1, len(lo) + 1, dtype=np.uint64), 25, jellyfish_like=False)
+    qf = capi.QueryMerFile(path)
+    try:
+        assert qf.info["layout"] == capi.LAYOUT_WIDE
+        glo, _, gcnt = qf.dump()
+        odb = helpers.OracleDB(path)
+        rlo, _, rcnt = odb.records()
+        assert np.array_equal(glo, rlo) and np.array_equal(gcnt.astype(np.uint64), rcnt)
+    finally:
+        qf.close()
+
+
+def test_compact_k37_table_at_bench_density(tmp_path):
+    """k = 37 needs >= 2^21 lines before the 74-bit key quotients into an 8-byte slot: a 26 Mb genome's database
+    (what bench.py loads, smaller) must come up compact, ~11.4 bytes per record, and count every window like the CPU oracle."""
+    import torch
+    from jasper_b200 import synth_gpu
+    w = synth_gpu.make_workload(str(tmp_path), 26_000_000, 37, seed=3, err_kmers_per_bp=0.2)
+    qf = capi.QueryMerFile(w["db"])
+    try:
+        info = qf.info
+        assert info["layout"] == capi.LAYOUT_COMPACT and info["slot_bytes"] == 8 and info["n_stash"] == 0
+        assert 0.6 < info["load_factor"] < 0.75 and info["bytes_per_record"] < 12.5
+        assert info["max_displacement"] <= 4 * 16
+        g = w["genome"]
+        odb = helpers.OracleDB(w["db"])
+        rng = np.random.default_rng(2)
+        for at in rng.integers(0, len(g) - 300_000, 3):
+            s = synth.codes_to_bytes(g[int(at):int(at) + 200_000]).decode()
+            s = s[:1000] + "N" + s[1001:5000] + "acgtn" + s[5005:]               # invalid windows, lowercase
+            got = qf.count_positions(s)
+            assert np.array_equal(got, odb.count_positions(s))
+        # mutated windows: mostly absent keys
+        s = bytearray(synth.codes_to_bytes(g[1000:101000]))
+        for i in range(0, len(s), 41):
+            s[i] = ord("ACGT"[("ACGT".index(chr(s[i])) + 1) % 4])
+        s = s.decode()
+        assert np.array_equal(qf.count_positions(s), odb.count_positions(s))
+        sectors = capi.counter("probe_steps")
+    finally:
+        qf.close()
+    del torch
 
 
 def test_errors_mirror_the_binding(tmp_path, golden_cases):

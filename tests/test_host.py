@@ -272,3 +272,38 @@ def test_fix_rows_assembled_on_several_threads(golden_cases, hostsim_lib, name, 
         monkeypatch.setenv("JB_ROW_THREADS", n)
         assert helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], 300) == base
     monkeypatch.delenv("JB_ROW_THREADS", raising=False)
+
+
+# ----------------------------------------------------------------------------- compact table arithmetic (CPU twin)
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+@pytest.mark.parametrize("load", [0.0, 0.9])
+def test_compact_table_arithmetic_on_golden_dbs(golden_cases, name, load):
+    """Sequential placement + the probe rule + the low-block inversion, on the real `jellyfish count` files."""
+    sim = helpers.table_sim_lib()
+    st, msg = helpers.table_sim_check(sim, golden_cases[name]["db"], load=load)
+    if name == "k37_mix":                       # 74-bit keys in a 2^17 hash: the remainder alone takes 57 bits
+        assert st["layout"] == 0 and "no room" in msg
+        return
+    assert st["layout"] == 1 and st["records"] > 0
+    assert st["n_stash"] == 0 if st["cnt_bits"] >= 20 else st["n_stash"] < st["records"] // 100      # (k31_dirty: a 9-bit count field, 22 counts beyond it)
+    assert st["max_disp_lines"] <= (3 if load == 0.0 else 12)
+    if load == 0.0:
+        assert st["lines_per_hit_x1000"] < 1160 and st["lines_per_miss_x1000"] < 1420      # 32-byte sectors read per lookup, default load
+    # a 3-bit count field: most records escape to the stash and are still found with their exact counts
+    st2, _ = helpers.table_sim_check(sim, golden_cases[name]["db"], load=load, max_cval_bits=3)
+    assert st2["n_stash"] > 0
+
+
+def test_compact_table_tombstones_and_singular_matrix(tmp_path):
+    sim = helpers.table_sim_lib()
+    p = str(tmp_path / "collide.jf")
+    helpers.colliding_db(p, big_counts=50)
+    st, _ = helpers.table_sim_check(sim, p)
+    assert st["layout"] == 1 and st["max_disp_lines"] > 3 and st["n_stash"] >= 50
+    # a matrix whose low block is singular cannot be quotiented: wide layout, with the reason
+    rng = np.random.default_rng(4)
+    lo = np.unique(rng.integers(0, 1 << 50, 5000, dtype=np.uint64))
+    q = str(tmp_path / "singular.jf")
+    synth.write_jf(q, lo, np.zeros(len(lo), dtype=np.uint64), np.ones(len(lo), dtype=np.uint64), 25, jellyfish_like=False)
+    st, msg = helpers.table_sim_check(sim, q)
+    assert st["layout"] == 0 and "singular" in msg
