@@ -193,7 +193,7 @@ class ReferenceRun(object):
                 a, b = l.split()
                 w += int(a); t += int(b)
             tallies[ite] = [w, t]
-        rows = ["".join(open(os.path.join(self.dir, "_iter%d_%s.fix.csv" % (ite, fn))).read() for fn in self.files) for ite in range(PASSES)]
+        rows = ["".join(open(os.path.join(self.dir, "_iter%d_%s.fix.csv" % (ite, fn)), newline="").read() for fn in self.files) for ite in range(PASSES)]
         return seqs, tallies, rows
 
 
@@ -443,27 +443,43 @@ def main():
                 "table": {k2: qf.info[k2] for k2 in ("layout", "slot_bytes", "remainder_bits", "tag_bits", "count_bits", "load_factor", "bytes_per_record", "n_stash", "table_bytes", "n_records", "max_displacement", "load_seconds", "read_seconds", "file_bytes")},
                 "launches_per_step": last_stats["full_scans"]}
 
-    # ---- CPU baseline beside it (bounded sample of the same workload, all host cores)
+    # ---- CPU baseline beside it: the reference itself on the box's host cores, over the WHOLE workload when it is installed
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cores = len(os.sched_getaffinity(0))
-        sample = (args.cpu_sample_kb * 1000) or min(total_bp, 3_000_000 * cores)
-        cb = cpu_baseline(db_path, chunks, sample, cores)
-        # the same slices through the GPU path: the baseline run doubles as a parity check on the bench workload itself
-        slices = [job[1][0] for job in cb["jobs"]]
-        got = qf.polish(slices, K, SOLID_THRE, PASSES)
-        same_bases = [s for _, s in got.seqs] == [o[5][0] for o in cb["outs"]]
-        want_t = [[sum(o[3][ite][q] for o in cb["outs"]) for q in (0, 1)] for ite in range(PASSES + 1)]
-        same_tallies = [list(t) for t in got.tallies] == want_t
-        if not (same_bases and same_tallies):
-            raise SystemExit("bench: the GPU path and the CPU baseline disagree on the bench workload (bases %s, tallies %s)" % (same_bases, same_tallies))
-        cpu = {"value": cb["bp"] * PASSES / cb["wall"], "unit": "bp polished/s", "cores": cb["procs"],
-               "parity": "polished bases and QV tallies of all %d slices (%d bp) identical to the GPU path" % (len(slices), cb["bp"]),
-               "kind": "reference" if cb["kind"] == "reference-binding" else "port",
-               "sample": "%d slices of %d bp of the same chunks, k=%d p=%d, python oracle over %s, %.1f s wall" % (
-                   cb["procs"], cb["bp"] // max(1, cb["procs"]), K, PASSES,
-                   "the reference's compiled Jellyfish binding (oracle/_ref)" if cb["kind"] == "reference-binding" else "oracle/libjf_oracle.so", cb["wall"]),
-               "lookups_per_s": cb["lookups"] / cb["wall"]}
+        if reference_available():
+            touch_reference_binding(db_path)
+            ref = ReferenceRun(base, db_path, chunks, cores)
+            wall = ref.step()
+            r_seqs, r_tallies, r_rows = ref.outputs()
+            # the step's own result (`res`: the last timed batch) against the reference's files: the bench doubles as a parity
+            # check of the whole workload -- polished bases, fix.csv bytes of every pass, QV tallies
+            same_bases = [x for _, x in res.seqs] == r_seqs
+            same_tallies = [list(res.tallies[0]), list(res.tallies[-1])] == [r_tallies[0], r_tallies[PASSES]]
+            same_rows = product_fix_csv_text(res, chunks) == r_rows
+            if not (same_bases and same_tallies and same_rows):
+                raise SystemExit("bench: the GPU path and the unmodified reference disagree on the bench workload (bases %s, tallies %s, fix rows %s)"
+                                 % (same_bases, same_tallies, same_rows))
+            cpu = {"value": total_bp * PASSES / wall, "unit": "bp polished/s", "cores": min(cores, len(chunks)), "kind": "reference",
+                   "parity": "all %d chunks (%d bp): polished bases, the fix.csv bytes of both passes (%d rows) and the QV tallies written by the unmodified "
+                             "src/jasper.py are identical to the GPU path's" % (len(chunks), total_bp, sum(len(r) for r in res.rows)),
+                   "sample": "the whole workload once: unmodified src/jasper.py per chunk file under `xargs -P %d` (src/jasper.sh:206-212) over the reference's "
+                             "compiled Jellyfish binding (oracle/_ref), %.1f s wall" % (cores, wall)}
+        else:
+            sample = (args.cpu_sample_kb * 1000) or min(total_bp, 3_000_000 * cores)
+            cb = cpu_port_baseline(db_path, chunks, sample, cores)
+            slices = [job[1][0] for job in cb["jobs"]]
+            got = qf.polish(slices, K, SOLID_THRE, PASSES)
+            same_bases = [s for _, s in got.seqs] == [o[5][0] for o in cb["outs"]]
+            want_t = [[sum(o[3][ite][q] for o in cb["outs"]) for q in (0, 1)] for ite in range(PASSES + 1)]
+            same_tallies = [list(t) for t in got.tallies] == want_t
+            if not (same_bases and same_tallies):
+                raise SystemExit("bench: the GPU path and the CPU port disagree on the bench workload (bases %s, tallies %s)" % (same_bases, same_tallies))
+            cpu = {"value": cb["bp"] * PASSES / cb["wall"], "unit": "bp polished/s", "cores": cb["procs"], "kind": "port",
+                   "parity": "polished bases and QV tallies of all %d slices (%d bp) identical to the GPU path" % (len(slices), cb["bp"]),
+                   "sample": "%d slices of %d bp of the same chunks, k=%d p=%d, python restatement (oracle/) over oracle/libjf_oracle.so (oracle/_ref not installed), %.1f s wall"
+                             % (cb["procs"], cb["bp"] // max(1, cb["procs"]), K, PASSES, cb["wall"]),
+                   "lookups_per_s": cb["lookups"] / cb["wall"]}
 
     line = {
         "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world, "steps": args.steps,
@@ -494,7 +510,9 @@ def main():
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the polishing stage of the
+    unmodified jasper.sh (xargs -P <cores> of the unmodified jasper.py) over the SAME chunks the GPU arm polishes; one step = the
+    whole workload once."""
     if rank != 0:
         return
     base = os.path.join(tempfile.gettempdir(), "jb_bench_ref")
@@ -504,24 +522,40 @@ def run_reference(args, rank, world):
     db_path = os.path.join(base, "db.jf")
     cores = len(os.sched_getaffinity(0))
     total_bp = sum(len(s) for _, s in chunks)
-    sample = (args.cpu_sample_kb * 1000) or min(total_bp, 1_000_000 * cores)
-    walls, bps, kind, procs = [], [], "port", cores
-    for step in range(args.warmup + args.steps):
-        cb = cpu_baseline(db_path, chunks, sample, cores)
-        if step >= args.warmup:
-            walls.append(cb["wall"]); bps.append(cb["bp"])
-        kind, procs = cb["kind"], cb["procs"]
-    wall = sum(walls)
-    value = sum(bps) * PASSES / wall
+    if reference_available():
+        touch_reference_binding(db_path)
+        ref = ReferenceRun(base, db_path, chunks, cores)
+        walls = []
+        for step in range(args.warmup + args.steps):
+            w = ref.step()
+            if step >= args.warmup:
+                walls.append(w)
+        _, tallies, rows = ref.outputs()
+        wall = sum(walls)
+        value = total_bp * PASSES * args.steps / wall
+        kind, procs = "reference", min(cores, len(chunks))
+        sample = ("each step: the whole workload (%d chunks, %d bp): unmodified src/jasper.py per chunk file under `xargs -P %d` (src/jasper.sh:206-212), "
+                  "the reference's compiled Jellyfish binding; QV tallies %s -> %s, %d fix rows"
+                  % (len(chunks), total_bp, cores, tallies[0], tallies[PASSES], sum(r.count("\n") - len(chunks) for r in rows)))
+    else:
+        sample_bp = (args.cpu_sample_kb * 1000) or min(total_bp, 1_000_000 * cores)
+        walls, bps = [], []
+        for step in range(args.warmup + args.steps):
+            cb = cpu_port_baseline(db_path, chunks, sample_bp, cores)
+            if step >= args.warmup:
+                walls.append(cb["wall"]); bps.append(cb["bp"])
+        wall = sum(walls)
+        value = sum(bps) * PASSES / wall
+        kind, procs = "port", cb["procs"]
+        sample = ("each step: %d worker processes x %d bp slices of the workload's chunks (python restatement of src/jasper.py over oracle/libjf_oracle.so; "
+                  "oracle/_ref not installed)" % (procs, bps[-1] // max(1, procs)))
     line = {
         "impl": "reference", "metric": "assembly bp polished/sec", "value": value, "unit": "bp polished/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "python int / uint64", "data": "synthetic",
         "config": {"workload": workload_text(args.genome_mb, meta, len(chunks)),
-                   "l2_policy": "CPU path: a bounded sample of the workload per step (see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": value, "unit": "bp polished/s", "cores": procs, "kind": "reference" if kind == "reference-binding" else "port",
-                         "sample": "each step: %d worker processes x %d bp slices of the workload's chunks (python restatement of src/jasper.py over %s)"
-                                   % (procs, bps[-1] // max(1, procs), "the reference's compiled Jellyfish binding" if kind == "reference-binding" else "oracle/libjf_oracle.so")},
+                   "l2_policy": "CPU path: the whole workload per step" if kind == "reference" else "CPU path: a bounded sample of the workload per step (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": "bp polished/s", "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "bp polished/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

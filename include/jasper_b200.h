@@ -105,7 +105,7 @@ const char* jb_last_error(void);
 const char* jb_version(void);
 
 /* ---- database ------------------------------------------------------------------------------ */
-/* Environment knobs of the loader (all optional): JB_TABLE_LAYOUT=wide|compact, JB_TABLE_LOAD=<0.05..0.95> (default 0.70
+/* Environment knobs of the loader (all optional): JB_TABLE_LAYOUT=wide|compact, JB_TABLE_LOAD=<0.05..0.95> (default 0.5
  * compact / 0.5 wide, raised until the table fits), JB_READERS=<threads> (default 4), JB_ODIRECT=1 (bypass the page cache). */
 int jb_db_open(const char* jf_path, int device, jb_db** out);
 int jb_db_info(const jb_db* db, jb_db_info_t* out);

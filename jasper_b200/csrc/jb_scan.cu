@@ -142,12 +142,12 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
     } else {
       // Compact table: the same loop over four 8-byte slots per sector.  (r2a probed whole 128-byte lines with four lanes
       // each: one line per lookup, but four times the landing registers per probe in flight -- 6.0 ms against 2.2.)
-      for (int q0 = 0; q0 < nr; q0 += kGroup) {
-        unsigned long long pat[kGroup];
-        const ulonglong4* sec[kGroup];
-        unsigned long long w[kGroup][4];
+      for (int q0 = 0; q0 < nr; q0 += kGroupCompact) {
+        unsigned long long pat[kGroupCompact];
+        const ulonglong4* sec[kGroupCompact];
+        unsigned long long w[kGroupCompact][4];
 #pragma unroll
-        for (int b = 0; b < kGroup; ++b) {
+        for (int b = 0; b < kGroupCompact; ++b) {
           const int q = q0 + b;
           if (q < nr) {
             const uint8_t c = s_seq[r0 + q + k - 1];
@@ -167,7 +167,7 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
           }
         }
 #pragma unroll
-        for (int b = 0; b < kGroup; ++b) {
+        for (int b = 0; b < kGroupCompact; ++b) {
           const int q = q0 + b;
           if (q < nr) {
             uint32_t cv = 0;

@@ -307,7 +307,7 @@ def test_compact_table_stash_tombstones_and_escapes(tmp_path, monkeypatch, cval_
 
 
 def test_compact_all_zero_pattern_is_not_shadowed_by_empty_slots(tmp_path):
-    """k = 8 in a 2^16 hash: the remainder is empty, so a key whose tag is 0 has the all-zero pattern that every EMPTY slot
+    """k = 8: the remainder is (almost) empty, so a key whose remainder and tag are 0 has the all-zero pattern that every EMPTY slot
     also shows (r2b: empty slots behind the record used to win).  Every one of the 4^8 k-mers against the CPU oracle."""
     k = 8
     rng = np.random.default_rng(21)
@@ -318,7 +318,7 @@ def test_compact_all_zero_pattern_is_not_shadowed_by_empty_slots(tmp_path):
     odb = helpers.OracleDB(path)
     qf = capi.QueryMerFile(path)
     try:
-        assert qf.info["layout"] == capi.LAYOUT_COMPACT and qf.info["remainder_bits"] == 0
+        assert qf.info["layout"] == capi.LAYOUT_COMPACT and qf.info["remainder_bits"] <= 1
         strings = ["".join("ACGT"[(x >> (2 * (k - 1 - i))) & 3] for i in range(k)) for x in range(1 << (2 * k))]
         got = qf.lookup(strings)
         want = [odb.count(s) for s in strings]
@@ -347,7 +347,7 @@ def test_singular_matrix_falls_back_to_the_wide_layout(tmp_path):
 
 def test_compact_k37_table_at_bench_density(tmp_path):
     """k = 37 needs >= 2^21 lines before the 74-bit key quotients into an 8-byte slot: a 26 Mb genome's database
-    (what bench.py loads, smaller) must come up compact, ~11.4 bytes per record, and count every window like the CPU oracle."""
+    (what bench.py loads, smaller) must come up compact, ~16 bytes per record at the default load 0.5, and count every window like the CPU oracle."""
     import torch
     from jasper_b200 import synth_gpu
     w = synth_gpu.make_workload(str(tmp_path), 26_000_000, 37, seed=3, err_kmers_per_bp=0.2)
@@ -355,7 +355,7 @@ def test_compact_k37_table_at_bench_density(tmp_path):
     try:
         info = qf.info
         assert info["layout"] == capi.LAYOUT_COMPACT and info["slot_bytes"] == 8 and info["n_stash"] == 0
-        assert 0.6 < info["load_factor"] < 0.75 and info["bytes_per_record"] < 12.5
+        assert 0.45 < info["load_factor"] < 0.55 and info["bytes_per_record"] < 16.5
         assert info["max_displacement"] <= 4 * 16
         g = w["genome"]
         odb = helpers.OracleDB(w["db"])

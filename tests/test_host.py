@@ -288,7 +288,7 @@ def test_compact_table_arithmetic_on_golden_dbs(golden_cases, name, load):
     assert st["n_stash"] == 0 if st["cnt_bits"] >= 20 else st["n_stash"] < st["records"] // 100      # (k31_dirty: a 9-bit count field, 22 counts beyond it)
     assert st["max_disp_lines"] <= (3 if load == 0.0 else 12)
     if load == 0.0:
-        assert st["lines_per_hit_x1000"] < 1160 and st["lines_per_miss_x1000"] < 1420      # 32-byte sectors read per lookup, default load
+        assert st["lines_per_hit_x1000"] < 1060 and st["lines_per_miss_x1000"] < 1100      # 32-byte sectors read per lookup, default load
     # a 3-bit count field: most records escape to the stash and are still found with their exact counts
     st2, _ = helpers.table_sim_check(sim, golden_cases[name]["db"], load=load, max_cval_bits=3)
     assert st2["n_stash"] > 0
