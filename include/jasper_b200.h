@@ -151,6 +151,12 @@ int jb_count_positions(const jb_db* db, const char* seq, size_t len, uint32_t* c
 int jb_polish(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, int k, uint32_t solid_thre,
               int passes, int fix, jb_result** out);
 
+/* How many bases one jb_polish / jb_batch_upload call can take on this handle's device right now (free device
+ * memory next to the resident table, minus the fixed scratch pools, over the per-base working set).  The host side
+ * groups pieces into calls below this bound -- the role BATCH_SIZE plays for the reference's workers
+ * (src/jasper.sh:132-139): it bounds the working set, it does not change any result. */
+int jb_polish_capacity(const jb_db* db, uint64_t* max_bases);
+
 /* Split form, for callers that keep contigs resident in HBM between calls (and for timing the
  * device part alone): upload once, polish (device only), then fetch. */
 int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, jb_batch** out);

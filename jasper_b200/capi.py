@@ -67,7 +67,7 @@ EXPORTS = [
     "jb_init", "jb_device_count", "jb_last_error", "jb_version",
     "jb_db_open", "jb_db_open_partitioned", "jb_db_open_part", "jb_db_part_handle", "jb_db_attach_parts", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
     "jb_lookup", "jb_lookup_flat", "jb_count_positions",
-    "jb_polish", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
+    "jb_polish", "jb_polish_capacity", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
     "jb_result_status", "jb_result_iterations", "jb_result_tally", "jb_result_num_rows", "jb_result_rows",
     "jb_result_num_seqs", "jb_result_seq", "jb_result_free",
     "jb_last_timing_ms", "jb_last_counter",
@@ -111,6 +111,7 @@ def load_library():
         "jb_lookup_flat": (C.c_int, [vp, C.c_char_p, u64p, C.c_size_t, u32p]),
         "jb_count_positions": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p]),
         "jb_polish": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]),
+        "jb_polish_capacity": (C.c_int, [vp, u64p]),
         "jb_batch_upload": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.POINTER(vp)]),
         "jb_batch_polish": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.c_int]),
         "jb_batch_fetch": (C.c_int, [vp, C.POINTER(vp)]),
@@ -176,6 +177,31 @@ class PolishResult:
     seqs: list                         # [(name, str)]
     timings: dict = field(default_factory=dict)
     counters: dict = field(default_factory=dict)
+
+
+def rows_as_lists(a, names):
+    """A raw row array (numpy, _FixRow layout) -> [[name, coord, field3, field4]] as src/jasper.py appends them."""
+    idx, coord = a["seq_index"].tolist(), a["coord"].tolist()
+    mut = [m.decode("latin-1") for m in a["mutation"].tolist()]
+    org = [o.decode("latin-1") for o in a["original"].tolist()]
+    return [[names[i], c, m, o] for i, c, m, o in zip(idx, coord, mut, org)]
+
+
+def rows_csv_bytes(a, names) -> bytes:
+    """The body of src/jasper.py's fix.csv (:114-119: csv.writer, delimiter ' ', "\\r\\n" line ends) for a raw row array.  The four
+    fields never hold a blank, a quote or a line break (names are first header tokens), so plain joining equals csv's quoting."""
+    if len(a) == 0:
+        return b""
+    idx, coord = a["seq_index"].tolist(), a["coord"].tolist()
+    mut, org = a["mutation"].tolist(), a["original"].tolist()
+    nb = [n.encode("utf-8") for n in names]
+    if any(b'"' in n for n in nb):               # csv would quote such a name: let the csv module do it
+        import csv
+        import io
+        buf = io.StringIO()
+        csv.writer(buf, delimiter=" ").writerows(rows_as_lists(a, names))
+        return buf.getvalue().encode("utf-8")
+    return b"".join(b"%s %d %s %s\r\n" % (nb[i], c, m, o) for i, c, m, o in zip(idx, coord, mut, org))
 
 
 class QueryMerFile(object):
@@ -307,6 +333,12 @@ class QueryMerFile(object):
         return gbps.value, gps.value
 
     # -- polishing ----------------------------------------------------------------------------
+    def polish_capacity(self) -> int:
+        """Bases one polish() call can take on this device right now (jb_polish_capacity)."""
+        n = C.c_uint64()
+        _check(self._lib.jb_polish_capacity(self._h, C.byref(n)))
+        return n.value
+
     def _seq_array(self, seqs):
         n = len(seqs)
         arr = (_Seq * max(1, n))()
@@ -320,7 +352,9 @@ class QueryMerFile(object):
             arr[i].len = len(b)
         return arr, keep
 
-    def _collect(self, res, names) -> PolishResult:
+    def _collect(self, res, names, raw: bool = False) -> PolishResult:
+        """raw=True keeps the result in bulk form: sequences as `bytes`, the rows of a pass as one numpy structured array
+        (fields seq_index, coord, mutation, original) -- no per-row / per-base Python objects (64 Mb: ~15 ms instead of ~120)."""
         lib = self._lib
         n_it = lib.jb_result_iterations(res)
         tallies, rows = [], []
@@ -329,15 +363,17 @@ class QueryMerFile(object):
             _check(lib.jb_result_tally(res, ite, C.byref(w), C.byref(t)))
             tallies.append((w.value, t.value))
             nr = lib.jb_result_num_rows(res, ite)
+            if raw and _FIXROW_DTYPE is not None:
+                import numpy as np
+                a = np.empty(nr, dtype=_FIXROW_DTYPE)
+                _check(lib.jb_result_rows(res, ite, a.ctypes.data_as(C.POINTER(_FixRow)), nr))
+                rows.append(a)
+                continue
             buf = (_FixRow * max(1, nr))()
             _check(lib.jb_result_rows(res, ite, buf, nr))
             if nr > 256 and _FIXROW_DTYPE is not None:                           # bulk conversion through numpy: per-field ctypes access costs ~2 us each
                 import numpy as np
-                a = np.frombuffer(buf, dtype=_FIXROW_DTYPE, count=nr)
-                idx, coord = a["seq_index"].tolist(), a["coord"].tolist()
-                mut = [m.decode("latin-1") for m in a["mutation"].tolist()]
-                org = [o.decode("latin-1") for o in a["original"].tolist()]
-                rows.append([[names[i], c, m, o] for i, c, m, o in zip(idx, coord, mut, org)])
+                rows.append(rows_as_lists(np.frombuffer(buf, dtype=_FIXROW_DTYPE, count=nr), names))
             else:
                 rows.append([[names[buf[i].seq_index], buf[i].coord, buf[i].mutation.decode("latin-1"), buf[i].original.decode("latin-1")]
                              for i in range(nr)])
@@ -345,7 +381,8 @@ class QueryMerFile(object):
         for i in range(lib.jb_result_num_seqs(res)):
             p, ln = C.c_void_p(), C.c_uint64()
             _check(lib.jb_result_seq(res, i, C.byref(p), C.byref(ln)))
-            seqs.append((names[i], C.string_at(p, ln.value).decode("latin-1") if ln.value else ""))
+            b = C.string_at(p, ln.value) if ln.value else b""
+            seqs.append((names[i], b if raw else b.decode("latin-1")))
         out = PolishResult(status=lib.jb_result_status(res), tallies=tallies, rows=rows, seqs=seqs)
         for key in ("polish", "polish_scan", "polish_plan", "polish_walk", "polish_kwalk", "polish_recount", "polish_verdicts", "h2d", "d2h"):
             out.timings[key] = timing_ms(key)
@@ -355,13 +392,13 @@ class QueryMerFile(object):
             out.counters[key] = counter(key)
         return out
 
-    def polish(self, seqs, k: int, solid_thre: int, passes: int, fix: bool = True) -> PolishResult:
-        """seqs: [(name, str)].  One call = the whole per-batch loop of src/jasper.py main()."""
+    def polish(self, seqs, k: int, solid_thre: int, passes: int, fix: bool = True, raw: bool = False) -> PolishResult:
+        """seqs: [(name, str or bytes)].  One call = the whole per-batch loop of src/jasper.py main().  raw: see _collect."""
         arr, keep = self._seq_array(seqs)
         res = C.c_void_p()
         _check(self._lib.jb_polish(self._h, arr, len(seqs), k, solid_thre, passes, 1 if fix else 0, C.byref(res)))
         try:
-            return self._collect(res, [n for n, _ in seqs])
+            return self._collect(res, [n for n, _ in seqs], raw=raw)
         finally:
             self._lib.jb_result_free(res)
 
@@ -380,11 +417,11 @@ class _Batch(object):
     def polish(self, k, solid_thre, passes, fix=True):
         _check(self.qf._lib.jb_batch_polish(self.h, k, solid_thre, passes, 1 if fix else 0))
 
-    def fetch(self) -> PolishResult:
+    def fetch(self, raw: bool = False) -> PolishResult:
         res = C.c_void_p()
         _check(self.qf._lib.jb_batch_fetch(self.h, C.byref(res)))
         try:
-            return self.qf._collect(res, self.names)
+            return self.qf._collect(res, self.names, raw=raw)
         finally:
             self.qf._lib.jb_result_free(res)
 

@@ -415,6 +415,19 @@ struct jb_result {
 namespace {
 int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out, bool prescan);
 }
+// device bytes upload_impl allocates per base: three base buffers, two count and two validity arrays (each over the padded
+// regions, x 1.125), the bit masks, verdict arrays, fix rows, copy jobs
+constexpr uint64_t kDeviceBytesPerBase = 26;
+extern "C" int jb_polish_capacity(const jb_db* db, uint64_t* max_bases) {
+  if (!db || !max_bases) return fail(JB_E_ARG, "jb_polish_capacity: null argument");
+  JB_CUDA(cudaSetDevice(db->device));
+  size_t free_b = 0, total_b = 0;
+  JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t pools = (uint64_t)kPoolSlots * ((uint64_t)kTrieCap * 4 + kPatchCap) + (1ull << 30);     // bridging scratch + slack
+  *max_bases = free_b > pools ? (free_b - pools) / kDeviceBytesPerBase : 0;
+  return JB_OK;
+}
+
 extern "C" int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out) {
   return upload_impl(db, seqs, n, out, false);
 }

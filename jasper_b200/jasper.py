@@ -67,24 +67,51 @@ def write_fasta(path: str, seqs, width: int = 60) -> None:
                 of.write(s[i:i + width] + "\n")
 
 
+def fasta_bytes(name: str, seq: bytes, width: int = 60) -> bytes:
+    """One record as src/jasper.py:120-128 writes it (split_output: `width` bases per line), built in bulk."""
+    head = b">" + name.encode("utf-8") + b"\n"
+    full = len(seq) // width * width
+    try:
+        import numpy as np
+    except ImportError:
+        return head + b"".join(seq[i:i + width] + b"\n" for i in range(0, len(seq), width))
+    body = b""
+    if full:
+        a = np.empty((full // width, width + 1), dtype=np.uint8)
+        a[:, :width] = np.frombuffer(seq, dtype=np.uint8, count=full).reshape(-1, width)
+        a[:, width] = 10
+        body = a.tobytes()
+    tail = seq[full:] + b"\n" if len(seq) > full else b""
+    return head + body + tail
+
+
+def write_outputs_raw(res, names, num_iter, test, fix, fout, fixedout) -> None:
+    """The files of one src/jasper.py run from a raw PolishResult (capi._collect(raw=True)), byte for byte."""
+    for ite in range(num_iter + 1):
+        it_fix = fix and ite != num_iter
+        if test and (ite == 0 or ite == num_iter):
+            with open(str(ite) + "qValCalcHelper.csv", "a") as f:
+                f.write("{} {}\n".format(*res.tallies[ite]))
+        if it_fix:
+            with open(_prefixed(fout, ite), "wb") as f:
+                f.write(b"Contig Base_coord Original Mutation\r\n")
+                f.write(capi.rows_csv_bytes(res.rows[ite], names))
+        if ite == num_iter and fix:
+            with open(_prefixed(fixedout, ite - 1), "wb") as of:
+                for name, s in res.seqs:
+                    of.write(fasta_bytes(name, s))
+
+
 def main(contigs, query_path, k, test, fix, fout, fixedout, db, thre, num_iter):
     try:
         device = int(os.environ.get("JASPER_B200_DEVICE", "0"))
         qf = capi.QueryMerFile(db, device=device)
         seq_dict = parse_fasta(query_path)
         seqs = list(seq_dict.items())
-        res = qf.polish(seqs, k, thre, num_iter, fix=bool(fix))
+        res = qf.polish(seqs, k, thre, num_iter, fix=bool(fix), raw=True)
         if res.status != 0:
             raise capi.JasperError(res.status, "the reference polisher raises on this input (exit 1)")
-        for ite in range(num_iter + 1):
-            it_fix = fix and ite != num_iter
-            if test and (ite == 0 or ite == num_iter):
-                with open(str(ite) + "qValCalcHelper.csv", "a") as f:
-                    f.write("{} {}\n".format(*res.tallies[ite]))
-            if it_fix:
-                write_fix_csv(_prefixed(fout, ite), res.rows[ite])
-            if ite == num_iter and fix:
-                write_fasta(_prefixed(fixedout, ite - 1), res.seqs)
+        write_outputs_raw(res, [n for n, _ in seqs], num_iter, test, fix, fout, fixedout)
         qf.close()
     except SystemExit:
         raise

@@ -14,10 +14,14 @@ must then be on PATH: DB construction is out of scope here).  Same files written
                            mangles it                                               src/jasper.sh:222-226
 and the two "Q value" log lines (src/jasper.sh:235-257, GNU bc's fixed-point steps emulated with `decimal`).
 
-What differs, deliberately: nothing is spilled to batch files (pieces go to the GPUs from memory, sharded by length
-over the devices in JASPER_B200_DEVICES, default all; the table is read once and replicated over NVLink); contigs come
-out in input order (the reference's order is perl's hash order, i.e. random per run); the jasper.*.success restart
-markers are not written.  There is no CPU fallback: without the library and a GPU this exits 1.
+The intermediate protocol is the reference's too: every polishing call leaves the files a reference worker leaves for its
+batch file (_iter<i>_<asm>.batch.<g>.fa.fix.csv, _iter<last>_<asm>.batch.<g>.fa.fixed.fa, lines in *qValCalcHelper.csv),
+the join reads them back, and the jasper.split/histo/correct/join.success markers make a rerun skip finished stages
+exactly as src/jasper.sh does.  What differs, deliberately: the INPUT batch files are not written (pieces go to the GPUs
+from memory, sharded by length over the devices in JASPER_B200_DEVICES, default all, and cut into calls that fit each
+device, jb_polish_capacity; the table is read once and replicated over NVLink); contigs come out in input order (the
+reference's order is perl's hash order, i.e. random per run).  There is no CPU fallback: without the library and a GPU
+this exits 1.
 """
 from __future__ import annotations
 
@@ -71,15 +75,29 @@ def merge_fix_rows(rows_per_pass):
     Returns the bytes of <asm>.fixes.csv."""
     import csv
     import io
-    lines = []
-    buf = io.StringIO()
-    w = csv.writer(buf, delimiter=" ")                        # the dialect src/jasper.py:114-119 writes with (CRLF ends)
-    w.writerow(["Contig", "Base_coord", "Original", "Mutation"])
+    texts = []
     for rows in rows_per_pass:
+        buf = io.StringIO()
+        w = csv.writer(buf, delimiter=" ")                    # the dialect src/jasper.py:114-119 writes with (CRLF ends)
+        w.writerow(["Contig", "Base_coord", "Original", "Mutation"])
         w.writerows(rows)
-    for line in buf.getvalue().split("\n")[:-1]:              # awk reads \n-terminated records; the \r stays in the last field
-        f = line.split(":")                                   # awk -F ':' '{print $1" "$2}'
-        lines.append(f[0] + " " + (f[1] if len(f) > 1 else ""))
+        texts.append(buf.getvalue())
+    return merge_fix_csv_texts(texts)
+
+
+def merge_fix_csv_texts(texts):
+    """src/jasper.sh:222-226 on the per-batch fix.csv files (their contents, in `ls` order): `awk 'NR==1 || FNR>1'` keeps the
+    first file's header and every file's rows; then the ':' split, the sort and the re-join.  -> bytes of <asm>.fixes.csv."""
+    lines = []
+    for fi, text in enumerate(texts):
+        recs = text.split("\n")
+        if recs and recs[-1] == "":
+            recs.pop()
+        for li, line in enumerate(recs):                      # awk reads \n-terminated records; the \r stays in the last field
+            if li == 0 and fi > 0:
+                continue
+            f = line.split(":")                               # awk -F ':' '{print $1" "$2}'
+            lines.append(f[0] + " " + (f[1] if len(f) > 1 else ""))
 
     def num(s: str) -> float:                                 # sort -n: leading blanks, optional '-', digits, optional fraction
         s = s.lstrip(" \t")
@@ -143,45 +161,109 @@ def q_value(wrong: int, total: int, k: int) -> str:
 
 
 # ----------------------------------------------------------------------------- the run
-def polish_pieces(pieces, k, thre, passes, qfs):
-    """pieces [(name, seq)] over the open tables `qfs` (one per GPU): (tallies first/last summed, rows per pass, seqs in piece order)."""
-    shards = batching.shard_units([len(s) for _, s in pieces], len(qfs))
-    results = [None] * len(qfs)
+def group_by_capacity(indices, lengths, capacity):
+    """Consecutive groups of piece indices whose bases stay below `capacity` (None = one group).  What BATCH_SIZE does for the
+    reference's workers: it bounds the working set of one polishing call, nothing else."""
+    if not capacity:
+        return [list(indices)] if indices else []
+    groups, cur, used = [], [], 0
+    for i in indices:
+        if cur and used + lengths[i] > capacity:
+            groups.append(cur)
+            cur, used = [], 0
+        cur.append(i)
+        used += lengths[i]
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def _batch_file(qfn, g):
+    return "%s.batch.%d.fa" % (qfn, g)
+
+
+def _spill_group(workdir, qfn, g, names, res, passes):
+    """The files one reference worker leaves for its batch file (src/jasper.py:107-128 through run_jasper.sh,
+    src/jasper.sh:207-208): _iter<i>_<batch>.fix.csv per fixing pass, _iter<last>_<batch>.fixed.fa, and one line appended
+    to 0qValCalcHelper.csv / <p>qValCalcHelper.csv."""
+    from . import jasper as dropin
+    from . import capi
+    bf = _batch_file(qfn, g)
+    for ite in range(passes):
+        rows = res.rows[ite]
+        path = os.path.join(workdir, "_iter%d_%s.fix.csv" % (ite, bf))
+        if isinstance(rows, list):
+            dropin.write_fix_csv(path, rows)
+        else:
+            with open(path, "wb") as f:
+                f.write(b"Contig Base_coord Original Mutation\r\n")
+                f.write(capi.rows_csv_bytes(rows, names))
+    with open(os.path.join(workdir, "_iter%d_%s.fixed.fa" % (passes - 1, bf)), "wb") as f:
+        for name, seq in res.seqs:
+            f.write(dropin.fasta_bytes(name, seq if isinstance(seq, (bytes, bytearray)) else seq.encode("latin-1")))
+    for ite in (0, passes):
+        with open(os.path.join(workdir, "%dqValCalcHelper.csv" % ite), "a") as f:
+            f.write("%d %d\n" % tuple(res.tallies[ite if ite == 0 else -1]))
+
+
+def polish_pieces(pieces, k, thre, passes, qfs, workdir, qfn):
+    """pieces [(name, seq)] over the open tables `qfs` (one per GPU): sharded by length over the tables, every shard cut into
+    calls that fit the device (jb_polish_capacity), every call's outputs spilled like a reference worker's."""
+    lengths = [len(s) for _, s in pieces]
+    shards = batching.shard_units(lengths, len(qfs))
+    plans, g = [], 0
+    for r, qf in enumerate(qfs):
+        cap = qf.capacity() if hasattr(qf, "capacity") else None
+        groups = group_by_capacity(shards[r], lengths, cap)
+        plans.append([(g + j, grp) for j, grp in enumerate(groups)])
+        g += len(groups)
     errors = []
+    lock = threading.Lock()
 
     def work(r):
         try:
-            results[r] = qfs[r].polish([pieces[i] for i in shards[r]], k, thre, passes)
+            for gi, grp in plans[r]:
+                seqs = [pieces[i] for i in grp]
+                res = qfs[r].polish(seqs, k, thre, passes)
+                if res.status != 0:
+                    raise RuntimeError("the reference polisher raises on this input (exit 1)")
+                with lock:                                    # (the qValCalcHelper files are shared, like the workers' appends)
+                    _spill_group(workdir, qfn, gi, [n for n, _ in seqs], res, passes)
         except BaseException as e:                            # noqa: BLE001 -- reported below
             errors.append(e)
 
-    threads = [threading.Thread(target=work, args=(r,)) for r in range(len(qfs)) if shards[r]]
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(len(qfs)) if plans[r]]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     if errors:
         raise errors[0]
-    seqs = [None] * len(pieces)
-    rows = [[] for _ in range(passes)]
-    t4 = [0, 0, 0, 0]
-    for r, res in enumerate(results):
-        if res is None:
-            continue
-        if res.status != 0:
-            raise RuntimeError("the reference polisher raises on this input (exit 1)")
-        for j, i in enumerate(shards[r]):
-            seqs[i] = res.seqs[j]
-        for ite in range(passes):
-            rows[ite].extend(res.rows[ite])
-        t4[0] += res.tallies[0][0]; t4[1] += res.tallies[0][1]
-        t4[2] += res.tallies[-1][0]; t4[3] += res.tallies[-1][1]
-    return t4, rows, seqs
+    return g
+
+
+def _touch(workdir, name):
+    open(os.path.join(workdir, name), "a").close()
+
+
+def _rm(workdir, *names):
+    for n in names:
+        try:
+            os.remove(os.path.join(workdir, n))
+        except FileNotFoundError:
+            pass
+
+
+def _glob(workdir, pattern):
+    import glob
+    return sorted(glob.glob(os.path.join(workdir, pattern)))  # the shell's `ls` / glob order (C locale)
 
 
 def run(assembly, jf_db, k=37, passes=2, threads=2, batch=0, debug=False, devices=None, open_tables=None, workdir="."):
-    """The stages of src/jasper.sh.  open_tables(path, devices) -> [table-like objects with .histogram() and .polish()]
-    (default: one jasper_b200.capi.QueryMerFile per device, read once, replicated); tests inject a stand-in."""
+    """The stages of src/jasper.sh, with its restart markers (jasper.split/histo/correct/join.success: a stage whose marker
+    exists is skipped, a stage that runs invalidates the markers behind it, src/jasper.sh:152-158,187-195,214-218,227).
+    open_tables(path, devices) -> [table-like objects with .histogram(), .solid_threshold(), .polish(), .close(), optionally
+    .capacity()] (default: one jasper_b200.capi.QueryMerFile per device, read once, replicated); tests inject a stand-in."""
     qfn = os.path.basename(assembly)
     if not os.path.isfile(assembly) or os.path.getsize(assembly) == 0:
         raise SystemExit("The query file does not exist. Please supply a valid fasta file to be polished with -a option.")
@@ -189,50 +271,116 @@ def run(assembly, jf_db, k=37, passes=2, threads=2, batch=0, debug=False, device
         raise SystemExit("The number of passes supplied by -p must be a positive integer")
     if k < 1:
         raise SystemExit("The k-mer size supplied by -k must be a positive integer")
+    have = lambda name: os.path.exists(os.path.join(workdir, name))
     contigs, total = read_assembly(assembly)
     bs = batching.batch_size(total, threads, batch)
     log("Using BATCH SIZE %d" % bs)
-    log("Splitting query into batches for parallel execution")
-    pieces = batching.split_contigs(contigs, bs)
+    last = passes - 1
+    # ---- split (src/jasper.sh:152-159).  Pieces go to the GPUs from memory: nothing to write, but the marker protocol stays.
+    pieces = None
+    if not have("jasper.split.success"):
+        log("Splitting query into batches for parallel execution")
+        _rm(workdir, "jasper.correct.success")
+        _touch(workdir, "jasper.split.success")
     if open_tables is None:
         open_tables = open_gpu_tables
-    qfs = open_tables(jf_db, devices)
+    qfs = []
+    histo_path = os.path.join(workdir, "jfhisto%d.csv" % k)
+    thre = None
     try:
-        log("Computing K-mer histogram")
-        rows = qfs[0].histogram(10000)
-        with open(os.path.join(workdir, "jfhisto%d.csv" % k), "w") as f:
-            f.write("".join("%d %d\n" % (c, n) for c, n in rows))
-        log("Polishing")
-        try:
-            thre = qfs[0].solid_threshold(rows)
-        except Exception:
-            thre = None
-        with open(os.path.join(workdir, "threshold.txt"), "w") as f:
-            f.write("" if thre is None else str(thre))
-        if thre is None:
-            raise SystemExit("Local min of kmer counts is smaller than 4. The input read data is not suitable for polishing.")
-        log("Lower threshold for unreliable kmers is %d" % thre)
-        t4, fix_rows, seqs = polish_pieces(pieces, k, thre, passes, qfs)
+        # ---- histogram (src/jasper.sh:187-193)
+        if not have("jasper.histo.success") or not (os.path.isfile(histo_path) and os.path.getsize(histo_path)):
+            log("Computing K-mer histogram")
+            qfs = qfs or open_tables(jf_db, devices)
+            rows = qfs[0].histogram(10000)
+            with open(histo_path + ".tmp", "w") as f:
+                f.write("".join("%d %d\n" % (c, n) for c, n in rows))
+            os.replace(histo_path + ".tmp", histo_path)
+            _rm(workdir, "jasper.correct.success")
+            _touch(workdir, "jasper.histo.success")
+        # ---- polish (src/jasper.sh:195-216)
+        if not have("jasper.correct.success"):
+            log("Polishing")
+            rows = [tuple(int(x) for x in line.split()) for line in open(histo_path) if line.strip()]
+            qfs = qfs or open_tables(jf_db, devices)
+            try:
+                thre = qfs[0].solid_threshold(rows)
+            except Exception:
+                thre = None
+            with open(os.path.join(workdir, "threshold.txt"), "w") as f:
+                f.write("" if thre is None else str(thre))
+            if thre is None:
+                raise SystemExit("Local min of kmer counts is smaller than 4. The input read data is not suitable for polishing.")
+            log("Lower threshold for unreliable kmers is %d" % thre)
+            for stale in _glob(workdir, "_iter*_%s.batch.*.fa.fix*" % qfn) + _glob(workdir, "*qValCalcHelper.csv"):
+                os.remove(stale)                              # (a worker appends to the tallies: leftovers of a failed run would be summed twice)
+            pieces = batching.split_contigs(contigs, bs)
+            polish_pieces(pieces, k, thre, passes, qfs, workdir, qfn)
+            _rm(workdir, "jasper.join.success")
+            _touch(workdir, "jasper.correct.success")
     finally:
         for qf in qfs:
             qf.close()
-    log("Joining")
-    joined = batching.join_pieces(seqs, bs)
-    with open(os.path.join(workdir, qfn + ".polished.fasta"), "w") as f:
-        seen = set()
-        for name, _ in contigs:
-            if name in joined and name not in seen:           # (the reference prints perl's hash order)
-                seen.add(name)
-                f.write(">%s\n%s\n" % (name, joined[name]))
-    with open(os.path.join(workdir, qfn + ".fixes.csv"), "wb") as f:
-        f.write(merge_fix_rows(fix_rows))
-    q0, q1 = q_value(t4[0], t4[1], k), q_value(t4[2], t4[3], k)
-    log("Before Polishing: Q value = %s" % q0)
-    log("After Polishing: Q value = %s" % q1)
+    if thre is None:
+        try:
+            thre = int(open(os.path.join(workdir, "threshold.txt")).read().strip())
+        except (OSError, ValueError):
+            thre = None
+    # ---- join (src/jasper.sh:218-233)
+    if not have("jasper.join.success"):
+        log("Joining")
+        named = []
+        for path in _glob(workdir, "_iter%d_%s.batch.*.fa.fixed.fa" % (last, qfn)):
+            name, parts = None, []
+            with open(path, "r") as f:
+                for line in f:
+                    tok = line.split()
+                    if not tok:
+                        continue
+                    if tok[0].startswith(">"):
+                        if name is not None:
+                            named.append((name, "".join(parts)))
+                        name, parts = tok[0][1:], []
+                    else:
+                        parts.append(tok[0])
+            if name is not None:
+                named.append((name, "".join(parts)))
+        joined = batching.join_pieces(named, bs)
+        with open(os.path.join(workdir, qfn + ".fixed.fasta.tmp"), "w") as f:
+            seen = set()
+            for name, _ in contigs:
+                if name in joined and name not in seen:       # (the reference prints perl's hash order)
+                    seen.add(name)
+                    f.write(">%s\n%s\n" % (name, joined[name]))
+        os.replace(os.path.join(workdir, qfn + ".fixed.fasta.tmp"), os.path.join(workdir, qfn + ".polished.fasta"))
+        for path in _glob(workdir, "_iter*_%s.batch.*.fa.fixed.fa" % qfn) + _glob(workdir, "_iter*_%s.batch.*.fa.fixed.fa.tmp" % qfn):
+            os.remove(path)
+        csvs = _glob(workdir, "_iter*_%s.batch.*.fa.fix.csv" % qfn)
+        with open(os.path.join(workdir, qfn + ".fixes.csv.tmp"), "wb") as f:
+            f.write(merge_fix_csv_texts([open(p, "r", newline="").read() for p in csvs]))
+        os.replace(os.path.join(workdir, qfn + ".fixes.csv.tmp"), os.path.join(workdir, qfn + ".fixes.csv"))
+        _touch(workdir, "jasper.join.success")
+        if not debug:
+            for path in csvs:
+                os.remove(path)
+    # ---- Q values (src/jasper.sh:235-259)
+    t4 = [0, 0, 0, 0]
+    q0 = q1 = None
+    try:
+        for j, ite in enumerate((0, passes)):
+            for line in open(os.path.join(workdir, "%dqValCalcHelper.csv" % ite)):
+                a, b = line.split()
+                t4[2 * j] += int(a); t4[2 * j + 1] += int(b)
+        q0, q1 = q_value(t4[0], t4[1], k), q_value(t4[2], t4[3], k)
+        log("Before Polishing: Q value = %s" % q0)
+        log("After Polishing: Q value = %s" % q1)
+    except OSError:
+        log("Q values: the *qValCalcHelper.csv files of the polishing stage are gone (removed by an earlier complete run)")
+    for path in _glob(workdir, "*qValCalcHelper.csv"):
+        os.remove(path)
     log("Polished sequence is in %s.polished.fasta" % qfn)
-    if not debug:
-        pass                                                  # nothing was spilled: no batch files to remove
-    return {"batch_size": bs, "threshold": thre, "tallies": t4, "q_before": q0, "q_after": q1, "pieces": len(pieces)}
+    return {"batch_size": bs, "threshold": thre, "tallies": t4, "q_before": q0, "q_after": q1,
+            "pieces": len(pieces) if pieces is not None else None}
 
 
 class _GpuTable(object):
@@ -247,7 +395,11 @@ class _GpuTable(object):
         return capi.solid_threshold(rows)
 
     def polish(self, seqs, k, thre, passes):
-        return self.qf.polish(seqs, k, thre, passes)
+        return self.qf.polish(seqs, k, thre, passes, raw=True)
+
+    def capacity(self):
+        env = os.environ.get("JASPER_B200_MAX_CALL_BP")       # tests: force several calls per device
+        return int(env) if env else self.qf.polish_capacity()
 
     def close(self):
         self.qf.close()

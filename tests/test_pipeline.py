@@ -123,3 +123,47 @@ def test_pipeline_shards_pieces_over_several_tables(golden_cases, tmp_path):
     pipeline.run(case["fasta"], case["db"], k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=str(tmp_path), open_tables=two)
     assert len(two.calls) == 2 and all(n > 0 for n in two.calls)          # both tables got work
     _check_outputs(case, str(tmp_path), meta["k"])
+
+
+def test_pipeline_restart_markers_and_capacity_groups(golden_cases, tmp_path):
+    """src/jasper.sh's restart protocol: a finished stage (jasper.<stage>.success) is skipped on the next run, a stage that
+    runs invalidates the ones behind it; and a table that reports a small capacity gets its shard in several calls, each
+    leaving the files of one reference worker -- the joined outputs do not change."""
+    case = golden_cases["k31_dirty"]
+    meta = json.load(open(os.path.join(case["dir"], "expected_sh", "meta.json")))
+    histo = [tuple(int(x) for x in l.split()) for l in open(os.path.join(case["dir"], "histo.csv"))]
+    work = str(tmp_path)
+    calls = []
+
+    def tables(path, devices):
+        t = _OracleTable(path, histo)
+        orig = t.polish
+        t.polish = lambda seqs, k, thre, passes: (calls.append(sum(len(s) for _, s in seqs)), orig(seqs, k, thre, passes))[1]
+        t.capacity = lambda: 9000
+        return [t]
+
+    kw = dict(k=meta["k"], passes=meta["passes"], threads=meta["threads"], workdir=work)
+    out = pipeline.run(case["fasta"], case["db"], open_tables=tables, debug=True, **kw)
+    assert len(calls) >= 3 and max(calls) <= 9000 + meta["batch_size"]            # several calls, none far above the capacity
+    _check_outputs(case, work, meta["k"])
+    for m in ("split", "histo", "correct", "join"):
+        assert os.path.exists(os.path.join(work, "jasper.%s.success" % m))
+    kept = sorted(f for f in os.listdir(work) if f.endswith(".fix.csv"))
+    assert len(kept) == len(calls) * meta["passes"]                                # -d keeps the per-batch fix.csv files
+    assert not [f for f in os.listdir(work) if f.endswith(".fixed.fa") or f.endswith("qValCalcHelper.csv")]
+
+    # everything done: a rerun touches neither the table nor the outputs
+    def no_tables(path, devices):
+        raise AssertionError("a finished run must not open the database again")
+    before = {f: os.path.getmtime(os.path.join(work, f)) for f in ("asm.fa.polished.fasta", "asm.fa.fixes.csv")}
+    pipeline.run(case["fasta"], case["db"], open_tables=no_tables, debug=True, **kw)
+    assert before == {f: os.path.getmtime(os.path.join(work, f)) for f in before}
+    # the join stage alone (its inputs: the per-batch fix.csv kept by -d; the polished pieces are gone, like in the reference,
+    # so only the fixes are rebuilt here) -- and a lost polish marker re-polishes and re-joins
+    os.remove(os.path.join(work, "jasper.correct.success"))
+    os.remove(os.path.join(work, "asm.fa.polished.fasta"))
+    n0 = len(calls)
+    out2 = pipeline.run(case["fasta"], case["db"], open_tables=tables, **kw)
+    assert len(calls) > n0 and out2["tallies"] == out["tallies"]
+    _check_outputs(case, work, meta["k"])
+    assert not [f for f in os.listdir(work) if f.endswith(".fix.csv")]             # without -d the per-batch files are removed
