@@ -394,11 +394,18 @@ class QueryMerFile(object):
 
     def polish(self, seqs, k: int, solid_thre: int, passes: int, fix: bool = True, raw: bool = False) -> PolishResult:
         """seqs: [(name, str or bytes)].  One call = the whole per-batch loop of src/jasper.py main().  raw: see _collect."""
+        import time
+        t0 = time.perf_counter()
         arr, keep = self._seq_array(seqs)
         res = C.c_void_p()
+        t1 = time.perf_counter()
         _check(self._lib.jb_polish(self._h, arr, len(seqs), k, solid_thre, passes, 1 if fix else 0, C.byref(res)))
+        t2 = time.perf_counter()
         try:
-            return self._collect(res, [n for n, _ in seqs], raw=raw)
+            out = self._collect(res, [n for n, _ in seqs], raw=raw)
+            self.last_wall_ms = {"marshal": (t1 - t0) * 1e3, "jb_polish": (t2 - t1) * 1e3, "collect": (time.perf_counter() - t2) * 1e3,
+                                 "jb_upload": timing_ms("wall_upload"), "jb_device": timing_ms("wall_polish"), "jb_fetch": timing_ms("wall_fetch")}
+            return out
         finally:
             self._lib.jb_result_free(res)
 

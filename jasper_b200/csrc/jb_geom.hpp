@@ -69,7 +69,8 @@ inline GeomChoice choose_geometry(const JfHeader& h, uint64_t n_records, double 
   if (layout_pref != kLayoutWide) {
     const double ld = load > 0 ? load : kDefaultLoadCompact;
     const uint64_t lines = std::max<uint64_t>(64, (uint64_t)((double)n / (kCompactSlots * ld)) + 1);     // sectors
-    const int ext = std::max(0, std::min({ceil_log2_u64(lines) + 4 - r, h.key_bits, 64 - r}));
+    // 4-8 posx values per sector: fine enough for an even spread, coarse enough for a short tag (every tag bit is a count bit less)
+    const int ext = std::max(0, std::min({ceil_log2_u64(lines) + 2 - r, h.key_bits, 64 - r}));
     const int bits = r + ext;
     // posx values per sector; a probe may meet records of kMaxHops + 1 consecutive home sectors
     const long double per_line = (long double)(bits >= 64 ? 18446744073709551616.0L : (long double)(1ull << bits)) / (long double)lines;

@@ -140,7 +140,7 @@ JB_HD uint64_t hash_lut(const uint64_t* lut, int nbytes, const Key& key) {
 //    {key.lo : 64, key.hi : 32, count : 32} per sector, count == 0 marks an empty slot, linear probing.
 enum : int { kLayoutWide = 0, kLayoutCompact = 1 };
 constexpr int kCompactSlots = 4;       // 8-byte slots per 32-byte sector
-constexpr int kMaxHops = 15;           // a compact probe reads the home sector and at most this many more
+constexpr int kMaxHops = 7;            // a compact probe reads the home sector and at most this many more (load <= 0.65: 3-4 seen)
 constexpr int kMaxCvalBits = 28;
 
 struct TableGeom {

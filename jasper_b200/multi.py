@@ -17,6 +17,18 @@ def shard_chunks(chunks, world: int):
     return batching.shard_units([len(s) for _, s in chunks], world)
 
 
+def polish_shard(my_chunks, k: int, solid_thre: int, passes: int, polish_fn, world: int, allreduce_tallies=None, fix: bool = True):
+    """One rank's part of a sharded run, for callers that hold only their own chunks (a 3.1 Gb assembly is not copied to
+    every rank): polish the shard, sum the first/last tallies over the ranks.  -> (result of polish_fn, [w0, t0, wp, tp] of the
+    whole assembly)."""
+    res = polish_fn(my_chunks, k, solid_thre, passes, fix)
+    first, last = res.tallies[0], res.tallies[-1]
+    t4 = [first[0], first[1], last[0], last[1]]
+    if allreduce_tallies is not None and world > 1:
+        t4 = list(allreduce_tallies(t4))
+    return res, t4
+
+
 def polish_sharded(chunks, k: int, solid_thre: int, passes: int, polish_fn, rank: int, world: int,
                    allreduce_tallies=None, gather=None, fix: bool = True):
     """polish_fn(chunk_list, k, solid_thre, passes, fix) -> object with .status, .tallies [(wrong, total)] per
@@ -27,11 +39,7 @@ def polish_sharded(chunks, k: int, solid_thre: int, passes: int, polish_fn, rank
     order of `chunks`); on other ranks: dict(status, tallies) only."""
     shards = shard_chunks(chunks, world)
     mine = shards[rank]
-    res = polish_fn([chunks[i] for i in mine], k, solid_thre, passes, fix)
-    first, last = res.tallies[0], res.tallies[-1]
-    t4 = [first[0], first[1], last[0], last[1]]
-    if allreduce_tallies is not None and world > 1:
-        t4 = list(allreduce_tallies(t4))
+    res, t4 = polish_shard([chunks[i] for i in mine], k, solid_thre, passes, polish_fn, world, allreduce_tallies, fix)
     local = {"status": res.status, "index": mine, "rows": res.rows, "seqs": res.seqs}
     parts = gather(local) if (gather is not None and world > 1) else [local]
     out = {"status": res.status, "tallies": [(t4[0], t4[1]), (t4[2], t4[3])]}
