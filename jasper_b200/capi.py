@@ -174,9 +174,25 @@ class PolishResult:
     status: int
     tallies: list                      # [(wrong, total)] per iteration 0..p
     rows: list                         # per iteration: [[name, coord, mutation, original], ...]
-    seqs: list                         # [(name, str)]
+    seqs: list                         # [(name, str)]; raw mode: [(name, memoryview over the library's pinned result buffer)]
     timings: dict = field(default_factory=dict)
     counters: dict = field(default_factory=dict)
+    _owner: object = None              # raw mode: keeps the jb_result (and with it the memoryviews) alive
+
+
+class _ResultOwner(object):
+    """Frees a jb_result when the last PolishResult / memoryview user lets go of it."""
+
+    def __init__(self, lib, res):
+        self.lib, self.res = lib, res
+
+    def __del__(self):
+        try:
+            if self.res:
+                self.lib.jb_result_free(self.res)
+                self.res = None
+        except Exception:
+            pass
 
 
 def rows_as_lists(a, names):
@@ -353,8 +369,9 @@ class QueryMerFile(object):
         return arr, keep
 
     def _collect(self, res, names, raw: bool = False) -> PolishResult:
-        """raw=True keeps the result in bulk form: sequences as `bytes`, the rows of a pass as one numpy structured array
-        (fields seq_index, coord, mutation, original) -- no per-row / per-base Python objects (64 Mb: ~15 ms instead of ~120)."""
+        """raw=True keeps the result in bulk form: sequences as memoryviews of the library's pinned result buffer (valid while the
+        PolishResult lives), the rows of a pass as one numpy structured array (fields seq_index, coord, mutation, original) -- no
+        per-row / per-base Python objects and no copy of the bases.  raw results own `res`; otherwise the caller frees it."""
         lib = self._lib
         n_it = lib.jb_result_iterations(res)
         tallies, rows = [], []
@@ -381,9 +398,13 @@ class QueryMerFile(object):
         for i in range(lib.jb_result_num_seqs(res)):
             p, ln = C.c_void_p(), C.c_uint64()
             _check(lib.jb_result_seq(res, i, C.byref(p), C.byref(ln)))
-            b = C.string_at(p, ln.value) if ln.value else b""
-            seqs.append((names[i], b if raw else b.decode("latin-1")))
+            if raw:                                          # no copy: a view of the pinned buffer the device wrote into
+                seqs.append((names[i], memoryview((C.c_char * ln.value).from_address(p.value)).cast("B") if ln.value else memoryview(b"")))
+            else:
+                seqs.append((names[i], C.string_at(p, ln.value).decode("latin-1") if ln.value else ""))
         out = PolishResult(status=lib.jb_result_status(res), tallies=tallies, rows=rows, seqs=seqs)
+        if raw:
+            out._owner = _ResultOwner(lib, res)
         for key in ("polish", "polish_scan", "polish_plan", "polish_walk", "polish_kwalk", "polish_recount", "polish_verdicts", "h2d", "d2h"):
             out.timings[key] = timing_ms(key)
         for key in ("scan_lookups", "walk_lookups", "kernel_launches", "events", "probe_steps", "h2d_bytes", "d2h_bytes",
@@ -395,6 +416,7 @@ class QueryMerFile(object):
     def polish(self, seqs, k: int, solid_thre: int, passes: int, fix: bool = True, raw: bool = False) -> PolishResult:
         """seqs: [(name, str or bytes)].  One call = the whole per-batch loop of src/jasper.py main().  raw: see _collect."""
         import time
+        out = None
         t0 = time.perf_counter()
         arr, keep = self._seq_array(seqs)
         res = C.c_void_p()
@@ -407,7 +429,8 @@ class QueryMerFile(object):
                                  "jb_upload": timing_ms("wall_upload"), "jb_device": timing_ms("wall_polish"), "jb_fetch": timing_ms("wall_fetch")}
             return out
         finally:
-            self._lib.jb_result_free(res)
+            if not (raw and out is not None):
+                self._lib.jb_result_free(res)
 
     # split form: keep the batch resident and time the device part alone
     def upload(self, seqs):
@@ -427,10 +450,13 @@ class _Batch(object):
     def fetch(self, raw: bool = False) -> PolishResult:
         res = C.c_void_p()
         _check(self.qf._lib.jb_batch_fetch(self.h, C.byref(res)))
+        out = None
         try:
-            return self.qf._collect(res, self.names, raw=raw)
+            out = self.qf._collect(res, self.names, raw=raw)
+            return out
         finally:
-            self.qf._lib.jb_result_free(res)
+            if not (raw and out is not None):
+                self.qf._lib.jb_result_free(res)
 
     def free(self):
         if self.h:

@@ -67,21 +67,21 @@ def write_fasta(path: str, seqs, width: int = 60) -> None:
                 of.write(s[i:i + width] + "\n")
 
 
-def fasta_bytes(name: str, seq: bytes, width: int = 60) -> bytes:
-    """One record as src/jasper.py:120-128 writes it (split_output: `width` bases per line), built in bulk."""
+def fasta_bytes(name: str, seq, width: int = 60) -> bytes:
+    """One record as src/jasper.py:120-128 writes it (split_output: `width` bases per line), built in bulk.  seq: bytes-like."""
     head = b">" + name.encode("utf-8") + b"\n"
     full = len(seq) // width * width
     try:
         import numpy as np
     except ImportError:
-        return head + b"".join(seq[i:i + width] + b"\n" for i in range(0, len(seq), width))
+        return head + b"".join(bytes(seq[i:i + width]) + b"\n" for i in range(0, len(seq), width))
     body = b""
     if full:
         a = np.empty((full // width, width + 1), dtype=np.uint8)
         a[:, :width] = np.frombuffer(seq, dtype=np.uint8, count=full).reshape(-1, width)
         a[:, width] = 10
         body = a.tobytes()
-    tail = seq[full:] + b"\n" if len(seq) > full else b""
+    tail = bytes(seq[full:]) + b"\n" if len(seq) > full else b""
     return head + body + tail
 
 

@@ -200,7 +200,7 @@ def _spill_group(workdir, qfn, g, names, res, passes):
                 f.write(capi.rows_csv_bytes(rows, names))
     with open(os.path.join(workdir, "_iter%d_%s.fixed.fa" % (passes - 1, bf)), "wb") as f:
         for name, seq in res.seqs:
-            f.write(dropin.fasta_bytes(name, seq if isinstance(seq, (bytes, bytearray)) else seq.encode("latin-1")))
+            f.write(dropin.fasta_bytes(name, seq.encode("latin-1") if isinstance(seq, str) else seq))
     for ite in (0, passes):
         with open(os.path.join(workdir, "%dqValCalcHelper.csv" % ite), "a") as f:
             f.write("%d %d\n" % tuple(res.tallies[ite if ite == 0 else -1]))

@@ -18,6 +18,10 @@ import jasper_oracle as jo  # noqa: E402
 from jasper_b200 import synth  # noqa: E402
 
 GOLDEN_NAMES = ["k25_mix", "k37_mix", "k31_dirty", "k21_even"]
+# fuzz cases through the UNMODIFIED reference, chosen for the rare branches (tests/golden/make_golden_branches.py)
+BRANCH_GOLDENS = ["branches/s32", "branches/s99", "branches/s278", "branches/s377", "branches/s5", "branches/s9", "branches/s39", "branches/s66"]
+ALL_BRANCHES = ["add_base", "bridge", "drop_base", "grow_run", "grow_single", "rolling_ok", "rolling_weak", "shrink_run", "shrink_single", "substitution",
+                "two_ended_e", "two_ended_s", "unfixed_k", "unfixed_long", "unfixed_short"]
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
@@ -228,14 +232,15 @@ def product_rows_text(rows_per_pass, names):
 def load_golden(name, tmpdir):
     d = os.path.join(GOLDEN_DIR, name)
     meta = json.load(open(os.path.join(d, "case.json")))
-    db = os.path.join(tmpdir, name + ".jf")
+    db = os.path.join(tmpdir, name.replace("/", "_") + ".jf")
     if not os.path.exists(db):
         with gzip.open(os.path.join(d, "db.jf.gz")) as f, open(db, "wb") as o:
             o.write(f.read())
     meta["db"] = db
     meta["dir"] = d
     meta["fasta"] = os.path.join(d, "asm.fa")
-    meta["lookups"] = json.load(open(os.path.join(d, "lookups.json")))
+    lk = os.path.join(d, "lookups.json")
+    meta["lookups"] = json.load(open(lk)) if os.path.exists(lk) else []
     return meta
 
 

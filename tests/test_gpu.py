@@ -96,6 +96,32 @@ def test_polish_reproduces_reference_bytes(golden_cases, dbs, name):
     assert res.counters["kernel_launches"] >= 2 * (case["passes"] + 1)
 
 
+@pytest.mark.parametrize("name", helpers.BRANCH_GOLDENS)
+@pytest.mark.parametrize("layout", ["compact", "wide"])
+def test_polish_reproduces_reference_bytes_on_rare_branches(tmp_path, monkeypatch, name, layout):
+    """tests/golden/branches/*: the unmodified reference on fuzz cases that take fixdiploid's "s" side, grow_single, unfixed_k and the
+    rolling threshold (every branch >= 5 times in all, tests/test_oracle.py checks the counts): same bytes from the CUDA path,
+    through both table layouts, with and without the verdict kernels."""
+    monkeypatch.setenv("JB_TABLE_LAYOUT", layout)
+    case = helpers.load_golden(name, str(tmp_path))
+    seqs = jo.read_fasta(case["fasta"])
+    qf = capi.QueryMerFile(case["db"])
+    try:
+        for no_verdicts in (None, "1"):
+            if no_verdicts:
+                monkeypatch.setenv("JB_NO_VERDICTS", no_verdicts)
+            res = qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+            assert res.status == 0
+            for ite in range(case["passes"]):
+                assert jo.format_fix_csv(res.rows[ite]) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+            assert jo.format_fasta(res.seqs) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+            assert ("%d %d\n" % res.tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
+            assert ("%d %d\n" % res.tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+    finally:
+        monkeypatch.delenv("JB_NO_VERDICTS", raising=False)
+        qf.close()
+
+
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 @pytest.mark.parametrize("seg_block,margin", [("0", None), ("64", None), ("256", "0"), ("2048", None)])
 def test_polish_golden_is_independent_of_segmentation(golden_cases, dbs, name, seg_block, margin, monkeypatch):

@@ -144,6 +144,24 @@ def test_walker_source_matches_golden(golden_cases, hostsim_lib, name, use_event
     assert jo.format_fasta(list(zip(names, out))) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
 
 
+@pytest.mark.parametrize("name", helpers.BRANCH_GOLDENS)
+def test_walker_source_matches_rare_branch_goldens(tmp_path, hostsim_lib, name):
+    """The device walker's source, built for the host, against the unmodified reference's files on the rare-branch cases."""
+    case = helpers.load_golden(name, str(tmp_path))
+    odb = helpers.OracleDB(case["db"])
+    seqs = jo.read_fasta(case["fasta"])
+    names = [n for n, _ in seqs]
+    for use_events in (0, 300):
+        st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events)
+        assert st == 0
+        for ite in range(case["passes"]):
+            rows = [[names[int(f[1])], int(f[2]), f[3], f[4]] for f in (l.split("\t") for l in txt.splitlines()) if f[0] == str(ite)]
+            assert jo.format_fix_csv(rows) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+        assert jo.format_fasta(list(zip(names, out))) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+        assert ("%d %d\n" % tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
+        assert ("%d %d\n" % tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_walker_source_fuzz(tmp_path, hostsim_lib, seed):
     """Random dirty genomes (N runs, lower case, IUPAC, repeats, heterozygosity, clustered errors)."""

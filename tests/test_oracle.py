@@ -30,6 +30,32 @@ def test_polish_oracle_reproduces_reference_run(golden_cases, name):
     assert jo.format_tally(res.passes[-1]) == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
 
 
+def _check_against_expected(case, res):
+    for ite in range(case["passes"]):
+        assert jo.format_fix_csv(res.passes[ite].rows) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+    assert jo.format_fasta(res.seqs) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+    assert jo.format_tally(res.passes[0]) == helpers.expected_file(case, "0qValCalcHelper.csv")
+    assert jo.format_tally(res.passes[-1]) == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+
+
+def test_rare_branches_are_pinned_by_reference_runs(tmp_path):
+    """tests/golden/branches/*: outputs of the unmodified src/jasper.py on fuzz cases picked for the branches the big goldens
+    miss -- fixdiploid's "s" side, a single inserted base (grow_single), substitution and deletion both failing (unfixed_k), the
+    rolling threshold.  The restatement reproduces every file, and together the cases take EVERY branch at least five times."""
+    total = {}
+    for name in helpers.BRANCH_GOLDENS:
+        case = helpers.load_golden(name, str(tmp_path))
+        odb = helpers.OracleDB(case["db"])
+        oracle = jo.PolishOracle(odb.count, case["k"], case["threshold"])
+        res = oracle.polish(jo.read_fasta(case["fasta"]), case["passes"])
+        _check_against_expected(case, res)
+        assert oracle.branch_report() == case["branches"]
+        for b, n in oracle.branch_report().items():
+            total[b] = total.get(b, 0) + n
+    assert sorted(total) == sorted(helpers.ALL_BRANCHES)
+    assert min(total.values()) >= 5, total
+
+
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 def test_lookup_oracle_matches_binding_vectors(golden_cases, name):
     """C(s) and the canonical k-mer text for edge-case strings recorded from the real binding."""
