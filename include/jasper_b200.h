@@ -157,6 +157,11 @@ int jb_polish(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, int k, uint3
  * (src/jasper.sh:132-139): it bounds the working set, it does not change any result. */
 int jb_polish_capacity(const jb_db* db, uint64_t* max_bases);
 
+/* Page-locked host memory.  jb_polish / jb_batch_upload recognise contigs that lie in page-locked memory (from here, from
+ * cudaHostAlloc, or registered with cudaHostRegister) and copy them to the device without a staging copy. */
+int jb_host_alloc(size_t bytes, void** out);
+void jb_host_free(void* p);
+
 /* Split form, for callers that keep contigs resident in HBM between calls (and for timing the
  * device part alone): upload once, polish (device only), then fetch. */
 int jb_batch_upload(const jb_db* db, const jb_seq_t* seqs, size_t n_seqs, jb_batch** out);

@@ -42,7 +42,7 @@ LAYOUT_WIDE, LAYOUT_COMPACT = 0, 1
 
 
 class _Seq(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("seq", C.c_char_p), ("len", C.c_uint64)]
+    _fields_ = [("name", C.c_char_p), ("seq", C.c_void_p), ("len", C.c_uint64)]
 
 
 class _FixRow(C.Structure):
@@ -67,7 +67,7 @@ EXPORTS = [
     "jb_init", "jb_device_count", "jb_last_error", "jb_version",
     "jb_db_open", "jb_db_open_partitioned", "jb_db_open_part", "jb_db_part_handle", "jb_db_attach_parts", "jb_db_info", "jb_db_replicate", "jb_db_close", "jb_db_dump", "jb_db_histogram", "jb_solid_threshold",
     "jb_lookup", "jb_lookup_flat", "jb_count_positions",
-    "jb_polish", "jb_polish_capacity", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
+    "jb_polish", "jb_polish_capacity", "jb_host_alloc", "jb_host_free", "jb_batch_upload", "jb_batch_polish", "jb_batch_fetch", "jb_batch_free",
     "jb_result_status", "jb_result_iterations", "jb_result_tally", "jb_result_num_rows", "jb_result_rows",
     "jb_result_num_seqs", "jb_result_seq", "jb_result_free",
     "jb_last_timing_ms", "jb_last_counter",
@@ -112,6 +112,8 @@ def load_library():
         "jb_count_positions": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p]),
         "jb_polish": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(vp)]),
         "jb_polish_capacity": (C.c_int, [vp, u64p]),
+        "jb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+        "jb_host_free": (None, [vp]),
         "jb_batch_upload": (C.c_int, [vp, C.POINTER(_Seq), C.c_size_t, C.POINTER(vp)]),
         "jb_batch_polish": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.c_int]),
         "jb_batch_fetch": (C.c_int, [vp, C.POINTER(vp)]),
@@ -218,6 +220,44 @@ def rows_csv_bytes(a, names) -> bytes:
         csv.writer(buf, delimiter=" ").writerows(rows_as_lists(a, names))
         return buf.getvalue().encode("utf-8")
     return b"".join(b"%s %d %s %s\r\n" % (nb[i], c, m, o) for i, c, m, o in zip(idx, coord, mut, org))
+
+
+class PinnedBuffer(object):
+    """Page-locked host memory from the library (jb_host_alloc).  Contigs placed in it (`place`) travel to the GPU without a
+    staging copy; `view` is a writable memoryview over the whole buffer."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        p = C.c_void_p()
+        _check(self._lib.jb_host_alloc(nbytes, C.byref(p)))
+        self._p = p
+        self.nbytes = nbytes
+        self.view = memoryview((C.c_char * max(1, nbytes)).from_address(p.value)).cast("B")[:nbytes]
+
+    def place(self, seqs):
+        """Copy [(name, str / bytes-like)] into the buffer back to back -> [(name, memoryview slice)] for polish() / upload()."""
+        out, at = [], 0
+        for name, s in seqs:
+            b = s.encode("latin-1") if isinstance(s, str) else s
+            n = len(b)
+            if at + n > self.nbytes:
+                raise ValueError("PinnedBuffer of %d bytes is too small" % self.nbytes)
+            self.view[at:at + n] = b
+            out.append((name, self.view[at:at + n]))
+            at += n
+        return out
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p:
+            # (views handed out by place() point into this memory: the caller must be done with them)
+            self._lib.jb_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class QueryMerFile(object):
@@ -360,11 +400,18 @@ class QueryMerFile(object):
         arr = (_Seq * max(1, n))()
         keep = []
         for i, (name, s) in enumerate(seqs):
-            b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
             nb = name.encode("utf-8")
-            keep.append((b, nb))
             arr[i].name = nb
-            arr[i].seq = b
+            if isinstance(s, memoryview):                    # e.g. a slice of a PinnedBuffer: passed by address, no copy
+                s = s.cast("B") if s.format != "B" else s
+                view = (C.c_char * len(s)).from_buffer(s) if len(s) else None
+                keep.append((s, view, nb))
+                arr[i].seq = C.addressof(view) if view is not None else None
+                arr[i].len = len(s)
+                continue
+            b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
+            keep.append((b, nb))
+            arr[i].seq = C.cast(C.c_char_p(b), C.c_void_p)
             arr[i].len = len(b)
         return arr, keep
 

@@ -485,24 +485,39 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
   JB_CUDA(cudaEventRecord(e0, s));
   // stage through pinned memory in slices: a few host threads copy slices while the DMA engine drains the
   // ones already staged (one thread saturates at ~9 GB/s, the link takes 3x that)
-  struct Slice { const char* src; uint64_t dev_off, pin_off, len; size_t unit; bool last; };
+  // A contig that already lies in page-locked memory (jb_host_alloc, cudaHostAlloc, cudaHostRegister) goes to the device
+  // straight from where it is: no staging copy, the link runs at its own speed (~50 GB/s instead of the ~20 GB/s of memcpy + DMA).
+  struct Slice { const char* src; uint64_t dev_off, pin_off, len; size_t unit; bool last; bool direct; };
   std::vector<Slice> slices;
   constexpr uint64_t kSlice = 4ull << 20;
   uint64_t p = 0;
-  for (size_t i = 0; i < n; ++i)
+  size_t n_staged = 0;
+  for (size_t i = 0; i < n; ++i) {
+    bool direct = false;
+    if (seqs[i].len) {
+      cudaPointerAttributes pa{};
+      if (cudaPointerGetAttributes(&pa, seqs[i].seq) == cudaSuccess) direct = pa.type == cudaMemoryTypeHost;
+      else cudaGetLastError();
+    }
     for (uint64_t at = 0; at < seqs[i].len; at += kSlice) {
       const uint64_t m = std::min<uint64_t>(kSlice, seqs[i].len - at);
-      slices.push_back(Slice{seqs[i].seq + at, b->off[i] + at, p, m, i, at + m == seqs[i].len});
-      p += m;
+      slices.push_back(Slice{seqs[i].seq + at, b->off[i] + at, p, m, i, at + m == seqs[i].len, direct});
+      if (!direct) { p += m; ++n_staged; }
     }
-  const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, slices.size() / 2));
+  }
+  note_counter("h2d_direct_bytes", (int64_t)(total_len - p));
+  const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, n_staged / 2));
   std::vector<std::atomic<int>> ready(slices.size());
   for (auto& r : ready) r.store(0);
   std::vector<std::thread> copiers;
   uint8_t* pin = w.h_in.p;
+  // staged slices are dealt to the copier threads round robin by their rank among the staged ones
+  std::vector<int> owner(slices.size(), -1);
+  { size_t q = 0; for (size_t j = 0; j < slices.size(); ++j) if (!slices[j].direct) owner[j] = (int)(q++ % (size_t)n_thr); }
   for (int t = 1; t < n_thr; ++t)
     copiers.emplace_back([&, t]() {
-      for (size_t j = (size_t)t; j < slices.size(); j += (size_t)n_thr) {
+      for (size_t j = 0; j < slices.size(); ++j) {
+        if (owner[j] != t) continue;
         std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
         ready[j].store(1, std::memory_order_release);
       }
@@ -542,10 +557,13 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
   cudaError_t copy_err = cudaSuccess;
   size_t g = 0, g_first = 0;
   for (size_t j = 0; j < slices.size(); ++j) {
-    if (j % (size_t)n_thr == 0) std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
-    else while (!ready[j].load(std::memory_order_acquire)) std::this_thread::yield();
+    if (!slices[j].direct) {
+      if (owner[j] == 0) std::memcpy(pin + slices[j].pin_off, slices[j].src, slices[j].len);
+      else while (!ready[j].load(std::memory_order_acquire)) std::this_thread::yield();
+    }
     if (copy_err == cudaSuccess)
-      copy_err = cudaMemcpyAsync(w.buf[0].p + slices[j].dev_off, pin + slices[j].pin_off, slices[j].len, cudaMemcpyHostToDevice, cs);
+      copy_err = cudaMemcpyAsync(w.buf[0].p + slices[j].dev_off, slices[j].direct ? (const uint8_t*)slices[j].src : pin + slices[j].pin_off, slices[j].len,
+                                 cudaMemcpyHostToDevice, cs);
     if (!prescan) continue;
     if (!slices[j].last) continue;
     size_t done_units = slices[j].unit + 1;               // contigs fully enqueued (empty ones have no slices)
@@ -586,6 +604,18 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
 }  // namespace
 
 extern "C" void jb_batch_free(jb_batch* b) { delete b; }
+
+// page-locked host memory for callers that want their contigs to travel without a staging copy
+extern "C" int jb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(JB_E_ARG, "jb_host_alloc: null argument");
+  *out = nullptr;
+  if (cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(JB_E_NOMEM, "cannot page-lock " + std::to_string(bytes) + " bytes of host memory");
+  }
+  return JB_OK;
+}
+extern "C" void jb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 namespace {
 
