@@ -275,7 +275,7 @@ struct PinBuf {
 struct Workspace {
   int device = -1;
   DevBuf<uint8_t> buf[2], stage;
-  DevBuf<uint32_t> counts[2], events, weak, events_l1, order, tile_first, block_first, slot_unit, vmap;
+  DevBuf<uint32_t> counts[2], events, weak, events_l1, events_l2, order, tile_first, block_first, slot_unit, vmap;
   DevBuf<Verdict> verdicts;
   DevBuf<Verdict2> verdicts2;
   DevBuf<uint32_t> verdict_unit;
@@ -306,7 +306,7 @@ struct Workspace {
   ~Workspace() {
     if (device < 0) return;
     cudaSetDevice(device);
-    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); dry_out.release(); order.release();
+    buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); events_l2.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); dry_out.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release();
@@ -463,7 +463,7 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
   JB_TRY(w.buf[0].ensure(total + 64)); JB_TRY(w.buf[1].ensure(total + 64)); JB_TRY(w.stage.ensure(total + 64));
   for (int q = 0; q < 2; ++q) { JB_TRY(w.counts[q].ensure(total + 64)); JB_TRY(w.okb[q].ensure(total + 64)); }
   JB_TRY(w.scan_units_new.ensure(n + 1));
-  JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64));
+  JB_TRY(w.events.ensure(total / 32 + 64)); JB_TRY(w.weak.ensure(total / 32 + 64)); JB_TRY(w.events_l1.ensure(total / 32768 + 64)); JB_TRY(w.events_l2.ensure(total / (32768 * 32) + 64));
   JB_TRY(w.vmap.ensure(total / 32 + 64)); JB_TRY(w.verdicts.ensure(total / 64 + 4096));
   JB_TRY(w.verdicts2.ensure(total / 64 + 4096)); JB_TRY(w.verdict_unit.ensure(total / 64 + 4096));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
@@ -650,7 +650,7 @@ UnitIO make_seg(const jb_batch* b, const SegPlan& p, uint8_t* in, uint32_t gen, 
   u.okb = w.okb[cidx].p + b->off[i];
   u.weak = w.weak.p + b->off[i] / 32; u.vmap = b->use_verdicts ? w.vmap.p : nullptr; u.verdicts = w.verdicts.p;
   u.verdicts2 = b->use_verdicts2 ? w.verdicts2.p : nullptr;
-  u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_bit_base = b->off[i];
+  u.ev = w.events.p + b->off[i] / 32; u.ev_l1 = w.events_l1.p; u.ev_l2 = getenv("JB_NO_L2") ? nullptr : w.events_l2.p; u.ev_bit_base = b->off[i];
   u.base = p.base; u.next_anchor = p.next_anchor;
   u.unit = p.unit; u.seg = p.seg; u.gen = gen; u.slot = slot;
   u.materialize_all = gen ? 1u : 0u;               // re-runs take the conservative path
@@ -805,6 +805,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
     JB_CUDA(cudaMemsetAsync(w.used.p, 0, 64, s));        // (the previous pass's counters are on the host already)
     JB_CUDA(cudaMemsetAsync(w.events_l1.p, 0, (b->flat_bytes / 32768 + 64) * 4, s));
+    JB_CUDA(cudaMemsetAsync(w.events_l2.p, 0, (b->flat_bytes / (32768 * 32) + 64) * 4, s));
     ScanArgs a{};
     a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
     a.counts = w.counts[cidx].p; a.okb = w.okb[cidx].p; a.probe_steps = w.used.p + 2;
@@ -821,7 +822,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaEventRecord(ev_b, s));
     EventArgs ea{};
     ea.units = w.scan_units.p; ea.tile_first = w.tile_first.p; ea.n_units = (uint32_t)n; ea.n_tiles = tile_first[n];
-    ea.counts = w.counts[cidx].p; ea.okb = w.okb[cidx].p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p;
+    ea.counts = w.counts[cidx].p; ea.okb = w.okb[cidx].p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p; ea.events_l2 = w.events_l2.p;
     ea.solid_thre = solid_thre; ea.k = k;
     if (int rc = launch_events(ea, s)) return rc;
     ++launches;
@@ -1024,7 +1025,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
         JB_CUDA(cudaEventRecord(ev_r0, s));
         if (int rc = launch_recount(view, ra, rt, used[3], s)) return rc;
         JB_CUDA(cudaEventRecord(ev_r1, s));
-        launches += 2;
+        launches += 3;
         // (not while the polished bases travel on the side stream: a device-to-host copy on this stream would queue behind
         //  them in the copy engine and hold the stream for the whole transfer; the statistic of that pass is dropped)
         used[4] = 0;

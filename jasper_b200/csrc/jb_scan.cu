@@ -247,65 +247,197 @@ k_events(EventArgs a) {
     if (lane == 0) {
       const uint64_t f = f0 + w0;                                   // contig offsets are multiples of 32, not of 1024:
       a.events[f >> 5] = word; a.weak[f >> 5] = wword;              // a tile can straddle two summary blocks
-      if (word) atomicOr(&a.events_l1[f >> 15], 1u << ((f >> 10) & 31));
+      if (word) {
+        const uint32_t bit = 1u << ((f >> 10) & 31);
+        if (!(atomicOr(&a.events_l1[f >> 15], bit))) atomicOr(&a.events_l2[f >> 20], 1u << ((f >> 15) & 31));   // first bit of its level-1 word
+      }
     }
   }
 }
 
 
-// one grid row per copy job, gridDim.x CTAs share it
+// ---- k_recount ----------------------------------------------------------------------------------------------------
+// 32 two-bit codes, one per lane (lane 0 = first base), as a 64-bit word with the first base most significant
+__device__ __forceinline__ uint64_t spread32(uint32_t v) {
+  uint64_t x = v;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x;
+}
+// one round: every lane contributes one base; -> the packed word (same in all lanes) and the validity ballot (bit i = lane i)
+__device__ __forceinline__ uint64_t pack_round(uint8_t c, bool in_contig, uint32_t* valid) {
+  const bool v = in_contig && base_valid(c);
+  const uint32_t code = v ? base_code(c) : 0u;
+  *valid = __ballot_sync(0xffffffffu, v);
+  const uint32_t p0 = __brev(__ballot_sync(0xffffffffu, code & 1u)), p1 = __brev(__ballot_sync(0xffffffffu, (code >> 1) & 1u));
+  return spread32(p0) | (spread32(p1) << 1);
+}
+// the k bases that start `q` bases into the packed stream a:b:c (32 bases per word, first base most significant), 0 <= q < 32
+__device__ __forceinline__ Key key_at(uint64_t a, uint64_t b, uint64_t c, int q, int k, const Key& mask) {
+  const int sh = 192 - 2 * q - 2 * k;            // k <= 48, q <= 31: 34 <= sh <= 190
+  Key r;
+  if (sh >= 128) { const int s = sh - 128; r.lo = a >> s; r.hi = 0; }
+  else if (sh >= 64) { const int s = sh - 64; r.lo = s ? (b >> s) | (a << (64 - s)) : b; r.hi = a >> s; }
+  else { r.lo = (c >> sh) | (b << (64 - sh)); r.hi = (b >> sh) | (a << (64 - sh)); }
+  r.lo &= mask.lo; r.hi &= mask.hi;
+  return r;
+}
+// bits [q, q + k) of the validity stream v0:v1:v2 (bit i of word w = base 32 w + i) all set?
+__device__ __forceinline__ bool valid_at(uint32_t v0, uint32_t v1, uint32_t v2, int q, int k) {
+  const uint32_t lo = __funnelshift_r(v0, v1, q), mid = __funnelshift_r(v1, v2, q);
+  if (k <= 32) { const uint32_t m = k == 32 ? 0xffffffffu : ((1u << k) - 1u); return (lo & m) == m; }
+  const uint32_t m = (1u << (k - 32)) - 1u;
+  return lo == 0xffffffffu && (mid & m) == m;
+}
+
+__device__ __noinline__ Key recount_rare_key(const uint8_t* s, int64_t avail, int k, Key mask) {
+  return key_canonical(key_from_chars(s, avail, k, mask), k);
+}
+
+struct ProbeInFlight { uint64_t posx; const ulonglong4* sec; unsigned long long w0, w1, w2, w3; };
+__device__ __forceinline__ void probe_issue(const TableView& t, const Key& m, ProbeInFlight& p) {
+  p.posx = key_posx(t.g, hash_lut(t.lut, t.g.key_bytes, m), m);
+  p.sec = reinterpret_cast<const ulonglong4*>(unit_ptr(t, home_unit_of_posx(t.g, p.posx)));
+  ldg256(p.sec, p.w0, p.w1, p.w2, p.w3);
+}
+__device__ __forceinline__ uint32_t probe_finish(const TableView& t, const Key& m, ProbeInFlight& p) {
+  if (t.g.layout == kLayoutCompact) {
+    const CompactProbe pr = compact_probe_of(t.g, p.posx, m);
+    uint32_t cv = 0;
+    int hop = 0;
+    while (!compact_step(pr, p.w0, p.w1, p.w2, p.w3, &cv)) {
+      if (++hop > kMaxHops) { cv = pr.cmask; break; }
+      ++p.sec;
+      ldg256(p.sec, p.w0, p.w1, p.w2, p.w3);
+    }
+    return cv == pr.cmask ? stash_find(t, m, p.posx) : cv;
+  }
+  while (true) {
+    const uint32_t c0 = (uint32_t)(p.w1 >> 32), c1 = (uint32_t)(p.w3 >> 32);
+    if (c0 == 0) return 0;
+    if (p.w0 == m.lo && (uint32_t)p.w1 == (uint32_t)m.hi) return c0;
+    if (c1 == 0) return 0;
+    if (p.w2 == m.lo && (uint32_t)p.w3 == (uint32_t)m.hi) return c1;
+    ++p.sec;
+    ldg256(p.sec, p.w0, p.w1, p.w2, p.w3);
+  }
+}
+
+// Counts of the next pass's sequence, two kernels over the same job list.  k_recount_copy: a job's windows that lie inside
+// an untouched stretch keep their counts (streamed, eight independent loads per thread in flight).  k_recount_probe: the
+// other windows -- the last k-1 of an untouched stretch, every window of a materialised one -- are cut from a 2-bit packed
+// copy of the new bases that the warp builds with ballots, 64 windows per trip, two probes in flight per lane.
+// Work split in both: a.team threads per job on a 1-D grid (many short jobs), or the CTAs of one grid row per job (few
+// long ones).
+struct RecountJobView { int64_t D, dirty0, dend, cend, O; bool live; };
+__device__ __forceinline__ RecountJobView recount_job(const RecountArgs& a, unsigned long long j, int k) {
+  RecountJobView v;
+  const CopyJob job = a.jobs[j];
+  const int64_t off = a.dst_off[job.slot];
+  v.live = off >= 0;
+  if (!v.live) return v;
+  const ScanUnit u = a.units_new[a.slot_unit[job.slot]];
+  v.D = off + job.rel;                                            // flat position of the job's first base
+  v.cend = (int64_t)u.seq_off + (int64_t)u.len;                   // flat end of the new contig
+  v.dend = v.D + job.len;
+  v.dirty0 = v.D; v.O = -1;
+  if (job.src >= a.in_buf && job.src < a.in_buf + a.flat_bytes) { // an untouched stretch: windows inside it keep their counts
+    v.O = job.src - a.in_buf;
+    v.dirty0 = v.D + (job.len - k + 1 > 0 ? job.len - k + 1 : 0);
+  }
+  return v;
+}
+struct RecountSplit { int64_t tid, nth; unsigned long long j0, jstep; };
+__device__ __forceinline__ RecountSplit recount_split(int team) {
+  RecountSplit r;
+  if (team) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    r.tid = (int64_t)(g % (unsigned)team); r.nth = team;
+    r.j0 = g / (unsigned)team; r.jstep = (unsigned long long)gridDim.x * blockDim.x / (unsigned)team;
+  } else {
+    r.tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r.nth = (int64_t)gridDim.x * blockDim.x;
+    r.j0 = blockIdx.y; r.jstep = gridDim.y;
+  }
+  return r;
+}
+
+constexpr int kRecountUnroll = 8;
 __global__ void __launch_bounds__(256)
-k_recount(TableView t, RecountArgs a) {
+k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
+  const unsigned long long n = *a.n_jobs;
+  const RecountSplit sp = recount_split(a.team);
+  for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
+    const RecountJobView v = recount_job(a, j, k);
+    if (!v.live || v.O < 0) continue;
+    const int64_t ncopy = v.dirty0 - v.D;
+    const uint32_t* __restrict__ co = a.cnt_old + v.O;
+    const uint8_t* __restrict__ oo = a.okb_old + v.O;
+    uint32_t* __restrict__ cn = a.cnt_new + v.D;
+    uint8_t* __restrict__ on = a.okb_new + v.D;
+    for (int64_t q0 = sp.tid; q0 < ncopy; q0 += sp.nth * kRecountUnroll) {
+      uint32_t c[kRecountUnroll];
+      uint8_t o[kRecountUnroll];
+#pragma unroll
+      for (int x = 0; x < kRecountUnroll; ++x) {
+        const int64_t q = q0 + x * sp.nth;
+        if (q < ncopy) { c[x] = __ldg(co + q); o[x] = __ldg(oo + q); }
+      }
+#pragma unroll
+      for (int x = 0; x < kRecountUnroll; ++x) {
+        const int64_t q = q0 + x * sp.nth;
+        if (q < ncopy) { cn[q] = c[x]; on[q] = o[x]; }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_recount_probe(const __grid_constant__ TableView t, const __grid_constant__ RecountArgs a) {
   const unsigned long long n = *a.n_jobs;
   const int k = t.g.k;
-  // many short jobs (a fixing pass over a dirty assembly: ~3 jobs per edit, a few hundred positions each): a team of
-  // a.team threads per job, teams spread over a 1-D grid.  Few long jobs: the CTAs of one grid row share a job.
-  int64_t tid, nth;
-  unsigned long long j0, jstep;
-  if (a.team) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    tid = (int64_t)(g % (unsigned)a.team); nth = a.team;
-    j0 = g / (unsigned)a.team; jstep = (unsigned long long)gridDim.x * blockDim.x / (unsigned)a.team;
-  } else {
-    tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nth = (int64_t)gridDim.x * blockDim.x;
-    j0 = blockIdx.y; jstep = gridDim.y;
-  }
+  const int lane = threadIdx.x & 31;
+  const RecountSplit sp = recount_split(a.team);
+  const int64_t wi = sp.tid >> 5, nw = sp.nth >> 5;               // this warp among the job's warps
   unsigned long long probes = 0;
-  for (unsigned long long j = j0; j < n; j += jstep) {
-    const CopyJob job = a.jobs[j];
-    const int64_t off = a.dst_off[job.slot];
-    if (off < 0) continue;
-    const ScanUnit u = a.units_new[a.slot_unit[job.slot]];
-    const int64_t D = off + job.rel;                              // flat position of the job's first base
-    const int64_t cend = (int64_t)u.seq_off + (int64_t)u.len;     // flat end of the new contig
-    int64_t dirty0 = D;
-    if (job.src >= a.in_buf && job.src < a.in_buf + a.flat_bytes) {
-      // an untouched stretch: windows that lie inside it keep their counts
-      const int64_t O = job.src - a.in_buf;
-      const int64_t ncopy = job.len - k + 1 > 0 ? job.len - k + 1 : 0;
-      for (int64_t q = tid; q < ncopy; q += nth) { a.cnt_new[D + q] = a.cnt_old[O + q]; a.okb_new[D + q] = a.okb_old[O + q]; }
-      dirty0 = D + ncopy;
-    }
-    for (int64_t p = dirty0 + tid; p < D + job.len; p += nth) {
-      const uint8_t* s = a.new_bases + p;
-      const int64_t avail = cend - p;
-      Key key = {0, 0};
-      int got = 0;
-      while (got < k && got < avail) {
-        const uint8_t c = s[got];
-        if (!base_valid(c)) break;
-        key = key_push(key, base_code(c), t.mask);
-        ++got;
+  for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
+    const RecountJobView jv = recount_job(a, j, k);
+    if (!jv.live) continue;
+    const int64_t cend = jv.cend, dend = jv.dend;
+    for (int64_t c0 = jv.dirty0 + wi * 64; c0 < dend; c0 += nw * 64) {
+      // bases [c0, c0 + 128) packed: windows c0 + lane (words 0-2) and c0 + 32 + lane (words 1-3)
+      uint64_t w[4];
+      uint32_t v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t p = c0 + 32 * r + lane;
+        const bool in = p < cend;
+        w[r] = pack_round(in ? a.new_bases[p] : (uint8_t)0, in, &v[r]);
       }
-      key = key_shl_bases(key, k - got, t.mask);
-      a.cnt_new[p] = table_count(t, key_canonical(key, k));
-      a.okb_new[p] = got == k ? 1 : 0;
-      ++probes;
+      const int64_t pa = c0 + lane, pb = c0 + 32 + lane;
+      const bool doa = pa < dend, dob = pb < dend;
+      const bool oka = valid_at(v[0], v[1], v[2], lane, k), okb = valid_at(v[1], v[2], v[3], lane, k);
+      Key ka = {0, 0}, kb = {0, 0};
+      ProbeInFlight fa, fb;
+      if (doa) {
+        if (oka) { const Key f = key_at(w[0], w[1], w[2], lane, k, t.mask); ka = key_canonical(f, k); }
+        else ka = recount_rare_key(a.new_bases + pa, cend - pa, k, t.mask);
+        probe_issue(t, ka, fa);
+      }
+      if (dob) {
+        if (okb) { const Key f = key_at(w[1], w[2], w[3], lane, k, t.mask); kb = key_canonical(f, k); }
+        else kb = recount_rare_key(a.new_bases + pb, cend - pb, k, t.mask);
+        probe_issue(t, kb, fb);
+      }
+      if (doa) { a.cnt_new[pa] = probe_finish(t, ka, fa); a.okb_new[pa] = oka ? 1 : 0; ++probes; }
+      if (dob) { a.cnt_new[pb] = probe_finish(t, kb, fb); a.okb_new[pb] = okb ? 1 : 0; ++probes; }
     }
   }
   if (a.probes) {
     for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
-    if ((threadIdx.x & 31) == 0 && probes) atomicAdd(a.probes, probes);
+    if (lane == 0 && probes) atomicAdd(a.probes, probes);
   }
 }
 
@@ -350,9 +482,12 @@ int launch_recount(const TableView& view, const RecountArgs& a, const RecountTai
     a2.team = 64;
     g = dim3((unsigned)std::min<unsigned long long>((nj * 64 + 255) / 256, 148ull * 64), 1);
   }
-  k_recount<<<g, 256, 0, s>>>(view, a2);
+  k_recount_copy<<<g, 256, 0, s>>>(a2, view.g.k);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount launch: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_copy launch: ") + cudaGetErrorString(e));
+  k_recount_probe<<<g, 256, 0, s>>>(view, a2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_probe launch: ") + cudaGetErrorString(e));
   if (t.n_units) {
     k_recount_tail<<<(t.n_units + 127) / 128, 128, 0, s>>>(t);
     e = cudaGetLastError();

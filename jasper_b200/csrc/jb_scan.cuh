@@ -90,6 +90,7 @@ struct EventArgs {
   uint32_t* events;
   uint32_t* weak;
   uint32_t* events_l1;      // pre-zeroed
+  uint32_t* events_l2;      // pre-zeroed: bit w = level-1 word w is not empty
   uint32_t solid_thre;
   int k;
 };

@@ -117,6 +117,7 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   const Verdict2* verdicts2; // k_verdicts2 output, same index; may be null
   const uint32_t* ev;        // event words of this contig (bit p of the pass-start sequence); may be null
   const uint32_t* ev_l1;     // level-1 summary over FLAT bit positions (1 bit per 1024); may be null
+  const uint32_t* ev_l2;     // level-2 summary (1 bit per 32768 flat positions = one level-1 word); may be null
   uint64_t ev_bit_base;      // flat bit index of contig position 0
   int64_t base;              // old coordinate where this segment starts (0 or an anchor)
   int64_t next_anchor;       // old coordinate of the next segment's anchor, or -1 for the last segment
@@ -1124,6 +1125,31 @@ struct Walker {
       int m = 0;
       while (m < 32 && !s.flag[m]) ++m;
 #endif
+      if (m == 32 && c.ev_l2) {
+        // 32 empty blocks: the level-2 summary leaps over event-free level-1 words (1 M positions per step); the blocks
+        // looked at above run up to (blk + 31), so the search starts at the level-1 word that holds blk + 32
+        const uint64_t w0 = (blk + 32) >> 5, last_w = last_blk >> 5;
+#if defined(__CUDA_ARCH__)
+        int m2;
+        {
+          const uint64_t wq = w0 + (uint64_t)lane;
+          const bool f = wq > last_w || ((c.ev_l2[wq >> 5] >> (wq & 31)) & 1u);
+          const unsigned mm = __ballot_sync(0xffffffffu, f);
+          m2 = mm ? __ffs(mm) - 1 : 32;
+        }
+#else
+        JB_LANES(l2) {
+          uint64_t wq = w0 + (uint64_t)l2;
+          s.flag[l2] = wq > last_w ? 1u : ((c.ev_l2[wq >> 5] >> (wq & 31)) & 1u);
+        }
+        int m2 = 0;
+        while (m2 < 32 && !s.flag[m2]) ++m2;
+#endif
+        // blocks [blk, (w0 + m2) << 5) are empty: [blk, blk + 32) by level 1, whole level-1 words w0 .. w0 + m2 - 1 by level 2,
+        // and the blocks of word (blk + 32) >> 5 below blk + 32 are among the 32 seen above
+        const uint64_t nb = (w0 + (uint64_t)m2) << 5;
+        if (nb > blk + 32) m = (int)(nb - blk);                     // at most 32 + 31 + 32 * 32 blocks
+      }
       if (m >= 2) {
         const int64_t T = (int64_t)(((blk + (uint64_t)m) << 10) - c.ev_bit_base);   // first position of a non-empty block
         if (T - 1 > p2) i += ((T - 1 - p2) / stride) * stride;

@@ -88,7 +88,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
     std::vector<CopyJob> jobv(1 << 18);
     JobSink jobs{jobv.data(), jobv.size(), &jobs_used};
     std::vector<int64_t> len(n);
-    std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n), cnts(n);
+    std::vector<std::vector<uint32_t>> ev(n), weak(n), l1(n), l2(n), cnts(n);
     std::vector<std::vector<uint8_t>> stage(n), okbs(n);
     for (size_t i = 0; i < n; ++i) {
       len[i] = (int64_t)cur[i].size();
@@ -100,6 +100,8 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       l1[i].assign((size_t)(len[i] + 1) / 32768 + 2, 0);
       for (int64_t p = 0; p <= len[i]; ++p)
         if (bit_at(ev[i].data(), p)) l1[i][p >> 15] |= 1u << ((p >> 10) & 31);
+      l2[i].assign(l1[i].size() / 32 + 2, 0);
+      for (size_t w = 0; w < l1[i].size(); ++w) if (l1[i][w]) l2[i][w >> 5] |= 1u << (w & 31);
     }
     // verdicts, the way k_verdicts builds them: one per weak run, published under the run's end
     std::vector<std::vector<uint32_t>> vmaps(n);
@@ -172,7 +174,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       u.weak = use_events ? weak[i].data() : nullptr;
       u.vmap = use_verdicts ? vmaps[i].data() : nullptr; u.verdicts = verdicts[i].data();
       u.verdicts2 = (use_verdicts && use_verdicts2) ? verdicts2[i].data() : nullptr;
-      u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_bit_base = 0;
+      u.ev = use_events ? ev[i].data() : nullptr; u.ev_l1 = use_events ? l1[i].data() : nullptr; u.ev_l2 = (use_events && !getenv("JB_SIM_NO_L2")) ? l2[i].data() : nullptr; u.ev_bit_base = 0;
       u.base = p.base; u.next_anchor = p.next_anchor; u.unit = p.unit; u.seg = p.seg; u.gen = gen;
       u.slot = slot; u.materialize_all = gen ? 1u : 0u;
   u.keep_margin = keep_margin;

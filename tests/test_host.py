@@ -325,3 +325,37 @@ def test_compact_table_tombstones_and_singular_matrix(tmp_path):
     synth.write_jf(q, lo, np.zeros(len(lo), dtype=np.uint64), np.ones(len(lo), dtype=np.uint64), 25, jellyfish_like=False)
     st, msg = helpers.table_sim_check(sim, q)
     assert st["layout"] == 0 and "singular" in msg
+
+
+def test_long_clean_stretches_hop_by_the_level2_summary(tmp_path, hostsim_lib, monkeypatch):
+    """A 0.8 Mb contig with a handful of errors: the walker leaps the clean megabases through the 1-per-32768 summary
+    (fast_hop); with and without it, and against the oracle, the result is the same."""
+    rng = np.random.default_rng(77)
+    k, thr = 25, 3
+    g = synth.random_genome(800_000, rng)
+    lo, hi = synth.canonical_keys(g, k)
+    lo, hi, cnt = synth.unique_keys(lo, hi, np.full(len(lo), 20, dtype=np.int64))
+    path = os.path.join(str(tmp_path), "clean.jf")
+    synth.write_jf(path, lo, hi, cnt, k, seed=5)
+    a = g.copy()
+    for at in (40_011, 41_500, 500_007, 799_950):          # substitutions: two near each other, hundreds of kilobases between the rest
+        a[at] = (a[at] + 1) % 4
+    a = np.delete(a, [230_123])                                     # and one deletion
+    recs = [("long", synth.codes_to_bytes(a).decode()), ("short", synth.codes_to_bytes(g[:5000]).decode())]
+    odb = helpers.OracleDB(path)
+    res, _ = helpers.oracle_polish(odb, recs, k, thr, 2)
+    assert res is not None and res.seqs[0][1] == synth.codes_to_bytes(g).decode()
+    got = {}
+    for no_l2 in ("", "1"):
+        if no_l2:
+            monkeypatch.setenv("JB_SIM_NO_L2", "1")
+        else:
+            monkeypatch.delenv("JB_SIM_NO_L2", raising=False)
+        for use_events in (1, 4096):
+            st, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, recs, k, thr, 2, use_events)
+            assert st == 0
+            assert txt == helpers.rows_text(res.passes, [n for n, _ in recs])
+            assert out == [s for _, s in res.seqs]
+            assert tallies == [(p.wrong, p.total) for p in res.passes]
+            got[(no_l2, use_events)] = (txt, out, tallies)
+    assert len(set(map(repr, got.values()))) == 1
