@@ -294,6 +294,10 @@ struct Workspace {
   DevBuf<unsigned int> next;
   DevBuf<BridgeScratch> pool; DevBuf<uint32_t> trie; DevBuf<uint8_t> patch; DevBuf<uint32_t> busy;
   bool pool_ready = false;
+  // grown bridging pool: a few slots with a much larger trie, allocated when a search outgrew a standard slot (kTrieFull)
+  DevBuf<BridgeScratch> pool_big; DevBuf<uint32_t> trie_big; DevBuf<uint8_t> patch_big; DevBuf<uint32_t> busy_big;
+  uint32_t big_nodes = 0;
+  void release_big_pool() { pool_big.release(); trie_big.release(); patch_big.release(); busy_big.release(); big_nodes = 0; }
   PinBuf<uint8_t> h_in;                     // staged input bases
   PinBuf<UnitIO> h_segs;
   PinBuf<long long> h_anchors;
@@ -309,7 +313,7 @@ struct Workspace {
     buf[0].release(); buf[1].release(); stage.release(); counts[0].release(); counts[1].release(); okb[0].release(); okb[1].release(); slot_unit.release(); scan_units_new.release(); events.release(); weak.release(); events_l1.release(); events_l2.release(); vmap.release(); verdicts.release(); verdicts2.release(); verdict_unit.release(); dry_out.release(); order.release();
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
-    trie.release(); patch.release(); busy.release();
+    trie.release(); patch.release(); busy.release(); release_big_pool();
     h_in.release(); h_segs.release(); h_anchors.release(); h_rows[0].release(); h_rows[1].release(); h_aux[0].release(); h_aux[1].release(); h_used.release();
     if (s2) cudaStreamDestroy(s2);
     if (ev_walk) cudaEventDestroy(ev_walk);
@@ -629,6 +633,29 @@ int small_d2h(void* dst, const void* src, size_t n, bool by_kernel, cudaStream_t
   return JB_OK;
 }
 
+// The grown bridging pool: kBigPoolSlots slots whose tries take up to half of the free device memory (at most 2^30 - 1 nodes
+// each: a node id occupies 30 bits of its child's entry).  Released when the batch has been polished.
+constexpr uint32_t kBigPoolSlots = 4;
+int ensure_big_pool(Workspace& w, cudaStream_t s) {
+  if (w.big_nodes) return JB_OK;
+  size_t free_b = 0, total_b = 0;
+  JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t nodes = std::min<uint64_t>((1ull << 30) - 1, free_b / 2 / ((uint64_t)kBigPoolSlots * 4));
+  if (const char* e = getenv("JB_BIG_TRIE_NODES")) nodes = std::min<uint64_t>(nodes, (uint64_t)atoll(e));    // tests: exhaust the grown pool too
+  if (nodes <= kTrieCap) return fail(JB_E_NOMEM, "no device memory left to grow the de-Bruijn path pool");
+  if (w.pool_big.ensure(kBigPoolSlots) || w.trie_big.ensure((size_t)kBigPoolSlots * nodes) || w.patch_big.ensure((size_t)kBigPoolSlots * kPatchCap) ||
+      w.busy_big.ensure(kBigPoolSlots)) {
+    w.release_big_pool();
+    return fail(JB_E_NOMEM, "out of device memory while growing the de-Bruijn path pool");
+  }
+  JB_CUDA(cudaMemsetAsync(w.busy_big.p, 0, (size_t)kBigPoolSlots * 4, s));
+  k_init_pool<<<1, 128, 0, s>>>(w.pool_big.p, (int)kBigPoolSlots, w.trie_big.p, (uint32_t)nodes, w.patch_big.p, kPatchCap);
+  JB_CUDA(cudaGetLastError());
+  w.big_nodes = (uint32_t)nodes;
+  add_counter("pool_growths", 1);
+  return JB_OK;
+}
+
 int64_t pick_seg_block(int64_t total_len, int sms) {
   // (multiples of 32: k_find_anchors walks whole bitmask words)
   if (const char* e = getenv("JB_SEG_BLOCK")) { long v = atol(e); if (v >= 64) return (v + 31) / 32 * 32; if (v == 0) return 0; }
@@ -872,8 +899,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     mark("scan+anchors done", ite);
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
     const size_t n_first = plan.size();
-    JB_TRY(w.segs.ensure(n_first + n)); JB_TRY(w.h_segs.ensure(n_first + n));     // room for whole-contig re-runs behind the plan
-    JB_TRY(w.order.ensure(n_first + n)); JB_TRY(w.dst_off.ensure(n_first + n));
+    JB_TRY(w.segs.ensure(n_first + 2 * n)); JB_TRY(w.h_segs.ensure(n_first + 2 * n));     // room for two rounds of whole-contig re-runs behind the plan
+    JB_TRY(w.order.ensure(n_first + 2 * n)); JB_TRY(w.dst_off.ensure(n_first + 2 * n));
     UnitIO* hs = w.h_segs.p;
     for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin, cidx);
     // queue order: the few long segments (stretches without an anchor) first, the rest as planned
@@ -906,49 +933,75 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     mark("walk done", ite);
     { float m2 = 0; cudaEventElapsedTime(&m2, ev_c, ev_e); kwalk_ms += m2; }
     n_segments += (int64_t)n_first;
-    // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment
+    // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment; a contig whose
+    // de-Bruijn search outgrew a standard trie (kTrieFull) is walked again with the grown pool
     std::vector<uint8_t> redo(n, 0);
-    size_t n_redo = 0, n_slots = n_first;
+    std::vector<uint32_t> todo;
+    bool need_big = false;
+    size_t n_slots = n_first;
     for (size_t q = 0; q < n_first; ++q) {
       const UnitIO& u = hs[q];
       if (!u.status) continue;
       const bool split = plan[q].n_segs > 1;
-      if (u.status == kFarBack || (split && (u.status == kSeamViolation || u.status == JB_E_SCRATCH))) { if (!redo[u.unit]) { redo[u.unit] = 1; ++n_redo; } continue; }
+      if (u.status == kTrieFull || u.status == kFarBack || (split && (u.status == kSeamViolation || u.status == JB_E_SCRATCH))) {
+        need_big = need_big || u.status == kTrieFull;
+        if (!redo[u.unit]) { redo[u.unit] = 1; todo.push_back(u.unit); }
+        continue;
+      }
       b->status = u.status;
       return fail(JB_E_SCRATCH, "contig " + std::to_string(u.unit) + ": a device work pool overflowed during polishing "
-                                "(output slack, fix-row arena, or de-Bruijn path pool; status " + std::to_string(u.status) + ")");
+                                "(output slack, fix-row arena, or copy-job arena; status " + std::to_string(u.status) + ")");
     }
     std::vector<UnitIO> segs;                            // accepted segments in (contig, segment) order
-    if (n_redo) {
-      size_t na = 0;
-      UnitIO* again = hs + n_first;
-      for (size_t i = 0; i < n; ++i) if (redo[i]) { again[na] = make_seg(b, whole_contig((uint32_t)i, caps[i]), in, 1, (uint32_t)(n_first + na), keep_margin, cidx); ++na; }
-      std::vector<uint32_t> ord2(na);
-      for (size_t q = 0; q < na; ++q) ord2[q] = (uint32_t)(n_first + q);
-      JB_CUDA(cudaMemcpyAsync(w.segs.p + n_first, again, na * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
-      JB_CUDA(cudaMemcpyAsync(w.order.p, ord2.data(), na * 4, cudaMemcpyHostToDevice, s));
-      JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
-      k_walk<<<walk_grid(na), kWalkWarps * 32, 0, s>>>(view, w.segs.p, w.order.p, (uint32_t)na, c2, pool, sink, jobs, w.next.p);
-      JB_CUDA(cudaGetLastError());
-      ++launches;
-      JB_CUDA(cudaMemcpyAsync(again, w.segs.p + n_first, na * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
-      JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
-      JB_CUDA(cudaStreamSynchronize(s));
-      n_reruns += (int64_t)na;
-      size_t ai = 0;
+    if (!todo.empty()) {
+      std::sort(todo.begin(), todo.end());
+      std::vector<UnitIO> redone(n);
+      bool use_big = need_big;
+      for (uint32_t round = 1; !todo.empty(); ++round) {
+        BridgePool rp = pool;
+        if (use_big) {
+          if (int rc = ensure_big_pool(w, s)) return rc;
+          rp = BridgePool{w.pool_big.p, kBigPoolSlots, w.busy_big.p};
+        }
+        const size_t na = todo.size();
+        UnitIO* again = hs + n_slots;
+        std::vector<uint32_t> ord2(na);
+        for (size_t q = 0; q < na; ++q) {
+          again[q] = make_seg(b, whole_contig(todo[q], caps[todo[q]]), in, round, (uint32_t)(n_slots + q), keep_margin, cidx);
+          ord2[q] = (uint32_t)(n_slots + q);
+        }
+        JB_CUDA(cudaMemcpyAsync(w.segs.p + n_slots, again, na * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaMemcpyAsync(w.order.p, ord2.data(), na * 4, cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
+        k_walk<<<walk_grid(na), kWalkWarps * 32, 0, s>>>(view, w.segs.p, w.order.p, (uint32_t)na, c2, rp, sink, jobs, w.next.p);
+        JB_CUDA(cudaGetLastError());
+        ++launches;
+        JB_CUDA(cudaMemcpyAsync(again, w.segs.p + n_slots, na * sizeof(UnitIO), cudaMemcpyDeviceToHost, s));
+        JB_CUDA(cudaMemcpyAsync(used, w.used.p, 32, cudaMemcpyDeviceToHost, s));
+        JB_CUDA(cudaStreamSynchronize(s));
+        n_reruns += (int64_t)na;
+        std::vector<uint32_t> next_todo;
+        for (size_t q = 0; q < na; ++q) {
+          const UnitIO& u = again[q];
+          if (!u.status) { redone[u.unit] = u; continue; }
+          if (u.status == kTrieFull && !use_big) { next_todo.push_back(u.unit); continue; }
+          b->status = u.status;
+          if (u.status == kTrieFull)
+            return fail(JB_E_SCRATCH, "contig " + std::to_string(u.unit) + ": the de-Bruijn path search (src/jasper.py:527-583) needs more than " +
+                                      std::to_string(w.big_nodes) + " path extensions for one stretch; the grown pool is exhausted");
+          return fail(JB_E_SCRATCH, "contig " + std::to_string(u.unit) + ": a device work pool overflowed during polishing (status " + std::to_string(u.status) + ")");
+        }
+        n_slots += na;
+        todo.swap(next_todo);
+        use_big = true;
+      }
       for (size_t q = 0; q < n_first;) {
         const uint32_t unit = hs[q].unit;
         if (redo[unit]) {
-          const UnitIO& u = again[ai++];
-          if (u.status) {
-            b->status = u.status;
-            return fail(JB_E_SCRATCH, "contig " + std::to_string(unit) + ": a device work pool overflowed during polishing (status " + std::to_string(u.status) + ")");
-          }
-          segs.push_back(u);
+          segs.push_back(redone[unit]);
           while (q < n_first && hs[q].unit == unit) ++q;
         } else segs.push_back(hs[q++]);
       }
-      n_slots = n_first + na;
     } else {
       segs.assign(hs, hs + n_first);
     }
@@ -1089,6 +1142,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   }
   note_counter("verdicts", n_verdicts); note_timing("polish_verdicts", verdict_ms); note_counter("verdict2_events", n_v2); note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
   cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
+  w.release_big_pool();
   b->polished = true;
   while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});
   return JB_OK;

@@ -95,6 +95,7 @@ struct BridgeScratch {       // global memory, one per resident walker
 constexpr uint8_t kTagBridge = 0xFF;      // Verdict2.tag of a bridged multi-error patch
 enum PostKind : int { kPostNone = 0, kPostSub = 1, kPostDel = 2, kPostIns = 3 };
 constexpr int kFarBack = -102;            // walker status: it needed bases behind its materialised window
+constexpr int kTrieFull = -103;           // walker status: the de-Bruijn search outgrew its trie (the host re-walks the contig with a grown pool)
 constexpr int64_t kMinGap = 256;          // clean stretches longer than this are not materialised
 JB_HD int default_keep_margin(int k) { return 2 * k + 32; }
 
@@ -608,7 +609,7 @@ struct Walker {
   // (k chars), s.b holds good_k_mer_after (k chars).  Returns patch length (>= 1) with the patch in
   // bs->patch, 0 for "None".
   JB_W uint32_t trie_new(uint32_t parent, uint32_t base, uint32_t& n_nodes) {
-    if (n_nodes >= bs->trie_cap) { status = JB_E_SCRATCH; return 0; }
+    if (n_nodes >= bs->trie_cap) { status = kTrieFull; return 0; }
     uint32_t id = n_nodes++;
     JB_LANES(l) { if (l == 0) bs->trie[id] = (parent << 2) | base; }
     return id;

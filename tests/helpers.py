@@ -19,6 +19,7 @@ from jasper_b200 import synth  # noqa: E402
 
 GOLDEN_NAMES = ["k25_mix", "k37_mix", "k31_dirty", "k21_even"]
 # fuzz cases through the UNMODIFIED reference, chosen for the rare branches (tests/golden/make_golden_branches.py)
+DEEP_BRIDGE = "branches/deep_bridge"     # a de-Bruijn search of > 1 M path extensions (tests/golden/make_golden_deep_bridge.py)
 BRANCH_GOLDENS = ["branches/s32", "branches/s99", "branches/s278", "branches/s377", "branches/s5", "branches/s9", "branches/s39", "branches/s66"]
 ALL_BRANCHES = ["add_base", "bridge", "drop_base", "grow_run", "grow_single", "rolling_ok", "rolling_weak", "shrink_run", "shrink_single", "substitution",
                 "two_ended_e", "two_ended_s", "unfixed_k", "unfixed_long", "unfixed_short"]
@@ -125,6 +126,8 @@ def hostsim_lib():
     sim.hostsim_segments.argtypes = [C.c_void_p]
     sim.hostsim_reruns.restype = C.c_ulonglong
     sim.hostsim_reruns.argtypes = [C.c_void_p]
+    sim.hostsim_pool_growths.restype = C.c_ulonglong
+    sim.hostsim_pool_growths.argtypes = [C.c_void_p]
     for fn in (sim.hostsim_events, sim.hostsim_fast, sim.hostsim_post, sim.hostsim_v2):
         fn.restype = C.c_ulonglong
         fn.argtypes = [C.c_void_p]
@@ -203,6 +206,7 @@ def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=No
         if stats is not None:
             stats["segments"] = sim.hostsim_segments(r)
             stats["reruns"] = sim.hostsim_reruns(r)
+            stats["pool_growths"] = sim.hostsim_pool_growths(r)
             stats["events"] = sim.hostsim_events(r)
             stats["fast"] = sim.hostsim_fast(r)
             stats["post"] = sim.hostsim_post(r)

@@ -26,7 +26,7 @@ struct SimResult {
   std::vector<PassOut> passes;
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
-  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0, v2 = 0;
+  unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0, v2 = 0, pool_growths = 0;
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
@@ -188,7 +188,7 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, segs[q], ws, pool, sink, jobs);
       w.run();
       if (segs[q].status) {
-        if (segs[q].status == kFarBack || (plan[q].n_segs > 1 && (segs[q].status == kSeamViolation || segs[q].status == JB_E_SCRATCH))) {
+        if (segs[q].status == kTrieFull || segs[q].status == kFarBack || (plan[q].n_segs > 1 && (segs[q].status == kSeamViolation || segs[q].status == JB_E_SCRATCH))) {
           redo[plan[q].unit] = 1; any_redo = true;
           if (segs[q].status == kFarBack) ++res->far_backs;
         }
@@ -209,8 +209,18 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
         const uint32_t unit = segs[q].unit;
         if (!redo[unit]) { merged.push_back(segs[q++]); continue; }
         UnitIO u = make_seg(whole_contig(unit, caps[unit]), 1, (uint32_t)n_slots++);
-        Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink, jobs);
-        w.run();
+        {
+          Walker<HostDB> w(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink, jobs);
+          w.run();
+        }
+        if (u.status == kTrieFull && trie.size() < (1u << 26)) {      // the product's ladder: once more with the grown pool
+          trie.assign(1u << 26, 0);
+          bs.trie = trie.data(); bs.trie_cap = (uint32_t)trie.size();
+          ++res->pool_growths;
+          u = make_seg(whole_contig(unit, caps[unit]), 2, (uint32_t)n_slots++);
+          Walker<HostDB> w2(db, k, sampling_step(k), solid, do_fix, u, ws, pool, sink, jobs);
+          w2.run();
+        }
         if (u.status) { res->status = u.status; return res; }
         merged.push_back(u);
         ++res->reruns;
@@ -291,6 +301,7 @@ extern "C" unsigned long long hostsim_post(const SimResult* r) { return r->post;
 extern "C" unsigned long long hostsim_v2(const SimResult* r) { return r->v2; }
 extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->segments; }
 extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
+extern "C" unsigned long long hostsim_pool_growths(const SimResult* r) { return r->pool_growths; }
 extern "C" unsigned long long hostsim_far_backs(const SimResult* r) { return r->far_backs; }
 extern "C" void hostsim_free(SimResult* r) { delete r; }
 

@@ -122,6 +122,33 @@ def test_polish_reproduces_reference_bytes_on_rare_branches(tmp_path, monkeypatc
         qf.close()
 
 
+def test_deep_bridge_rewalks_with_the_grown_pool(tmp_path, monkeypatch):
+    """tests/golden/branches/deep_bridge (bytes of the unmodified reference): one de-Bruijn search of more than a million path
+    extensions.  A standard bridging slot (1 M trie nodes) overflows, the walker reports kTrieFull, the library grows the pool and
+    re-walks that contig alone -- same bytes as the reference; with the grown pool capped too, the call fails with JB_E_SCRATCH and
+    says which contig."""
+    case = helpers.load_golden(helpers.DEEP_BRIDGE, str(tmp_path))
+    seqs = jo.read_fasta(case["fasta"])
+    qf = capi.QueryMerFile(case["db"])
+    try:
+        before = capi.counter("pool_growths")
+        res = qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+        assert res.status == 0
+        assert capi.counter("pool_growths") > before
+        assert res.counters["segment_reruns"] >= 1
+        for ite in range(case["passes"]):
+            assert jo.format_fix_csv(res.rows[ite]) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+        assert jo.format_fasta(res.seqs) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+        assert ("%d %d\n" % res.tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
+        assert ("%d %d\n" % res.tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
+        monkeypatch.setenv("JB_BIG_TRIE_NODES", str((1 << 20) + 4096))
+        with pytest.raises(capi.JasperError) as ei:
+            qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+        assert ei.value.code == -8 and "contig 0" in str(ei.value)          # JB_E_SCRATCH
+    finally:
+        qf.close()
+
+
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 @pytest.mark.parametrize("seg_block,margin", [("0", None), ("64", None), ("256", "0"), ("2048", None)])
 def test_polish_golden_is_independent_of_segmentation(golden_cases, dbs, name, seg_block, margin, monkeypatch):

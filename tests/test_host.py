@@ -359,3 +359,22 @@ def test_long_clean_stretches_hop_by_the_level2_summary(tmp_path, hostsim_lib, m
             assert tallies == [(p.wrong, p.total) for p in res.passes]
             got[(no_l2, use_events)] = (txt, out, tallies)
     assert len(set(map(repr, got.values()))) == 1
+
+
+def test_deep_bridge_outgrows_the_standard_trie(tmp_path, hostsim_lib):
+    """tests/golden/branches/deep_bridge (bytes of the unmodified reference): thousands of live paths for hundreds of rounds.
+    The walker source runs out of the standard 1 M-node trie, reports kTrieFull, and the re-walk with the grown pool gives the
+    reference's bytes."""
+    case = helpers.load_golden(helpers.DEEP_BRIDGE, str(tmp_path))
+    seqs = jo.read_fasta(case["fasta"])
+    odb = helpers.OracleDB(case["db"])
+    names = [n for n, _ in seqs]
+    st = {}
+    status, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], 300, stats=st)
+    assert status == 0 and st["pool_growths"] >= 1
+    for ite in range(case["passes"]):
+        rows = [[names[int(f[1])], int(f[2]), f[3], f[4]] for f in (l.split("\t") for l in txt.splitlines()) if f[0] == str(ite)]
+        assert jo.format_fix_csv(rows) == helpers.expected_file(case, "_iter%d_asm.fa.fix.csv" % ite)
+    assert jo.format_fasta(list(zip(names, out))) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
+    assert ("%d %d\n" % tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
+    assert ("%d %d\n" % tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
