@@ -3,14 +3,17 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <new>
 
 namespace jb {
 namespace {
 
 constexpr int kMatch = 0, kMismatch = -1, kOpen = -1, kExtend = -1;
 
-inline long gap_cost(long length, long open) {       // open + extend*length - extend, 0 for length <= 0
-  return length <= 0 ? 0 : open + (long)kExtend * length - kExtend;
+// scores stay within +-(la + lb + 2): 32 bits are plenty (patches are capped at 256 K bases)
+using score_t = int32_t;
+inline score_t gap_cost(score_t length, score_t open) {       // open + extend*length - extend, 0 for length <= 0
+  return length <= 0 ? 0 : open + (score_t)kExtend * length - kExtend;
 }
 
 struct Frame {
@@ -38,36 +41,38 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
     if (unique) { *out_a = A; *out_b = B; return true; }
   }
   const int W = lb + 1;
+  // 5 bytes per cell: a patch of tens of kb against its original would need gigabytes -- refuse cleanly (the row thread reports it)
+  if ((uint64_t)(la + 1) * (uint64_t)W > (1ull << 31)) throw std::bad_alloc();
   // (thousands of short alignments per pass on the row threads: keep the matrices between calls)
-  static thread_local std::vector<long> score_tl;
+  static thread_local std::vector<score_t> score_tl;
   static thread_local std::vector<uint8_t> trace_tl;
-  static thread_local std::vector<long> col_score_tl;
+  static thread_local std::vector<score_t> col_score_tl;
   score_tl.assign((size_t)(la + 1) * W, 0);
   trace_tl.assign((size_t)(la + 1) * W, 0);
   col_score_tl.assign(lb + 1, 0);
-  long* const score = score_tl.data();                  // (one TLS lookup each, not one per matrix access)
+  score_t* const score = score_tl.data();                  // (one TLS lookup each, not one per matrix access)
   uint8_t* const trace = trace_tl.data();
-  long* const col_score = col_score_tl.data();
-  const long first_gap = gap_cost(1, kOpen);
+  score_t* const col_score = col_score_tl.data();
+  const score_t first_gap = gap_cost(1, kOpen);
   for (int i = 0; i <= la; ++i) score[(size_t)i * W] = gap_cost(i, kOpen);
   for (int j = 0; j <= lb; ++j) score[j] = gap_cost(j, kOpen);
   for (int j = 1; j <= lb; ++j) col_score[j] = gap_cost(j, 2 * kOpen);
   for (int row = 1; row <= la; ++row) {
-    long row_score = gap_cost(row, 2 * kOpen);
-    const long* up = score + (size_t)(row - 1) * W;     // (row pointers: the index arithmetic was a third of the loop)
-    long* cur = score + (size_t)row * W;
+    score_t row_score = gap_cost(row, 2 * kOpen);
+    const score_t* up = score + (size_t)(row - 1) * W;     // (row pointers: the index arithmetic was a third of the loop)
+    score_t* cur = score + (size_t)row * W;
     uint8_t* tcur = trace + (size_t)row * W;
     const char ar = A[row - 1];
     for (int col = 1; col <= lb; ++col) {
-      const long nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
-      const long row_open = cur[col - 1] + first_gap;
-      const long row_extend = row_score + kExtend;
+      const score_t nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
+      const score_t row_open = cur[col - 1] + first_gap;
+      const score_t row_extend = row_score + kExtend;
       row_score = row_open > row_extend ? row_open : row_extend;
-      const long col_open = up[col] + first_gap;
-      const long col_extend = col_score[col] + kExtend;
-      const long cs = col_open > col_extend ? col_open : col_extend;
+      const score_t col_open = up[col] + first_gap;
+      const score_t col_extend = col_score[col] + kExtend;
+      const score_t cs = col_open > col_extend ? col_open : col_extend;
       col_score[col] = cs;
-      long best = nogap > cs ? nogap : cs;
+      score_t best = nogap > cs ? nogap : cs;
       if (row_score > best) best = row_score;
       cur[col] = best;
       int t = nogap == best ? 2 : 0;
@@ -125,11 +130,11 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
         else {
           col_gap = !in_a;
           const int target = in_a ? col : row;
-          const long target_score = sc(row, col);
+          const score_t target_score = sc(row, col);
           for (int n = 0; n < target; ++n) {
             if (in_a) { --col; a.push_back('-'); b.push_back(B[col]); }
             else { --row; a.push_back(A[row]); b.push_back('-'); }
-            long actual = sc(row, col) + gap_cost(n + 1, kOpen);
+            score_t actual = sc(row, col) + gap_cost(n + 1, kOpen);
             if (actual == target_score && n > 0) {
               if (!tr(row, col)) break;
               stack.push_back(Frame{a, b, row, col, col_gap, tr(row, col)});

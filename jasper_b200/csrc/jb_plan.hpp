@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <atomic>
 #include <functional>
+#include <new>
+#include <stdexcept>
 #include <cstdint>
 #include <cstdlib>
 #include <thread>
@@ -157,7 +159,10 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
         while (sl >= slot0[q + 1]) ++q;
         if (at[sl] == 0xFFFFFFFFu) continue;
         const DevRow& r = rows[at[sl]];
-        if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)t])) part_ok[(size_t)t] = 0;
+        // (nothing may throw past this point: the other workers wait at the barrier, and an exception that leaves a thread
+        //  ends the process -- the alignment matrices of a very long bridged patch are the realistic std::bad_alloc)
+        try { if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)t])) part_ok[(size_t)t] = 0; }
+        catch (const std::exception&) { part_ok[(size_t)t] = 2; }
       }
     }
     barrier(2);
@@ -187,7 +192,10 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
     for (auto& th : pool) th.join();
   }
   bool ok = true;
-  for (int t = 0; t < n_thr; ++t) ok = ok && part_ok[(size_t)t];
+  for (int t = 0; t < n_thr; ++t) {
+    if (part_ok[(size_t)t] == 2) throw std::bad_alloc();          // on the calling thread, where the caller catches it
+    ok = ok && part_ok[(size_t)t];
+  }
   return ok;
 }
 

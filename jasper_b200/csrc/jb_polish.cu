@@ -705,6 +705,7 @@ struct RowJob {
   std::vector<size_t> first_seg;
   PassOut out;
   bool ok = true;
+  bool nomem = false;        // the host-side alignment of a bridged patch ran out of memory
   size_t pass = 0;
   int buf = 0;
   std::atomic<bool> copied{true};
@@ -727,7 +728,9 @@ int finish_rows(jb_batch* b, PendingRows* pr, std::vector<std::unique_ptr<RowJob
   j->th = std::thread([raw, src_rows, src_aux, n_rows, trace]() {
     // straight from the pinned log (the next pass's log is not copied into it before `copied` is set)
     const auto t0 = std::chrono::steady_clock::now();
-    raw->ok = rows_in_order(src_rows, n_rows, src_aux, raw->segs, raw->place, raw->first_seg, &raw->out);
+    // (an exception must not leave this thread: std::terminate would take the host process down)
+    try { raw->ok = rows_in_order(src_rows, n_rows, src_aux, raw->segs, raw->place, raw->first_seg, &raw->out); }
+    catch (const std::exception&) { raw->ok = false; raw->nomem = true; }
     raw->copied.store(true, std::memory_order_release);
     if (trace) fprintf(stderr, "[jb trace] row thread: %zu log rows -> %zu csv rows in %.3f ms\n", n_rows, raw->out.rows.size(),
                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
@@ -741,7 +744,7 @@ void join_rows(jb_batch* b, std::vector<std::unique_ptr<RowJob>>* jobs) {
   for (auto& j : *jobs) {
     if (j->th.joinable()) j->th.join();
     if (j->pass < b->passes.size()) { b->passes[j->pass].rows.swap(j->out.rows); b->passes[j->pass].spill.swap(j->out.spill); }
-    if (!j->ok) b->status = JB_E_REFERENCE_CRASH;          // exit 1 in the reference
+    if (!j->ok) b->status = j->nomem ? JB_E_NOMEM : JB_E_REFERENCE_CRASH;          // (the latter: exit 1 in the reference)
   }
   jobs->clear();
 }
