@@ -456,7 +456,7 @@ class QueryMerFile(object):
             out.timings[key] = timing_ms(key)
         for key in ("scan_lookups", "walk_lookups", "kernel_launches", "events", "probe_steps", "h2d_bytes", "d2h_bytes",
                     "segments", "segment_reruns", "seg_block", "full_scans", "full_scan_lookups", "recount_probes", "max_seg_events", "max_seg_lookups", "max_seg_span",
-                    "verdicts", "fast_events", "fast_steps", "verdict2_events"):
+                    "verdicts", "fast_events", "fast_steps", "verdict2_events", "speculative_passes"):
             out.counters[key] = counter(key)
         return out
 

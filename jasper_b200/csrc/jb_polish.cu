@@ -185,13 +185,12 @@ __global__ void k_store_host(uint8_t* __restrict__ dst, const uint8_t* __restric
   for (size_t q = nv * 16 + i; q < n; q += nth) dst[q] = src[q];
 }
 
-// dst[0:n) = src[0:n), the CTAs of one grid row share the job; 16-byte stores, byte-funnelled loads when
-// the two streams are misaligned against each other (indels shift them)
-__device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int64_t n) {
+// dst[0:n) = src[0:n) by threads tid of nth; 16-byte stores, byte-funnelled loads when the two streams are misaligned
+// against each other (indels shift them)
+__device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int64_t n, int64_t tid, int64_t nth) {
   if (n <= 0) return;
   int64_t head = (int64_t)((16 - ((uintptr_t)dst & 15)) & 15);
   if (head > n) head = n;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = tid; q < head; q += nth) dst[q] = src[q];
   const int64_t nvec = (n - head) / 16;
   const uint8_t* s2 = src + head;
@@ -214,15 +213,89 @@ __device__ __forceinline__ void copy_span(const uint8_t* src, uint8_t* dst, int6
   for (int64_t q = head + nvec * 16 + tid; q < n; q += nth) dst[q] = src[q];
 }
 
-// every copy job of an accepted segment: outb[dst_off[slot] + rel ...) = src[0:len); superseded slots have dst_off < 0
-__global__ void k_concat(const CopyJob* jobs, const unsigned long long* n_jobs, const int64_t* dst_off, uint8_t* outb) {
-  const unsigned long long n = *n_jobs;
-  for (unsigned long long j = blockIdx.y; j < n; j += gridDim.y) {
+// every copy job of an accepted segment: outb[dst_off[slot] + rel ...) = src[0:len); superseded slots have dst_off < 0.
+// Fixed 1-D grid, the job list shared out on the device (job_split): launched right behind k_place, no host in between.
+__global__ void __launch_bounds__(256)
+k_concat(const CopyJob* jobs, const unsigned long long* n_jobs, unsigned long long jobs_cap, const int64_t* dst_off, uint8_t* outb) {
+  const unsigned long long n = min(*n_jobs, jobs_cap);
+  const JobSplit sp = job_split(n, false, 128u);
+  for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
     const CopyJob job = jobs[j];
     const int64_t off = dst_off[job.slot];
     if (off < 0) continue;
-    copy_span(job.src, outb + off + job.rel, job.len);
+    copy_span(job.src, outb + off + job.rel, job.len, sp.tid, sp.nth);
   }
+}
+
+// ---- placement on the device: between k_walk and k_concat nothing waits for the host ------------------------------------
+// what a walker reports about its segment, compact (the descriptors are 200+ bytes apiece)
+struct SegOut {
+  int64_t end_old, new_len, wrong;
+  int32_t status; uint32_t n_rows, n_fast, n_post, n_v2, pad;
+  unsigned long long lookups, events, cycles;
+};
+__global__ void k_seg_gather(const UnitIO* __restrict__ segs, uint32_t n, SegOut* __restrict__ out, unsigned long long* flag) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const UnitIO& u = segs[q];
+  SegOut o;
+  o.end_old = u.end_old; o.new_len = u.new_len; o.wrong = u.wrong; o.status = u.status; o.n_rows = u.n_rows; o.n_fast = u.n_fast;
+  o.n_post = u.n_post; o.n_v2 = u.n_v2; o.pad = 0; o.lookups = u.lookups; o.events = u.events; o.cycles = u.cycles;
+  out[q] = o;
+  if (u.status) atomicOr(flag, 1ull);
+}
+
+// One CTA.  Segments are in (contig, segment) order, slot q = segment q: the offset of a segment's new bases inside its
+// new contig is the running sum of the new lengths before it (jb_plan.hpp, place_segments); the contigs' new lengths fall
+// out of the same sums.  If any segment failed, or a contig outgrew its region, nothing is placed (every dst_off < 0, the
+// old lengths kept): k_concat and the recount behind this launch then do nothing and the host takes the slow path.
+struct PlaceArgs {
+  const SegOut* so; uint32_t n_segs;
+  const uint32_t* seg_unit;      // per segment: its contig
+  const uint32_t* unit_first;    // per contig: index of its first segment; [n_units] = n_segs
+  const ScanUnit* units_old; const int64_t* caps; uint32_t n_units;
+  int64_t* prefix;               // scratch, n_segs + 1
+  int64_t* dst_off; uint32_t* slot_unit; ScanUnit* units_new;
+  unsigned long long* flag;      // in: bit 0 = a segment failed; out: bit 1 = a contig outgrew its region
+};
+constexpr int kPlaceThreads = 1024;
+__global__ void __launch_bounds__(kPlaceThreads)
+k_place(PlaceArgs a) {
+  __shared__ int64_t part[kPlaceThreads];
+  __shared__ unsigned int bad;
+  const uint32_t t = threadIdx.x, n = a.n_segs;
+  const uint32_t per = (n + kPlaceThreads - 1) / kPlaceThreads;
+  const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+  int64_t sum = 0;
+  for (uint32_t q = lo; q < hi; ++q) sum += a.so[q].new_len;
+  part[t] = sum;
+  if (t == 0) bad = (*a.flag & 1ull) ? 1u : 0u;
+  __syncthreads();
+  for (int d = 1; d < kPlaceThreads; d <<= 1) {         // inclusive scan of the per-thread sums
+    const int64_t add = t >= (uint32_t)d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  int64_t run = part[t] - sum;
+  for (uint32_t q = lo; q < hi; ++q) { a.prefix[q] = run; run += a.so[q].new_len; }
+  if (t == kPlaceThreads - 1) a.prefix[n] = part[t];
+  __syncthreads();
+  for (uint32_t u = t; u < a.n_units; u += kPlaceThreads)
+    if (a.prefix[a.unit_first[u + 1]] - a.prefix[a.unit_first[u]] > a.caps[u]) atomicOr(&bad, 2u);
+  __syncthreads();
+  const bool ok = bad == 0;
+  for (uint32_t q = t; q < n; q += kPlaceThreads) {
+    const uint32_t u = a.seg_unit[q];
+    a.dst_off[q] = ok ? (int64_t)a.units_old[u].seq_off + a.prefix[q] - a.prefix[a.unit_first[u]] : -1;
+    a.slot_unit[q] = u;
+  }
+  for (uint32_t u = t; u < a.n_units; u += kPlaceThreads) {
+    ScanUnit nu = a.units_old[u];
+    if (ok) nu.len = (uint64_t)(a.prefix[a.unit_first[u + 1]] - a.prefix[a.unit_first[u]]);
+    a.units_new[u] = nu;
+  }
+  if (t == 0 && (bad & 2u)) atomicOr(a.flag, 2ull);
 }
 
 __global__ void k_init_pool(BridgeScratch* pool, int n, uint32_t* trie, uint32_t trie_cap, uint8_t* patch, uint32_t patch_cap) {
@@ -304,6 +377,11 @@ struct Workspace {
   PinBuf<DevRow> h_rows[2];                 // double-buffered: a host thread reads one log while the next lands
   PinBuf<uint8_t> h_aux[2];
   PinBuf<unsigned long long> h_used;
+  // placement on the device (k_seg_gather, k_place) and the pinned staging of everything a pass uploads: the host never
+  // hands the driver pageable memory inside the pass loop (such a copy would wait for the stream first)
+  DevBuf<SegOut> seg_out; PinBuf<SegOut> h_seg_out;
+  DevBuf<uint32_t> seg_unit, unit_first; DevBuf<int64_t> caps_d, prefix;
+  PinBuf<uint8_t> h_geom; PinBuf<uint32_t> h_order, h_seg_unit; PinBuf<int64_t> h_dst_off; PinBuf<unsigned long long> h_probes;
   cudaStream_t s2 = nullptr;                // side stream: fix rows travel while the next pass scans
   cudaEvent_t ev_walk = nullptr, ev_rows = nullptr, ev_concat = nullptr, ev_group = nullptr;
   DevBuf<uint32_t> tile_first_groups;
@@ -314,6 +392,8 @@ struct Workspace {
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release(); release_big_pool();
+    seg_out.release(); h_seg_out.release(); seg_unit.release(); unit_first.release(); caps_d.release(); prefix.release();
+    h_geom.release(); h_order.release(); h_seg_unit.release(); h_dst_off.release(); h_probes.release();
     h_in.release(); h_segs.release(); h_anchors.release(); h_rows[0].release(); h_rows[1].release(); h_aux[0].release(); h_aux[1].release(); h_used.release();
     if (s2) cudaStreamDestroy(s2);
     if (ev_walk) cudaEventDestroy(ev_walk);
@@ -471,7 +551,9 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
   JB_TRY(w.vmap.ensure(total / 32 + 64)); JB_TRY(w.verdicts.ensure(total / 64 + 4096));
   JB_TRY(w.verdicts2.ensure(total / 64 + 4096)); JB_TRY(w.verdict_unit.ensure(total / 64 + 4096));
   JB_TRY(w.scan_units.ensure(n + 1)); JB_TRY(w.seg_units.ensure(n + 1)); JB_TRY(w.tile_first.ensure(n + 2)); JB_TRY(w.block_first.ensure(n + 2));
-  JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(8)); JB_TRY(w.h_used.ensure(8));
+  JB_TRY(w.next.ensure(4)); JB_TRY(w.used.ensure(16)); JB_TRY(w.h_used.ensure(16));
+  JB_TRY(w.unit_first.ensure(n + 2)); JB_TRY(w.caps_d.ensure(n + 1));
+  JB_TRY(w.h_geom.ensure((n + 2) * (4 + 4 + 4 + sizeof(ScanUnit) + sizeof(SegUnit) + 8) + 64));
   JB_TRY(w.rows.ensure(total_len / 32 + 4096)); JB_TRY(w.aux.ensure(total_len / 4 + (1u << 20)));
   for (int q = 0; q < 2; ++q) { JB_TRY(w.h_rows[q].ensure(total_len / 32 + 4096)); JB_TRY(w.h_aux[q].ensure(total_len / 4 + (1u << 20))); }
   JB_TRY(w.jobs.ensure(total_len / 16 + 4 * n + 65536));
@@ -764,15 +846,28 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   cudaStream_t s = db->stream;
   Workspace& w = *b->ws;
   const size_t n = b->n;
-  cudaEvent_t ev_begin, ev_end, ev_a, ev_b, ev_c, ev_d, ev_e;
-  JB_CUDA(cudaEventCreate(&ev_begin)); JB_CUDA(cudaEventCreate(&ev_end)); JB_CUDA(cudaEventCreate(&ev_e));
-  JB_CUDA(cudaEventCreate(&ev_a)); JB_CUDA(cudaEventCreate(&ev_b)); JB_CUDA(cudaEventCreate(&ev_c)); JB_CUDA(cudaEventCreate(&ev_d));
+  // events: destroyed on every way out; one set of timing events per pass (nothing is read before the last pass has run:
+  // the host does not wait for the stream between passes)
+  struct EventBag {
+    std::vector<cudaEvent_t> all;
+    ~EventBag() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+    cudaError_t make(cudaEvent_t* e, unsigned flags = cudaEventDefault) {
+      cudaError_t rc = cudaEventCreateWithFlags(e, flags);
+      if (rc == cudaSuccess) all.push_back(*e);
+      return rc;
+    }
+  } evs;
+  struct PassEvents { cudaEvent_t a, b, c, d, e, r0, r1, v0, v1; bool recount = false, verdicts = false; };
+  std::vector<PassEvents> pev((size_t)passes + 1);
+  for (PassEvents& pe : pev)
+    for (cudaEvent_t* e : {&pe.a, &pe.b, &pe.c, &pe.d, &pe.e, &pe.r0, &pe.r1, &pe.v0, &pe.v1}) JB_CUDA(evs.make(e));
+  cudaEvent_t ev_begin, ev_end, ev_anchors, ev_res;
+  JB_CUDA(evs.make(&ev_begin)); JB_CUDA(evs.make(&ev_end));
+  JB_CUDA(evs.make(&ev_anchors, cudaEventDisableTiming)); JB_CUDA(evs.make(&ev_res, cudaEventDisableTiming));
   double scan_ms = 0, walk_ms = 0, plan_ms = 0, kwalk_ms = 0;
   int64_t scan_lookups = 0, walk_lookups = 0, launches = 0, n_events = 0, probe_steps = 0, n_segments = 0, n_reruns = 0;
-  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0, n_fast = 0, n_post = 0, n_v2 = 0;
+  int64_t max_seg_events = 0, max_seg_lookups = 0, max_seg_span = 0, n_fast = 0, n_post = 0, n_v2 = 0, n_speculative = 0;
   int64_t slow_cycles[3] = {0, 0, 0}, slow_events[3] = {0, 0, 0}, slow_lookups[3] = {0, 0, 0}, slow_span[3] = {0, 0, 0}, sum_cycles[3] = {0, 0, 0};
-  std::vector<ScanUnit> sunits(n);
-  std::vector<SegUnit> gunits(n);
   std::vector<int64_t> caps(n);
   const WalkCfg cfg{k, sampling_step(k), solid_thre, 0};
   const TableView view = db->view();
@@ -790,9 +885,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   double recount_ms = 0;
   const bool full_rescan = getenv("JB_FULL_RESCAN") != nullptr;      // tests: scan every pass from scratch
   const bool verify_recount = getenv("JB_VERIFY_RECOUNT") != nullptr; // tests: check k_recount against a full scan
-  cudaEvent_t ev_r0, ev_r1, ev_v0, ev_v1, ev_anchors;
-  JB_CUDA(cudaEventCreateWithFlags(&ev_anchors, cudaEventDisableTiming));
-  JB_CUDA(cudaEventCreate(&ev_r0)); JB_CUDA(cudaEventCreate(&ev_r1)); JB_CUDA(cudaEventCreate(&ev_v0)); JB_CUDA(cudaEventCreate(&ev_v1));
+  // tests: JB_NO_SPECULATION makes the host place the segments and launch k_concat / the recount itself, as the slow path does
+  const bool speculate = getenv("JB_NO_SPECULATION") == nullptr && !verify_recount;
   const bool do_fix_verdicts = getenv("JB_NO_VERDICTS") == nullptr;      // tests: walkers decide everything themselves
   double verdict_ms = 0;
   int64_t n_verdicts = 0;
@@ -813,9 +907,20 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     b->passes.push_back(PassOut{});
     uint8_t* in = w.buf[b->cur].p;
     uint8_t* outb = w.buf[b->cur ^ 1].p;
-    std::vector<uint32_t> tile_first(n + 1, 0), block_first(n + 1, 0);
+    PassEvents& pe = pev[(size_t)ite];
+    // the pass's per-contig geometry, staged in pinned memory (the copies below run when the stream gets there; the area is
+    // written again only after this pass's ev_res has been waited for)
+    uint8_t* geom = w.h_geom.p;
+    int64_t* caps_h = reinterpret_cast<int64_t*>(geom); geom += (n + 1) * 8;          // (the 8-byte aligned arrays first)
+    ScanUnit* sunits = reinterpret_cast<ScanUnit*>(geom); geom += (n + 1) * sizeof(ScanUnit);
+    SegUnit* gunits = reinterpret_cast<SegUnit*>(geom); geom += (n + 1) * sizeof(SegUnit);
+    uint32_t* tile_first = reinterpret_cast<uint32_t*>(geom); geom += (n + 2) * 4;
+    uint32_t* block_first = reinterpret_cast<uint32_t*>(geom); geom += (n + 2) * 4;
+    uint32_t* unit_first = reinterpret_cast<uint32_t*>(geom);
+    tile_first[0] = 0; block_first[0] = 0;
     int64_t pass_total = 0, pass_lookups = 0;
     for (size_t i = 0; i < n; ++i) {
+      caps_h[i] = caps[i];
       pass_total += b->len[i] - k + 1;                                  // may be negative (src/jasper.py:51)
       sunits[i] = ScanUnit{b->off[i], (uint64_t)b->len[i], b->off[i]};
       gunits[i] = SegUnit{b->off[i], (uint64_t)b->len[i]};
@@ -828,18 +933,19 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     std::vector<BlockRef> blocks;
     if (seg_block > 0) blocks = make_blocks(b->len, seg_block);
     JB_TRY(w.anchors.ensure(blocks.size() + 1)); JB_TRY(w.h_anchors.ensure(blocks.size() + 1));
-    JB_CUDA(cudaMemcpyAsync(w.tile_first.p, tile_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.block_first.p, block_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.scan_units.p, sunits.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.seg_units.p, gunits.data(), n * sizeof(SegUnit), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.tile_first.p, tile_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.block_first.p, block_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.scan_units.p, sunits, n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.seg_units.p, gunits, n * sizeof(SegUnit), cudaMemcpyHostToDevice, s));
+    if (ite == 0) JB_CUDA(cudaMemcpyAsync(w.caps_d.p, caps_h, n * 8, cudaMemcpyHostToDevice, s));
     JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
-    JB_CUDA(cudaMemsetAsync(w.used.p, 0, 64, s));        // (the previous pass's counters are on the host already)
+    JB_CUDA(cudaMemsetAsync(w.used.p, 0, 128, s));       // (the previous pass's counters are on the host already, or on their way)
     JB_CUDA(cudaMemsetAsync(w.events_l1.p, 0, (b->flat_bytes / 32768 + 64) * 4, s));
     JB_CUDA(cudaMemsetAsync(w.events_l2.p, 0, (b->flat_bytes / (32768 * 32) + 64) * 4, s));
     ScanArgs a{};
     a.bases = in; a.units = w.scan_units.p; a.tile_first = w.tile_first.p; a.n_units = (uint32_t)n; a.n_tiles = tile_first[n];
     a.counts = w.counts[cidx].p; a.okb = w.okb[cidx].p; a.probe_steps = w.used.p + 2;
-    JB_CUDA(cudaEventRecord(ev_a, s));
+    JB_CUDA(cudaEventRecord(pe.a, s));
     if (ite == 0 && b->prescanned && !have_counts) {      // jb_polish: scanned group by group behind the upload
       have_counts = true;
       ++full_scans; full_scan_lookups += b->prescan_lookups;
@@ -849,7 +955,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       ++launches; ++full_scans;
       full_scan_lookups += pass_lookups;
     }
-    JB_CUDA(cudaEventRecord(ev_b, s));
+    JB_CUDA(cudaEventRecord(pe.b, s));
     EventArgs ea{};
     ea.units = w.scan_units.p; ea.tile_first = w.tile_first.p; ea.n_units = (uint32_t)n; ea.n_tiles = tile_first[n];
     ea.counts = w.counts[cidx].p; ea.okb = w.okb[cidx].p; ea.events = w.events.p; ea.weak = w.weak.p; ea.events_l1 = w.events_l1.p; ea.events_l2 = w.events_l2.p;
@@ -882,7 +988,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       va.dry_out = w.dry_out.p; va.dry_post = getenv("JB_NO_V2_POST") ? 0 : (getenv("JB_NO_POST2") ? 2 : 1);
       va.k = k; va.step = cfg.step; va.solid = solid_thre;
       const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
-      JB_CUDA(cudaEventRecord(ev_v0, s));
+      JB_CUDA(cudaEventRecord(pe.v0, s));
       k_verdicts<<<std::max(1u, vgrid), kVerdictWarps * 32, 0, s>>>(view, va);
       JB_CUDA(cudaGetLastError());
       ++launches;
@@ -892,7 +998,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
         JB_CUDA(cudaGetLastError());
         ++launches;
       }
-      JB_CUDA(cudaEventRecord(ev_v1, s));
+      JB_CUDA(cudaEventRecord(pe.v1, s));
+      pe.verdicts = true;
     }
     // while the scan runs: turn the previous pass's fix log into csv rows
     mark("scan launched", ite);
@@ -903,39 +1010,105 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
     const size_t n_first = plan.size();
     JB_TRY(w.segs.ensure(n_first + 2 * n)); JB_TRY(w.h_segs.ensure(n_first + 2 * n));     // room for two rounds of whole-contig re-runs behind the plan
-    JB_TRY(w.order.ensure(n_first + 2 * n)); JB_TRY(w.dst_off.ensure(n_first + 2 * n));
+    JB_TRY(w.order.ensure(n_first + 2 * n)); JB_TRY(w.dst_off.ensure(n_first + 2 * n)); JB_TRY(w.h_dst_off.ensure(n_first + 2 * n));
+    JB_TRY(w.h_order.ensure(n_first + 2 * n)); JB_TRY(w.seg_unit.ensure(n_first + 1)); JB_TRY(w.h_seg_unit.ensure(n_first + 1));
+    JB_TRY(w.seg_out.ensure(n_first + 1)); JB_TRY(w.h_seg_out.ensure(n_first + 1)); JB_TRY(w.prefix.ensure(n_first + 2));
+    JB_TRY(w.slot_unit.ensure(n_first + 2 * n + 1)); JB_TRY(w.h_probes.ensure((size_t)passes + 2));
     UnitIO* hs = w.h_segs.p;
-    for (size_t q = 0; q < n_first; ++q) hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin, cidx);
+    uint32_t* seg_unit = w.h_seg_unit.p;
+    for (size_t q = 0; q < n_first; ++q) {
+      hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin, cidx);
+      seg_unit[q] = plan[q].unit;
+      if (plan[q].seg == 0) unit_first[plan[q].unit] = (uint32_t)q;
+    }
+    unit_first[n] = (uint32_t)n_first;
     // queue order: the few long segments (stretches without an anchor) first, the rest as planned
-    std::vector<uint32_t> order;
-    order.reserve(n_first);
-    auto seg_span = [&](size_t q) { return (hs[q].next_anchor >= 0 ? hs[q].next_anchor : hs[q].in_len) - hs[q].base; };
-    const int64_t long_span = 4 * std::max<int64_t>(seg_block, 1024);
-    std::vector<uint32_t> longs;
-    for (size_t q = 0; q < n_first; ++q) if (seg_span(q) > long_span) longs.push_back((uint32_t)q);
-    std::sort(longs.begin(), longs.end(), [&](uint32_t x, uint32_t y) { return seg_span(x) > seg_span(y); });
-    order = longs;
-    for (size_t q = 0; q < n_first; ++q) if (seg_span(q) <= long_span) order.push_back((uint32_t)q);
+    uint32_t* order = w.h_order.p;
+    {
+      auto seg_span = [&](size_t q) { return (hs[q].next_anchor >= 0 ? hs[q].next_anchor : hs[q].in_len) - hs[q].base; };
+      const int64_t long_span = 4 * std::max<int64_t>(seg_block, 1024);
+      std::vector<uint32_t> longs;
+      for (size_t q = 0; q < n_first; ++q) if (seg_span(q) > long_span) longs.push_back((uint32_t)q);
+      std::sort(longs.begin(), longs.end(), [&](uint32_t x, uint32_t y) { return seg_span(x) > seg_span(y); });
+      size_t at = 0;
+      for (uint32_t q : longs) order[at++] = q;
+      for (size_t q = 0; q < n_first; ++q) if (seg_span(q) <= long_span) order[at++] = (uint32_t)q;
+    }
     JB_CUDA(cudaMemcpyAsync(w.segs.p, hs, n_first * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.order.p, order.data(), n_first * 4, cudaMemcpyHostToDevice, s));
+    JB_CUDA(cudaMemcpyAsync(w.order.p, order, n_first * 4, cudaMemcpyHostToDevice, s));
+    if (do_fix) {
+      JB_CUDA(cudaMemcpyAsync(w.seg_unit.p, seg_unit, n_first * 4, cudaMemcpyHostToDevice, s));
+      JB_CUDA(cudaMemcpyAsync(w.unit_first.p, unit_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    }
     // ---- walk (the previous pass's rows have left the arena: the stream waited for ev_rows)
     WalkCfg c2 = cfg; c2.fix = do_fix ? 1 : 0;
     RowSink sink{w.rows.p, w.rows.cap, w.used.p, w.aux.p, w.aux.cap, w.used.p + 1};
     JobSink jobs{w.jobs.p, w.jobs.cap, w.used.p + 3};
     auto walk_grid = [&](size_t cnt) { return (unsigned)std::min<size_t>((cnt + kWalkWarps - 1) / kWalkWarps, (size_t)b->sms * kWalkCtasPerSm); };
-    JB_CUDA(cudaEventRecord(ev_c, s));
+    JB_CUDA(cudaEventRecord(pe.c, s));
     k_walk<<<walk_grid(n_first), kWalkWarps * 32, 0, s>>>(view, w.segs.p, w.order.p, (uint32_t)n_first, c2, pool, sink, jobs, w.next.p);
     JB_CUDA(cudaGetLastError());
     ++launches;
-    JB_CUDA(cudaEventRecord(ev_e, s));
+    JB_CUDA(cudaEventRecord(pe.e, s));
+    JB_CUDA(cudaEventRecord(w.ev_walk, s));              // the fix log may leave on the side stream from here on
+    // ---- the segments' results, compact; placement of their new bases on the device; then -- without waiting for the
+    // host -- the stitching and the recount.  The host reads the results meanwhile; if a segment failed (k_place then placed
+    // nothing and the kernels behind it found nothing to do) it re-walks and launches them again itself.
+    k_seg_gather<<<(unsigned)((n_first + 255) / 256), 256, 0, s>>>(w.segs.p, (uint32_t)n_first, w.seg_out.p, w.used.p + 8);
+    JB_CUDA(cudaGetLastError());
+    ++launches;
+    if (do_fix) {
+      PlaceArgs pa{};
+      pa.so = w.seg_out.p; pa.n_segs = (uint32_t)n_first; pa.seg_unit = w.seg_unit.p; pa.unit_first = w.unit_first.p;
+      pa.units_old = w.scan_units.p; pa.caps = w.caps_d.p; pa.n_units = (uint32_t)n; pa.prefix = w.prefix.p;
+      pa.dst_off = w.dst_off.p; pa.slot_unit = w.slot_unit.p; pa.units_new = w.scan_units_new.p; pa.flag = w.used.p + 8;
+      k_place<<<1, kPlaceThreads, 0, s>>>(pa);
+      JB_CUDA(cudaGetLastError());
+      ++launches;
+    }
     const bool engine_busy = b->early != nullptr;        // the polished bases are travelling on the side stream
-    if (int rc = small_d2h(hs, w.segs.p, n_first * sizeof(UnitIO), engine_busy, s)) return rc;
-    if (int rc = small_d2h(used, w.used.p, 64, engine_busy, s)) return rc;
+    SegOut* so = w.h_seg_out.p;
+    if (int rc = small_d2h(so, w.seg_out.p, n_first * sizeof(SegOut), engine_busy, s)) return rc;
+    if (int rc = small_d2h(used, w.used.p, 128, engine_busy, s)) return rc;
+    JB_CUDA(cudaEventRecord(ev_res, s));
+    const bool keep_counts = !full_rescan && ite + 1 <= passes;
+    // k_concat, then the counts of the new sequence: copied for untouched stretches, probed again around the edits
+    auto stitch_and_recount = [&]() -> int {
+      k_concat<<<(unsigned)b->sms * 8, 256, 0, s>>>(w.jobs.p, w.used.p + 3, (unsigned long long)w.jobs.cap, w.dst_off.p, outb);
+      JB_CUDA(cudaGetLastError());
+      ++launches;
+      JB_CUDA(cudaEventRecord(w.ev_concat, s));
+      if (!keep_counts) return JB_OK;
+      RecountArgs ra{};
+      ra.jobs = w.jobs.p; ra.n_jobs = w.used.p + 3; ra.jobs_cap = (unsigned long long)w.jobs.cap; ra.dst_off = w.dst_off.p; ra.slot_unit = w.slot_unit.p;
+      ra.units_new = w.scan_units_new.p;
+      ra.in_buf = in; ra.flat_bytes = b->flat_bytes; ra.new_bases = outb;
+      ra.cnt_old = w.counts[cidx].p; ra.okb_old = w.okb[cidx].p; ra.cnt_new = w.counts[cidx ^ 1].p; ra.okb_new = w.okb[cidx ^ 1].p;
+      ra.probes = w.used.p + 4;
+      RecountTailArgs rt{w.scan_units.p, w.scan_units_new.p, (uint32_t)n, w.counts[cidx].p, w.counts[cidx ^ 1].p, w.okb[cidx ^ 1].p};
+      JB_CUDA(cudaMemsetAsync(w.used.p + 4, 0, 8, s));
+      JB_CUDA(cudaEventRecord(pe.r0, s));
+      if (int rc = launch_recount(view, ra, rt, s)) return rc;
+      JB_CUDA(cudaEventRecord(pe.r1, s));
+      pe.recount = true;
+      launches += 3;
+      // (not while the polished bases travel on the side stream: a device-to-host copy on this stream would queue behind
+      //  them in the copy engine and hold the stream for the whole transfer; the statistic of that pass is dropped)
+      w.h_probes.p[ite] = 0;
+      if (!(b->early && ite == passes - 1)) JB_CUDA(cudaMemcpyAsync(w.h_probes.p + ite, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
+      return JB_OK;
+    };
+    if (do_fix && speculate) { if (int rc = stitch_and_recount()) return rc; }
     mark("walk launched", ite);
-    JB_CUDA(cudaStreamSynchronize(s));
+    JB_CUDA(cudaEventSynchronize(ev_res));
     mark("walk done", ite);
-    { float m2 = 0; cudaEventElapsedTime(&m2, ev_c, ev_e); kwalk_ms += m2; }
     n_segments += (int64_t)n_first;
+    for (size_t q = 0; q < n_first; ++q) {               // the results join the descriptors the host built
+      UnitIO& u = hs[q];
+      const SegOut& o = so[q];
+      u.end_old = o.end_old; u.new_len = o.new_len; u.wrong = o.wrong; u.status = o.status; u.n_rows = o.n_rows; u.n_fast = o.n_fast;
+      u.n_post = o.n_post; u.n_v2 = o.n_v2; u.lookups = o.lookups; u.events = o.events; u.cycles = o.cycles;
+    }
     // ---- contigs whose seams did not hold (or whose segment slack ran out) are walked again as one segment; a contig whose
     // de-Bruijn search outgrew a standard trie (kTrieFull) is walked again with the grown pool
     std::vector<uint8_t> redo(n, 0);
@@ -956,6 +1129,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
                                 "(output slack, fix-row arena, or copy-job arena; status " + std::to_string(u.status) + ")");
     }
     std::vector<UnitIO> segs;                            // accepted segments in (contig, segment) order
+    const bool rewalked = !todo.empty();
+    if (do_fix && speculate && !rewalked) ++n_speculative;
     if (!todo.empty()) {
       std::sort(todo.begin(), todo.end());
       std::vector<UnitIO> redone(n);
@@ -1020,40 +1195,48 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       sum_cycles[ite < 3 ? ite : 2] += (int64_t)u.cycles;
     }
     probe_steps += (int64_t)used[2];
+    if (b->use_verdicts) n_verdicts += (int64_t)used[6];
     if (do_fix) {
-      // ---- stitch the segments into the other buffer; the fix log follows on the side stream
+      // ---- the segments' new bases are stitched into the other buffer (launched above, or here after a re-walk); the fix
+      // log follows on the side stream
       if (used[0] > w.rows.cap || used[1] > w.aux.cap || used[3] > w.jobs.cap) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "fix-row / copy-job arena overflow"); }
       std::vector<int64_t> new_lens(b->len);
       pending.place = place_segments(segs, &new_lens);
-      std::vector<int64_t> dst_off(n_slots, -1);        // by launch slot; superseded attempts stay at -1
       pending.first_seg.assign(n, 0);
-      for (size_t q = 0; q < segs.size(); ++q) {
-        dst_off[segs[q].slot] = (int64_t)b->off[segs[q].unit] + pending.place[q].new_off;
+      for (size_t q = 0; q < segs.size(); ++q)
         if (segs[q].seg == 0) pending.first_seg[segs[q].unit] = q;
-      }
       for (size_t i = 0; i < n; ++i)
         if (new_lens[i] > caps[i]) { b->status = JB_E_SCRATCH; return fail(JB_E_SCRATCH, "contig " + std::to_string(i) + " outgrew its output slack"); }
+      if (rewalked || !speculate) {
+        // the host's own placement goes to the device (by launch slot; superseded attempts stay at -1)
+        int64_t* dst_off = w.h_dst_off.p;
+        uint32_t* slot_unit = w.h_order.p;                // (the queue order has been consumed: its staging area is free)
+        ScanUnit* units_new = sunits;                     // (likewise this pass's staged geometry)
+        for (size_t q = 0; q < n_slots; ++q) { dst_off[q] = -1; slot_unit[q] = 0; }
+        for (size_t q = 0; q < segs.size(); ++q) {
+          dst_off[segs[q].slot] = (int64_t)b->off[segs[q].unit] + pending.place[q].new_off;
+          slot_unit[segs[q].slot] = segs[q].unit;
+        }
+        for (size_t i = 0; i < n; ++i) units_new[i] = ScanUnit{b->off[i], (uint64_t)new_lens[i], b->off[i]};
+        JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off, n_slots * 8, cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaMemcpyAsync(w.slot_unit.p, slot_unit, n_slots * 4, cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaMemcpyAsync(w.scan_units_new.p, units_new, n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
+        JB_CUDA(cudaEventRecord(w.ev_walk, s));           // (the re-walks wrote rows too)
+        if (int rc = stitch_and_recount()) return rc;
+      }
       const int hb = ite & 1;                            // the log of pass ite-2 must have been read out of this buffer
       for (auto& rj : row_jobs) if (rj->buf == hb) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
-      JB_CUDA(cudaEventRecord(w.ev_walk, s));
       JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
       if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows[hb].p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
       if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux[hb].p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
       JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
-      JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, s));
-      const unsigned long long nj = std::max<unsigned long long>(used[3], 1);
-      dim3 g((unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(4, 65536 / nj)), (unsigned)std::min<unsigned long long>(nj, 16384));
-      k_concat<<<g, 256, 0, s>>>(w.jobs.p, w.used.p + 3, w.dst_off.p, outb);
-      JB_CUDA(cudaGetLastError());
-      ++launches;
       if (ite == passes - 1 && !b->early && b->fetch_follows && getenv("JB_NO_EARLY_FETCH") == nullptr) {
         uint64_t total_new = 0;
         for (size_t i = 0; i < n; ++i) total_new += (uint64_t)new_lens[i];
         b->early = take_out_buffer(std::max<uint64_t>(total_new, 1), &b->early_cap);
         if (b->early) {
           if (!b->ev_early) JB_CUDA(cudaEventCreateWithFlags(&b->ev_early, cudaEventDisableTiming));
-          JB_CUDA(cudaEventRecord(w.ev_concat, s));
-          JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_concat, 0));
+          JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_concat, 0));      // (recorded behind the k_concat that counts)
           uint64_t at = 0;
           for (size_t i = 0; i < n; ++i) {
             if (new_lens[i]) JB_CUDA(cudaMemcpyAsync(b->early + at, outb + b->off[i], (size_t)new_lens[i], cudaMemcpyDeviceToHost, w.s2));
@@ -1062,30 +1245,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
           JB_CUDA(cudaEventRecord(b->ev_early, w.s2));
         }
       }
-      // ---- counts of the new sequence: copied for untouched stretches, probed again around the edits
       have_counts = false;
-      if (!full_rescan && ite + 1 <= passes) {
-        std::vector<uint32_t> slot_unit(n_slots, 0);
-        for (size_t q = 0; q < segs.size(); ++q) slot_unit[segs[q].slot] = segs[q].unit;
-        std::vector<ScanUnit> units_new(n);
-        for (size_t i = 0; i < n; ++i) units_new[i] = ScanUnit{b->off[i], (uint64_t)new_lens[i], b->off[i]};
-        JB_TRY(w.slot_unit.ensure(n_slots + 1));
-        JB_CUDA(cudaMemcpyAsync(w.slot_unit.p, slot_unit.data(), n_slots * 4, cudaMemcpyHostToDevice, s));
-        JB_CUDA(cudaMemcpyAsync(w.scan_units_new.p, units_new.data(), n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-        RecountArgs ra{};
-        ra.jobs = w.jobs.p; ra.n_jobs = w.used.p + 3; ra.dst_off = w.dst_off.p; ra.slot_unit = w.slot_unit.p; ra.units_new = w.scan_units_new.p;
-        ra.in_buf = in; ra.flat_bytes = b->flat_bytes; ra.new_bases = outb;
-        ra.cnt_old = w.counts[cidx].p; ra.okb_old = w.okb[cidx].p; ra.cnt_new = w.counts[cidx ^ 1].p; ra.okb_new = w.okb[cidx ^ 1].p;
-        ra.probes = w.used.p + 4;
-        RecountTailArgs rt{w.scan_units.p, w.scan_units_new.p, (uint32_t)n, w.counts[cidx].p, w.counts[cidx ^ 1].p, w.okb[cidx ^ 1].p};
-        JB_CUDA(cudaEventRecord(ev_r0, s));
-        if (int rc = launch_recount(view, ra, rt, used[3], s)) return rc;
-        JB_CUDA(cudaEventRecord(ev_r1, s));
-        launches += 3;
-        // (not while the polished bases travel on the side stream: a device-to-host copy on this stream would queue behind
-        //  them in the copy engine and hold the stream for the whole transfer; the statistic of that pass is dropped)
-        used[4] = 0;
-        if (!(b->early && ite == passes - 1)) JB_CUDA(cudaMemcpyAsync(used + 4, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
+      if (keep_counts) {
         if (verify_recount) {
           // full scan of the new sequence into the buffer the old counts lived in, then compare
           ScanArgs va = a;
@@ -1109,17 +1270,11 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       b->len = new_lens;
       b->cur ^= 1;
     }
-    JB_CUDA(cudaEventRecord(ev_d, s));
+    JB_CUDA(cudaEventRecord(pe.d, s));
     mark("concat launched", ite);
     // this pass's fix log lands while k_concat / k_recount run: hand it to its row thread now, not at the next pass
     if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
-    JB_CUDA(cudaStreamSynchronize(s));                   // dst_off (a host vector) must stay alive until k_concat has read it
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev_a, ev_b); scan_ms += ms;
-    cudaEventElapsedTime(&ms, ev_b, ev_c); plan_ms += ms;
-    cudaEventElapsedTime(&ms, ev_c, ev_d); walk_ms += ms;
-    if (do_fix && have_counts) { cudaEventElapsedTime(&ms, ev_r0, ev_r1); recount_ms += ms; recount_probes += (int64_t)used[4]; }
-    if (b->use_verdicts) { cudaEventElapsedTime(&ms, ev_v0, ev_v1); verdict_ms += ms; n_verdicts += (int64_t)used[6]; }
+    // (no wait for the stream here: the next pass is queued behind this one's kernels straight away)
     mark("pass done", ite);
   }
   if (int rc = finish_rows(b, &pending, &row_jobs)) return rc;
@@ -1128,13 +1283,21 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   JB_CUDA(cudaEventRecord(ev_end, s));
   JB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
+  for (size_t q = 0; q < b->passes.size() && q < pev.size(); ++q) {
+    const PassEvents& pe = pev[q];
+    cudaEventElapsedTime(&ms, pe.a, pe.b); scan_ms += ms;
+    cudaEventElapsedTime(&ms, pe.b, pe.c); plan_ms += ms;
+    cudaEventElapsedTime(&ms, pe.c, pe.d); walk_ms += ms;
+    cudaEventElapsedTime(&ms, pe.c, pe.e); kwalk_ms += ms;
+    if (pe.recount) { cudaEventElapsedTime(&ms, pe.r0, pe.r1); recount_ms += ms; recount_probes += (int64_t)w.h_probes.p[q]; }
+    if (pe.verdicts) { cudaEventElapsedTime(&ms, pe.v0, pe.v1); verdict_ms += ms; }
+  }
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
   note_timing("polish", ms); note_timing("polish_scan", scan_ms); note_timing("polish_walk", walk_ms); note_timing("polish_plan", plan_ms);
   note_timing("polish_kwalk", kwalk_ms);
   note_timing("polish_recount", recount_ms);
   note_counter("scan_lookups", full_scan_lookups + recount_probes); note_counter("walk_lookups", walk_lookups);
   note_counter("full_scans", full_scans); note_counter("full_scan_lookups", full_scan_lookups); note_counter("recount_probes", recount_probes);
-  cudaEventDestroy(ev_r0); cudaEventDestroy(ev_r1); cudaEventDestroy(ev_v0); cudaEventDestroy(ev_v1); cudaEventDestroy(ev_anchors);
   note_counter("kernel_launches", launches); note_counter("events", n_events); note_counter("probe_steps", probe_steps);
   note_counter("max_seg_events", max_seg_events); note_counter("max_seg_lookups", max_seg_lookups); note_counter("max_seg_span", max_seg_span);
   for (int q = 0; q < 3; ++q) {
@@ -1144,7 +1307,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     note_counter(("sum_cycles" + sfx).c_str(), sum_cycles[q]);
   }
   note_counter("verdicts", n_verdicts); note_timing("polish_verdicts", verdict_ms); note_counter("verdict2_events", n_v2); note_counter("fast_events", n_fast); note_counter("fast_steps", n_post); note_counter("segments", n_segments); note_counter("segment_reruns", n_reruns); note_counter("seg_block", seg_block);
-  cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_c); cudaEventDestroy(ev_d); cudaEventDestroy(ev_e);
+  note_counter("speculative_passes", n_speculative);
   w.release_big_pool();
   b->polished = true;
   while ((int)b->passes.size() <= passes) b->passes.push_back(PassOut{});

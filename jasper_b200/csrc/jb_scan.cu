@@ -330,8 +330,8 @@ __device__ __forceinline__ uint32_t probe_finish(const TableView& t, const Key& 
 // an untouched stretch keep their counts (streamed, eight independent loads per thread in flight).  k_recount_probe: the
 // other windows -- the last k-1 of an untouched stretch, every window of a materialised one -- are cut from a 2-bit packed
 // copy of the new bases that the warp builds with ballots, 64 windows per trip, two probes in flight per lane.
-// Work split in both: a.team threads per job on a 1-D grid (many short jobs), or the CTAs of one grid row per job (few
-// long ones).
+// Work split in both: decided on the device from the job count (job_split, jb_jobs.cuh); the launch does not wait for the
+// host to learn how many jobs the walkers wrote.
 struct RecountJobView { int64_t D, dirty0, dend, cend, O; bool live; };
 __device__ __forceinline__ RecountJobView recount_job(const RecountArgs& a, unsigned long long j, int k) {
   RecountJobView v;
@@ -350,25 +350,11 @@ __device__ __forceinline__ RecountJobView recount_job(const RecountArgs& a, unsi
   }
   return v;
 }
-struct RecountSplit { int64_t tid, nth; unsigned long long j0, jstep; };
-__device__ __forceinline__ RecountSplit recount_split(int team) {
-  RecountSplit r;
-  if (team) {
-    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    r.tid = (int64_t)(g % (unsigned)team); r.nth = team;
-    r.j0 = g / (unsigned)team; r.jstep = (unsigned long long)gridDim.x * blockDim.x / (unsigned)team;
-  } else {
-    r.tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r.nth = (int64_t)gridDim.x * blockDim.x;
-    r.j0 = blockIdx.y; r.jstep = gridDim.y;
-  }
-  return r;
-}
-
 constexpr int kRecountUnroll = 8;
 __global__ void __launch_bounds__(256)
 k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
-  const unsigned long long n = *a.n_jobs;
-  const RecountSplit sp = recount_split(a.team);
+  const unsigned long long n = min(*a.n_jobs, a.jobs_cap);
+  const JobSplit sp = job_split(n, a.force_rows != 0, 128u);
   for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
     const RecountJobView v = recount_job(a, j, k);
     if (!v.live || v.O < 0) continue;
@@ -396,10 +382,11 @@ k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
 
 __global__ void __launch_bounds__(256, 3)
 k_recount_probe(const __grid_constant__ TableView t, const __grid_constant__ RecountArgs a) {
-  const unsigned long long n = *a.n_jobs;
+  const unsigned long long n = min(*a.n_jobs, a.jobs_cap);
   const int k = t.g.k;
   const int lane = threadIdx.x & 31;
-  const RecountSplit sp = recount_split(a.team);
+  // (rows of at most 8 CTAs: a job rarely has more than a few dozen windows to probe)
+  const JobSplit sp = job_split(n, a.force_rows != 0, 8u);
   const int64_t wi = sp.tid >> 5, nw = sp.nth >> 5;               // this warp among the job's warps
   unsigned long long probes = 0;
   for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
@@ -471,21 +458,16 @@ int compare_counts(const ScanUnit* d_units, uint32_t n_units, const uint32_t* cn
   return JB_OK;
 }
 
-int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, unsigned long long n_jobs_hint, cudaStream_t s) {
-  // few jobs = long untouched stretches: give each job more CTAs for the count copy
-  const unsigned long long nj = std::max<unsigned long long>(n_jobs_hint, 1);
-  const unsigned gx = (unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(2, 65536 / nj));
-  dim3 g(gx, (unsigned)std::min<unsigned long long>(nj, 32768));
+int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   RecountArgs a2 = a;
-  a2.team = 0;
-  if (nj >= 16384 && getenv("JB_RECOUNT_ROWS") == nullptr) {     // short jobs: 64 threads each
-    a2.team = 64;
-    g = dim3((unsigned)std::min<unsigned long long>((nj * 64 + 255) / 256, 148ull * 64), 1);
-  }
-  k_recount_copy<<<g, 256, 0, s>>>(a2, view.g.k);
+  a2.force_rows = getenv("JB_RECOUNT_ROWS") != nullptr;           // tests: rows of CTAs whatever the job count
+  k_recount_copy<<<(unsigned)sms * 8, 256, 0, s>>>(a2, view.g.k);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_copy launch: ") + cudaGetErrorString(e));
-  k_recount_probe<<<g, 256, 0, s>>>(view, a2);
+  k_recount_probe<<<(unsigned)sms * 6, 256, 0, s>>>(view, a2);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_probe launch: ") + cudaGetErrorString(e));
   if (t.n_units) {

@@ -23,6 +23,7 @@
 // coalesced.  Warps drift apart, so probe latency of one overlaps key arithmetic of another.
 #pragma once
 #include "jb_internal.cuh"
+#include "jb_jobs.cuh"
 
 namespace jb {
 
@@ -102,6 +103,7 @@ struct CopyJob;
 struct RecountArgs {
   const CopyJob* jobs;
   const unsigned long long* n_jobs;
+  unsigned long long jobs_cap;  // arena size: the walkers' counter may run past it (the host then fails the call)
   const int64_t* dst_off;       // by launch slot: flat offset of the segment's new bases; < 0 = superseded
   const uint32_t* slot_unit;    // by launch slot: contig
   const ScanUnit* units_new;    // per contig: seq_off (= flat offset, unchanged between passes) and the NEW length
@@ -111,7 +113,7 @@ struct RecountArgs {
   const uint32_t* cnt_old; const uint8_t* okb_old;
   uint32_t* cnt_new; uint8_t* okb_new;
   unsigned long long* probes;   // statistics
-  int team;                     // threads per job (multiple of 32) on a 1-D grid; 0 = one grid row of CTAs per job
+  int force_rows;               // tests: never split into teams (jb_jobs.cuh, job_split)
 };
 struct RecountTailArgs {
   const ScanUnit* units_old; const ScanUnit* units_new; uint32_t n_units;
@@ -122,7 +124,7 @@ struct RecountTailArgs {
 // number of positions p in [0, len_u] of any contig where (count, ok) differ between two flat arrays (test aid)
 int compare_counts(const ScanUnit* d_units, uint32_t n_units, const uint32_t* cnt_a, const uint8_t* okb_a, const uint32_t* cnt_b,
                    const uint8_t* okb_b, unsigned long long* d_scratch, unsigned long long* mismatches, cudaStream_t s);
-int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, unsigned long long n_jobs_hint, cudaStream_t s);
+int launch_recount(const TableView& view, const RecountArgs& a, const RecountTailArgs& t, cudaStream_t s);
 int scan_grid(uint32_t n_tiles);
 int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s);
 int launch_events(const EventArgs& a, cudaStream_t s);

@@ -203,6 +203,27 @@ def test_polish_big_fuzz_segmented_matches_hostsim_and_oracle(tmp_path, hostsim_
 
 
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
+def test_device_side_placement_changes_nothing(golden_cases, dbs, name, monkeypatch):
+    """k_place puts the segments' new bases on the device and k_concat / the recount are queued behind it before the host has
+    seen the walkers' results; with JB_NO_SPECULATION the host places and launches them itself (the path a re-walk takes).
+    Same result either way, also when every seam is forced to fail (margin 0: the speculative launches then find nothing to
+    do and the host's placement counts)."""
+    case = golden_cases[name]
+    seqs = jo.read_fasta(case["fasta"])
+    fast = dbs[name].polish(seqs, case["k"], case["threshold"], 3)
+    assert fast.status == 0 and fast.counters["speculative_passes"] >= 1
+    monkeypatch.setenv("JB_NO_SPECULATION", "1")
+    slow = dbs[name].polish(seqs, case["k"], case["threshold"], 3)
+    monkeypatch.delenv("JB_NO_SPECULATION")
+    assert slow.counters["speculative_passes"] == 0
+    monkeypatch.setenv("JB_SEG_BLOCK", "256"); monkeypatch.setenv("JB_ANCHOR_MARGIN", "0")
+    seams = dbs[name].polish(seqs, case["k"], case["threshold"], 3)
+    for other in (slow, seams):
+        assert other.status == 0
+        assert other.seqs == fast.seqs and other.tallies == fast.tallies and other.rows == fast.rows
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 def test_incremental_recount_equals_full_scan(golden_cases, dbs, name, monkeypatch):
     """Passes 2.. inherit window counts through k_recount: (a) the device checks every inherited count against a
     full scan of the new sequence (JB_VERIFY_RECOUNT), (b) forcing full rescans gives the same bytes."""
