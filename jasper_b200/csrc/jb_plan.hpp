@@ -123,7 +123,8 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
   const size_t n_slots = at.size();
   // Three phases on a few threads spawned once (the 63 k rows of a 64 Mb pass cost ~8 ms on one, and this runs beside the
   // GPU work of the following passes): index the log by (segment, emission order), convert slot ranges, splice in order.
-  int n_thr = n_slots > 8192 ? 4 : 1;
+  // (the alignments of bridged patches dominate: ~10 ms of one core per 64 Mb pass; with four threads this finished after the GPU)
+  int n_thr = n_slots > 8192 ? (int)std::min<unsigned>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 2)) : 1;
   if (const char* e = getenv("JB_ROW_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 16) n_thr = v; }   // tests
   // the few per-segment facts the index phase needs, packed (the descriptors are 250 bytes apiece)
   std::vector<uint32_t> seg_gen(segs.size()), seg_rows(segs.size());

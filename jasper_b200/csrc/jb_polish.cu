@@ -184,6 +184,11 @@ __global__ void k_store_host(uint8_t* __restrict__ dst, const uint8_t* __restric
   for (size_t v = i; v < nv; v += nth) reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(src)[v];
   for (size_t q = nv * 16 + i; q < n; q += nth) dst[q] = src[q];
 }
+// ... and the other way: a pass's small uploads are read straight out of the mapped pinned staging area (4-byte words)
+__global__ void k_load_host(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n_words) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = i; v < n_words; v += nth) dst[v] = src[v];
+}
 
 // dst[0:n) = src[0:n) by threads tid of nth; 16-byte stores, byte-funnelled loads when the two streams are misaligned
 // against each other (indels shift them)
@@ -738,6 +743,16 @@ int ensure_big_pool(Workspace& w, cudaStream_t s) {
   return JB_OK;
 }
 
+// dst: device memory, src: pinned host memory (mapped), both 4-byte aligned, n a multiple of 4
+int small_h2d(void* dst, const void* src, size_t n, bool by_kernel, cudaStream_t s) {
+  if (n == 0) return JB_OK;
+  if (!by_kernel || (n & 3)) { JB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s)); return JB_OK; }
+  const unsigned blocks = (unsigned)std::min<size_t>(64, (n / 4 + 255) / 256);
+  k_load_host<<<blocks, 256, 0, s>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src), n / 4);
+  JB_CUDA(cudaGetLastError());
+  return JB_OK;
+}
+
 int64_t pick_seg_block(int64_t total_len, int sms) {
   // (multiples of 32: k_find_anchors walks whole bitmask words)
   if (const char* e = getenv("JB_SEG_BLOCK")) { long v = atol(e); if (v >= 64) return (v + 31) / 32 * 32; if (v == 0) return 0; }
@@ -933,10 +948,13 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     std::vector<BlockRef> blocks;
     if (seg_block > 0) blocks = make_blocks(b->len, seg_block);
     JB_TRY(w.anchors.ensure(blocks.size() + 1)); JB_TRY(w.h_anchors.ensure(blocks.size() + 1));
-    JB_CUDA(cudaMemcpyAsync(w.tile_first.p, tile_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.block_first.p, block_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.scan_units.p, sunits, n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.seg_units.p, gunits, n * sizeof(SegUnit), cudaMemcpyHostToDevice, s));
+    // (while the polished bases travel on the side stream the copy engine is taken: a 64 MB transfer in front of these few
+    //  bytes would hold the whole count pass back, so a kernel fetches them from the mapped staging area instead)
+    const bool up_by_kernel = b->early != nullptr;
+    if (int rc = small_h2d(w.tile_first.p, tile_first, (n + 1) * 4, up_by_kernel, s)) return rc;
+    if (int rc = small_h2d(w.block_first.p, block_first, (n + 1) * 4, up_by_kernel, s)) return rc;
+    if (int rc = small_h2d(w.scan_units.p, sunits, n * sizeof(ScanUnit), up_by_kernel, s)) return rc;
+    if (int rc = small_h2d(w.seg_units.p, gunits, n * sizeof(SegUnit), up_by_kernel, s)) return rc;
     if (ite == 0) JB_CUDA(cudaMemcpyAsync(w.caps_d.p, caps_h, n * 8, cudaMemcpyHostToDevice, s));
     JB_CUDA(cudaMemsetAsync(w.next.p, 0, 4, s));
     JB_CUDA(cudaMemsetAsync(w.used.p, 0, 128, s));       // (the previous pass's counters are on the host already, or on their way)
@@ -1034,8 +1052,8 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       for (uint32_t q : longs) order[at++] = q;
       for (size_t q = 0; q < n_first; ++q) if (seg_span(q) <= long_span) order[at++] = (uint32_t)q;
     }
-    JB_CUDA(cudaMemcpyAsync(w.segs.p, hs, n_first * sizeof(UnitIO), cudaMemcpyHostToDevice, s));
-    JB_CUDA(cudaMemcpyAsync(w.order.p, order, n_first * 4, cudaMemcpyHostToDevice, s));
+    if (int rc = small_h2d(w.segs.p, hs, n_first * sizeof(UnitIO), up_by_kernel, s)) return rc;
+    if (int rc = small_h2d(w.order.p, order, n_first * 4, up_by_kernel, s)) return rc;
     if (do_fix) {
       JB_CUDA(cudaMemcpyAsync(w.seg_unit.p, seg_unit, n_first * 4, cudaMemcpyHostToDevice, s));
       JB_CUDA(cudaMemcpyAsync(w.unit_first.p, unit_first, (n + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -1282,6 +1300,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
   mark("rows joined", passes);
   JB_CUDA(cudaEventRecord(ev_end, s));
   JB_CUDA(cudaStreamSynchronize(s));
+  mark("stream drained", passes);
   float ms = 0;
   for (size_t q = 0; q < b->passes.size() && q < pev.size(); ++q) {
     const PassEvents& pe = pev[q];

@@ -213,40 +213,58 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
   }
 }
 
-// one warp per 1024-position tile, one position per lane and step
+// one warp per 1024-position tile; a lane takes four consecutive positions per step (one 16-byte load of counts, one 4-byte
+// load of validity bytes), eight lanes make one 32-bit word of the masks with a single warp reduction (r2d: the per-position
+// version issued 59 instructions per 32 positions and was bound by issue slots, not by memory)
 __global__ void __launch_bounds__(256)
-k_events(EventArgs a) {
+k_events(const __grid_constant__ EventArgs a) {
   const uint32_t ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ti >= a.n_tiles) return;
   const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
   const ScanUnit u = a.units[tile.unit];
-  const int64_t n_out = (int64_t)min((uint64_t)kTile, u.len + 1 - tile.start);
-  const uint32_t* cnt = a.counts + u.out_off;
-  const uint64_t f0 = u.out_off + tile.start;                       // flat bit index of the tile, multiple of 1024
-  // branch-free per position (the 1/50 test reads its second count unconditionally: an L1/L2 hit k positions back),
-  // four words per trip so that the loads of one trip are in flight together
-  const uint32_t* cnt_t = cnt + tile.start;
+  const int n = (int)min((uint64_t)kTile, u.len + 1 - tile.start);  // positions of this tile
+  const uint64_t f0 = u.out_off + tile.start;                       // flat index of the tile's first position: a multiple of 32
+  const uint32_t* cnt_t = a.counts + f0;                            // (16-byte aligned: out_off is a multiple of 32, tile.start of 1024)
   const uint8_t* okb_t = a.okb + f0;
-  const int n = (int)n_out;
   const int k = a.k;
-  const bool head = tile.start == 0;                                  // only the first tile of a contig holds positions < k
-#pragma unroll 4
-  for (int w0 = 0; w0 < n; w0 += 32) {
-    const int q = w0 + lane;
-    const bool in = q < n;
-    const uint32_t c = in ? cnt_t[q] : 0u;
-    const bool ok = in && okb_t[q] != 0;
-    const bool early = head && q < k;
-    const uint32_t prev = (in && !early) ? cnt_t[q - k] : 0u;          // (q - k < 0 reaches into the previous tile of the same contig)
-    const bool low = c < a.solid_thre;
-    const bool wk = ok && low;
-    const bool ev = in && (!ok || early || low || (unsigned long long)c * JB_DIVISOR < (unsigned long long)prev);
-    const unsigned int word = __ballot_sync(0xffffffffu, ev);
-    const unsigned int wword = __ballot_sync(0xffffffffu, wk);
-    if (lane == 0) {
-      const uint64_t f = f0 + w0;                                   // contig offsets are multiples of 32, not of 1024:
-      a.events[f >> 5] = word; a.weak[f >> 5] = wword;              // a tile can straddle two summary blocks
+  const bool head = tile.start == 0;                                // only the first tile of a contig holds positions < k
+  const unsigned group = 0xFFu << (lane & 24);                      // the eight lanes that share a word
+  const int sh = 4 * (lane & 7);
+#pragma unroll 2
+  for (int w0 = 0; w0 < n; w0 += 128) {
+    const int q0 = w0 + 4 * lane;
+    uint32_t c[4] = {0, 0, 0, 0}, prev[4] = {0, 0, 0, 0};
+    uint32_t okw = 0;
+    if (q0 + 3 < n) {
+      const uint4 cv = *reinterpret_cast<const uint4*>(cnt_t + q0);
+      c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
+      okw = *reinterpret_cast<const uint32_t*>(okb_t + q0);
+    } else {
+#pragma unroll
+      for (int x = 0; x < 4; ++x) if (q0 + x < n) { c[x] = cnt_t[q0 + x]; okw |= (uint32_t)okb_t[q0 + x] << (8 * x); }
+    }
+    // the count k positions back (the 1/50 test); it reaches into the previous tile of the same contig, never before position 0
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int q = q0 + x;
+      if (q < n && !(head && q < k)) prev[x] = cnt_t[q - k];
+    }
+    uint32_t ev = 0, wk = 0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int q = q0 + x;
+      const bool in = q < n;
+      const bool ok = in && ((okw >> (8 * x)) & 0xFFu) != 0;
+      const bool early = head && q < k;
+      const bool low = c[x] < a.solid_thre;
+      if (ok && low) wk |= 1u << x;
+      if (in && (!ok || early || low || (unsigned long long)c[x] * JB_DIVISOR < (unsigned long long)prev[x])) ev |= 1u << x;
+    }
+    const uint32_t word = __reduce_or_sync(group, ev << sh), wword = __reduce_or_sync(group, wk << sh);
+    if ((lane & 7) == 0 && w0 + 4 * lane < n) {                     // (contig offsets are multiples of 32, not of 1024:
+      const uint64_t f = f0 + (uint64_t)(w0 + 4 * lane);            //  a tile can straddle two summary blocks)
+      a.events[f >> 5] = word; a.weak[f >> 5] = wword;
       if (word) {
         const uint32_t bit = 1u << ((f >> 10) & 31);
         if (!(atomicOr(&a.events_l1[f >> 15], bit))) atomicOr(&a.events_l2[f >> 20], 1u << ((f >> 15) & 31));   // first bit of its level-1 word

@@ -85,20 +85,63 @@ def _unique_sum(lo, hi, w):
     return lo[idx], hi[idx], tot
 
 
+DIRT = {"repeat_copies": 150, "repeat_len": 400, "repeat_divergence": 0.02, "homopolymer_every": 2000, "homopolymer_len": (6, 16),
+        "heterozygosity": 0.004, "n_runs": 24, "n_run_len": (20, 400), "lower_stretches": 200, "lower_len": (200, 2000)}
+
+
+def dirty_genome(G: int, seed: int, dev) -> torch.Tensor:
+    """A random genome with what real assemblies hold and iid bases do not: a repeat family (DIRT["repeat_copies"] diverged
+    copies of one unit) and homopolymer runs.  int64 codes on `dev`."""
+    rng = np.random.default_rng(seed + 77)
+    g = rng.integers(0, 4, G, dtype=np.uint8)
+    L = DIRT["repeat_len"]
+    unit = rng.integers(0, 4, L, dtype=np.uint8)
+    for p in rng.integers(0, max(1, G - L), DIRT["repeat_copies"]):
+        c = unit.copy()
+        m = rng.random(L) < DIRT["repeat_divergence"]
+        c[m] = (c[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) % 4
+        g[p:p + L] = c[:max(0, min(L, G - p))]
+    lo, hi = DIRT["homopolymer_len"]
+    for p in rng.integers(0, max(1, G - hi), max(1, G // DIRT["homopolymer_every"])):
+        g[p:p + int(rng.integers(lo, hi))] = rng.integers(0, 4)
+    return torch.from_numpy(g).to(dev).to(torch.int64)
+
+
 def make_workload(out_dir: str, genome_bp: int, k: int, seed: int, coverage: float = 30.0, read_len: int = 150,
-                  err_kmers_per_bp: float = 2.2, device: str | None = None, r_bits: int | None = None) -> dict:
-    """Writes out_dir/db.jf and returns {"genome": uint8 codes (cpu numpy), "db": path, "n_records": N, ...}."""
+                  err_kmers_per_bp: float = 2.2, device: str | None = None, r_bits: int | None = None, dirty: bool = False) -> dict:
+    """Writes out_dir/db.jf and returns {"genome": uint8 codes (cpu numpy), "db": path, "n_records": N, ...}.
+    dirty: the genome carries a repeat family and homopolymer runs (dirty_genome) and the reads come from TWO haplotypes that
+    differ at DIRT["heterozygosity"] of the sites, half of the coverage each; the assembly is made from the first."""
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     G = int(genome_bp)
-    g = torch.randint(0, 4, (G,), dtype=torch.int64, device=dev, generator=gen)
-    flo, fhi, rlo, rhi = _keys_from_codes(g, k)
-    take = _ult(rlo, rhi, flo, fhi)
-    clo = torch.where(take, rlo, flo)
-    chi = torch.where(take, rhi, fhi)
     lam = coverage * (read_len - k + 1) / read_len
-    w = torch.poisson(torch.full((clo.numel(),), lam, device=dev), generator=gen).to(torch.int64).clamp_(min=1)
+    if dirty:
+        g = dirty_genome(G, seed, dev)
+        h2 = g.clone()
+        het = torch.rand(G, device=dev, generator=gen) < DIRT["heterozygosity"]
+        h2[het] = (h2[het] + torch.randint(1, 4, (int(het.sum()),), device=dev, generator=gen)) & 3
+        flo, fhi, rlo, rhi = _keys_from_codes(g, k)              # (error k-mers below are cut from the first haplotype)
+        take = _ult(rlo, rhi, flo, fhi)
+        clo = torch.where(take, rlo, flo)
+        chi = torch.where(take, rhi, fhi)
+        w = torch.poisson(torch.full((clo.numel(),), lam / 2, device=dev), generator=gen).to(torch.int64)
+        f2lo, f2hi, r2lo, r2hi = _keys_from_codes(h2, k)
+        take = _ult(r2lo, r2hi, f2lo, f2hi)
+        clo = torch.cat([clo, torch.where(take, r2lo, f2lo)]); chi = torch.cat([chi, torch.where(take, r2hi, f2hi)])
+        w = torch.cat([w, torch.poisson(torch.full((f2lo.numel(),), lam / 2, device=dev), generator=gen).to(torch.int64)])
+        del h2, het, f2lo, f2hi, r2lo, r2hi
+        keep = w > 0                                             # (a window no read covers is not in the database)
+        clo, chi, w = clo[keep], chi[keep], w[keep]
+        del keep
+    else:
+        g = torch.randint(0, 4, (G,), dtype=torch.int64, device=dev, generator=gen)
+        flo, fhi, rlo, rhi = _keys_from_codes(g, k)
+        take = _ult(rlo, rhi, flo, fhi)
+        clo = torch.where(take, rlo, flo)
+        chi = torch.where(take, rhi, fhi)
+        w = torch.poisson(torch.full((clo.numel(),), lam, device=dev), generator=gen).to(torch.int64).clamp_(min=1)
     # singleton error k-mers: a genome window with one base substituted
     E = int(err_kmers_per_bp * G)
     if E > 0:
@@ -174,8 +217,9 @@ def make_workload(out_dir: str, genome_bp: int, k: int, seed: int, coverage: flo
     return {"genome": genome, "db": path, "n_records": int(N), "r": r, "lambda": lam, "err_kmers": E}
 
 
-def make_assembly(genome: np.ndarray, rate: float, seed: int, device: str | None = None) -> bytes:
-    """synth.inject_errors (0.5 substitution / 0.25 deletion / 0.25 insertion) with torch ops."""
+def make_assembly(genome: np.ndarray, rate: float, seed: int, device: str | None = None, dirty: bool = False) -> bytes:
+    """synth.inject_errors (0.5 substitution / 0.25 deletion / 0.25 insertion) with torch ops; dirty: plus runs of N / n and
+    lower-case stretches (the reference keeps case and skips windows with N, src/jasper.py:56-69)."""
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
@@ -195,5 +239,16 @@ def make_assembly(genome: np.ndarray, rate: float, seed: int, device: str | None
     at = (torch.cumsum(rep, 0) - 1)[ins]
     a2[at] = insb[ins]
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    out = lut[a2].cpu().numpy().tobytes()
-    return out
+    if not dirty:
+        return lut[a2].cpu().numpy().tobytes()
+    out = lut[a2].cpu().numpy().copy()
+    rng = np.random.default_rng(seed + 5)
+    lo, hi = DIRT["n_run_len"]
+    per = out.size / 64e6                                                             # (the counts are per 64 Mb)
+    for p in rng.integers(0, max(1, out.size - hi), max(1, int(round(DIRT["n_runs"] * per)))):                  # runs of N (and a few of n)
+        out[p:p + int(rng.integers(lo, hi))] = ord("N") if rng.random() < 0.8 else ord("n")
+    lo, hi = DIRT["lower_len"]
+    for p in rng.integers(0, max(1, out.size - hi), max(1, int(round(DIRT["lower_stretches"] * per)))):         # soft-masked stretches
+        e = p + int(rng.integers(lo, hi))
+        out[p:e] |= 0x20
+    return out.tobytes()
