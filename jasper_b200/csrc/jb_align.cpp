@@ -47,39 +47,55 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
   static thread_local std::vector<score_t> score_tl;
   static thread_local std::vector<uint8_t> trace_tl;
   static thread_local std::vector<score_t> col_score_tl;
-  score_tl.assign((size_t)(la + 1) * W, 0);
-  trace_tl.assign((size_t)(la + 1) * W, 0);
-  col_score_tl.assign(lb + 1, 0);
-  score_t* const score = score_tl.data();                  // (one TLS lookup each, not one per matrix access)
-  uint8_t* const trace = trace_tl.data();
-  score_t* const col_score = col_score_tl.data();
-  const score_t first_gap = gap_cost(1, kOpen);
-  for (int i = 0; i <= la; ++i) score[(size_t)i * W] = gap_cost(i, kOpen);
-  for (int j = 0; j <= lb; ++j) score[j] = gap_cost(j, kOpen);
-  for (int j = 1; j <= lb; ++j) col_score[j] = gap_cost(j, 2 * kOpen);
-  for (int row = 1; row <= la; ++row) {
-    score_t row_score = gap_cost(row, 2 * kOpen);
-    const score_t* up = score + (size_t)(row - 1) * W;     // (row pointers: the index arithmetic was a third of the loop)
-    score_t* cur = score + (size_t)row * W;
-    uint8_t* tcur = trace + (size_t)row * W;
-    const char ar = A[row - 1];
-    for (int col = 1; col <= lb; ++col) {
-      const score_t nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
-      const score_t row_open = cur[col - 1] + first_gap;
-      const score_t row_extend = row_score + kExtend;
-      row_score = row_open > row_extend ? row_open : row_extend;
-      const score_t col_open = up[col] + first_gap;
-      const score_t col_extend = col_score[col] + kExtend;
-      const score_t cs = col_open > col_extend ? col_open : col_extend;
-      col_score[col] = cs;
-      score_t best = nogap > cs ? nogap : cs;
-      if (row_score > best) best = row_score;
-      cur[col] = best;
-      int t = nogap == best ? 2 : 0;
-      if (row_score == best) t += (row_open == row_score ? 1 : 0) + (row_extend == row_score ? 8 : 0);
-      if (cs == best) t += (col_open == cs ? 4 : 0) + (col_extend == cs ? 16 : 0);
-      tcur[col] = (uint8_t)t;
+  score_t* score = nullptr;
+  uint8_t* trace = nullptr;
+  // Only a band around the diagonal is computed.  With these penalties every gap character and every mismatch costs 1, so
+  // a cell (i, j) lies on an optimal alignment of cost d only if |i - j| <= d, and the trace-back below only ever stands on
+  // such cells (it moves from a cell to predecessors that achieve the cell's best score, starting at the end).  Cells
+  // outside the band keep a score no path can reach and a trace value no branch acts on; in-band cells that depend on them
+  // come out too low, never too high, and none of those can be on an optimal alignment while the band is wider than d.
+  // So: half-width `band`, accept when the cost found is below it, else widen (the second round is the whole matrix).
+  constexpr score_t kNever = -(1 << 28);
+  int band = std::abs(la - lb) + 3;
+  if (getenv("JB_ALIGN_NO_BAND")) band = la + lb + 1;
+  while (true) {
+    score_tl.assign((size_t)(la + 1) * W, kNever);
+    trace_tl.assign((size_t)(la + 1) * W, 32);             // (32: none of the move bits)
+    col_score_tl.assign(lb + 1, 0);
+    score = score_tl.data();                               // (one TLS lookup each, not one per matrix access)
+    trace = trace_tl.data();
+    score_t* const col_score = col_score_tl.data();
+    const score_t first_gap = gap_cost(1, kOpen);
+    for (int i = 0; i <= la; ++i) { score[(size_t)i * W] = gap_cost(i, kOpen); trace[(size_t)i * W] = 0; }
+    for (int j = 0; j <= lb; ++j) { score[j] = gap_cost(j, kOpen); trace[j] = 0; }
+    for (int j = 1; j <= lb; ++j) col_score[j] = j <= band + 1 ? gap_cost(j, 2 * kOpen) : kNever;
+    for (int row = 1; row <= la; ++row) {
+      const int c_lo = row - band > 1 ? row - band : 1, c_hi = row + band < lb ? row + band : lb;
+      score_t row_score = c_lo == 1 ? gap_cost(row, 2 * kOpen) : kNever;
+      const score_t* up = score + (size_t)(row - 1) * W;   // (row pointers: the index arithmetic was a third of the loop)
+      score_t* cur = score + (size_t)row * W;
+      uint8_t* tcur = trace + (size_t)row * W;
+      const char ar = A[row - 1];
+      for (int col = c_lo; col <= c_hi; ++col) {
+        const score_t nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
+        const score_t row_open = cur[col - 1] + first_gap;
+        const score_t row_extend = row_score + kExtend;
+        row_score = row_open > row_extend ? row_open : row_extend;
+        const score_t col_open = up[col] + first_gap;
+        const score_t col_extend = col_score[col] + kExtend;
+        const score_t cs = col_open > col_extend ? col_open : col_extend;
+        col_score[col] = cs;
+        score_t best = nogap > cs ? nogap : cs;
+        if (row_score > best) best = row_score;
+        cur[col] = best;
+        int t = nogap == best ? 2 : 0;
+        if (row_score == best) t += (row_open == row_score ? 1 : 0) + (row_extend == row_score ? 8 : 0);
+        if (cs == best) t += (col_open == cs ? 4 : 0) + (col_extend == cs ? 16 : 0);
+        tcur[col] = (uint8_t)t;
+      }
     }
+    if (band > la + lb || -score[(size_t)la * W + lb] < band) break;
+    band = la + lb + 1;
   }
   auto tr = [&](int r, int c) { return (int)trace[(size_t)r * W + c]; };
   auto sc = [&](int r, int c) { return score[(size_t)r * W + c]; };

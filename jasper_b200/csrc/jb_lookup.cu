@@ -128,7 +128,7 @@ extern "C" int jb_count_positions(const jb_db* db, const char* seq, size_t len, 
   uint8_t* d_seq = nullptr; uint32_t* d_cnt = nullptr; ScanUnit* d_units = nullptr; uint32_t* d_tiles = nullptr;
   cudaEvent_t e0, e1, e2, e3;
   JB_CUDA(cudaEventCreate(&e0)); JB_CUDA(cudaEventCreate(&e1)); JB_CUDA(cudaEventCreate(&e2)); JB_CUDA(cudaEventCreate(&e3));
-  JB_CUDA(cudaMalloc(&d_seq, len + 16));
+  JB_CUDA(cudaMalloc(&d_seq, len + kSeqSlice + 16));      // (k_scan fetches whole tile slices: room behind the last base)
   JB_CUDA(cudaMalloc(&d_cnt, (len + 1) * 4));
   JB_CUDA(cudaMalloc(&d_units, sizeof(ScanUnit)));
   JB_CUDA(cudaMalloc(&d_tiles, tiles.size() * sizeof(uint32_t)));

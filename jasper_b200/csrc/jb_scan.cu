@@ -40,23 +40,66 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* s_lut = reinterpret_cast<uint64_t*>(smem);
   const int lut_n = t.g.key_bytes * 256;
-  uint8_t* s_seq = smem + (size_t)lut_n * 8 + (size_t)warp * kScanSmemPerWarp;
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_seq + kSeqSlice);
+  uint8_t* s_warp = smem + (size_t)lut_n * 8 + (size_t)warp * kScanSmemPerWarp;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_warp + kSeqBufs * kSeqSlice);
   for (int i = threadIdx.x; i < lut_n; i += kScanThreads) s_lut[i] = t.lut[i];
+#if JB_SCAN_TMA
+  // one mbarrier per tile buffer, owned by this warp: lane 0 asks the TMA unit for a tile's bases (one 1-D bulk copy, the
+  // source is 16-byte aligned: contig offsets are multiples of 32, tile starts of 1024) and every lane waits on the barrier
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_cnt + kCntSlice);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t phase = 0;                                // bit b = parity the next wait on buffer b expects
+  int buf = 0;
+  auto tile_fetch = [&](uint32_t ti, int into) {     // lane 0 only
+    const ScanTile nt = decode_tile(a.tile_first, a.n_units, ti);
+    const ScanUnit nu = a.units[nt.unit];
+    const uint8_t* src = a.bases + nu.seq_off + nt.start;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_warp + into * kSeqSlice), bar = bar0 + 8 * into;
+    // (always the whole slice: a contig's region extends 4096 bytes past its last base, the bytes behind the end are cleared below)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kSeqSlice) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"((uint32_t)kSeqSlice), "r"(bar) : "memory");
+  };
+#endif
   __syncthreads();                                   // the only block-wide barrier
   unsigned long long steps_total = 0;
   const int top_shift = 2 * k - 2;
   const uint32_t warps_total = gridDim.x * kScanWarps;
   const unsigned long long lim = 1ull << t.g.cnt_bits;
   const uint32_t cmask = cval_mask(t.g);
+#if JB_SCAN_TMA
+  if (lane == 0 && blockIdx.x * kScanWarps + warp < a.n_tiles) tile_fetch(blockIdx.x * kScanWarps + warp, 0);
+#endif
 
   for (uint32_t ti = blockIdx.x * kScanWarps + warp; ti < a.n_tiles; ti += warps_total) {
     const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
     const ScanUnit u = a.units[tile.unit];
     const int64_t n_out = (int64_t)min((uint64_t)kTile, u.len + 1 - tile.start);   // positions produced
     const int n_chars = (int)n_out + k - 1;
-    const uint8_t* src = a.bases + u.seq_off + tile.start;
     const int64_t avail = (int64_t)u.len - (int64_t)tile.start;                    // real bases from tile.start on
+#if JB_SCAN_TMA
+    uint8_t* s_seq = s_warp + buf * kSeqSlice;
+    __syncwarp();                                                                  // the other buffer's readers (previous tile) are done
+    if (lane == 0 && ti + warps_total < a.n_tiles) tile_fetch(ti + warps_total, buf ^ 1);
+    {
+      const uint32_t bar = bar0 + 8 * buf, par = (phase >> buf) & 1u;
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(par) : "memory");
+      phase ^= 1u << buf;
+    }
+    if (avail < n_chars + 1)                                                       // past the contig end: zeros, as MerDNA sees them
+      for (int i = (int)(avail > 0 ? avail : 0) + lane; i < n_chars + 1; i += 32) s_seq[i] = 0;
+    __syncwarp();
+    buf ^= 1;
+#else
+    uint8_t* s_seq = s_warp;
+    const uint8_t* src = a.bases + u.seq_off + tile.start;
     __syncwarp();                                                                  // previous tile's smem reads are done
     // ---- stage bases: 16-byte loads where the source is aligned, zero-fill past the contig end
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -75,6 +118,7 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
       for (int i = lane; i < n_chars + 1; i += 32) s_seq[i] = (i < avail) ? src[i] : (uint8_t)0;
     }
     __syncwarp();
+#endif
 
     // ---- each lane: 32 consecutive windows starting at r0
     const int r0 = lane * kLanePos;

@@ -43,9 +43,13 @@ constexpr int kTile = 32 * kLanePos;                // 1024 positions per warp t
 constexpr int kGroup = JB_SCAN_GROUP;               // probes in flight per lane, wide table
 constexpr int kGroupCompact = JB_SCAN_GROUP_COMPACT;
 constexpr int kScanCtasPerSm = JB_SCAN_MINBLOCKS;
+#ifndef JB_SCAN_TMA
+#define JB_SCAN_TMA 1                               // tiles arrive by cp.async.bulk (TMA), the next one while the current one is probed
+#endif
 constexpr int kSeqSlice = kTile + JB_MAX_K + 16;    // staged bases per warp (multiple of 16)
+constexpr int kSeqBufs = JB_SCAN_TMA ? 2 : 1;       // TMA: double-buffered
 constexpr int kCntSlice = 33 * 32;                  // counts, row-padded against bank conflicts
-constexpr size_t kScanSmemPerWarp = (size_t)kSeqSlice + (size_t)kCntSlice * 4;
+constexpr size_t kScanSmemPerWarp = (size_t)kSeqBufs * kSeqSlice + (size_t)kCntSlice * 4 + (JB_SCAN_TMA ? 16 : 0);   // (+ two mbarriers)
 
 struct ScanUnit {          // one contig
   uint64_t seq_off;        // first base in the flat base buffer

@@ -125,6 +125,43 @@ def test_alignment_shortcut_equals_the_matrix(hostsim_lib, monkeypatch):
     assert fast == slow
 
 
+def test_alignment_band_equals_the_matrix(hostsim_lib, monkeypatch):
+    """The matrix is only filled in a band around the diagonal (every gap character and mismatch costs 1, so an optimal
+    alignment of cost d stays within |i - j| <= d; the band is widened when the cost found does not fit).  Same first
+    alignment as the full matrix on pairs with substitutions, insertions and deletions, small alphabets (ties) included, and
+    on pairs that need the widened band."""
+    rng = np.random.default_rng(9)
+    pairs = []
+    for it in range(5000):
+        n = int(rng.integers(1, 120))
+        alpha = "ACGT"[:int(rng.integers(1, 5))]
+        a = [alpha[int(x)] for x in rng.integers(0, len(alpha), n)]
+        b = list(a)
+        for _ in range(int(rng.integers(0, 5)) if it % 10 else int(rng.integers(5, 40))):      # every tenth pair: many edits
+            op, at = int(rng.integers(0, 3)), int(rng.integers(0, max(1, len(b))))
+            if op == 0 and b:
+                b[at] = "ACGT"[int(rng.integers(0, 4))]
+            elif op == 1:
+                b.insert(at, "ACGT"[int(rng.integers(0, 4))])
+            elif b:
+                del b[at]
+        if b:
+            pairs.append(("".join(a).encode(), "".join(b).encode()))
+
+    def run():
+        out = []
+        oa, ob = C.create_string_buffer(512), C.create_string_buffer(512)
+        for a, b in pairs:
+            ok = hostsim_lib.hostsim_align(a, b, oa, ob, 512)
+            out.append((ok, oa.value, ob.value) if ok else (0, b"", b""))
+        return out
+    banded = run()
+    monkeypatch.setenv("JB_ALIGN_NO_BAND", "1")
+    full = run()
+    monkeypatch.delenv("JB_ALIGN_NO_BAND")
+    assert banded == full
+
+
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
 @pytest.mark.parametrize("use_events", [0, 1, 64, 300, 2048])
 def test_walker_source_matches_golden(golden_cases, hostsim_lib, name, use_events):
