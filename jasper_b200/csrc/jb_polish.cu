@@ -1110,11 +1110,10 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       JB_CUDA(cudaEventRecord(pe.r1, s));
       pe.recount = true;
       launches += 3;
-      // (not while the polished bases travel on the side stream: a device-to-host copy on this stream would queue behind
-      //  them in the copy engine and hold the stream for the whole transfer; the statistic of that pass is dropped)
+      // (by kernel, never by the copy engine: behind the last fixing pass the polished bases start travelling on the side
+      //  stream, and a device-to-host copy on this stream would queue behind them and hold the stream for the whole transfer)
       w.h_probes.p[ite] = 0;
-      if (!(b->early && ite == passes - 1)) JB_CUDA(cudaMemcpyAsync(w.h_probes.p + ite, w.used.p + 4, 8, cudaMemcpyDeviceToHost, s));
-      return JB_OK;
+      return small_d2h(w.h_probes.p + ite, w.used.p + 4, 8, true, s);
     };
     if (do_fix && speculate) { if (int rc = stitch_and_recount()) return rc; }
     mark("walk launched", ite);
@@ -1339,7 +1338,8 @@ extern "C" int jb_batch_fetch(jb_batch* b, jb_result** out) {
   cudaStream_t s = b->db->stream;
   std::unique_ptr<jb_result> r(new jb_result());
   r->status = b->status;
-  r->passes = b->passes;
+  if (b->fetch_follows) r->passes = std::move(b->passes);      // jb_polish frees the batch right behind this call: no copy of the rows
+  else r->passes = b->passes;
   r->seq_off.resize(b->n); r->seq_len.resize(b->n);
   uint64_t total = 0;
   for (size_t i = 0; i < b->n; ++i) { r->seq_off[i] = total; r->seq_len[i] = (uint64_t)b->len[i]; total += (uint64_t)b->len[i]; }

@@ -43,8 +43,12 @@ constexpr int kTile = 32 * kLanePos;                // 1024 positions per warp t
 constexpr int kGroup = JB_SCAN_GROUP;               // probes in flight per lane, wide table
 constexpr int kGroupCompact = JB_SCAN_GROUP_COMPACT;
 constexpr int kScanCtasPerSm = JB_SCAN_MINBLOCKS;
+// 1: tiles arrive by cp.async.bulk (TMA) into a double buffer with an mbarrier per buffer, the next tile in flight while the
+// current one is probed.  Measured against the per-lane staging on one box (profiles/r2g_scan_tma_ab.txt): k_scan 2.32 ms
+// against 1.87 ms -- the second tile buffer takes the shared-memory carve-out from 196 KB to 228 KB per SM and the staging was
+// never on the critical path (a warp spends ~1 us of a ~35 us tile on it).  Kept as a build option, off by default.
 #ifndef JB_SCAN_TMA
-#define JB_SCAN_TMA 1                               // tiles arrive by cp.async.bulk (TMA), the next one while the current one is probed
+#define JB_SCAN_TMA 0
 #endif
 constexpr int kSeqSlice = kTile + JB_MAX_K + 16;    // staged bases per warp (multiple of 16)
 constexpr int kSeqBufs = JB_SCAN_TMA ? 2 : 1;       // TMA: double-buffered
