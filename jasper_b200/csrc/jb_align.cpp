@@ -32,6 +32,7 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
   // matrix: a column with a gap costs as much as a mismatch and gaps come in pairs, so the gapless alignment (score -h)
   // is the only optimal one unless h == 2 and one deletion plus one insertion line everything else up
   // (A[m1+1 : m2+1] == B[m1 : m2] or A[m1 : m2] == B[m1+1 : m2+1]); only that tie needs the traceback order below.
+  // (tests switch the shortcuts off through the environment; it is read per call, but only these two short names)
   if (la == lb && !getenv("JB_ALIGN_NO_FAST")) {
     int h = 0, m1 = -1, m2 = -1;
     for (int i = 0; i < la && h <= 2; ++i)
@@ -58,16 +59,18 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
   constexpr score_t kNever = -(1 << 28);
   int band = std::abs(la - lb) + 3;
   if (getenv("JB_ALIGN_NO_BAND")) band = la + lb + 1;
+  // (thousands of these per pass on the row threads: the matrices are kept between calls and only the band, the cells that
+  //  border it and the matrix borders inside it are written -- nothing else is ever read, see the gap-extension walk below)
+  if (score_tl.size() < (size_t)(la + 1) * W) { score_tl.resize((size_t)(la + 1) * W); trace_tl.resize((size_t)(la + 1) * W); }
+  if (col_score_tl.size() < (size_t)lb + 1) col_score_tl.resize((size_t)lb + 1);
+  score = score_tl.data();                                 // (one TLS lookup each, not one per matrix access)
+  trace = trace_tl.data();
+  score_t* const col_score = col_score_tl.data();
+  const score_t first_gap = gap_cost(1, kOpen);
   while (true) {
-    score_tl.assign((size_t)(la + 1) * W, kNever);
-    trace_tl.assign((size_t)(la + 1) * W, 32);             // (32: none of the move bits)
-    col_score_tl.assign(lb + 1, 0);
-    score = score_tl.data();                               // (one TLS lookup each, not one per matrix access)
-    trace = trace_tl.data();
-    score_t* const col_score = col_score_tl.data();
-    const score_t first_gap = gap_cost(1, kOpen);
-    for (int i = 0; i <= la; ++i) { score[(size_t)i * W] = gap_cost(i, kOpen); trace[(size_t)i * W] = 0; }
-    for (int j = 0; j <= lb; ++j) { score[j] = gap_cost(j, kOpen); trace[j] = 0; }
+    const int edge = band + 1;                             // border cells up to here lie inside the band or next to it
+    for (int i = 0; i <= la && i <= edge; ++i) { score[(size_t)i * W] = gap_cost(i, kOpen); trace[(size_t)i * W] = 0; }
+    for (int j = 0; j <= lb && j <= edge; ++j) { score[j] = gap_cost(j, kOpen); trace[j] = 0; }
     for (int j = 1; j <= lb; ++j) col_score[j] = j <= band + 1 ? gap_cost(j, 2 * kOpen) : kNever;
     for (int row = 1; row <= la; ++row) {
       const int c_lo = row - band > 1 ? row - band : 1, c_hi = row + band < lb ? row + band : lb;
@@ -75,6 +78,8 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
       const score_t* up = score + (size_t)(row - 1) * W;   // (row pointers: the index arithmetic was a third of the loop)
       score_t* cur = score + (size_t)row * W;
       uint8_t* tcur = trace + (size_t)row * W;
+      if (c_lo > 1) { cur[c_lo - 1] = kNever; tcur[c_lo - 1] = 32; }      // the cells next to the band: never reached,
+      if (c_hi < lb) { cur[c_hi + 1] = kNever; tcur[c_hi + 1] = 32; }     // and no move bit set (32)
       const char ar = A[row - 1];
       for (int col = c_lo; col <= c_hi; ++col) {
         const score_t nogap = up[col - 1] + (ar == B[col - 1] ? kMatch : kMismatch);
@@ -97,6 +102,7 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
     if (band > la + lb || -score[(size_t)la * W + lb] < band) break;
     band = la + lb + 1;
   }
+  const int band_used = band;
   auto tr = [&](int r, int c) { return (int)trace[(size_t)r * W + c]; };
   auto sc = [&](int r, int c) { return score[(size_t)r * W + c]; };
 
@@ -150,6 +156,10 @@ bool first_global_alignment(const std::string& A, const std::string& B, std::str
           for (int n = 0; n < target; ++n) {
             if (in_a) { --col; a.push_back('-'); b.push_back(B[col]); }
             else { --row; a.push_back(A[row]); b.push_back('-'); }
+            // Outside the band nothing can match (such a cell is on no optimal alignment) and the walk would only run on
+            // to the matrix border, where the trace value 0 kills this branch: same outcome, without reading cells that
+            // were never written.
+            if (col - row > band_used || row - col > band_used) { dead = true; break; }
             score_t actual = sc(row, col) + gap_cost(n + 1, kOpen);
             if (actual == target_score && n > 0) {
               if (!tr(row, col)) break;
