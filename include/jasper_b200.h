@@ -80,6 +80,12 @@ typedef struct {
   double bytes_per_record;   /* table_bytes / n_records                             */
   double read_seconds;       /* busiest reader thread's time inside read()          */
   uint64_t file_bytes;
+  /* the scan index: the records once more, grouped by minimizer, for the every-window-of-a-contig access pattern (0 = not built) */
+  uint64_t index_bytes;
+  uint64_t index_buckets;
+  int32_t index_mmer;     /* minimizer length */
+  int32_t pad_;
+  double index_seconds;
 } jb_db_info_t;
 
 typedef struct {

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjasper_b200.so")
-SOURCES = ["jb_api.cu", "jb_table.cu", "jb_lookup.cu", "jb_scan.cu", "jb_polish.cu", "jb_header.cpp", "jb_align.cpp"]
+SOURCES = ["jb_api.cu", "jb_table.cu", "jb_index.cu", "jb_lookup.cu", "jb_scan.cu", "jb_polish.cu", "jb_header.cpp", "jb_align.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

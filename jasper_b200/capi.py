@@ -35,7 +35,8 @@ class _DbInfo(C.Structure):
                 ("build_kernel_ms", C.c_double), ("layout", C.c_int32), ("slot_bytes", C.c_int32), ("remainder_bits", C.c_int32),
                 ("tag_bits", C.c_int32), ("count_bits", C.c_int32), ("n_parts", C.c_int32), ("home_units", C.c_uint64),
                 ("n_stash", C.c_uint64), ("load_factor", C.c_double), ("bytes_per_record", C.c_double), ("read_seconds", C.c_double),
-                ("file_bytes", C.c_uint64)]
+                ("file_bytes", C.c_uint64), ("index_bytes", C.c_uint64), ("index_buckets", C.c_uint64), ("index_mmer", C.c_int32),
+                ("pad_", C.c_int32), ("index_seconds", C.c_double)]
 
 
 LAYOUT_WIDE, LAYOUT_COMPACT = 0, 1

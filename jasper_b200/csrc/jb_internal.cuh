@@ -10,6 +10,7 @@
 #include "../../include/jasper_b200.h"
 #include "jb_header.hpp"
 #include "jb_kmer.cuh"
+#include "jb_index.cuh"
 
 namespace jb {
 
@@ -54,6 +55,7 @@ struct TableView {
   // compact only: records whose count exceeds the count field, or that were displaced beyond kMaxHops
   const Slot* stash;                               // wide slots, 2 per sector, linear probing; replicated on every device
   uint64_t stash_units;                            // 0 = no stash
+  ScanIndex ix;                                    // the records once more, grouped by minimizer, for k_scan (jb_index.cuh); bucket_bits 0 = none
 };
 
 // the bytes of probe unit `unit`, wherever they live
@@ -159,6 +161,10 @@ __device__ __forceinline__ uint32_t table_count(const TableView& t, const Key& c
 }  // namespace jb
 
 struct jb_db;
+namespace jb {
+int build_scan_index(jb_db* db);       // jb_index.cu: JB_OK also when no index is built (switched off, does not fit, partitioned table)
+void free_scan_index(jb_db* db);
+}
 int jb_check_ready(const jb_db* db);   // JB_OK, or an error while a part-wise opened table still lacks its other parts
 
 struct jb_db {
@@ -187,6 +193,12 @@ struct jb_db {
   uint64_t part_overlap = 0;           // units
   uint8_t* parts[jb::kMaxParts] = {};
   uint64_t part_first[jb::kMaxParts + 1] = {};     // units
+  // the scan index (jb_index.cuh)
+  void* idx_slots = nullptr; void* idx_off = nullptr;
+  int idx_bits = 0, idx_m = 0;
+  uint64_t idx_n_slots = 0;
+  bool idx_wide_off = false;
+  double idx_seconds = 0;
   int unit_bytes() const { return 32; }
   uint64_t my_units() const {          // units resident behind `mem`
     return n_parts > 1 ? part_first[my_part + 1] - part_first[my_part] + (my_part + 1 < n_parts ? part_overlap : 0) : n_units;
@@ -199,6 +211,10 @@ struct jb_db {
     for (int q = 0; q < jb::kMaxParts; ++q) v.part[q] = parts[q];
     for (int q = 0; q <= jb::kMaxParts; ++q) v.part_first[q] = part_first[q];
     v.stash = stash; v.stash_units = stash_units;
+    v.ix.slots = reinterpret_cast<const uint4*>(idx_slots);
+    v.ix.off32 = idx_wide_off ? nullptr : reinterpret_cast<const uint32_t*>(idx_off);
+    v.ix.off64 = idx_wide_off ? reinterpret_cast<const uint64_t*>(idx_off) : nullptr;
+    v.ix.bucket_bits = idx_bits; v.ix.m = idx_m;
     return v;
   }
 };

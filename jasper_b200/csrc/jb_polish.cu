@@ -1425,6 +1425,7 @@ extern "C" int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** ou
   for (int i = 0; i < n; ++i) {
     auto d = new jb_db(*src);
     d->device = devices[i]; d->mem = nullptr; d->lut = nullptr; d->stream = nullptr; d->stash = nullptr; d->stash_list = nullptr;
+    d->idx_slots = nullptr; d->idx_off = nullptr; d->idx_bits = 0;
     for (int q = 0; q < kMaxParts; ++q) { d->parts[q] = nullptr; d->ipc_mapped[q] = false; }
     outs[i] = d;
     cudaError_t e = cudaSetDevice(devices[i]);
@@ -1441,6 +1442,17 @@ extern "C" int jb_db_replicate(jb_db* src, int n, const int* devices, jb_db** ou
     if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
     if (e != cudaSuccess) { undo(); cudaGetLastError(); return fail(JB_E_CUDA, std::string("jb_db_replicate: ") + cudaGetErrorString(e)); }
     d->parts[0] = d->mem;
+    if (src->idx_bits) {                                  // the scan index travels too when it fits (else this replica scans through the hash table)
+      const size_t off_bytes = ((size_t)1 << src->idx_bits) * (src->idx_wide_off ? 8 : 4) + (src->idx_wide_off ? 8 : 4);
+      const size_t slot_bytes = (size_t)std::max<uint64_t>(src->idx_n_slots, 1) * 16;
+      cudaError_t e2 = cudaMalloc(&d->idx_slots, slot_bytes);
+      if (e2 == cudaSuccess) e2 = cudaMalloc(&d->idx_off, off_bytes);
+      if (e2 == cudaSuccess) e2 = cudaMemcpyPeerAsync(d->idx_slots, devices[i], src->idx_slots, src->device, slot_bytes, d->stream);
+      if (e2 == cudaSuccess) e2 = cudaMemcpyPeerAsync(d->idx_off, devices[i], src->idx_off, src->device, off_bytes, d->stream);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(d->stream);
+      if (e2 == cudaSuccess) d->idx_bits = src->idx_bits;
+      else { cudaGetLastError(); free_scan_index(d); }
+    }
   }
   return JB_OK;
 }

@@ -32,6 +32,11 @@ Key scan_rare_window_key(const uint8_t* window, int k, Key mask) {
   return key_canonical(key_from_chars(window, k, k, mask), k);
 }
 
+// rare, index scan: the minimizer of such a window's (padded) key, from scratch
+__device__ __noinline__ uint32_t scan_rare_min_hash(Key canonical, int k, int m) {
+  return window_min_hash(canonical, key_revcomp(canonical, k), k, m, nullptr);
+}
+
 template <int kLayout>
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
 k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) {
@@ -180,6 +185,75 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
                            : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(sec[b]));
             }
             s_cnt[lane * 33 + q] = r;
+          }
+        }
+      }
+    } else if (kLayout == kScanByIndex) {
+      // Scan index (jb_index.cuh): the bucket comes from the window's minimizer, kept up to date as the window rolls (the
+      // newest m-mer against the current minimum; a rescan of the k-m+1 m-mers when the minimum has left the window), the
+      // bucket's bounds stay in registers while the minimizer does, and the slot is one 16-byte load per window.
+      const ScanIndex& ix = t.ix;
+      const int m = ix.m, w1 = k - m;
+      const uint64_t mmask = (1ull << (2 * m)) - 1;
+      uint32_t minh = 0;
+      int min_off = -1;                                   // offset of the minimum m-mer inside the current window; < 0 = unknown
+      uint64_t c_bucket = ~0ull, c_beg = 0;
+      uint32_t c_cap = 0;
+      for (int q0 = 0; q0 < nr; q0 += kGroupIndex) {
+        Key keys[kGroupIndex];
+        uint64_t begs[kGroupIndex];
+        uint32_t caps[kGroupIndex], at[kGroupIndex];
+        uint4 rec[kGroupIndex];
+#pragma unroll
+        for (int b = 0; b < kGroupIndex; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            const uint8_t c = s_seq[r0 + q + k - 1];
+            const bool v = base_valid(c);
+            const uint32_t code = v ? base_code(c) : 0u;
+            nv = v ? nv + 1 : 0;
+            fwd = key_push(fwd, code, t.mask);
+            rc = rc_push(rc, code, top_shift);
+            Key mk;
+            uint32_t mh;
+            if (nv >= k) {
+              okmask |= 1u << q;
+              mk = key_less(rc, fwd) ? rc : fwd;
+              --min_off;                                   // the window moved on by one base
+              const uint32_t hn = mmer_hash_at(fwd, rc, k, m, w1, mmask);
+              if (nv == k || min_off < 0) minh = window_min_hash(fwd, rc, k, m, &min_off);
+              else if (hn <= minh) { minh = hn; min_off = w1; }
+              mh = minh;
+            } else {
+              mk = scan_rare_window_key(s_seq + r0 + q, k, t.mask);   // rare: N / IUPAC / contig tail
+              mh = scan_rare_min_hash(mk, k, m);
+              min_off = -1;
+            }
+            keys[b] = mk;
+            const uint64_t bucket = index_bucket(mh, ix.bucket_bits);
+            if (bucket != c_bucket) { index_bounds(ix, bucket, &c_beg, &c_cap); c_bucket = bucket; }
+            begs[b] = c_beg; caps[b] = c_cap;
+            at[b] = c_cap ? __umulhi(index_slot_hash(mk), c_cap) : 0u;
+            if (c_cap) rec[b] = __ldg(ix.slots + c_beg + at[b]);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < kGroupIndex; ++b) {
+          const int q = q0 + b;
+          if (q < nr) {
+            uint32_t cv = 0;
+            if (caps[b]) {
+              ++steps_total;
+              while (true) {
+                const uint4 r = rec[b];
+                if (r.w == 0) break;
+                if ((((uint64_t)r.y << 32) | r.x) == keys[b].lo && r.z == (uint32_t)keys[b].hi) { cv = r.w; break; }
+                at[b] = at[b] + 1 == caps[b] ? 0u : at[b] + 1;
+                ++steps_total;
+                rec[b] = __ldg(ix.slots + begs[b] + at[b]);
+              }
+            }
+            s_cnt[lane * 33 + q] = cv;
           }
         }
       }
@@ -562,11 +636,13 @@ int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s) {
   if (configured_device != dev) {
     cudaError_t e = cudaFuncSetAttribute(k_scan<kLayoutWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kLayoutCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kScanByIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
     if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("cudaFuncSetAttribute(k_scan): ") + cudaGetErrorString(e));
     configured_device = dev;
   }
   if (a.n_tiles == 0) return JB_OK;
-  if (view.g.layout == kLayoutCompact) k_scan<kLayoutCompact><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  if (view.ix.bucket_bits && getenv("JB_SCAN_NO_INDEX") == nullptr) k_scan<kScanByIndex><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  else if (view.g.layout == kLayoutCompact) k_scan<kLayoutCompact><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   else k_scan<kLayoutWide><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_scan launch: ") + cudaGetErrorString(e));

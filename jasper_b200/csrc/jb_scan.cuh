@@ -40,6 +40,11 @@ constexpr int kTile = 32 * kLanePos;                // 1024 positions per warp t
 #ifndef JB_SCAN_GROUP_COMPACT
 #define JB_SCAN_GROUP_COMPACT 3                     // (r2c: 4 in flight spill in the compact loop: 2.28 ms against 1.88)
 #endif
+#ifndef JB_SCAN_GROUP_INDEX
+#define JB_SCAN_GROUP_INDEX 4
+#endif
+constexpr int kScanByIndex = 2;                     // k_scan<kScanByIndex>: lookups through the scan index (jb_index.cuh) instead of a table layout
+constexpr int kGroupIndex = JB_SCAN_GROUP_INDEX;
 constexpr int kGroup = JB_SCAN_GROUP;               // probes in flight per lane, wide table
 constexpr int kGroupCompact = JB_SCAN_GROUP_COMPACT;
 constexpr int kScanCtasPerSm = JB_SCAN_MINBLOCKS;

@@ -651,7 +651,12 @@ int open_any(const char* path, int n_dev, const int* devices, jb_db** outs, int 
 extern "C" int jb_db_open(const char* path, int device, jb_db** out) {
   if (!path || !out) return fail(JB_E_ARG, "jb_db_open: null argument");
   *out = nullptr;
-  return open_any(path, 1, &device, out, -1);
+  int rc = open_any(path, 1, &device, out, -1);
+  if (rc == JB_OK) {
+    rc = build_scan_index(*out);
+    if (rc != JB_OK) { jb_db_close(*out); *out = nullptr; }
+  }
+  return rc;
 }
 
 // ---- one process per GPU: build the own part, swap CUDA IPC handles through the host, attach the others
@@ -717,6 +722,7 @@ extern "C" void jb_db_close(jb_db* db) {
   cudaSetDevice(db->device);
   jb_release_cached_workspaces(db->device);
   for (int p = 0; p < kMaxParts; ++p) if (db->ipc_mapped[p] && db->parts[p]) cudaIpcCloseMemHandle(db->parts[p]);
+  free_scan_index(db);
   if (db->mem) cudaFree(db->mem);
   if (db->stash) cudaFree(db->stash);
   if (db->stash_list) cudaFree(db->stash_list);
@@ -742,6 +748,11 @@ extern "C" int jb_db_info(const jb_db* db, jb_db_info_t* o) {
   o->load_factor = db->home_units ? (double)db->n_records / ((double)db->home_units * spu) : 0.0;
   o->bytes_per_record = db->n_records ? (double)db->table_bytes() / (double)db->n_records : 0.0;
   o->read_seconds = db->read_seconds; o->file_bytes = db->file_bytes;
+  if (db->idx_bits) {
+    o->index_buckets = 1ull << db->idx_bits;
+    o->index_bytes = db->idx_n_slots * 16 + (o->index_buckets + 1) * (db->idx_wide_off ? 8 : 4);
+    o->index_mmer = db->idx_m; o->index_seconds = db->idx_seconds;
+  }
   return JB_OK;
 }
 

@@ -72,13 +72,46 @@ def test_lookup_matches_binding_vectors_and_oracle(golden_cases, dbs, name):
 
 
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
-def test_count_positions_matches_oracle(golden_cases, dbs, name):
+@pytest.mark.parametrize("index", ["index", "table"])
+def test_count_positions_matches_oracle(golden_cases, dbs, name, index, monkeypatch):
+    """k_scan against the oracle for every window, through the scan index (records grouped by minimizer, jb_index.cuh) and,
+    with JB_SCAN_NO_INDEX, through the hash table."""
     case = golden_cases[name]
     odb = helpers.OracleDB(case["db"])
+    if index == "table":
+        monkeypatch.setenv("JB_SCAN_NO_INDEX", "1")
+    else:
+        assert dbs[name].info["index_bytes"] > 0
     for _, s in jo.read_fasta(case["fasta"]):
         got = dbs[name].count_positions(s)
         assert np.array_equal(got, odb.count_positions(s))
     assert np.array_equal(dbs[name].count_positions(""), odb.count_positions(""))
+
+
+@pytest.mark.parametrize("seed", [3, 7, 12, 21, 30])
+@pytest.mark.parametrize("layout", ["compact", "wide"])
+def test_scan_index_equals_the_table_on_dirty_input(tmp_path, monkeypatch, seed, layout):
+    """Fuzz genomes (N runs, lower case, IUPAC, repeats; k = 20 ... 48): the counts of every window through the index equal
+    those through the hash table, and the polished result is the same, from a compact and from a wide table."""
+    monkeypatch.setenv("JB_TABLE_LAYOUT", layout)
+    k = helpers.FUZZ_KS[seed % len(helpers.FUZZ_KS)]
+    if k < 15:
+        pytest.skip("no scan index below k = 15")
+    recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k, big=True)
+    qf = capi.QueryMerFile(path)
+    try:
+        assert qf.info["index_bytes"] > 0
+        with_index = [qf.count_positions(s) for _, s in recs]
+        pol_index = qf.polish(recs, k, thr, 2)
+        monkeypatch.setenv("JB_SCAN_NO_INDEX", "1")
+        without = [qf.count_positions(s) for _, s in recs]
+        pol_table = qf.polish(recs, k, thr, 2)
+        for a, b in zip(with_index, without):
+            assert np.array_equal(a, b)
+        assert pol_index.status == pol_table.status
+        assert pol_index.seqs == pol_table.seqs and pol_index.rows == pol_table.rows and pol_index.tallies == pol_table.tallies
+    finally:
+        qf.close()
 
 
 @pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
