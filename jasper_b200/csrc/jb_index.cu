@@ -25,8 +25,8 @@ __device__ __forceinline__ void index_visit(const IndexBuild& b, const Key& key,
   uint64_t beg; uint32_t cap;
   index_bounds(b.ix, bucket, &beg, &cap);
   uint4* slots = const_cast<uint4*>(b.ix.slots);
-  uint32_t s = __umulhi(index_slot_hash(key), cap);
-  // claim the first empty slot from the home on (the count word is the claim; the keys of a table are distinct, so nobody
+  uint32_t s = 2 * __umulhi(index_slot_hash(key), cap / 2);
+  // claim the first empty slot from the home pair on (the count word is the claim; the keys of a table are distinct, so nobody
   // compares keys during the build)
   while (atomicCAS(&slots[beg + s].w, 0u, count) != 0u) s = s + 1 == cap ? 0 : s + 1;
   slots[beg + s].x = (uint32_t)key.lo; slots[beg + s].y = (uint32_t)(key.lo >> 32); slots[beg + s].z = (uint32_t)key.hi;
@@ -147,7 +147,7 @@ int build_scan_index(jb_db* db) {
   int bits = 8;
   while (bits < 28 && (N >> (bits + 1)) >= 12) ++bits;            // ~12-24 records per bucket
   const uint64_t n_buckets = 1ull << bits;
-  const uint64_t slots_bound = N + N / 4 + n_buckets + 64;        // sum of (n + n/4 + 1) over the non-empty buckets
+  const uint64_t slots_bound = N + N / 4 + 2 * n_buckets + 64;    // sum of (n + n/4 + 2) over the non-empty buckets
   const bool wide_off = slots_bound >= (1ull << 32);
   size_t free_b = 0, total_b = 0;
   JB_CUDA(cudaMemGetInfo(&free_b, &total_b));

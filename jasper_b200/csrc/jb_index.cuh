@@ -9,9 +9,10 @@
 // records by minimizer:
 //     bucket(key)  = mix(min over the m-mers x of key of hash(min(x, revcomp x)))  >> (32 - bucket_bits)
 //     off[b]       = first slot of bucket b (exclusive prefix sums of the bucket capacities)
-//     a bucket     = a small open-addressing table of its own: capacity = records * 5/4 + 1 sixteen-byte slots
-//                    {key.lo : 64, key.hi : 32, count : 32}, slot = off[b] + mulhi32(hash2(key), capacity), linear probing
-//                    with wrap-around inside the bucket, count == 0 = empty (every bucket keeps at least one empty slot)
+//     a bucket     = a small open-addressing table of its own: an even number (records * 5/4 + 2) of sixteen-byte slots
+//                    {key.lo : 64, key.hi : 32, count : 32}, probed a PAIR (one 32-byte sector) at a time:
+//                    pair = mulhi32(hash2(key), pairs), linear probing with wrap-around inside the bucket, count == 0 =
+//                    empty (every bucket keeps at least one empty slot; records fill a pair front to back)
 // A lookup is one offset pair (16 M x 4 bytes at the bench size: resident in the 126 MB L2, and a lane that walks a contig
 // keeps the pair in registers while the minimizer stays) and one slot -- still a single independent load per window, like
 // the hash probe, so the probes of several windows stay in flight together; but the ~9 windows of a minimizer run land in
@@ -70,7 +71,7 @@ JB_HD uint32_t index_slot_hash(const Key& canonical) {
   x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32;
   return (uint32_t)x;
 }
-JB_HD uint64_t index_bucket_capacity(uint64_t records) { return records ? records + records / 4 + 1 : 0; }
+JB_HD uint64_t index_bucket_capacity(uint64_t records) { return records ? (records + records / 4 + 2) & ~1ull : 0; }   // slots, even
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void index_bounds(const ScanIndex& ix, uint64_t bucket, uint64_t* beg, uint32_t* cap) {
@@ -84,7 +85,7 @@ static __device__ __noinline__ uint32_t index_find(const ScanIndex& ix, const Ke
   uint64_t beg; uint32_t cap;
   index_bounds(ix, bucket, &beg, &cap);
   if (cap == 0) return 0;
-  uint32_t s = __umulhi(index_slot_hash(canonical), cap);
+  uint32_t s = 2 * __umulhi(index_slot_hash(canonical), cap / 2);
   while (true) {
     const uint4 r = __ldg(ix.slots + beg + s);
     if (r.w == 0) return 0;

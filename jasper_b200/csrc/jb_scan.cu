@@ -44,10 +44,13 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
   const int k = t.g.k;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* s_lut = reinterpret_cast<uint64_t*>(smem);
-  const int lut_n = t.g.key_bytes * 256;
+  const int lut_n = kLayout == kScanByIndex ? 0 : t.g.key_bytes * 256;        // (the index scan never hashes with the matrix)
   uint8_t* s_warp = smem + (size_t)lut_n * 8 + (size_t)warp * kScanSmemPerWarp;
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_warp + kSeqBufs * kSeqSlice);
   for (int i = threadIdx.x; i < lut_n; i += kScanThreads) s_lut[i] = t.lut[i];
+  // index scan: every lane's ring of the m-mer hashes of its current window (odd stride: no bank conflicts)
+  uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem + (size_t)lut_n * 8 + (size_t)kScanWarps * kScanSmemPerWarp) +
+                     (size_t)threadIdx.x * (size_t)scan_ring_stride(k, t.ix.m);
 #if JB_SCAN_TMA
   // one mbarrier per tile buffer, owned by this warp: lane 0 asks the TMA unit for a tile's bases (one 1-D bulk copy, the
   // source is 16-byte aligned: contig offsets are multiples of 32, tile starts of 1024) and every lane waits on the barrier
@@ -193,17 +196,17 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
       // newest m-mer against the current minimum; a rescan of the k-m+1 m-mers when the minimum has left the window), the
       // bucket's bounds stay in registers while the minimizer does, and the slot is one 16-byte load per window.
       const ScanIndex& ix = t.ix;
-      const int m = ix.m, w1 = k - m;
+      const int m = ix.m, w1 = k - m, wn = w1 + 1;       // wn m-mers per window
       const uint64_t mmask = (1ull << (2 * m)) - 1;
-      uint32_t minh = 0;
-      int min_off = -1;                                   // offset of the minimum m-mer inside the current window; < 0 = unknown
+      int rp = 0;                                         // ring slot of the oldest m-mer hash
       uint64_t c_bucket = ~0ull, c_beg = 0;
       uint32_t c_cap = 0;
       for (int q0 = 0; q0 < nr; q0 += kGroupIndex) {
         Key keys[kGroupIndex];
-        uint64_t begs[kGroupIndex];
-        uint32_t caps[kGroupIndex], at[kGroupIndex];
-        uint4 rec[kGroupIndex];
+        const ulonglong4* pp[kGroupIndex];                // the pair (32-byte sector) in flight, and the bucket's pairs
+        const ulonglong4* pbeg[kGroupIndex];
+        uint32_t npair[kGroupIndex], at[kGroupIndex];
+        unsigned long long w[kGroupIndex][4];
 #pragma unroll
         for (int b = 0; b < kGroupIndex; ++b) {
           const int q = q0 + b;
@@ -219,22 +222,34 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
             if (nv >= k) {
               okmask |= 1u << q;
               mk = key_less(rc, fwd) ? rc : fwd;
-              --min_off;                                   // the window moved on by one base
-              const uint32_t hn = mmer_hash_at(fwd, rc, k, m, w1, mmask);
-              if (nv == k || min_off < 0) minh = window_min_hash(fwd, rc, k, m, &min_off);
-              else if (hn <= minh) { minh = hn; min_off = w1; }
-              mh = minh;
+              // The minimizer hash = the smallest of the window's wn m-mer hashes.  They live in this lane's ring: a window
+              // that follows a valid one replaces the oldest with its newest m-mer; the first valid window after a break
+              // (every lane's first window, then only behind an N) fills the ring.  The minimum is taken over the whole ring
+              // each time: wn shared-memory loads, but the same instructions in every lane (r2i kept a running minimum and
+              // rescanned when it expired -- 8.8 of 32 lanes active on average, 3.5x the instructions).
+              if (nv == k) {
+                for (int tt = 0; tt < wn; ++tt) s_ring[tt] = mmer_hash_at(fwd, rc, k, m, tt, mmask);
+                rp = 0;
+              } else {
+                s_ring[rp] = mmer_hash_at(fwd, rc, k, m, w1, mmask);
+                rp = rp + 1 == wn ? 0 : rp + 1;
+              }
+              mh = 0xFFFFFFFFu;
+              for (int tt = 0; tt < wn; ++tt) mh = min(mh, s_ring[tt]);
             } else {
               mk = scan_rare_window_key(s_seq + r0 + q, k, t.mask);   // rare: N / IUPAC / contig tail
               mh = scan_rare_min_hash(mk, k, m);
-              min_off = -1;
             }
             keys[b] = mk;
             const uint64_t bucket = index_bucket(mh, ix.bucket_bits);
             if (bucket != c_bucket) { index_bounds(ix, bucket, &c_beg, &c_cap); c_bucket = bucket; }
-            begs[b] = c_beg; caps[b] = c_cap;
-            at[b] = c_cap ? __umulhi(index_slot_hash(mk), c_cap) : 0u;
-            if (c_cap) rec[b] = __ldg(ix.slots + c_beg + at[b]);
+            pbeg[b] = reinterpret_cast<const ulonglong4*>(ix.slots + c_beg);     // (bucket offsets and capacities are even: 32-byte aligned)
+            npair[b] = c_cap >> 1;
+            at[b] = c_cap ? __umulhi(index_slot_hash(mk), c_cap >> 1) : 0u;
+            if (c_cap) {
+              pp[b] = pbeg[b] + at[b];
+              asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(pp[b]));
+            }
           }
         }
 #pragma unroll
@@ -242,15 +257,21 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
           const int q = q0 + b;
           if (q < nr) {
             uint32_t cv = 0;
-            if (caps[b]) {
+            if (npair[b]) {
               ++steps_total;
+              const unsigned long long klo = keys[b].lo;
+              const uint32_t khi = (uint32_t)keys[b].hi;
               while (true) {
-                const uint4 r = rec[b];
-                if (r.w == 0) break;
-                if ((((uint64_t)r.y << 32) | r.x) == keys[b].lo && r.z == (uint32_t)keys[b].hi) { cv = r.w; break; }
-                at[b] = at[b] + 1 == caps[b] ? 0u : at[b] + 1;
+                // slot = {key.lo, key.hi | count << 32}; the records of a pair fill it front to back
+                const uint32_t c0 = (uint32_t)(w[b][1] >> 32), c1 = (uint32_t)(w[b][3] >> 32);
+                if (c0 == 0) break;
+                if (w[b][0] == klo && (uint32_t)w[b][1] == khi) { cv = c0; break; }
+                if (c1 == 0) break;
+                if (w[b][2] == klo && (uint32_t)w[b][3] == khi) { cv = c1; break; }
+                at[b] = at[b] + 1 == npair[b] ? 0u : at[b] + 1;
                 ++steps_total;
-                rec[b] = __ldg(ix.slots + begs[b] + at[b]);
+                pp[b] = pbeg[b] + at[b];
+                asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[b][0]), "=l"(w[b][1]), "=l"(w[b][2]), "=l"(w[b][3]) : "l"(pp[b]));
               }
             }
             s_cnt[lane * 33 + q] = cv;
@@ -629,19 +650,20 @@ int scan_grid(uint32_t n_tiles) {
 
 // k_scan needs more than the default 48 KB of dynamic shared memory (hash LUT + 8 warp slices)
 int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s) {
-  const size_t smem = scan_smem_bytes(view.g.key_bytes);
+  const bool by_index = view.ix.bucket_bits && getenv("JB_SCAN_NO_INDEX") == nullptr;
+  const size_t smem = by_index ? scan_smem_bytes_index(view.g.k, view.ix.m) : scan_smem_bytes(view.g.key_bytes);
   static thread_local int configured_device = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
     cudaError_t e = cudaFuncSetAttribute(k_scan<kLayoutWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kLayoutCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kScanByIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(kMaxKeyBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan<kScanByIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes_index(JB_MAX_K, index_mmer_len(JB_MAX_K)));
     if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("cudaFuncSetAttribute(k_scan): ") + cudaGetErrorString(e));
     configured_device = dev;
   }
   if (a.n_tiles == 0) return JB_OK;
-  if (view.ix.bucket_bits && getenv("JB_SCAN_NO_INDEX") == nullptr) k_scan<kScanByIndex><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
+  if (by_index) k_scan<kScanByIndex><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   else if (view.g.layout == kLayoutCompact) k_scan<kLayoutCompact><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   else k_scan<kLayoutWide><<<scan_grid(a.n_tiles), kScanThreads, smem, s>>>(view, a);
   cudaError_t e = cudaGetLastError();

@@ -41,7 +41,7 @@ constexpr int kTile = 32 * kLanePos;                // 1024 positions per warp t
 #define JB_SCAN_GROUP_COMPACT 3                     // (r2c: 4 in flight spill in the compact loop: 2.28 ms against 1.88)
 #endif
 #ifndef JB_SCAN_GROUP_INDEX
-#define JB_SCAN_GROUP_INDEX 4
+#define JB_SCAN_GROUP_INDEX 3
 #endif
 constexpr int kScanByIndex = 2;                     // k_scan<kScanByIndex>: lookups through the scan index (jb_index.cuh) instead of a table layout
 constexpr int kGroupIndex = JB_SCAN_GROUP_INDEX;
@@ -93,6 +93,9 @@ struct ScanArgs {
 };
 
 inline size_t scan_smem_bytes(int key_bytes) { return (size_t)key_bytes * 256 * 8 + kScanWarps * kScanSmemPerWarp; }
+// index scan: no hash LUT, but a ring of m-mer hashes per thread (k - m + 1 words, odd stride)
+__host__ __device__ inline int scan_ring_stride(int k, int m) { return (k - m + 1) | 1; }
+inline size_t scan_smem_bytes_index(int k, int m) { return kScanWarps * kScanSmemPerWarp + (size_t)kScanThreads * scan_ring_stride(k, m) * 4; }
 
 struct EventArgs {
   const ScanUnit* units;
