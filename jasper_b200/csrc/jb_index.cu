@@ -137,8 +137,13 @@ void free_scan_index(jb_db* db) {
 int build_scan_index(jb_db* db) {
   db->idx_bits = 0;
   const int k = db->hdr.k();
+  // Off unless asked for (JB_SCAN_INDEX=1, or 2 = build it even when little memory is left): measured on the bench workload
+  // (profiles/r2j_scan_index_ab.txt) the index scan takes 3.2 ms against the hash table's 1.88 ms.  It does cut DRAM traffic (5.9 GB
+  // against 8.2 GB per launch) but not to the ~3 GB the layout promises -- a bucket mixes several minimizers and a run's windows
+  // land on 4-5 lines of it -- and it pays for that with 1.5x the instructions and twice the exposed load latency (bucket bounds,
+  // then the slot).  Kept as an option with its tests: the records and the counts are the table's either way.
   const char* env = getenv("JB_SCAN_INDEX");
-  if (env && atoi(env) == 0) return JB_OK;
+  if (!env || atoi(env) == 0) return JB_OK;
   if (db->n_parts > 1 || k < 15 || db->n_records == 0) return JB_OK;
   JB_CUDA(cudaSetDevice(db->device));
   cudaStream_t s = db->stream;

@@ -78,14 +78,21 @@ def test_count_positions_matches_oracle(golden_cases, dbs, name, index, monkeypa
     with JB_SCAN_NO_INDEX, through the hash table."""
     case = golden_cases[name]
     odb = helpers.OracleDB(case["db"])
-    if index == "table":
-        monkeypatch.setenv("JB_SCAN_NO_INDEX", "1")
+    qf = dbs[name]
+    if index == "index":                                  # (the index is an option: JB_SCAN_INDEX at open time)
+        monkeypatch.setenv("JB_SCAN_INDEX", "1")
+        qf = capi.QueryMerFile(case["db"])
+        assert qf.info["index_bytes"] > 0
     else:
-        assert dbs[name].info["index_bytes"] > 0
-    for _, s in jo.read_fasta(case["fasta"]):
-        got = dbs[name].count_positions(s)
-        assert np.array_equal(got, odb.count_positions(s))
-    assert np.array_equal(dbs[name].count_positions(""), odb.count_positions(""))
+        assert qf.info["index_bytes"] == 0
+    try:
+        for _, s in jo.read_fasta(case["fasta"]):
+            got = qf.count_positions(s)
+            assert np.array_equal(got, odb.count_positions(s))
+        assert np.array_equal(qf.count_positions(""), odb.count_positions(""))
+    finally:
+        if index == "index":
+            qf.close()
 
 
 @pytest.mark.parametrize("seed", [3, 7, 12, 21, 30])
@@ -98,6 +105,7 @@ def test_scan_index_equals_the_table_on_dirty_input(tmp_path, monkeypatch, seed,
     if k < 15:
         pytest.skip("no scan index below k = 15")
     recs, path, thr = helpers.write_fuzz_db(tmp_path, seed, k, big=True)
+    monkeypatch.setenv("JB_SCAN_INDEX", "1")
     qf = capi.QueryMerFile(path)
     try:
         assert qf.info["index_bytes"] > 0
