@@ -5,8 +5,9 @@ The package holds only what the path needs:
   capi.py          ctypes binding of libjasper_b200.so, mirroring the reference's
                    dna_jellyfish interface (QueryMerFile / MerDNA) for this path
   jasper.py        host side of the reference's src/jasper.py (same CLI, same output files)
-  jasper.sh        drop-in driver for the reference's src/jasper.sh
-  synth.py         synthetic genomes / .jf writer for tests and bench.py (tooling)
+  pipeline.py      the reference's src/jasper.sh in one process (split, histogram + threshold, polishing over the GPUs, join, fixes.csv, QV)
+  batching.py      jasper.sh's batch size and contig splitting; multi.py: one rank per GPU
+  synth*.py        synthetic genomes / .jf writers for tests and bench.py (tooling)
 There is no CPU fallback: without the CUDA library every compute call raises.
 """
 from .capi import (JasperError, QueryMerFile, MerDNA, PolishResult, load_library, library_path)  # noqa: F401
