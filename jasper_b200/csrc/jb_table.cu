@@ -404,13 +404,16 @@ int open_impl(const char* path, int n_dev, const int* devices, jb_db** outs, int
   const int n_local = only_part >= 0 ? 1 : n_dev;       // handles (and devices) of this process
   for (int i = 0; i < n_local; ++i) {
     if (devices[i] < 0 || devices[i] >= ndev) return fail(JB_E_ARG, "jb_db_open: bad device index");
-    for (int j = 0; j < i; ++j) if (devices[j] == devices[i]) return fail(JB_E_ARG, "jb_db_open_partitioned: a device is listed twice");
+    // (tests on a one-GPU box: JB_PARTS_SAME_DEVICE lets the parts share a device -- separate allocations, the same partition
+    //  arithmetic and probe routing, "peer" loads that happen to be local)
+    for (int j = 0; j < i; ++j)
+      if (devices[j] == devices[i] && getenv("JB_PARTS_SAME_DEVICE") == nullptr) return fail(JB_E_ARG, "jb_db_open_partitioned: a device is listed twice");
   }
   const int device = devices[0];
   if (n_dev > 1 && only_part < 0) {
     for (int i = 0; i < n_dev; ++i)
       for (int j = 0; j < n_dev; ++j) {
-        if (i == j) continue;
+        if (i == j || devices[i] == devices[j]) continue;
         int can = 0;
         JB_CUDA(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
         if (!can) return fail(JB_E_UNSUPPORTED, "jb_db_open_partitioned: devices " + std::to_string(devices[i]) + " and " + std::to_string(devices[j]) + " have no peer access");

@@ -568,6 +568,34 @@ def test_partitioned_table_equals_the_whole_one(golden_cases, dbs, name, monkeyp
             qf.close()
 
 
+@pytest.mark.parametrize("name", ["k37_mix", "k25_mix"])
+@pytest.mark.parametrize("layout", ["compact", "wide"])
+def test_partitioned_table_arithmetic_on_one_gpu(golden_cases, name, layout, tmp_path, monkeypatch):
+    """The same check on a box with ONE GPU (the driver's): three parts of one table as three allocations on device 0
+    (JB_PARTS_SAME_DEVICE).  What it covers: the partition boundaries and overlaps, the routing of every probe to the part that
+    owns its sector, the loader's stores into the owning part; what it cannot cover: that the loads really cross NVLink."""
+    monkeypatch.setenv("JB_PARTS_SAME_DEVICE", "1")
+    monkeypatch.setenv("JB_TABLE_LAYOUT", layout)
+    case = helpers.load_golden(name, str(tmp_path))
+    whole = capi.QueryMerFile(case["db"])
+    parts = capi.QueryMerFile.open_partitioned(case["db"], [0, 0, 0])
+    try:
+        strings = [s for s, _, _ in case["lookups"]]
+        seqs = jo.read_fasta(case["fasta"])
+        want = whole.polish(seqs, case["k"], case["threshold"], case["passes"])
+        for qf in parts:
+            assert qf.info["n_parts"] == 3
+            assert qf.lookup(strings) == [c for _, _, c in case["lookups"]]
+            assert (qf.count_positions(seqs[0][1]) == whole.count_positions(seqs[0][1])).all()
+            assert list(qf.histogram(1000)) == list(whole.histogram(1000))
+            got = qf.polish(seqs, case["k"], case["threshold"], case["passes"])
+            assert (got.rows, got.seqs, got.tallies) == (want.rows, want.seqs, want.tallies)
+    finally:
+        for qf in parts:
+            qf.close()
+        whole.close()
+
+
 def test_bench_contract_on_a_small_genome(tmp_path):
     """bench.py end to end on a 4 Mb genome: one JSON line with the contract's keys, and its built-in parity check
     (the CPU-baseline slices also go through the GPU path and must agree) passes."""
