@@ -80,8 +80,7 @@ struct VerdictArgs {
   Verdict2* verdicts2;
   uint8_t* dry_out;             // k_verdicts2: kDryOut bytes of edit scratch per resident warp
   int dry_post;                 // k_verdicts2 also evaluates the scan step behind the fix
-  unsigned long long* next;     // k_verdicts2: work queue heads of the two sweeps (zeroed before the launch)
-  unsigned long long* next2;
+  unsigned long long* next;     // k_verdicts2: work queue head (zeroed before the launch)
   int k, step; uint32_t solid;
 };
 constexpr int kVerdictWarps = 4;
@@ -146,20 +145,17 @@ k_verdicts2(TableView t, VerdictArgs a, BridgePool pool) {
   const unsigned long long n = min(*a.used, a.cap);
   const RowSink no_rows{nullptr, 0, nullptr, nullptr, 0, nullptr};
   const JobSink no_jobs{nullptr, 0, nullptr};
-  // events cost anything from a few to hundreds of microseconds: dynamic queue, and two sweeps over it -- the multi-error
-  // stretches (a de-Bruijn search each) first, so that the longest jobs do not start last
-  for (int sweep = 0; sweep < 2; ++sweep)
-  while (true) {
+  while (true) {                                       // events cost anything from a few to hundreds of microseconds: dynamic queue
     unsigned long long id = 0;
-    if (lane == 0) id = atomicAdd(sweep == 0 ? a.next : a.next2, 1ull);
+    if (lane == 0) id = atomicAdd(a.next, 1ull);
     id = __shfl_sync(0xffffffffu, id, 0);
     if (id >= n) break;
     const Verdict v = a.verdicts[id];
     Verdict2* out = a.verdicts2 + id;
     const ScanUnit su = a.units[a.verdict_unit[id]];
     const int nbad = (int)v.d_ga - (int)v.d_s0;
-    if (v.kind != kVDelimit || su.len >= 0xFFFFFFFFull) { if (lane == 0 && sweep == 0) out->valid = 0; continue; }
-    if ((nbad > a.k) != (sweep == 0)) continue;
+    (void)nbad;
+    if (v.kind != kVDelimit || su.len >= 0xFFFFFFFFull) { if (lane == 0) out->valid = 0; continue; }
     UnitIO& u = units[warp];
     __syncwarp();
     if (lane == 0) {
@@ -1006,7 +1002,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       va.verdicts = w.verdicts.p; va.cap = std::min(w.verdicts.cap, std::min(w.verdicts2.cap, w.verdict_unit.cap)); va.used = w.used.p + 6; va.vmap = w.vmap.p;
       va.verdict_unit = w.verdict_unit.p; va.verdicts2 = w.verdicts2.p;
       JB_TRY(w.dry_out.ensure((size_t)b->sms * kWalkCtasPerSm * kWalkWarps * kDryOut));
-      va.next = w.used.p + 7; va.next2 = w.used.p + 9;
+      va.next = w.used.p + 7;
       va.dry_out = w.dry_out.p; va.dry_post = getenv("JB_NO_V2_POST") ? 0 : (getenv("JB_NO_POST2") ? 2 : 1);
       va.k = k; va.step = cfg.step; va.solid = solid_thre;
       const unsigned vgrid = (unsigned)std::min<uint64_t>((tile_first[n] + kVerdictWarps - 1) / kVerdictWarps, (uint64_t)b->sms * 8);
