@@ -8,6 +8,8 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <functional>
 #include <new>
 #include <stdexcept>
@@ -129,15 +131,21 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
   // the few per-segment facts the index phase needs, packed (the descriptors are 250 bytes apiece)
   std::vector<uint32_t> seg_gen(segs.size()), seg_rows(segs.size());
   for (size_t q = 0; q < segs.size(); ++q) { seg_gen[q] = segs[q].gen; seg_rows[q] = segs[q].n_rows; }
-  std::vector<PassOut> part((size_t)n_thr);
-  std::vector<char> part_ok((size_t)n_thr, 1);
-  std::vector<size_t> row_at((size_t)n_thr + 1, out->rows.size());
-  std::vector<uint32_t> spill_at((size_t)n_thr + 1, (uint32_t)out->spill.size());
-  std::atomic<int> arrived{0};
+  // phases 2 and 3 work on chunks of the slot range handed out dynamically: the alignments of bridged patches are what costs, and
+  // they are not spread evenly (r2q: with one static range per thread the first thread was done at 0.64 ms, the last at 1.26)
+  const int n_chunks = n_thr == 1 ? 1 : n_thr * 8;
+  std::vector<PassOut> part((size_t)n_chunks);
+  std::vector<char> part_ok((size_t)n_chunks, 1);
+  std::vector<size_t> row_at((size_t)n_chunks + 1, out->rows.size());
+  std::vector<uint32_t> spill_at((size_t)n_chunks + 1, (uint32_t)out->spill.size());
+  std::atomic<int> arrived{0}, next_convert{0}, next_splice{0};
   auto barrier = [&](int phase) {                      // all workers reach phase `phase`; the threads are spawned once
     arrived.fetch_add(1, std::memory_order_acq_rel);
     while (arrived.load(std::memory_order_acquire) < phase * n_thr) std::this_thread::yield();
   };
+  const bool trace = getenv("JB_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   auto work = [&](int t) {
     {                                                   // 1. index: every live row has its own slot, the scatter needs no locks
       const size_t lo = n_rows * (size_t)t / (size_t)n_thr, hi = n_rows * (size_t)(t + 1) / (size_t)n_thr;
@@ -151,37 +159,39 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
       }
     }
     barrier(1);
-    {                                                   // 2. convert a range of slots
-      const size_t lo = n_slots * (size_t)t / (size_t)n_thr, hi = n_slots * (size_t)(t + 1) / (size_t)n_thr;
+    if (trace && t == 0) fprintf(stderr, "[jb trace]   rows: indexed at %.3f ms (%d threads)\n", since(), n_thr);
+    for (int c = next_convert.fetch_add(1); c < n_chunks; c = next_convert.fetch_add(1)) {   // 2. convert chunks of slots
+      const size_t lo = n_slots * (size_t)c / (size_t)n_chunks, hi = n_slots * (size_t)(c + 1) / (size_t)n_chunks;
       size_t q = (size_t)(std::upper_bound(slot0.begin(), slot0.end(), (uint64_t)lo) - slot0.begin());
       q = q ? q - 1 : 0;
-      part[(size_t)t].rows.reserve((hi - lo) + 16);
+      part[(size_t)c].rows.reserve((hi - lo) + 16);
       for (size_t sl = lo; sl < hi; ++sl) {
         while (sl >= slot0[q + 1]) ++q;
         if (at[sl] == 0xFFFFFFFFu) continue;
         const DevRow& r = rows[at[sl]];
         // (nothing may throw past this point: the other workers wait at the barrier, and an exception that leaves a thread
         //  ends the process -- the alignment matrices of a very long bridged patch are the realistic std::bad_alloc)
-        try { if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)t])) part_ok[(size_t)t] = 0; }
-        catch (const std::exception&) { part_ok[(size_t)t] = 2; }
+        try { if (!row_to_csv(r, r.coord + place[q].row_shift, aux, &part[(size_t)c])) part_ok[(size_t)c] = 0; }
+        catch (const std::exception&) { part_ok[(size_t)c] = 2; }
       }
     }
+    if (trace) fprintf(stderr, "[jb trace]   rows: thread %d converted at %.3f ms\n", t, since());
     barrier(2);
     if (t == 0) {                                       // (sizes are known now: worker 0 lays the output out)
-      for (int u = 0; u < n_thr; ++u) {
+      for (int u = 0; u < n_chunks; ++u) {
         row_at[(size_t)u + 1] = row_at[(size_t)u] + part[(size_t)u].rows.size();
         spill_at[(size_t)u + 1] = spill_at[(size_t)u] + (uint32_t)part[(size_t)u].spill.size();
       }
-      out->rows.resize(row_at[(size_t)n_thr]);
-      for (int u = 0; u < n_thr; ++u) out->spill += part[(size_t)u].spill;
+      out->rows.resize(row_at[(size_t)n_chunks]);
+      for (int u = 0; u < n_chunks; ++u) out->spill += part[(size_t)u].spill;
     }
     barrier(3);
-    {                                                   // 3. splice in order
-      HostRow* dst = out->rows.data() + row_at[(size_t)t];
-      const std::vector<HostRow>& src = part[(size_t)t].rows;
+    for (int c = next_splice.fetch_add(1); c < n_chunks; c = next_splice.fetch_add(1)) {     // 3. splice in order
+      HostRow* dst = out->rows.data() + row_at[(size_t)c];
+      const std::vector<HostRow>& src = part[(size_t)c].rows;
       for (size_t i = 0; i < src.size(); ++i) {
         HostRow h = src[i];
-        if (h.mut_len + h.orig_len > (int)sizeof h.text) h.spill += spill_at[(size_t)t];
+        if (h.mut_len + h.orig_len > (int)sizeof h.text) h.spill += spill_at[(size_t)c];
         dst[i] = h;
       }
     }
@@ -193,10 +203,11 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
     for (auto& th : pool) th.join();
   }
   bool ok = true;
-  for (int t = 0; t < n_thr; ++t) {
-    if (part_ok[(size_t)t] == 2) throw std::bad_alloc();          // on the calling thread, where the caller catches it
-    ok = ok && part_ok[(size_t)t];
+  for (int c = 0; c < n_chunks; ++c) {
+    if (part_ok[(size_t)c] == 2) throw std::bad_alloc();          // on the calling thread, where the caller catches it
+    ok = ok && part_ok[(size_t)c];
   }
+  if (trace) fprintf(stderr, "[jb trace]   rows: done at %.3f ms\n", since());
   return ok;
 }
 

@@ -1027,6 +1027,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     mark("scan+anchors done", ite);
     std::vector<SegPlan> plan = plan_segments(b->len, caps, blocks, blocks.empty() ? nullptr : anchors);
     const size_t n_first = plan.size();
+    mark("  planned", ite);
     JB_TRY(w.segs.ensure(n_first + 2 * n)); JB_TRY(w.h_segs.ensure(n_first + 2 * n));     // room for two rounds of whole-contig re-runs behind the plan
     JB_TRY(w.order.ensure(n_first + 2 * n)); JB_TRY(w.dst_off.ensure(n_first + 2 * n)); JB_TRY(w.h_dst_off.ensure(n_first + 2 * n));
     JB_TRY(w.h_order.ensure(n_first + 2 * n)); JB_TRY(w.seg_unit.ensure(n_first + 1)); JB_TRY(w.h_seg_unit.ensure(n_first + 1));
@@ -1040,6 +1041,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       if (plan[q].seg == 0) unit_first[plan[q].unit] = (uint32_t)q;
     }
     unit_first[n] = (uint32_t)n_first;
+    mark("  descriptors", ite);
     // queue order: the few long segments (stretches without an anchor) first, the rest as planned
     uint32_t* order = w.h_order.p;
     {
@@ -1120,6 +1122,20 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_CUDA(cudaEventSynchronize(ev_res));
     mark("walk done", ite);
     n_segments += (int64_t)n_first;
+    mark("  results in", ite);
+    // the fix log leaves for the host right away, on the side stream (its row thread then starts while this thread still
+    // merges the results); a re-walk appends rows and sends it again
+    const int hb = ite & 1;                              // the log of pass ite-2 must have been read out of this buffer
+    auto send_fix_log = [&]() -> int {
+      for (auto& rj : row_jobs) if (rj->buf == hb) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
+      JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
+      if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows[hb].p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
+      if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux[hb].p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
+      JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
+      return JB_OK;
+    };
+    const bool log_fits = used[0] <= w.rows.cap && used[1] <= w.aux.cap;
+    if (do_fix && log_fits) { if (int rc = send_fix_log()) return rc; }
     for (size_t q = 0; q < n_first; ++q) {               // the results join the descriptors the host built
       UnitIO& u = hs[q];
       const SegOut& o = so[q];
@@ -1213,6 +1229,7 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     }
     probe_steps += (int64_t)used[2];
     if (b->use_verdicts) n_verdicts += (int64_t)used[6];
+    mark("  results merged", ite);
     if (do_fix) {
       // ---- the segments' new bases are stitched into the other buffer (launched above, or here after a re-walk); the fix
       // log follows on the side stream
@@ -1238,15 +1255,10 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
         JB_CUDA(cudaMemcpyAsync(w.dst_off.p, dst_off, n_slots * 8, cudaMemcpyHostToDevice, s));
         JB_CUDA(cudaMemcpyAsync(w.slot_unit.p, slot_unit, n_slots * 4, cudaMemcpyHostToDevice, s));
         JB_CUDA(cudaMemcpyAsync(w.scan_units_new.p, units_new, n * sizeof(ScanUnit), cudaMemcpyHostToDevice, s));
-        JB_CUDA(cudaEventRecord(w.ev_walk, s));           // (the re-walks wrote rows too)
+        JB_CUDA(cudaEventRecord(w.ev_walk, s));           // (the re-walks wrote rows too: the log travels again)
+        if (int rc = send_fix_log()) return rc;
         if (int rc = stitch_and_recount()) return rc;
       }
-      const int hb = ite & 1;                            // the log of pass ite-2 must have been read out of this buffer
-      for (auto& rj : row_jobs) if (rj->buf == hb) while (!rj->copied.load(std::memory_order_acquire)) std::this_thread::yield();
-      JB_CUDA(cudaStreamWaitEvent(w.s2, w.ev_walk, 0));
-      if (used[0]) JB_CUDA(cudaMemcpyAsync(w.h_rows[hb].p, w.rows.p, used[0] * sizeof(DevRow), cudaMemcpyDeviceToHost, w.s2));
-      if (used[1]) JB_CUDA(cudaMemcpyAsync(w.h_aux[hb].p, w.aux.p, used[1], cudaMemcpyDeviceToHost, w.s2));
-      JB_CUDA(cudaEventRecord(w.ev_rows, w.s2));
       if (ite == passes - 1 && !b->early && b->fetch_follows && getenv("JB_NO_EARLY_FETCH") == nullptr) {
         uint64_t total_new = 0;
         for (size_t i = 0; i < n; ++i) total_new += (uint64_t)new_lens[i];
