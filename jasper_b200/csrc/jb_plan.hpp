@@ -151,6 +151,7 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
     if (t == 0 && n_thr > 1) {
       // worker 0 makes room for the result while the others index: a fresh 2 MB vector costs ~0.4 ms of page faults, which used to
       // sit between the conversion and the splice with every other worker waiting (r2r); the size is an estimate, corrected below
+      if (rows_before == 0) out->rows = RowStore::take(n_slots + n_slots / 8 + 1024);      // (recycled pages when there are any)
       out->rows.resize(rows_before + n_slots + n_slots / 8 + 1024);
     } else {                                            // 1. index: every live row has its own slot, the scatter needs no locks
       const size_t nt = n_thr > 1 ? (size_t)n_thr - 1 : 1, me = n_thr > 1 ? (size_t)t - 1 : 0;
@@ -170,6 +171,7 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
       const size_t lo = n_slots * (size_t)c / (size_t)n_chunks, hi = n_slots * (size_t)(c + 1) / (size_t)n_chunks;
       size_t q = (size_t)(std::upper_bound(slot0.begin(), slot0.end(), (uint64_t)lo) - slot0.begin());
       q = q ? q - 1 : 0;
+      part[(size_t)c].rows = RowStore::take((hi - lo) + (hi - lo) / 4 + 16);
       part[(size_t)c].rows.reserve((hi - lo) + 16);
       for (size_t sl = lo; sl < hi; ++sl) {
         while (sl >= slot0[q + 1]) ++q;
@@ -201,6 +203,7 @@ inline bool rows_in_order(const DevRow* rows, size_t n_rows, const uint8_t* aux,
         if (h.mut_len + h.orig_len > (int)sizeof h.text) h.spill += spill_at[(size_t)c];
         dst[i] = h;
       }
+      if (n_thr > 1) RowStore::give(std::move(part[(size_t)c].rows));
     }
   };
   {

@@ -487,6 +487,7 @@ struct jb_batch {
     if (ev_early) { cudaEventSynchronize(ev_early); cudaEventDestroy(ev_early); }
     for (cudaEvent_t e : ev_tmp) if (e) { cudaEventSynchronize(e); cudaEventDestroy(e); }
     if (early) park_out_buffer(early, early_cap);
+    for (PassOut& po : passes) RowStore::give(std::move(po.rows));
     park_workspace(ws);
   }
 };
@@ -496,7 +497,10 @@ struct jb_result {
   std::vector<PassOut> passes;
   uint8_t* data = nullptr; size_t data_cap = 0;      // pinned: all sequences back to back
   std::vector<uint64_t> seq_off, seq_len;
-  ~jb_result() { park_out_buffer(data, data_cap); }
+  ~jb_result() {
+    park_out_buffer(data, data_cap);
+    for (PassOut& po : passes) RowStore::give(std::move(po.rows));
+  }
 };
 
 #define JB_TRY(expr) do { int rc_ = (expr); if (rc_ != JB_OK) return fail(rc_, "out of memory for polishing work buffers"); } while (0)
