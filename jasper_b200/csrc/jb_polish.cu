@@ -232,6 +232,35 @@ k_concat(const CopyJob* jobs, const unsigned long long* n_jobs, unsigned long lo
   }
 }
 
+// ---- segment descriptors on the device: the host uploads 40 bytes of plan per segment, not a 208-byte descriptor ----------
+struct SegPlanDev { uint32_t unit, seg; int64_t base, next_anchor, stage_off, stage_cap; };
+struct SegConsts {
+  const uint8_t* in; uint8_t* stage; const uint32_t* counts; const uint8_t* okb; const uint32_t* weak; const uint32_t* vmap;
+  const Verdict* verdicts; const Verdict2* verdicts2; const uint32_t* events; const uint32_t* ev_l1; const uint32_t* ev_l2;
+  const ScanUnit* units; int32_t keep_margin;
+};
+// (the same fields make_seg fills on the host for a re-walk)
+__global__ void k_make_segs(const SegPlanDev* __restrict__ plan, uint32_t n, SegConsts c, UnitIO* __restrict__ out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const SegPlanDev p = plan[q];
+  const ScanUnit su = c.units[p.unit];
+  const uint64_t off = su.seq_off;
+  UnitIO u;
+  u.status = 0; u.n_rows = 0; u.new_len = 0; u.end_old = 0; u.wrong = 0; u.lookups = 0; u.events = 0; u.n_fast = 0; u.n_post = 0; u.n_v2 = 0;
+  u.pad2 = 0; u.cycles = 0;
+  u.in = c.in + off; u.in_len = (int64_t)su.len;
+  u.out = c.stage + off + p.stage_off; u.out_cap = p.stage_cap;
+  u.cnt = c.counts + off; u.okb = c.okb + off;
+  u.weak = c.weak + off / 32; u.vmap = c.vmap; u.verdicts = c.verdicts; u.verdicts2 = c.verdicts2;
+  u.ev = c.events + off / 32; u.ev_l1 = c.ev_l1; u.ev_l2 = c.ev_l2; u.ev_bit_base = off;
+  u.base = p.base; u.next_anchor = p.next_anchor;
+  u.unit = p.unit; u.seg = p.seg; u.gen = 0; u.slot = q;
+  u.materialize_all = 0;
+  u.keep_margin = c.keep_margin;
+  out[q] = u;
+}
+
 // ---- placement on the device: between k_walk and k_concat nothing waits for the host ------------------------------------
 // what a walker reports about its segment, compact (the descriptors are 200+ bytes apiece)
 struct SegOut {
@@ -385,6 +414,7 @@ struct Workspace {
   // placement on the device (k_seg_gather, k_place) and the pinned staging of everything a pass uploads: the host never
   // hands the driver pageable memory inside the pass loop (such a copy would wait for the stream first)
   DevBuf<SegOut> seg_out; PinBuf<SegOut> h_seg_out;
+  DevBuf<SegPlanDev> plan_d; PinBuf<SegPlanDev> h_plan;
   DevBuf<uint32_t> seg_unit, unit_first; DevBuf<int64_t> caps_d, prefix;
   PinBuf<uint8_t> h_geom; PinBuf<uint32_t> h_order, h_seg_unit; PinBuf<int64_t> h_dst_off; PinBuf<unsigned long long> h_probes;
   cudaStream_t s2 = nullptr;                // side stream: fix rows travel while the next pass scans
@@ -397,7 +427,7 @@ struct Workspace {
     tile_first.release(); block_first.release(); segs.release(); dst_off.release(); anchors.release(); scan_units.release();
     seg_units.release(); rows.release(); aux.release(); jobs.release(); used.release(); next.release(); pool.release();
     trie.release(); patch.release(); busy.release(); release_big_pool();
-    seg_out.release(); h_seg_out.release(); seg_unit.release(); unit_first.release(); caps_d.release(); prefix.release();
+    seg_out.release(); h_seg_out.release(); plan_d.release(); h_plan.release(); seg_unit.release(); unit_first.release(); caps_d.release(); prefix.release();
     h_geom.release(); h_order.release(); h_seg_unit.release(); h_dst_off.release(); h_probes.release();
     h_in.release(); h_segs.release(); h_anchors.release(); h_rows[0].release(); h_rows[1].release(); h_aux[0].release(); h_aux[1].release(); h_used.release();
     if (s2) cudaStreamDestroy(s2);
@@ -1037,12 +1067,18 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
     JB_TRY(w.h_order.ensure(n_first + 2 * n)); JB_TRY(w.seg_unit.ensure(n_first + 1)); JB_TRY(w.h_seg_unit.ensure(n_first + 1));
     JB_TRY(w.seg_out.ensure(n_first + 1)); JB_TRY(w.h_seg_out.ensure(n_first + 1)); JB_TRY(w.prefix.ensure(n_first + 2));
     JB_TRY(w.slot_unit.ensure(n_first + 2 * n + 1)); JB_TRY(w.h_probes.ensure((size_t)passes + 2));
+    JB_TRY(w.plan_d.ensure(n_first + 1)); JB_TRY(w.h_plan.ensure(n_first + 1));
     UnitIO* hs = w.h_segs.p;
     uint32_t* seg_unit = w.h_seg_unit.p;
+    SegPlanDev* hp = w.h_plan.p;
     for (size_t q = 0; q < n_first; ++q) {
-      hs[q] = make_seg(b, plan[q], in, 0, (uint32_t)q, keep_margin, cidx);
-      seg_unit[q] = plan[q].unit;
-      if (plan[q].seg == 0) unit_first[plan[q].unit] = (uint32_t)q;
+      // the device builds the descriptor (k_make_segs); the host keeps the handful of fields it reads again later
+      const SegPlan& p = plan[q];
+      hp[q] = SegPlanDev{p.unit, p.seg, p.base, p.next_anchor, p.stage_off, p.stage_cap};
+      UnitIO& u = hs[q];
+      u.unit = p.unit; u.seg = p.seg; u.gen = 0; u.slot = (uint32_t)q; u.base = p.base; u.next_anchor = p.next_anchor; u.in_len = b->len[p.unit];
+      seg_unit[q] = p.unit;
+      if (p.seg == 0) unit_first[p.unit] = (uint32_t)q;
     }
     unit_first[n] = (uint32_t)n_first;
     mark("  descriptors", ite);
@@ -1058,7 +1094,17 @@ extern "C" int jb_batch_polish(jb_batch* b, int k, uint32_t solid_thre, int pass
       for (uint32_t q : longs) order[at++] = q;
       for (size_t q = 0; q < n_first; ++q) if (seg_span(q) <= long_span) order[at++] = (uint32_t)q;
     }
-    if (int rc = small_h2d(w.segs.p, hs, n_first * sizeof(UnitIO), up_by_kernel, s)) return rc;
+    if (int rc = small_h2d(w.plan_d.p, hp, n_first * sizeof(SegPlanDev), up_by_kernel, s)) return rc;
+    {
+      SegConsts sc{};
+      sc.in = in; sc.stage = w.stage.p; sc.counts = w.counts[cidx].p; sc.okb = w.okb[cidx].p; sc.weak = w.weak.p;
+      sc.vmap = b->use_verdicts ? w.vmap.p : nullptr; sc.verdicts = w.verdicts.p; sc.verdicts2 = b->use_verdicts2 ? w.verdicts2.p : nullptr;
+      sc.events = w.events.p; sc.ev_l1 = w.events_l1.p; sc.ev_l2 = getenv("JB_NO_L2") ? nullptr : w.events_l2.p;
+      sc.units = w.scan_units.p; sc.keep_margin = keep_margin;
+      k_make_segs<<<(unsigned)((n_first + 255) / 256), 256, 0, s>>>(w.plan_d.p, (uint32_t)n_first, sc, w.segs.p);
+      JB_CUDA(cudaGetLastError());
+      ++launches;
+    }
     if (int rc = small_h2d(w.order.p, order, n_first * 4, up_by_kernel, s)) return rc;
     if (do_fix) {
       JB_CUDA(cudaMemcpyAsync(w.seg_unit.p, seg_unit, n_first * 4, cudaMemcpyHostToDevice, s));
