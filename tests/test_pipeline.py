@@ -167,3 +167,23 @@ def test_pipeline_restart_markers_and_capacity_groups(golden_cases, tmp_path):
     assert len(calls) > n0 and out2["tallies"] == out["tallies"]
     _check_outputs(case, work, meta["k"])
     assert not [f for f in os.listdir(work) if f.endswith(".fix.csv")]             # without -d the per-batch files are removed
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` on a CPU-only box: the reference arm's JSON line (the unmodified src/jasper.py under xargs -P when
+    oracle/_ref is built, else the oracle port), with the keys the contract asks for and nothing else on stdout."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--genome-mb", "0.4", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "assembly bp polished/sec" and d["unit"] == "bp polished/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
