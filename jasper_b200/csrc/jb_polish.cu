@@ -85,7 +85,10 @@ struct VerdictArgs {
 };
 constexpr int kVerdictWarps = 4;
 constexpr int kDryOut = 1024;
-__global__ void __launch_bounds__(kVerdictWarps * 32)
+#ifndef JB_VERDICT_MINBLOCKS
+#define JB_VERDICT_MINBLOCKS 8       // (r2y: 64 registers, a few spilled words, twice the warps: 0.65 -> 0.50 ms on the clean workload; the walkers lose at 6 and 8)
+#endif
+__global__ void __launch_bounds__(kVerdictWarps * 32, JB_VERDICT_MINBLOCKS)
 k_verdicts(TableView t, VerdictArgs a) {
   __shared__ WarpScratch scratch[kVerdictWarps];
   __shared__ DevDB db;
