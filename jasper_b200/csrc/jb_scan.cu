@@ -537,7 +537,10 @@ k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
   }
 }
 
-__global__ void __launch_bounds__(256, 3)
+#ifndef JB_RECOUNT_MINBLOCKS
+#define JB_RECOUNT_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, JB_RECOUNT_MINBLOCKS)
 k_recount_probe(const __grid_constant__ TableView t, const __grid_constant__ RecountArgs a) {
   const unsigned long long n = min(*a.n_jobs, a.jobs_cap);
   const int k = t.g.k;
@@ -624,7 +627,7 @@ int launch_recount(const TableView& view, const RecountArgs& a, const RecountTai
   k_recount_copy<<<(unsigned)sms * 8, 256, 0, s>>>(a2, view.g.k);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_copy launch: ") + cudaGetErrorString(e));
-  k_recount_probe<<<(unsigned)sms * 6, 256, 0, s>>>(view, a2);
+  k_recount_probe<<<(unsigned)sms * 2 * JB_RECOUNT_MINBLOCKS, 256, 0, s>>>(view, a2);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_probe launch: ") + cudaGetErrorString(e));
   if (t.n_units) {
