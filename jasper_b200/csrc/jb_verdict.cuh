@@ -67,11 +67,29 @@ JB_FREE_NOINLINE bool make_verdict(const DB& db, WarpScratch& s, const uint8_t* 
   JB_LANES(l) { if (l == 0) { s.fbad[0] = -1; s.fbad[1] = W; } }
   JB_SYNC();
   JB_LANES(l) {
-    for (int q = l; q < W; q += 32) {
+    // every load of the staged window first (validity and count side by side, all rounds in flight: r2aa had a third of the
+    // kernel's stall samples on a validity load followed by a count load, round after round), then the bookkeeping
+    constexpr int kRounds = (kFastWin + 31) / 32;
+    uint8_t okv[kRounds];
+    uint32_t cv[kRounds];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < kRounds; ++r) {
+      const int q = l + 32 * r;
       const int64_t p = W0 + q;
-      bool ok = p >= 0 && p <= hi_p;
-      if (ok) ok = okb[p] != 0;
-      s.fc[q] = ok ? cnt[p] : 0u;
+      const bool in = q < W && p >= 0 && p <= hi_p;
+      okv[r] = in ? okb[p] : (uint8_t)0;
+      cv[r] = in ? cnt[p] : 0u;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < kRounds; ++r) {
+      const int q = l + 32 * r;
+      if (q >= W) continue;
+      const bool ok = okv[r] != 0;
+      s.fc[q] = ok ? cv[r] : 0u;
       if (!ok) {
 #if defined(__CUDA_ARCH__)
         if (q < kFastBack) atomicMax(&s.fbad[0], q); else atomicMin(&s.fbad[1], q);
