@@ -543,7 +543,7 @@ int upload_impl(const jb_db* db, const jb_seq_t* seqs, size_t n, jb_batch** out,
 }
 // device bytes upload_impl allocates per base: three base buffers, two count and two validity arrays (each over the padded
 // regions, x 1.125), the bit masks, verdict arrays, fix rows, copy jobs
-constexpr uint64_t kDeviceBytesPerBase = 27;
+constexpr uint64_t kDeviceBytesPerBase = 26;
 extern "C" int jb_polish_capacity(const jb_db* db, uint64_t* max_bases) {
   if (!db || !max_bases) return fail(JB_E_ARG, "jb_polish_capacity: null argument");
   JB_CUDA(cudaSetDevice(db->device));

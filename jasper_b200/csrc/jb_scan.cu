@@ -489,91 +489,33 @@ __device__ __forceinline__ uint32_t probe_finish(const TableView& t, const Key& 
 // copy of the new bases that the warp builds with ballots, 64 windows per trip, two probes in flight per lane.
 // Work split in both: decided on the device from the job count (job_split, jb_jobs.cuh); the launch does not wait for the
 // host to learn how many jobs the walkers wrote.
-// dirty0 / dend: the windows k_recount_probe looks up.  A materialised job that names the pass-start stretch it replaces
-// (kJobHasOld, jb_jobs.cuh) also accounts for the last windows of the untouched job in front of it; `Oa` / `Ob` are the flat
-// pass-start positions of that stretch's start and end, `lead` / `trail` as in the job.
-struct RecountJobView { int64_t D, copy_end, dirty0, dend, O, Oa, Ob; ScanUnit u; int lead, trail; bool live, has_old; };
+struct RecountJobView { int64_t D, dirty0, dend, cend, O; bool live; };
 __device__ __forceinline__ RecountJobView recount_job(const RecountArgs& a, unsigned long long j, int k) {
   RecountJobView v;
   const CopyJob job = a.jobs[j];
   const int64_t off = a.dst_off[job.slot];
   v.live = off >= 0;
   if (!v.live) return v;
-  v.u = a.units_new[a.slot_unit[job.slot]];                       // (seq_off + len = flat end of the new contig; only the probes need it,
-  v.D = off + job.rel;                                            //  so nothing waits for this load before them)
+  const ScanUnit u = a.units_new[a.slot_unit[job.slot]];
+  v.D = off + job.rel;                                            // flat position of the job's first base
+  v.cend = (int64_t)u.seq_off + (int64_t)u.len;                   // flat end of the new contig
   v.dend = v.D + job.len;
-  v.dirty0 = v.copy_end = v.D; v.O = -1;
-  v.has_old = false; v.Oa = v.Ob = 0; v.lead = v.trail = 0;
+  v.dirty0 = v.D; v.O = -1;
   if (job.src >= a.in_buf && job.src < a.in_buf + a.flat_bytes) { // an untouched stretch: windows inside it keep their counts
     v.O = job.src - a.in_buf;
-    v.dirty0 = v.copy_end = v.D + (job.len - k + 1 > 0 ? job.len - k + 1 : 0);
-    if ((job.info & kJobTailOwned) && !a.no_inherit) v.dirty0 = v.dend;   // ... and the job behind it accounts for the last ones
-  } else if ((job.info & kJobHasOld) && !a.no_inherit) {
-    v.has_old = true;
-    v.Oa = job.old - a.in_buf; v.Ob = v.Oa + job.old_len;
-    v.lead = job_lead(job.info); v.trail = job_trail(job.info);
+    v.dirty0 = v.D + (job.len - k + 1 > 0 ? job.len - k + 1 : 0);
   }
   return v;
 }
-// recount_walk's comparisons, by a whole warp: 32 bases per ballot, up to 128 per call (one round trip to memory)
-struct WarpMatch {
-  const uint8_t* x; const uint8_t* y; int lane;
-  __device__ __forceinline__ int first_set(const uint32_t (&mm)[4], int lim) const {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) if (mm[r]) { const int at = 32 * r + __ffs((int)mm[r]) - 1; return at < lim ? at : lim; }
-    return lim;
-  }
-  __device__ __forceinline__ int fwd(int xn, int yo, int lim) const {
-    uint32_t mm[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int q = 32 * r + lane;
-      mm[r] = __ballot_sync(0xffffffffu, q < lim ? x[xn + q] != y[yo + q] : true);
-    }
-    return first_set(mm, lim);
-  }
-  __device__ __forceinline__ int bwd(int xe, int ye, int lim) const {
-    uint32_t mm[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int q = 32 * r + lane;
-      mm[r] = __ballot_sync(0xffffffffu, q < lim ? x[xe - 1 - q] != y[ye - 1 - q] : true);
-    }
-    return first_set(mm, lim);
-  }
-  // behind a difference at (xn, yo): substituted (xn+1, yo+1), inserted (xn+1, yo), deleted (xn, yo+1); limits <= 64.
-  // All loads first, then the ballots: the three hypotheses cost one round trip together.
-  __device__ __forceinline__ void resync(int xn, int yo, int ls, int li, int ld, int* hs, int* hi, int* hd) const {
-    uint8_t xv[2][2], yv[2][2];                          // [round][offset 0 / 1]
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int q = 32 * r + lane;
-      const bool in0 = q < ld, in1 = q < ls || q < li;   // x[xn + q] is only needed by "deleted", x[xn + 1 + q] by the other two
-      xv[r][0] = in0 ? x[xn + q] : (uint8_t)0;
-      xv[r][1] = in1 ? x[xn + 1 + q] : (uint8_t)0;
-      yv[r][0] = q < li ? y[yo + q] : (uint8_t)0;
-      yv[r][1] = (q < ls || q < ld) ? y[yo + 1 + q] : (uint8_t)0;
-    }
-    uint32_t ms[4] = {0, 0, 0, 0}, mi[4] = {0, 0, 0, 0}, md[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int q = 32 * r + lane;
-      ms[r] = __ballot_sync(0xffffffffu, q < ls ? xv[r][1] != yv[r][1] : true);
-      mi[r] = __ballot_sync(0xffffffffu, q < li ? xv[r][1] != yv[r][0] : true);
-      md[r] = __ballot_sync(0xffffffffu, q < ld ? xv[r][0] != yv[r][1] : true);
-    }
-    *hs = first_set(ms, ls); *hi = first_set(mi, li); *hd = first_set(md, ld);
-  }
-};
 constexpr int kRecountUnroll = 8;
 __global__ void __launch_bounds__(256)
 k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
   const unsigned long long n = min(*a.n_jobs, a.jobs_cap);
-  const JobSplit sp = job_split(n, a.force_rows != 0, 128u, kJobTeam);
+  const JobSplit sp = job_split(n, a.force_rows != 0, 128u);
   for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
     const RecountJobView v = recount_job(a, j, k);
     if (!v.live || v.O < 0) continue;
-    const int64_t ncopy = v.copy_end - v.D;
+    const int64_t ncopy = v.dirty0 - v.D;
     const uint32_t* __restrict__ co = a.cnt_old + v.O;
     const uint8_t* __restrict__ oo = a.okb_old + v.O;
     uint32_t* __restrict__ cn = a.cnt_new + v.D;
@@ -598,94 +540,46 @@ k_recount_copy(const __grid_constant__ RecountArgs a, int k) {
 #ifndef JB_RECOUNT_MINBLOCKS
 #define JB_RECOUNT_MINBLOCKS 4
 #endif
-// One warp (or a team of warps: `wi` of `nw`) per job, two phases.  (1) The job's windows as stretches from RecountWalk
-// (jb_jobs.cuh), written to a short list in shared memory; (2) the list: inherited stretches copy count and validity of the
-// pass-start windows, probed ones are cut from a 2-bit packed copy of the new bases the warp builds with ballots, 64 windows
-// per trip, two probes in flight per lane.  (r2ac did both in one loop: the walk's state stayed live across the probes and the
-// kernel spilled 370 bytes -- 1.0 ms against 0.8 with the inheritance switched off.)
-struct RecountStretch { int64_t a, b, yo; int kind, pad; };
-constexpr int kMaxStretches = 12;          // header + 11
-// phase 1, out of line (its registers are its own): decode job j and list its stretches behind a header entry {a = flat
-// position of the job's first base, b = flat end of its contig}; returns the number of entries, 0 for a job without work
-__device__ __noinline__ int recount_plan_job(const RecountArgs& a, unsigned long long j, int k, RecountStretch* list, int lane) {
-  const RecountJobView jv = recount_job(a, j, k);
-  if (!jv.live) return 0;
-  const int64_t D = jv.D;
-  int n_list = 1;
-  if (jv.has_old) {
-    const WarpMatch match{a.new_bases + D, a.in_buf + jv.Oa, lane};
-    RecountWalk walk;
-    walk.init(jv.dend - D, jv.Ob - jv.Oa, jv.lead, jv.trail, k);
-    RecountRange r;
-    while (walk.next(match, &r)) {
-      if (lane == 0) { RecountStretch e; e.a = r.a; e.b = r.b; e.yo = jv.Oa + r.yo - r.a; e.kind = r.kind; e.pad = 0; list[n_list] = e; }
-      ++n_list;
-      if (n_list >= kMaxStretches - 2) walk.mode = 3;             // room for what is queued and the rest, which is probed
-    }
-  } else if (jv.dirty0 < jv.dend) {
-    if (lane == 0) { RecountStretch e; e.a = jv.dirty0 - D; e.b = jv.dend - D; e.yo = 0; e.kind = kRangeProbe; e.pad = 0; list[1] = e; }
-    n_list = 2;
-  }
-  if (n_list == 1) return 0;
-  if (lane == 0) { RecountStretch h; h.a = D; h.b = (int64_t)jv.u.seq_off + (int64_t)jv.u.len; h.yo = 0; h.kind = 0; h.pad = 0; list[0] = h; }
-  return n_list;
-}
-
 __global__ void __launch_bounds__(256, JB_RECOUNT_MINBLOCKS)
 k_recount_probe(const __grid_constant__ TableView t, const __grid_constant__ RecountArgs a) {
-  __shared__ RecountStretch s_list[8][kMaxStretches];
   const unsigned long long n = min(*a.n_jobs, a.jobs_cap);
   const int k = t.g.k;
   const int lane = threadIdx.x & 31;
-  RecountStretch* list = s_list[threadIdx.x >> 5];
   // (rows of at most 8 CTAs: a job rarely has more than a few dozen windows to probe)
-  const JobSplit sp = job_split(n, a.force_rows != 0, 8u, a.team);
+  const JobSplit sp = job_split(n, a.force_rows != 0, 8u);
   const int64_t wi = sp.tid >> 5, nw = sp.nth >> 5;               // this warp among the job's warps
   unsigned long long probes = 0;
   for (unsigned long long j = sp.j0; j < n; j += sp.jstep) {
-    __syncwarp();                                                 // (the previous job's list has been read)
-    const int n_list = recount_plan_job(a, j, k, list, lane);
-    __syncwarp();
-    if (!n_list) continue;
-    const int64_t D = list[0].a, cend = list[0].b;
-    for (int ri = 1; ri < n_list; ++ri) {
-      const RecountStretch e = list[ri];
-      if (e.kind == kRangeInherit) {
-        for (int64_t q = e.a + wi * 32 + lane; q < e.b; q += nw * 32) {
-          a.cnt_new[D + q] = a.cnt_old[e.yo + q];
-          a.okb_new[D + q] = a.okb_old[e.yo + q];
-        }
-        continue;
-      }
-      const int64_t dend = D + e.b;
-      for (int64_t c0 = D + e.a + wi * 64; c0 < dend; c0 += nw * 64) {
-        // bases [c0, c0 + 128) packed: windows c0 + lane (words 0-2) and c0 + 32 + lane (words 1-3)
-        uint64_t w[4];
-        uint32_t v[4];
+    const RecountJobView jv = recount_job(a, j, k);
+    if (!jv.live) continue;
+    const int64_t cend = jv.cend, dend = jv.dend;
+    for (int64_t c0 = jv.dirty0 + wi * 64; c0 < dend; c0 += nw * 64) {
+      // bases [c0, c0 + 128) packed: windows c0 + lane (words 0-2) and c0 + 32 + lane (words 1-3)
+      uint64_t w[4];
+      uint32_t v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t p = c0 + 32 * q + lane;
-          const bool in = p < cend;
-          w[q] = pack_round(in ? a.new_bases[p] : (uint8_t)0, in, &v[q]);
-        }
-        const int64_t pa = c0 + lane, pb = c0 + 32 + lane;
-        const bool doa = pa < dend, dob = pb < dend;
-        const bool oka = valid_at(v[0], v[1], v[2], lane, k), okb = valid_at(v[1], v[2], v[3], lane, k);
-        Key ka = {0, 0}, kb = {0, 0};
-        ProbeInFlight fa, fb;
-        if (doa) {
-          if (oka) { const Key f = key_at(w[0], w[1], w[2], lane, k, t.mask); ka = key_canonical(f, k); }
-          else ka = recount_rare_key(a.new_bases + pa, cend - pa, k, t.mask);
-          probe_issue(t, ka, fa);
-        }
-        if (dob) {
-          if (okb) { const Key f = key_at(w[1], w[2], w[3], lane, k, t.mask); kb = key_canonical(f, k); }
-          else kb = recount_rare_key(a.new_bases + pb, cend - pb, k, t.mask);
-          probe_issue(t, kb, fb);
-        }
-        if (doa) { a.cnt_new[pa] = probe_finish(t, ka, fa); a.okb_new[pa] = oka ? 1 : 0; ++probes; }
-        if (dob) { a.cnt_new[pb] = probe_finish(t, kb, fb); a.okb_new[pb] = okb ? 1 : 0; ++probes; }
+      for (int r = 0; r < 4; ++r) {
+        const int64_t p = c0 + 32 * r + lane;
+        const bool in = p < cend;
+        w[r] = pack_round(in ? a.new_bases[p] : (uint8_t)0, in, &v[r]);
       }
+      const int64_t pa = c0 + lane, pb = c0 + 32 + lane;
+      const bool doa = pa < dend, dob = pb < dend;
+      const bool oka = valid_at(v[0], v[1], v[2], lane, k), okb = valid_at(v[1], v[2], v[3], lane, k);
+      Key ka = {0, 0}, kb = {0, 0};
+      ProbeInFlight fa, fb;
+      if (doa) {
+        if (oka) { const Key f = key_at(w[0], w[1], w[2], lane, k, t.mask); ka = key_canonical(f, k); }
+        else ka = recount_rare_key(a.new_bases + pa, cend - pa, k, t.mask);
+        probe_issue(t, ka, fa);
+      }
+      if (dob) {
+        if (okb) { const Key f = key_at(w[1], w[2], w[3], lane, k, t.mask); kb = key_canonical(f, k); }
+        else kb = recount_rare_key(a.new_bases + pb, cend - pb, k, t.mask);
+        probe_issue(t, kb, fb);
+      }
+      if (doa) { a.cnt_new[pa] = probe_finish(t, ka, fa); a.okb_new[pa] = oka ? 1 : 0; ++probes; }
+      if (dob) { a.cnt_new[pb] = probe_finish(t, kb, fb); a.okb_new[pb] = okb ? 1 : 0; ++probes; }
     }
   }
   if (a.probes) {
@@ -730,9 +624,6 @@ int launch_recount(const TableView& view, const RecountArgs& a, const RecountTai
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   RecountArgs a2 = a;
   a2.force_rows = getenv("JB_RECOUNT_ROWS") != nullptr;           // tests: rows of CTAs whatever the job count
-  a2.no_inherit = getenv("JB_RECOUNT_NO_INHERIT") != nullptr;     // tests / A-B: probe every window of a materialised job
-  a2.team = 32;                                                   // one warp per job (many short jobs)
-  if (const char* e = getenv("JB_RECOUNT_TEAM")) a2.team = atoi(e) >= 64 ? 64 : 32;
   k_recount_copy<<<(unsigned)sms * 8, 256, 0, s>>>(a2, view.g.k);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_recount_copy launch: ") + cudaGetErrorString(e));

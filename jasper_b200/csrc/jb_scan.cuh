@@ -130,8 +130,6 @@ struct RecountArgs {
   uint32_t* cnt_new; uint8_t* okb_new;
   unsigned long long* probes;   // statistics
   int force_rows;               // tests: never split into teams (jb_jobs.cuh, job_split)
-  int no_inherit;               // tests (JB_RECOUNT_NO_INHERIT): every window of a materialised job is probed
-  int team;                     // k_recount_probe: threads per job when there are many jobs (32 or 64)
 };
 struct RecountTailArgs {
   const ScanUnit* units_old; const ScanUnit* units_new; uint32_t n_units;

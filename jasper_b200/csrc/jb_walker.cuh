@@ -143,12 +143,8 @@ struct UnitIO {               // one SEGMENT of one contig (a whole contig is th
   unsigned long long cycles;   // device clock ticks this segment took (profiling aid)
 };
 
-// append one copy job (out of line: the walker's call sites share it).
-// `own_tail` >= 0: the arena index of the untouched job in front of this (materialised) one, whose last windows it takes over
-// (r2ab tried job slots taken eight at a time -- one atomic per block instead of per job -- and the event's loads side by
-//  side: k_walk did not move, 1.29 ms either way, and the empty jobs that fill a block cost k_concat and the recount.)
-JB_FREE_NOINLINE bool push_job(JobSink jobs, uint32_t seg_slot, const uint8_t* src, int64_t rel, int64_t len, uint32_t info,
-                               const uint8_t* old, int64_t old_len, long long own_tail, unsigned long long* at) {
+// append one copy job (out of line: four call sites in the walker)
+JB_FREE_NOINLINE bool push_job(JobSink jobs, uint32_t seg_slot, const uint8_t* src, int64_t rel, int64_t len) {
   JB_SYNC();
   unsigned long long slot = 0;
 #if defined(__CUDA_ARCH__)
@@ -158,14 +154,8 @@ JB_FREE_NOINLINE bool push_job(JobSink jobs, uint32_t seg_slot, const uint8_t* s
   slot = (*jobs.used)++;
 #endif
   if (slot >= jobs.cap) return false;
-  JB_LANES(l) {
-    if (l == 0) {
-      CopyJob j; j.src = src; j.rel = rel; j.len = len; j.slot = seg_slot; j.info = info; j.old = old; j.old_len = old_len; jobs.jobs[slot] = j;
-      if (own_tail >= 0) jobs.jobs[own_tail].info |= kJobTailOwned;
-    }
-  }
+  JB_LANES(l) { if (l == 0) { CopyJob j; j.src = src; j.rel = rel; j.len = len; j.slot = seg_slot; j.pad = 0; jobs.jobs[slot] = j; } }
   JB_SYNC();
-  *at = slot;
   return true;
 }
 
@@ -188,9 +178,6 @@ struct Walker {
 
   int64_t i = 0, olen = 0, ipos = 0, L = 0, clean_from = 0;
   int64_t wstart = 0;                  // out[wstart:olen) is the materialised window; [0, wstart) is closed (copy jobs)
-  int64_t wstart_ipos = 0;             // the pass-start position out[wstart] stands for (the window replaces in[wstart_ipos:ipos))
-  int64_t lead_len = 0;                // length of the untouched copy job directly in front of the window (0: none) ...
-  long long lead_at = -1;              // ... and its index in the job arena
   int64_t keep_margin = 0;             // bases kept materialised in front of an edit
   bool far_back = false;
   int64_t base = 0, seam_margin = 0;   // seam_margin: how far before `base` this walker may read / how far before the
@@ -323,25 +310,9 @@ struct Walker {
   }
 
   // ---------------------------------------------------------------------------- edits
-  // an untouched stretch in[ipos:ipos+len) -> new bases [rel, rel+len)
   JB_W bool emit_job(const uint8_t* src, int64_t rel, int64_t len) {
-    lead_len = 0; lead_at = -1;
     if (len <= 0 || dry) return true;                 // (a dry run, k_verdicts2, describes no output)
-    unsigned long long at = 0;
-    if (!push_job(jobs, c.slot, src, rel, len, 0u, nullptr, 0, -1, &at)) { status = JB_E_SCRATCH; return false; }
-    lead_len = len; lead_at = (long long)at;
-    return true;
-  }
-  // the materialised window out[wstart:olen), which replaces in[wstart_ipos:ipos); `trail` untouched bases follow it
-  JB_W bool emit_window(int64_t trail) {
-    const int64_t len = olen - wstart;
-    if (len <= 0 || dry) return true;
-    const int64_t lead = lead_len < k - 1 ? lead_len : k - 1;
-    if (trail > k - 1) trail = k - 1;
-    if (trail < 0) trail = 0;
-    unsigned long long at = 0;
-    if (!push_job(jobs, c.slot, c.out + wstart, wstart, len, job_info(kJobHasOld, lead, trail), c.in + wstart_ipos, ipos - wstart_ipos,
-                  lead > 0 ? lead_at : -1, &at)) { status = JB_E_SCRATCH; return false; }
+    if (!push_job(jobs, c.slot, src, rel, len)) { status = JB_E_SCRATCH; return false; }
     return true;
   }
 
@@ -354,10 +325,10 @@ struct Walker {
     if (!c.materialize_all) {
       const int64_t keep_from = (a_abs - base) - keep_margin;
       if (keep_from > olen + kMinGap) {
+        if (!emit_job(c.out + wstart, wstart, olen - wstart)) return false;
         const int64_t gap = keep_from - olen;
-        if (!emit_window(gap)) return false;
         if (!emit_job(c.in + ipos, olen, gap)) return false;
-        ipos += gap; olen += gap; wstart = olen; wstart_ipos = ipos;
+        ipos += gap; olen += gap; wstart = olen;
       }
     }
     const int64_t n = upto - olen;
@@ -1235,8 +1206,7 @@ struct Walker {
     t_begin = clock64();
 #endif
     c = u;
-    base = c.base; seam_margin = seam_read_margin(k); keep_margin = c.keep_margin; wstart = 0; wstart_ipos = base; lead_len = 0; lead_at = -1;
-    far_back = false;
+    base = c.base; seam_margin = seam_read_margin(k); keep_margin = c.keep_margin; wstart = 0; far_back = false;
     i = base; olen = 0; ipos = base; L = c.in_len; clean_from = 0; wrong = 0; status = 0; brk = false; seam_bad = false; vflags = 0;
     publish();
     {
@@ -1262,7 +1232,7 @@ struct Walker {
     if (!status && ipos > end_old) status = kSeamViolation;
     // new bases of old [base, end_old) = closed jobs ++ out[wstart:olen) ++ in[ipos:end_old)
     if (fix && !status) {
-      emit_window(end_old - ipos);
+      emit_job(c.out + wstart, wstart, olen - wstart);
       emit_job(c.in + ipos, olen, end_old - ipos);
     }
     u.end_old = end_old;

@@ -122,7 +122,6 @@ def hostsim_lib():
     sim.hostsim_seq.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     sim.hostsim_tally.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     sim.hostsim_free.argtypes = [C.c_void_p]
-    sim.hostsim_recount_windows.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     sim.hostsim_segments.restype = C.c_ulonglong
     sim.hostsim_segments.argtypes = [C.c_void_p]
     sim.hostsim_reruns.restype = C.c_ulonglong
@@ -212,9 +211,6 @@ def hostsim_polish(sim, odb, seqs, k, thr, passes, use_events=1, fix=1, stats=No
             stats["fast"] = sim.hostsim_fast(r)
             stats["post"] = sim.hostsim_post(r)
             stats["v2"] = sim.hostsim_v2(r)
-            pr, inh = C.c_ulonglong(), C.c_ulonglong()
-            sim.hostsim_recount_windows(r, C.byref(pr), C.byref(inh))
-            stats["recount_probed"], stats["recount_inherited"] = pr.value, inh.value
         return st, txt, out, tallies
     finally:
         sim.hostsim_free(r)

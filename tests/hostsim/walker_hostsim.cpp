@@ -27,7 +27,6 @@ struct SimResult {
   std::vector<std::string> seqs;
   std::string text;     // rows as "ite\tseq\tcoord\tmutation\toriginal\n"
   unsigned long long lookups = 0, events = 0, segments = 0, reruns = 0, far_backs = 0, fast = 0, post = 0, v2 = 0, pool_growths = 0;
-  unsigned long long jobs_untouched = 0, windows_probed = 0, windows_inherited = 0;   // of materialised jobs, as k_recount_probe splits them
 };
 
 // event / weak bitmasks exactly as k_scan<.,true> defines them (jb_scan.cuh)
@@ -259,61 +258,8 @@ extern "C" SimResult* hostsim_polish(lookup_fn fn, const void* dbh, int k, uint3
       for (size_t i = 0; i < n; ++i) {
         if (new_lens[i] > caps[i]) { res->status = -100; return res; }
         for (int64_t q = 0; q < new_lens[i]; ++q) if (!covered[i][q]) { res->status = -100; return res; }
+        cur[i].swap(next[i]);
       }
-      // what k_recount_copy / k_recount_probe derive from the same jobs (jb_jobs.cuh): every window of the new contig is
-      // accounted for by exactly one job, and a window that inherits a pass-start count consists of the same k bases as
-      // the pass-start window it inherits from
-      {
-        std::vector<std::vector<uint8_t>> claimed(n);
-        for (size_t i = 0; i < n; ++i) claimed[i].assign((size_t)new_lens[i], 0);
-        bool ok = true;
-        auto claim = [&](uint32_t unit, int64_t q) { if (q < 0 || q >= new_lens[unit] || claimed[unit][q]++) ok = false; };
-        auto same = [&](uint32_t unit, int64_t o, int64_t q) {
-          if (o < 0 || q < 0 || o + k > len[unit] || q + k > new_lens[unit] || memcmp(cur[unit].data() + o, next[unit].data() + q, (size_t)k)) ok = false;
-        };
-        for (unsigned long long j = 0; j < jobs_used && ok; ++j) {
-          const CopyJob& job = jobv[j];
-          if (dst_off[job.slot] < 0 || job.len == 0) continue;      // (a superseded segment; the unused rest of a walker's block of job slots)
-          const uint32_t unit = slot_unit[job.slot];
-          const int64_t at = dst_off[job.slot] + job.rel;
-          const uint8_t* cb = (const uint8_t*)cur[unit].data();
-          if (job.src >= cb && job.src < cb + len[unit]) {
-            const int64_t O = job.src - cb, copy_end = at + (job.len - k + 1 > 0 ? job.len - k + 1 : 0);
-            if (job.info & kJobHasOld) ok = false;
-            for (int64_t q = at; q < copy_end; ++q) { claim(unit, q); same(unit, O + (q - at), q); }
-            if (!(job.info & kJobTailOwned)) for (int64_t q = copy_end; q < at + job.len; ++q) claim(unit, q);
-            ++res->jobs_untouched;
-          } else {
-            if (!(job.info & kJobHasOld)) { ok = false; break; }
-            const int64_t Oa = job.old - cb, m = job.old_len, Ob = Oa + m, both = std::min(job.len, m);
-            const int lead = job_lead(job.info), trail = job_trail(job.info);
-            if (Oa < 0 || m < 0 || Ob > len[unit]) { ok = false; break; }
-            struct HostMatch {
-              const char* x; const char* y;
-              int fwd(int xn, int yo, int lim) const { int r = 0; while (r < lim && x[xn + r] == y[yo + r]) ++r; return r; }
-              int bwd(int xe, int ye, int lim) const { int r = 0; while (r < lim && x[xe - 1 - r] == y[ye - 1 - r]) ++r; return r; }
-              void resync(int xn, int yo, int ls, int li, int ld, int* hs, int* hi, int* hd) const {
-                *hs = fwd(xn + 1, yo + 1, ls); *hi = fwd(xn + 1, yo, li); *hd = fwd(xn, yo + 1, ld);
-              }
-            } match{next[unit].data() + at, cur[unit].data() + Oa};
-            struct HostSink {
-              decltype(claim)& claim_; decltype(same)& same_; uint32_t unit; int64_t at, Oa; unsigned long long probed = 0, inherited = 0;
-              void inherit(int64_t a, int64_t b, int64_t yo) { for (int64_t q = a; q < b; ++q) { claim_(unit, at + q); same_(unit, Oa + yo + (q - a), at + q); } inherited += (unsigned long long)(b - a); }
-              void probe(int64_t a, int64_t b) { for (int64_t q = a; q < b; ++q) claim_(unit, at + q); probed += (unsigned long long)(b - a); }
-            } sink{claim, same, unit, at, Oa};
-            (void)both; (void)Ob;
-            RecountWalk walk;
-            walk.init(job.len, m, lead, trail, k);
-            RecountRange r;
-            while (walk.next(match, &r)) { if (r.kind == kRangeInherit) sink.inherit(r.a, r.b, r.yo); else sink.probe(r.a, r.b); }
-            res->windows_probed += sink.probed; res->windows_inherited += sink.inherited;
-          }
-        }
-        for (size_t i = 0; i < n && ok; ++i)
-          for (int64_t q = 0; q < new_lens[i]; ++q) if (claimed[i][q] != 1) { ok = false; break; }
-        if (!ok) { res->status = -101; return res; }
-      }
-      for (size_t i = 0; i < n; ++i) cur[i].swap(next[i]);
       std::vector<DevRow> got(rows.begin(), rows.begin() + used);
       std::vector<uint8_t> a2(aux.begin(), aux.begin() + aux_used);
       // the product's path (no copy, no sort) and the sorting path must agree
@@ -357,7 +303,6 @@ extern "C" unsigned long long hostsim_segments(const SimResult* r) { return r->s
 extern "C" unsigned long long hostsim_reruns(const SimResult* r) { return r->reruns; }
 extern "C" unsigned long long hostsim_pool_growths(const SimResult* r) { return r->pool_growths; }
 extern "C" unsigned long long hostsim_far_backs(const SimResult* r) { return r->far_backs; }
-extern "C" void hostsim_recount_windows(const SimResult* r, unsigned long long* probed, unsigned long long* inherited) { *probed = r->windows_probed; *inherited = r->windows_inherited; }
 extern "C" void hostsim_free(SimResult* r) { delete r; }
 
 // also expose the shared k-mer arithmetic for unit tests

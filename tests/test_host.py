@@ -415,29 +415,3 @@ def test_deep_bridge_outgrows_the_standard_trie(tmp_path, hostsim_lib):
     assert jo.format_fasta(list(zip(names, out))) == helpers.expected_file(case, "_iter%d_asm.fa.fixed.fa.tmp" % (case["passes"] - 1))
     assert ("%d %d\n" % tallies[0]).encode() == helpers.expected_file(case, "0qValCalcHelper.csv")
     assert ("%d %d\n" % tallies[-1]).encode() == helpers.expected_file(case, "%dqValCalcHelper.csv" % case["passes"])
-
-
-@pytest.mark.parametrize("name", helpers.GOLDEN_NAMES)
-def test_recount_inherits_only_identical_windows(golden_cases, hostsim_lib, name, monkeypatch):
-    """The copy jobs a fixing pass leaves also tell the incremental recount which windows of the new contig consist of the same
-    k bases as a pass-start window (jb_jobs.cuh: lead / trail / the stretch a materialised window replaces).  The host build
-    of the walker checks it on every pass (status -101 otherwise): every window accounted for by exactly one job, every
-    inherited window byte-identical to the one it inherits from -- with the default margins, with no kept margin (edits open
-    their own windows) and with every contig cut into small segments."""
-    case = golden_cases[name]
-    seqs = jo.read_fasta(case["fasta"])
-    odb = helpers.OracleDB(case["db"])
-    ref = None
-    for env, use_events in (({}, 1), ({}, 300), ({"JB_KEEP_MARGIN": "0"}, 1)):
-        for key, val in env.items():
-            monkeypatch.setenv(key, val)
-        st = {}
-        status, txt, out, tallies = helpers.hostsim_polish(hostsim_lib, odb, seqs, case["k"], case["threshold"], case["passes"], use_events, stats=st)
-        for key in env:
-            monkeypatch.delenv(key)
-        assert status == 0, (env, use_events)
-        if "JB_KEEP_MARGIN" not in env:
-            assert st["recount_inherited"] > 0 and st["recount_probed"] > 0, st
-            print(name, use_events, "windows of materialised jobs: probed", st["recount_probed"], "inherited", st["recount_inherited"])
-        ref = ref or (txt, out, tallies)
-        assert (txt, out, tallies) == ref
