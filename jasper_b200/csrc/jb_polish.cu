@@ -40,9 +40,20 @@ constexpr int kWalkWarps = 4;               // walkers per CTA
 #define JB_WALK_CTAS 4
 #endif
 constexpr int kWalkCtasPerSm = JB_WALK_CTAS;
-constexpr uint32_t kTrieCap = 1u << 20;     // de-Bruijn trie nodes per bridging slot
+// Bridging scratch: about one slot per resident walker (592 CTAs x 4 warps on a B200), so that a warp with a multi-error
+// stretch hardly ever waits for one.  With 512 slots of 1 M nodes k_verdicts2 spent 6 % of its samples asleep in
+// acquire_bridge and 7.5 % of its instructions polling (profiles/r2aa_*); 2048 x 256 K nodes: both verdict kernels
+// 1.60 -> 1.38 ms per step, no search of either bench workload outgrows a slot (profiles/r2ae_pool_ab.txt).  A search that
+// does reports kTrieFull and its contig is re-walked with the grown pool (ensure_big_pool below).
+#ifndef JB_TRIE_CAP_LOG2
+#define JB_TRIE_CAP_LOG2 18
+#endif
+#ifndef JB_POOL_SLOTS
+#define JB_POOL_SLOTS 2048
+#endif
+constexpr uint32_t kTrieCap = 1u << JB_TRIE_CAP_LOG2;   // de-Bruijn trie nodes per bridging slot
 constexpr uint32_t kPatchCap = 1u << 18;    // longest recoverable patch
-constexpr uint32_t kPoolSlots = 512;        // bridging scratch slots shared by all walkers
+constexpr uint32_t kPoolSlots = JB_POOL_SLOTS;          // bridging scratch slots shared by all walkers
 
 struct WalkCfg { int k, step; uint32_t solid; int fix; };
 
@@ -549,7 +560,7 @@ extern "C" int jb_polish_capacity(const jb_db* db, uint64_t* max_bases) {
   JB_CUDA(cudaSetDevice(db->device));
   size_t free_b = 0, total_b = 0;
   JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const uint64_t pools = (uint64_t)kPoolSlots * ((uint64_t)kTrieCap * 4 + kPatchCap) + (1ull << 30);     // bridging scratch + slack
+  const uint64_t pools = (uint64_t)kPoolSlots * ((uint64_t)kTrieCap * 4 + kPatchCap + sizeof(BridgeScratch)) + (1ull << 30);     // bridging scratch + slack
   *max_bases = free_b > pools ? (free_b - pools) / kDeviceBytesPerBase : 0;
   return JB_OK;
 }

@@ -165,7 +165,7 @@ def test_polish_reproduces_reference_bytes_on_rare_branches(tmp_path, monkeypatc
 
 def test_deep_bridge_rewalks_with_the_grown_pool(tmp_path, monkeypatch):
     """tests/golden/branches/deep_bridge (bytes of the unmodified reference): one de-Bruijn search of more than a million path
-    extensions.  A standard bridging slot (1 M trie nodes) overflows, the walker reports kTrieFull, the library grows the pool and
+    extensions.  A standard bridging slot (256 K trie nodes) overflows, the walker reports kTrieFull, the library grows the pool and
     re-walks that contig alone -- same bytes as the reference; with the grown pool capped too, the call fails with JB_E_SCRATCH and
     says which contig."""
     case = helpers.load_golden(helpers.DEEP_BRIDGE, str(tmp_path))
