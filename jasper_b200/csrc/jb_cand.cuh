@@ -36,6 +36,7 @@ namespace jb {
 
 constexpr int kStrCap = 4 * JB_MAX_K + 64;       // every tbf / trial / check string fits (<= 3k + 8)
 constexpr int kMaxCands = 64;
+constexpr int kSmallPaths = 32;                  // base_extension: paths kept in the warp's shared memory
 constexpr int kFastBack = 64;                    // make_verdict: staged windows in front of the event ...
 constexpr int kFastWin = kFastBack + 2 * JB_MAX_K + 24;   // ... and in all
 
@@ -112,6 +113,8 @@ struct WarpScratch {         // shared memory (device) / plain struct (host)
   uint32_t pr[32];
   uint32_t flag[32];
   uint32_t ext[32];          // extension verdicts of one bridging wave
+  Key pkm[2][kSmallPaths];   // base_extension: the path list while it is short (longer ones live in the bridging slot)
+  uint32_t pnode[2][kSmallPaths];
   Cand cand[kMaxCands];
   uint16_t cand_first[kMaxCands + 1];   // first work item of every candidate
   uint32_t failmask[2];

@@ -55,6 +55,24 @@ struct Verdict2 {
 };
 static_assert(sizeof(Verdict2) == 128, "Verdict2 is meant to be 128 bytes");      // two runs end inside the same 32 positions: no verdict for either
 
+// the last staged window q in (blo, from] whose count is solid, or blo: the reference walks back one window at a time
+// (src/jasper.py:152-158), a whole weak run of k-1 windows per event; the warp looks at 32 of them per step
+JB_FREE_INLINE int last_solid_back(const WarpScratch& s, int from, int blo, int64_t solid) {
+#if defined(__CUDA_ARCH__)
+  const int lane = (int)(threadIdx.x & 31);
+  for (int top = from; top > blo; top -= 32) {
+    const int q = top - lane;
+    const unsigned m = __ballot_sync(0xffffffffu, q > blo && (int64_t)s.fc[q] >= solid);
+    if (m) return top - (__ffs((int)m) - 1);
+  }
+  return blo;
+#else
+  int jq = from;
+  while (jq > blo && (int64_t)s.fc[jq] < solid) --jq;
+  return jq;
+#endif
+}
+
 // Verdict of the weak run that contains position a_pos (pass-start coordinates; the window at a_pos is valid and weak).
 // False: no verdict (the run touches invalid windows, a contig end, or is longer than the staged window).
 template <class DB>
@@ -106,8 +124,7 @@ JB_FREE_NOINLINE bool make_verdict(const DB& db, WarpScratch& s, const uint8_t* 
   const int a = kFastBack;
   if (a >= hi_lim || (int64_t)s.fc[a] >= solid) return false;
   // src/jasper.py:152-166: back to the last solid window, forward to the next one
-  int jq = a - 1;
-  while (jq > blo && (int64_t)s.fc[jq] < solid) --jq;
+  const int jq = last_solid_back(s, a - 1, blo, solid);
   if (jq <= blo) return false;
   int gq = a;
   while (gq < hi_lim && (int64_t)s.fc[gq] < solid) ++gq;

@@ -625,44 +625,62 @@ struct Walker {
     // Codes of "ACGT" upper case for the overlap test
     const char up[4] = {'A', 'C', 'G', 'T'};
     uint32_t n_nodes = 1;            // node 0 = root = the single start path (its char is G[k-1], kept raw)
-    int cur = 0;
+    // The path list (packed last k-1 bases, trie leaf) ping-pongs between two buffers.  While it is short -- nearly always:
+    // one path, now and then a bubble -- the buffers are the warp's own shared memory (s.pkm / s.pnode); a list that has
+    // more than kSmallPaths / 4 entries at the start of a round (a round can quadruple it) moves to the bridging slot's
+    // arrays in global memory for the rest of the search.  (r2aa: every round of a one-path search paid three or four
+    // dependent round trips to global memory for a 20-byte list.)
+    Key* km_cur = s.pkm[0]; Key* km_nxt = s.pkm[1];
+    uint32_t* nd_cur = s.pnode[0]; uint32_t* nd_nxt = s.pnode[1];
+    bool small = true;
+    // positions of G that are not ACGTacgt (bit q = G[q]); k <= 48
+    uint64_t g_inv = 0;
+    for (int q = 0; q < k; ++q) if (!base_valid(G[q])) g_inv |= 1ull << q;
     // km1 at round 1 = G[1:k]
     Key km0 = {0, 0};
     for (int q = 1; q < k; ++q) km0 = key_push(km0, base_valid(G[q]) ? base_code(G[q]) : 0u, mask);
     const Key mask_km1 = key_mask(k - 1);
     km0.lo &= mask_km1.lo; km0.hi &= mask_km1.hi;
     JB_SYNC();
-    JB_LANES(l) { if (l == 0) { bs->km[0][0] = km0; bs->node[0][0] = 0; bs->trie[0] = 0; } }
+    JB_LANES(l) { if (l == 0) { km_cur[0] = km0; nd_cur[0] = 0; bs->trie[0] = 0; } }
     JB_SYNC();
     int n_paths = 1;
     for (int64_t it = 1; it < max_ext; ++it) {
       // ---- paths = [l for l in paths if len(l) > 0]
       {
-        int nxt = cur ^ 1, w = 0;
+        int w = 0;
         for (int p0 = 0; p0 < n_paths; p0 += 32) {
           JB_SYNC();
-          JB_LANES(l) { s.flag[l] = (p0 + l < n_paths && bs->node[cur][p0 + l] != kDeadNode) ? 1u : 0u; }
+          JB_LANES(l) { s.flag[l] = (p0 + l < n_paths && nd_cur[p0 + l] != kDeadNode) ? 1u : 0u; }
           JB_SYNC();
           int run = w;
           JB_LANES(l) {
             if (s.flag[l]) {
               int off = 0;
               for (int q = 0; q < l; ++q) off += (int)s.flag[q];
-              bs->km[nxt][w + off] = bs->km[cur][p0 + l];
-              bs->node[nxt][w + off] = bs->node[cur][p0 + l];
+              km_nxt[w + off] = km_cur[p0 + l];
+              nd_nxt[w + off] = nd_cur[p0 + l];
             }
           }
           for (int q = 0; q < 32; ++q) run += (int)s.flag[q];
           w = run;
           JB_SYNC();
         }
-        cur = nxt; n_paths = w;
+        { Key* tk = km_cur; km_cur = km_nxt; km_nxt = tk; uint32_t* tn = nd_cur; nd_cur = nd_nxt; nd_nxt = tn; }
+        n_paths = w;
+        if (small && n_paths > kSmallPaths / 4) {        // too long for shared memory by the end of this round: move out
+          JB_SYNC();
+          JB_LANES(l) { for (int q = l; q < n_paths; q += 32) { bs->km[0][q] = km_cur[q]; bs->node[0][q] = nd_cur[q]; } }
+          JB_SYNC();
+          km_cur = bs->km[0]; km_nxt = bs->km[1]; nd_cur = bs->node[0]; nd_nxt = bs->node[1];
+          small = false;
+        }
       }
       if (n_paths > JB_MAX_PATHS) return 0;
       if (n_paths == 0) return 0;                      // the reference keeps looping over an empty list: None
       // first invalid base of km1 = G[it:k] ++ new bases (only G can hold invalid bytes)
       int first_inv = -1;
-      for (int q = (int)it; q < k; ++q) if (!base_valid(G[q])) { first_inv = q - (int)it; break; }
+      if (it < k && (g_inv >> it)) { int q = 0; while (!((g_inv >> (it + q)) & 1ull)) ++q; first_inv = q; }
       const bool overlap_round = it >= JB_MIN_OVERLAP && it >= min_patch;
       const int last_path = n_paths;
       for (int p0 = 0; p0 < last_path; p0 += 8) {
@@ -672,7 +690,7 @@ struct Walker {
           int p = p0 + (l >> 2);
           uint32_t ok = 0;
           if (p < last_path) {
-            Key full = key_push(bs->km[cur][p], (uint32_t)(l & 3), mask);   // km1 + base: k bases
+            Key full = key_push(km_cur[p], (uint32_t)(l & 3), mask);   // km1 + base: k bases
             if (first_inv >= 0) {                                          // MerDNA stops at the invalid byte
               int keep = first_inv;                                        // bases kept
               Key trimmed = {0, 0};
@@ -692,8 +710,8 @@ struct Walker {
         lookups += 4 * np;
         for (int pp = 0; pp < np; ++pp) {
           const int p = p0 + pp;
-          const uint32_t old_node = bs->node[cur][p];
-          const Key old_km = bs->km[cur][p];
+          const uint32_t old_node = nd_cur[p];
+          const Key old_km = km_cur[p];
           int extended = 0;
           for (int j = 0; j < 4; ++j) {
             if (!s.ext[pp * 4 + j]) continue;
@@ -751,18 +769,18 @@ struct Walker {
               uint32_t nn = trie_new(old_node, (uint32_t)j, n_nodes);
               if (status) return 0;
               JB_SYNC();
-              JB_LANES(l) { if (l == 0) { bs->km[cur][p] = nk; bs->node[cur][p] = nn; } }
+              JB_LANES(l) { if (l == 0) { km_cur[p] = nk; nd_cur[p] = nn; } }
               extended = 1;
             } else {
               if (n_paths >= kPathCap) { status = JB_E_SCRATCH; return 0; }
               uint32_t nn = trie_new(old_node, (uint32_t)j, n_nodes);
               if (status) return 0;
               JB_SYNC();
-              JB_LANES(l) { if (l == 0) { bs->km[cur][n_paths] = nk; bs->node[cur][n_paths] = nn; } }
+              JB_LANES(l) { if (l == 0) { km_cur[n_paths] = nk; nd_cur[n_paths] = nn; } }
               ++n_paths;
             }
           }
-          if (!extended) { JB_SYNC(); JB_LANES(l) { if (l == 0) bs->node[cur][p] = kDeadNode; } }
+          if (!extended) { JB_SYNC(); JB_LANES(l) { if (l == 0) nd_cur[p] = kDeadNode; } }
         }
         JB_SYNC();
       }
