@@ -354,7 +354,9 @@ k_scan(const __grid_constant__ TableView t, const __grid_constant__ ScanArgs a) 
 
 // one warp per 1024-position tile; a lane takes four consecutive positions per step (one 16-byte load of counts, one 4-byte
 // load of validity bytes), eight lanes make one 32-bit word of the masks with a single warp reduction (r2d: the per-position
-// version issued 59 instructions per 32 positions and was bound by issue slots, not by memory)
+// version issued 59 instructions per 32 positions and was bound by issue slots, not by memory; r2ah: a variant that stages the
+// tile's counts in shared memory and gives every lane one whole mask word -- a quarter of the instructions, no reduction --
+// measured the same step time, 6.53 ms either way, and was dropped)
 __global__ void __launch_bounds__(256)
 k_events(const __grid_constant__ EventArgs a) {
   const uint32_t ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -412,62 +414,6 @@ k_events(const __grid_constant__ EventArgs a) {
   }
 }
 
-
-// k_events2 (r2ah): the same masks, one WORD per lane.  A warp stages its tile's counts (and the k counts in front of it) in
-// shared memory, row-padded as in k_scan; lane l then owns positions [32 l, 32 l + 32) -- one event word, one weak word, both
-// stored coalesced -- and builds them with ~10 instructions per position in its own registers: no cross-lane reduction, a
-// fifth of the instructions k_events issues per position (that kernel is bound by issue slots, not by memory).
-constexpr int kEvHalo = 64;                           // counts staged in front of the tile (>= JB_MAX_K, multiple of 32)
-constexpr int kEvRows = (kTile + kEvHalo) / 32;       // rows of 32 counts, padded to 33
-__global__ void __launch_bounds__(256)
-k_events2(const __grid_constant__ EventArgs a) {
-  __shared__ uint32_t s_all[8][kEvRows * 33];
-  const uint32_t ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (ti >= a.n_tiles) return;                        // (whole warps: no block-wide barrier below)
-  uint32_t* s_cnt = s_all[threadIdx.x >> 5];
-  const ScanTile tile = decode_tile(a.tile_first, a.n_units, ti);
-  const ScanUnit u = a.units[tile.unit];
-  const int n = (int)min((uint64_t)kTile, u.len + 1 - tile.start);  // positions of this tile
-  const uint64_t f0 = u.out_off + tile.start;                       // flat index of the tile's first position: a multiple of 32
-  const uint32_t* cnt_t = a.counts + f0;
-  const int k = a.k;
-  const bool head = tile.start == 0;                                // only the first tile of a contig holds positions < k
-  // stage counts [-kEvHalo, n): row r holds positions 32 r - kEvHalo ...; the halo of a contig's first tile is never read
-#pragma unroll 4
-  for (int r = head ? kEvHalo / 32 : 0; r < kEvRows; ++r) {
-    const int p = 32 * r - kEvHalo + lane;
-    if (p < n) s_cnt[33 * r + lane] = cnt_t[p];
-  }
-  __syncwarp();
-  const int q0 = 32 * lane;
-  if (q0 >= n) return;
-  // validity bytes of this lane's 32 positions: two 16-byte loads (the arrays are padded past the last position)
-  const uint4 o0 = *reinterpret_cast<const uint4*>(a.okb + f0 + q0), o1 = *reinterpret_cast<const uint4*>(a.okb + f0 + q0 + 16);
-  const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-  uint32_t ev = 0, wk = 0;
-  const uint32_t* row = s_cnt + 33 * (lane + kEvHalo / 32);         // this lane's counts: row[x]
-#pragma unroll
-  for (int x = 0; x < 32; ++x) {
-    const int q = q0 + x;
-    const uint32_t c = row[x];
-    const bool in = q < n;
-    const bool ok = in && ((ow[x >> 2] >> (8 * (x & 3))) & 0xFFu) != 0;
-    const bool early = head && q < k;
-    const bool low = c < a.solid_thre;
-    // the count k positions back (the 1/50 test); it reaches into the halo, never before position 0
-    const int pb = q - k + kEvHalo;                                 // >= 0 unless early
-    const uint32_t prev = early ? 0u : s_cnt[pb + (pb >> 5)];
-    if (ok && low) wk |= 1u << x;
-    if (in && (!ok || early || low || (unsigned long long)c * JB_DIVISOR < (unsigned long long)prev)) ev |= 1u << x;
-  }
-  const uint64_t f = f0 + (uint64_t)q0;
-  a.events[f >> 5] = ev; a.weak[f >> 5] = wk;
-  if (ev) {
-    const uint32_t bit = 1u << ((f >> 10) & 31);
-    if (!(atomicOr(&a.events_l1[f >> 15], bit))) atomicOr(&a.events_l2[f >> 20], 1u << ((f >> 15) & 31));   // first bit of its level-1 word
-  }
-}
 
 // ---- k_recount ----------------------------------------------------------------------------------------------------
 // 32 two-bit codes, one per lane (lane 0 = first base), as a 64-bit word with the first base most significant
@@ -732,9 +678,7 @@ int launch_scan(const TableView& view, const ScanArgs& a, cudaStream_t s) {
 
 int launch_events(const EventArgs& a, cudaStream_t s) {
   if (a.n_tiles == 0) return JB_OK;
-  static const bool v1 = getenv("JB_EVENTS_V1") != nullptr;       // A/B: the four-positions-per-lane kernel
-  if (v1) k_events<<<(a.n_tiles + 7) / 8, 256, 0, s>>>(a);
-  else k_events2<<<(a.n_tiles + 7) / 8, 256, 0, s>>>(a);
+  k_events<<<(a.n_tiles + 7) / 8, 256, 0, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(JB_E_CUDA, std::string("k_events launch: ") + cudaGetErrorString(e));
   return JB_OK;
