@@ -35,9 +35,9 @@ import threading
 
 if __package__ in (None, ""):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from jasper_b200 import batching
+    from jasper_b200 import batching, bcmath
 else:
-    from . import batching
+    from . import batching, bcmath
 
 
 def log(msg: str) -> None:
@@ -139,25 +139,8 @@ def merge_fix_csv_texts(texts):
 
 
 def q_value(wrong: int, total: int, k: int) -> str:
-    """src/jasper.sh:239-246: GNU bc's scale-limited steps, digit for digit (truncation, no rounding)."""
-    from decimal import ROUND_DOWN, Decimal, getcontext
-    getcontext().prec = 120
-
-    def trunc(x, scale):
-        return x.quantize(Decimal(1).scaleb(-scale), rounding=ROUND_DOWN)
-
-    pgood = Decimal(1) - trunc(Decimal(wrong) / Decimal(total), 10)
-    inv_k = trunc(Decimal(1) / Decimal(k), 50)
-    err = Decimal(1) - trunc(trunc(trunc(pgood.ln(), 50) * inv_k, 50).exp(), 50)
-    if not err > 0:
-        return "Inf"
-    q = trunc(trunc(Decimal(-10) * trunc(err.ln(), 5), 5) / trunc(Decimal(10).ln(), 5), 5)
-    s = format(q, "f")
-    if s.startswith("0."):
-        s = s[1:]
-    elif s.startswith("-0."):
-        s = "-" + s[2:]
-    return s
+    """src/jasper.sh:239-246: the Q text of the log, through GNU bc's fixed-point rules and math-library series (bcmath.py)."""
+    return bcmath.q_value(wrong, total, k)
 
 
 # ----------------------------------------------------------------------------- the run

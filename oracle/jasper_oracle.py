@@ -496,9 +496,9 @@ def format_tally(rep: PassReport) -> bytes:
 
 
 # ------------------------------------------------------------------------------- QV (bc emulation)
-def qv_like_bc(wrong: int, total: int, k: int) -> str:
-    """src/jasper.sh:239-246 with GNU bc fixed-point truncation emulated by `decimal`
-    (bc is absent in this image: the last printed digit is itself unverified)."""
+def qv_exact_math(wrong: int, total: int, k: int) -> str:
+    """src/jasper.sh:239-246 with exact ln / exp truncated to bc's scales (the emulation of round 1): what bc would print if its
+    l() and e() were exact.  Kept as a cross-check of qv_like_bc: the two may differ in the last digit only."""
     from decimal import Decimal, getcontext, ROUND_DOWN
     getcontext().prec = 120
 
@@ -518,9 +518,110 @@ def qv_like_bc(wrong: int, total: int, k: int) -> str:
     ln_e = trunc(err.ln(), 5)
     ln_10 = trunc(Decimal(10).ln(), 5)
     q = trunc(trunc(Decimal(-10) * ln_e, 5) / ln_10, 5)
+    return _bc_text(q)
+
+
+def _bc_text(q) -> str:
     s = format(q, "f")
     if s.startswith("0."):
         s = s[1:]
     elif s.startswith("-0."):
         s = "-" + s[2:]
     return s
+
+
+class _BcDecimal:
+    """GNU bc's arithmetic on `decimal` numbers (a number's scale = its exponent): every result truncated to the scale POSIX
+    prescribes; l() and e() are the series of bc's own math library (libmath.b of GNU bc 1.06 / 1.07, restated from its
+    published source; bc is absent here, so parity is unpinned -- DESIGN.md section 2)."""
+
+    def __init__(self):
+        from decimal import Decimal, Context, ROUND_DOWN
+        self.D = Decimal
+        self.ctx = Context(prec=400, rounding=ROUND_DOWN)
+
+    def scale_of(self, x):
+        return max(0, -x.as_tuple().exponent)
+
+    def fix(self, x, scale):
+        return x.quantize(self.D(1).scaleb(-scale), context=self.ctx)
+
+    def add(self, a, b):
+        return self.fix(self.ctx.add(a, b), max(self.scale_of(a), self.scale_of(b)))
+
+    def sub(self, a, b):
+        return self.fix(self.ctx.subtract(a, b), max(self.scale_of(a), self.scale_of(b)))
+
+    def mul(self, a, b, scale):
+        sa, sb = self.scale_of(a), self.scale_of(b)
+        return self.fix(self.ctx.multiply(a, b), min(sa + sb, max(scale, sa, sb)))
+
+    def div(self, a, b, scale):
+        return self.fix(self.ctx.divide(a, b), scale)
+
+    def sqrt(self, a, scale):
+        # (exact square root truncated: context precision 400 digits is far beyond the 56 any caller keeps)
+        return self.fix(self.ctx.sqrt(a), max(scale, self.scale_of(a)))
+
+    def l(self, x, scale):            # libmath.b: define l(x)
+        D = self.D
+        if x <= 0:
+            return self.div(self.sub(D(1), D(10) ** scale), D(1), scale)
+        z, sc = scale, scale + 6
+        f = D(2)
+        while x >= 2:
+            f = self.mul(f, D(2), sc)
+            x = self.sqrt(x, sc)
+        while x <= D("0.5"):
+            f = self.mul(f, D(2), sc)
+            x = self.sqrt(x, sc)
+        n = self.div(self.sub(x, D(1)), self.add(x, D(1)), sc)
+        v, m, i = n, self.mul(n, n, sc), 3
+        while True:
+            n = self.mul(n, m, sc)
+            e = self.div(n, D(i), sc)
+            if e == 0:
+                return self.div(self.mul(f, v, sc), D(1), z)
+            v = self.add(v, e)
+            i += 2
+
+    def e(self, x, scale):            # libmath.b: define e(x)
+        D = self.D
+        neg = x < 0
+        if neg:
+            x = -x
+        z = scale
+        n = self.add(D(6 + z), self.mul(D("0.44"), x, scale))
+        sc, f = self.scale_of(x) + 1, 0
+        while x > 1:
+            f += 1
+            x = self.div(x, D(2), sc)
+            sc += 1
+        sc = int(n)                    # `scale = n` keeps the integer part
+        v, a, d, i = self.add(D(1), x), x, 1, 2
+        while True:
+            a = self.mul(a, x, sc)
+            d *= i
+            t = self.div(a, D(d), sc)
+            if t == 0:
+                for _ in range(f):
+                    v = self.mul(v, v, sc)
+                return self.div(D(1), v, z) if neg else self.div(v, D(1), z)
+            v = self.add(v, t)
+            i += 1
+
+
+def qv_like_bc(wrong: int, total: int, k: int) -> str:
+    """src/jasper.sh:239-246: the three bc invocations, each with bc's own scale rules and math-library series."""
+    bc = _BcDecimal()
+    D = bc.D
+    if total == 0:
+        raise ReferenceCrash("divide by zero in bc")
+    pgood = bc.sub(D(1), bc.div(D(wrong), D(total), 10))                        # scale=10; 1-$wrong/$total
+    if pgood <= 0:
+        raise ReferenceCrash("bc: log of non-positive number")
+    err = bc.sub(D(1), bc.e(bc.mul(bc.l(pgood, 50), bc.div(D(1), D(k), 50), 50), 50))   # scale=50; 1 - e(l($pgood)*(1/$KMER))
+    if not err > 0:
+        return "Inf"
+    q = bc.div(bc.mul(D(-10), bc.l(err, 5), 5), bc.l(D(10), 5), 5)              # scale=5; -10*l($error_rate) / l(10)
+    return _bc_text(q)

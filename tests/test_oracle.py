@@ -182,9 +182,10 @@ def test_threshold_restatement():
 
 def test_qv_bc_emulation():
     """5021/199962 at k=25 prints 29.92812; 1200/3.1e9 at k=37 prints 79.80504."""
-    assert jo.qv_like_bc(5021, 199962, 25) == "29.92812"
-    assert jo.qv_like_bc(1200, 3100000000, 37) == "79.80504"
-    assert jo.qv_like_bc(0, 1000, 25) == "Inf"
+    for fn in (jo.qv_like_bc, jo.qv_exact_math):
+        assert fn(5021, 199962, 25) == "29.92812"
+        assert fn(1200, 3100000000, 37) == "79.80504"
+        assert fn(0, 1000, 25) == "Inf"
 
 
 def test_pairwise_shim_basic():

@@ -89,9 +89,35 @@ def test_fix_row_merge_is_the_awk_sort_chain():
     ]
 
 
-def test_q_value_matches_the_oracle_emulation():
-    for wrong, total, k in ((2270316, 63999135, 37), (1627, 63999312, 37), (0, 1000, 25), (3284, 29980, 37)):
-        assert pipeline.q_value(wrong, total, k) == jo.qv_like_bc(wrong, total, k)
+def test_q_value_matches_the_oracle_restatement_of_bc():
+    """The Q text of src/jasper.sh:239-257 goes through GNU bc; bc is absent here, so both sides restate its published rules
+    (POSIX scale rules, the series of libmath.b) -- the product on integers (jasper_b200/bcmath.py), the oracle on `decimal`
+    numbers (oracle/jasper_oracle.py).  Same text on the tallies of the bench workloads, the survey's two constants and 300
+    seeded random tallies; the exact-math emulation of round 1 may differ in the last digit only."""
+    import random
+    from jasper_b200 import bcmath
+    cases = [(2270316, 63999135, 37), (1627, 63999312, 37), (0, 1000, 25), (3284, 29980, 37), (5021, 199962, 25), (1200, 3100000000, 37),
+             (110259410, 3099993862, 37), (49274, 3099993674, 37)]
+    rng = random.Random(20)
+    for _ in range(300):
+        total = rng.randint(10 ** 3, 4 * 10 ** 9)
+        cases.append((int(total * 10 ** rng.uniform(-8, -0.5)), total, rng.choice([21, 25, 31, 37, 48])))
+    for wrong, total, k in cases:
+        got = pipeline.q_value(wrong, total, k)
+        assert got == jo.qv_like_bc(wrong, total, k), (wrong, total, k)
+        exact = jo.qv_exact_math(wrong, total, k)
+        if got != exact:
+            assert got != "Inf" and exact != "Inf" and abs(float(got) - float(exact)) < 2.5e-5, (wrong, total, k, got, exact)
+    assert pipeline.q_value(5021, 199962, 25) == "29.92812" and pipeline.q_value(1200, 3100000000, 37) == "79.80504"
+    # what `bc -l` prints at its default scale of 20 (well-known outputs of the real program)
+    B = bcmath.Bc
+    assert bcmath.e(B(1), 20).text() == "2.71828182845904523536"
+    assert bcmath.e(B(2), 20).text() == "7.38905609893065022723"
+    assert bcmath.l(B(2), 20).text() == ".69314718055994530941"
+    assert bcmath.l(B(10), 20).text() == "2.30258509299404568401"
+    assert bcmath.sqrt(B(2), 20).text() == "1.41421356237309504880"
+    assert bcmath.div(B(1), B(3), 20).text() == ".33333333333333333333" and bcmath.div(B(-1), B(3), 5).text() == "-.33333"
+    assert bcmath.mul(B.parse("1.5"), B.parse("2.25"), 0).text() == "3.37"        # scale = min(1 + 2, max(0, 1, 2))
 
 
 @pytest.mark.gpu
