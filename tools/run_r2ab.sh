@@ -1,4 +1,5 @@
 # round-2 call ab (one B200): recount that inherits the windows outside the edits + walker with job slots in blocks; tests, A/B, full bench with parity
+# (ran against the recount-inheritance experiment, commit 6b7a964, since reverted: JB_RECOUNT_NO_INHERIT / JB_RECOUNT_TEAM and the build_m3 / build_old variants exist only there)
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2ab_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2ab_pytest_gpu.log
 tail -3 gpurun_out/r2ab_pytest_gpu.log

@@ -1,4 +1,5 @@
 # round-2 call ac (one B200): the recount that inherits windows outside the edits, one warp per job -- tests that verify the
+# (ran against the recount-inheritance experiment, commit 6b7a964, since reverted: JB_RECOUNT_NO_INHERIT / JB_RECOUNT_TEAM and the build_m3 / build_old variants exist only there)
 # recount against a full scan, then an A/B of {inherit on/off} x {32, 64 threads per job} x {4, 3 CTAs per SM} on one box
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q -k "recount or fuzz or reproduces" > gpurun_out/r2ac_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2ac_pytest_gpu.log

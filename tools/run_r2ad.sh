@@ -1,4 +1,5 @@
 # round-2 call ad (one B200): two-phase k_recount_probe (stretch list in shared memory, job decoding and walk out of line),
+# (ran against the recount-inheritance experiment, commit 6b7a964, since reverted: JB_RECOUNT_NO_INHERIT / JB_RECOUNT_TEAM and the build_m3 / build_old variants exist only there)
 # make_verdict's staging loads side by side; A/B against the committed build (build_old) on the same box
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q -k "recount or fuzz or reproduces or verdict" > gpurun_out/r2ad_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2ad_pytest_gpu.log

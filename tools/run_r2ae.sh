@@ -1,4 +1,5 @@
 # round-2 call ae (one B200): bridging pool of 2048 slots x 256 K trie nodes against 512 x 1 M (k_verdicts2 spent 6 % of its
+# (build_p2048 = -DJB_POOL_SLOTS=2048 -DJB_TRIE_CAP_LOG2=18, the default since)
 # samples asleep waiting for a slot and 7.5 % of its instructions polling, r2aa); clean and dirty workload, alternating
 mkdir -p gpurun_out
 run() {  # name, workload flag, env...

@@ -1,4 +1,5 @@
 # round-2 call af (one B200): bridging search keeps a short path list in shared memory, make_verdict walks back by ballot;
+# (build_old = the commit before, built by hand into jasper_b200/build_old/)
 # A/B against the previous commit (build_old) on the same box, clean and dirty workload, then the GPU tests that reach those paths
 mkdir -p gpurun_out
 run() {  # name, workload, env...

@@ -1,4 +1,5 @@
 # round-2 call ah (one B200): k_events2 (one mask word per lane from counts staged in shared memory) against k_events
+# (k_events2 and JB_EVENTS_V1 existed only in commit eac673c, removed in 1dd74e7: see profiles/r2ah_events_ab.txt)
 # (JB_EVENTS_V1); the full GPU test suite and smoke() run on the build with k_events2
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2ah_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2ah_pytest_gpu.log
