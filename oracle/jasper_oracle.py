@@ -10,7 +10,10 @@ Jellyfish binding (oracle/_ref); tests/test_oracle.py replays every golden case 
 this file and compares fix rows, tallies and polished sequences.  One piece stays
 PARITY-UNPINNED: the fix.csv *rows* of the multi-error (`nbad > k`) branch, which the
 reference derives from Bio.pairwise2 (absent here; restated from its published algorithm in
-oracle/Bio/pairwise2.py).  Polished sequences and tallies do not depend on it.
+oracle/Bio/pairwise2.py).  Polished sequences and tallies do not depend on it.  Likewise the
+"Q value" TEXT of src/jasper.sh:239-257 (qv_like_bc below): GNU bc is absent here and its
+scale rules and math-library series are restated from its published source; the integer
+tallies it is computed from are pinned.
 
 The restatement keeps the reference's observable semantics, including the ones that look
 like accidents: Python slice clamping and negative-start wrap-around,
